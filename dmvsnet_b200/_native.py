@@ -1,0 +1,89 @@
+"""ctypes binding of libdmvs_b200.so (declared in include/dmvs_b200.h).
+
+The library is the product; there is no Python/torch fallback for any entry point.
+If it is missing or fails to load, every op raises ``NativeLibraryError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
+
+MAX_SRC = 16
+REGNET_LAYERS = 11
+LAYER_NAMES = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11", "prob")
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class ConvLayer(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p)]
+
+
+class RegnetBranch(ctypes.Structure):
+    _fields_ = [("layer", ConvLayer * REGNET_LAYERS)]
+
+
+# name -> (restype, argtypes); mirrors include/dmvs_b200.h one to one
+SIGNATURES = {
+    "dmvs_abi_version": (c_int, []),
+    "dmvs_last_error": (c_char_p, []),
+    "dmvs_launch_count": (c_ulonglong, []),
+    "dmvs_warp_corr_f32": (c_int, [c_void_p, c_longlong, POINTER(c_void_p), c_longlong, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_regnet_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "dmvs_regnet_forward_f32": (c_int, [POINTER(RegnetBranch), c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_conv3d_f32": (c_int, [c_void_p, POINTER(ConvLayer), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_depth_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_refine_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_void_p]),
+    "dmvs_hypotheses_first_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_hypotheses_next_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library once; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            "libdmvs_b200.so is not built (%s). Run `python -m dmvsnet_b200.build` (needs nvcc); "
+            "there is no CPU/PyTorch fallback for the cost-volume path." % LIB_PATH)
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover - depends on the machine
+        raise NativeLibraryError("cannot load %s: %s" % (LIB_PATH, e)) from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError("%s does not export %s (stale build?)" % (LIB_PATH, name)) from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dmvs_abi_version() != 1:
+        raise NativeLibraryError("ABI version mismatch: library %d, binding 1" % lib.dmvs_abi_version())
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().dmvs_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count() -> int:
+    return int(load().dmvs_launch_count())

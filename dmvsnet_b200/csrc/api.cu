@@ -1,0 +1,22 @@
+// Library-wide pieces of the C ABI: version, error string, launch counter.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace dmvs {
+
+std::atomic<unsigned long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace dmvs
+
+extern "C" int dmvs_abi_version(void) { return DMVS_ABI_VERSION; }
+extern "C" const char* dmvs_last_error(void) { return dmvs::g_err; }
+extern "C" unsigned long long dmvs_launch_count(void) { return dmvs::g_launches.load(); }

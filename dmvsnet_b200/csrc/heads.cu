@@ -1,0 +1,262 @@
+// E1 / E2 / S1: the pointwise kernels around the regularisation nets (sm_100a).
+//
+//   E1 depth_head      <- DepthNet.forward   networks/mvsnet.py:15-66  (+ depth_regression module.py:454-460)
+//   E2 refine_head     <- DepthNet.refine    networks/mvsnet.py:67-100
+//   S1 hypotheses_*    <- get_depth_range_samples networks/module.py:476-649 (+ F.interpolate mvsnet.py:232-233)
+//
+// All three are bandwidth kernels: one thread per pixel, x fastest so every load/store of a
+// [.., h, w] plane is a coalesced 128-byte line per warp.
+#include "common.cuh"
+
+namespace dmvs {
+
+__device__ __forceinline__ float confidence_of(const float d[4], float interval) {
+  // 2 * (sigmoid(interval / (population-std over the 4 regressed depths + 1e-5)) - 0.5)   mvsnet.py:61-62
+  const float mean = (d[0] + d[1] + d[2] + d[3]) * 0.25f;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) var += (d[i] - mean) * (d[i] - mean);
+  var *= 0.25f;
+  const float z = interval / (sqrtf(var) + 1e-5f);
+  const float sig = 1.0f / (1.0f + expf(-z));
+  return 2.0f * (sig - 0.5f);
+}
+
+// ------------------------------------------------------------------------------------------ E1
+// Softmax over D for each of the 4 logit channels, expectation against the per-pixel hypotheses,
+// then the dual-depth bookkeeping.  Logits are streamed three times (max, sum, normalise); the
+// second and third pass hit L2 (a block's working set is 128 px x 4 x D floats).
+__global__ void __launch_bounds__(128) depth_head_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
+                                                         const float* __restrict__ interval_p, float* __restrict__ prob,
+                                                         float* __restrict__ d4o, float* __restrict__ hyp_c,
+                                                         float* __restrict__ conf, int D, int h, int w) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int b = blockIdx.z;
+  const long long hw = (long long)h * w;
+  const long long pix = (long long)y * w + x;
+  const float* hp = hyp + (long long)b * D * hw + pix;
+  float d4[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float* lp = logits + ((long long)(b * 4 + c) * D) * hw + pix;
+    float mx = -INFINITY;
+    for (int k = 0; k < D; ++k) mx = fmaxf(mx, __ldg(lp + k * hw));
+    float sum = 0.f;
+    for (int k = 0; k < D; ++k) sum += expf(__ldg(lp + k * hw) - mx);
+    float acc = 0.f;
+    float* pp = prob ? prob + ((long long)(b * 4 + c) * D) * hw + pix : nullptr;
+    for (int k = 0; k < D; ++k) {
+      const float pr = expf(__ldg(lp + k * hw) - mx) / sum;
+      if (pp) pp[k * hw] = pr;
+      acc += pr * __ldg(hp + k * hw);
+    }
+    d4[c] = acc;
+    d4o[(long long)(b * 4 + c) * hw + pix] = acc;
+  }
+  // row class: 0 small, 1 huge, 2 small with doubled range, 3 huge with doubled range   mvsnet.py:25-28,33-56
+  const int r = y & 3;
+  float lo = (r & 1) ? fminf(d4[2], d4[3]) : fminf(d4[0], d4[1]);
+  float hi = (r & 1) ? fmaxf(d4[2], d4[3]) : fmaxf(d4[0], d4[1]);
+  if (r & 2) {
+    const float lo2 = 2.f * lo - hi, hi2 = 2.f * hi - lo;
+    lo = lo2;
+    hi = hi2;
+  }
+  const float s6[6] = {3.f * lo - 2.f * hi, 2.f * lo - hi, lo, hi, 2.f * hi - lo, 3.f * hi - 2.f * lo};
+  const bool low_window = ((x & 1) == 0) == ((r & 1) == 0);
+  const int off = low_window ? 0 : 2;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) hyp_c[(long long)(b * 4 + j) * hw + pix] = s6[off + j];
+  conf[(long long)b * hw + pix] = confidence_of(d4, __ldg(interval_p));
+}
+
+// ------------------------------------------------------------------------------------------ E2
+__global__ void __launch_bounds__(128) refine_head_kernel(const float* __restrict__ logits, const float* __restrict__ hyp_c,
+                                                          const float* __restrict__ interval_p, float alpha,
+                                                          float* __restrict__ depth, float* __restrict__ conf,
+                                                          float* __restrict__ d4o, int h, int w) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int b = blockIdx.z;
+  const long long hw = (long long)h * w;
+  const long long pix = (long long)y * w + x;
+  float hv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) hv[k] = __ldg(hyp_c + (long long)(b * 4 + k) * hw + pix);
+  float d4[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) l[k] = __ldg(logits + ((long long)(b * 4 + c) * 4 + k) * hw + pix) * alpha;
+    const float mx = fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3]));
+    float e[4], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      e[k] = expf(l[k] - mx);
+      sum += e[k];
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc += (e[k] / sum) * hv[k];
+    d4[c] = acc;
+    d4o[(long long)(b * 4 + c) * hw + pix] = acc;
+  }
+  // (row%2, col%2): 00 small-min, 01 small-max, 10 huge-max, 11 huge-min       mvsnet.py:80-91
+  float out;
+  if ((y & 1) == 0)
+    out = ((x & 1) == 0) ? fminf(d4[0], d4[1]) : fmaxf(d4[0], d4[1]);
+  else
+    out = ((x & 1) == 0) ? fmaxf(d4[2], d4[3]) : fminf(d4[2], d4[3]);
+  depth[(long long)b * hw + pix] = out;
+  conf[(long long)b * hw + pix] = confidence_of(d4, __ldg(interval_p));
+}
+
+// ------------------------------------------------------------------------------------------ S1, stage 0
+// torch.linspace(start, end, n): start + step*i for i < n/2, end - step*(n-1-i) otherwise.
+__device__ __forceinline__ float linspace_at(float start, float end, int n, int i) {
+  const float step = __fdiv_rn(__fsub_rn(end, start), (float)(n - 1));
+  return (i < n / 2) ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
+__global__ void __launch_bounds__(128) hypotheses_first_kernel(const float* __restrict__ depth_values, int Nd,
+                                                               float* __restrict__ hyp, float* __restrict__ interval_out,
+                                                               int D, int h, int w, int inverse) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  const int b = blockIdx.z;
+  const float lo = __ldg(depth_values + (long long)b * Nd), hi = __ldg(depth_values + (long long)b * Nd + Nd - 1);
+  // the shift uses batch 0's interval (module.py:564,603)
+  const float lo0 = __ldg(depth_values), hi0 = __ldg(depth_values + Nd - 1);
+  const float si = __fdiv_rn(__fsub_rn(hi0, lo0), (float)(D - 1));
+  if (interval_out && b == 0 && x == 0 && y == 0) {
+    float out_si = si;
+    if (inverse) {  // recomputed from the shifted ends twice (module.py:606-621); equal up to rounding
+      const float s2 = __fdiv_rn(__fsub_rn(__fsub_rn(hi0, si), __fsub_rn(lo0, si)), (float)(D - 1));
+      out_si = __fdiv_rn(__fsub_rn(__fadd_rn(hi0, s2), __fadd_rn(lo0, s2)), (float)(D - 1));
+    }
+    *interval_out = out_si;
+  }
+  if (x >= w || y >= h) return;
+  const bool even = ((x + y) & 1) == 0;
+  const long long hw = (long long)h * w;
+  float* op = hyp + (long long)b * D * hw + (long long)y * w + x;
+  if (!inverse) {
+    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1));
+    for (int k = 0; k < D; ++k) {
+      const float plane = __fadd_rn(lo, __fmul_rn((float)k, step));
+      op[k * hw] = even ? __fsub_rn(plane, si) : __fadd_rn(plane, si);
+    }
+  } else {
+    const float s2 = __fdiv_rn(__fsub_rn(__fsub_rn(hi0, si), __fsub_rn(lo0, si)), (float)(D - 1));
+    const float a = even ? __fsub_rn(lo, si) : __fadd_rn(lo, s2);
+    const float e = even ? __fsub_rn(hi, si) : __fadd_rn(hi, s2);
+    const float ia = __fdiv_rn(1.0f, a), ie = __fdiv_rn(1.0f, e);
+    for (int k = 0; k < D; ++k) op[k * hw] = __fdiv_rn(1.0f, linspace_at(ia, ie, D, k));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ S1, stages > 0
+struct RangeSample {
+  float base, step;  // linear: lo, (hi-lo)/(D-1);  inverse: 1/lo, (1/hi-1/lo)/(D-1)
+};
+
+__device__ __forceinline__ RangeSample make_range(float last, bool even, int D, float ip, int inverse) {
+  // even pixels: "_n" range [last-(D+2)/2*ip, last+(D-2)/2*ip]; odd: "_p" (module.py:476-507,525-554)
+  const float big = (float)((D + 2) * 0.5), small = (float)((D - 2) * 0.5);
+  const float lo = __fsub_rn(last, __fmul_rn(even ? big : small, ip));
+  const float hi = __fadd_rn(last, __fmul_rn(even ? small : big, ip));
+  RangeSample r;
+  if (inverse) {
+    const float ilo = __fdiv_rn(1.0f, lo), ihi = __fdiv_rn(1.0f, hi);
+    r.base = ilo;
+    r.step = __fdiv_rn(__fsub_rn(ihi, ilo), (float)(D - 1));
+  } else {
+    r.base = lo;
+    r.step = __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1));
+  }
+  return r;
+}
+
+__device__ __forceinline__ float eval_range(const RangeSample& r, int k, int inverse) {
+  const float v = __fadd_rn(r.base, __fmul_rn((float)k, r.step));
+  return inverse ? __fdiv_rn(1.0f, v) : v;
+}
+
+__global__ void __launch_bounds__(128) hypotheses_next_kernel(const float* __restrict__ last_depth,
+                                                              const float* __restrict__ interval_pixel,
+                                                              float* __restrict__ hyp, float* __restrict__ interval_out,
+                                                              int D, int h0, int w0, int h, int w, int inverse) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  const int b = blockIdx.z;
+  const float ip = __ldg(interval_pixel);
+  if (interval_out && b == 0 && x == 0 && y == 0) *interval_out = __fdiv_rn(__fmul_rn((float)D, ip), (float)(D - 1));
+  if (x >= w || y >= h) return;
+  // F.interpolate(bilinear, align_corners=False): src = scale*(dst+0.5)-0.5 clamped at 0
+  const float sy = fmaxf(__fsub_rn(__fmul_rn((float)h0 / (float)h, (float)y + 0.5f), 0.5f), 0.f);
+  const float sx = fmaxf(__fsub_rn(__fmul_rn((float)w0 / (float)w, (float)x + 0.5f), 0.5f), 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + ((y0 < h0 - 1) ? 1 : 0), x1 = x0 + ((x0 < w0 - 1) ? 1 : 0);
+  const float ly1 = sy - (float)y0, ly0 = 1.0f - ly1;
+  const float lx1 = sx - (float)x0, lx0 = 1.0f - lx1;
+  const float* lp = last_depth + (long long)b * h0 * w0;
+  const RangeSample r00 = make_range(__ldg(lp + y0 * w0 + x0), ((y0 + x0) & 1) == 0, D, ip, inverse);
+  const RangeSample r01 = make_range(__ldg(lp + y0 * w0 + x1), ((y0 + x1) & 1) == 0, D, ip, inverse);
+  const RangeSample r10 = make_range(__ldg(lp + y1 * w0 + x0), ((y1 + x0) & 1) == 0, D, ip, inverse);
+  const RangeSample r11 = make_range(__ldg(lp + y1 * w0 + x1), ((y1 + x1) & 1) == 0, D, ip, inverse);
+  const long long hw = (long long)h * w;
+  float* op = hyp + (long long)b * D * hw + (long long)y * w + x;
+  for (int k = 0; k < D; ++k) {
+    const float top = __fadd_rn(__fmul_rn(lx0, eval_range(r00, k, inverse)), __fmul_rn(lx1, eval_range(r01, k, inverse)));
+    const float bot = __fadd_rn(__fmul_rn(lx0, eval_range(r10, k, inverse)), __fmul_rn(lx1, eval_range(r11, k, inverse)));
+    op[k * hw] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+  }
+}
+
+static inline dim3 pixel_grid(int B, int h, int w) { return dim3(ceil_div(w, 32), ceil_div(h, 4), B); }
+
+}  // namespace dmvs
+
+using namespace dmvs;
+
+extern "C" int dmvs_depth_head_f32(const float* logits, const float* hyp, const float* interval, float* prob, float* d4,
+                                   float* hyp_c, float* conf, int B, int D, int h, int w, void* stream) {
+  DMVS_REQUIRE(logits && hyp && interval && d4 && hyp_c && conf, DMVS_ERR_BAD_POINTER, "depth_head: null pointer");
+  DMVS_REQUIRE(B >= 1 && B <= 65535 && D >= 1 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE, "depth_head: bad dims");
+  depth_head_kernel<<<pixel_grid(B, h, w), dim3(32, 4), 0, (cudaStream_t)stream>>>(logits, hyp, interval, prob, d4, hyp_c,
+                                                                                 conf, D, h, w);
+  return check_launch("depth_head");
+}
+
+extern "C" int dmvs_refine_head_f32(const float* logits_c, const float* hyp_c, const float* interval, float alpha,
+                                    float* depth, float* conf, float* d4, int B, int h, int w, void* stream) {
+  DMVS_REQUIRE(logits_c && hyp_c && interval && depth && conf && d4, DMVS_ERR_BAD_POINTER, "refine_head: null pointer");
+  DMVS_REQUIRE(B >= 1 && B <= 65535 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE, "refine_head: bad dims");
+  refine_head_kernel<<<pixel_grid(B, h, w), dim3(32, 4), 0, (cudaStream_t)stream>>>(logits_c, hyp_c, interval, alpha, depth,
+                                                                                  conf, d4, h, w);
+  return check_launch("refine_head");
+}
+
+extern "C" int dmvs_hypotheses_first_f32(const float* depth_values, int Nd, float* hyp, float* interval_out, int B, int D,
+                                         int h, int w, int inverse, void* stream) {
+  DMVS_REQUIRE(depth_values && hyp, DMVS_ERR_BAD_POINTER, "hypotheses_first: null pointer");
+  DMVS_REQUIRE(B >= 1 && B <= 65535 && D >= 2 && Nd >= 2 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE, "hypotheses_first: bad dims");
+  hypotheses_first_kernel<<<pixel_grid(B, h, w), dim3(32, 4), 0, (cudaStream_t)stream>>>(depth_values, Nd, hyp, interval_out,
+                                                                                       D, h, w, inverse);
+  return check_launch("hypotheses_first");
+}
+
+extern "C" int dmvs_hypotheses_next_f32(const float* last_depth, const float* interval_pixel, float* hyp,
+                                        float* interval_out, int B, int D, int h0, int w0, int h, int w, int inverse,
+                                        void* stream) {
+  DMVS_REQUIRE(last_depth && interval_pixel && hyp, DMVS_ERR_BAD_POINTER, "hypotheses_next: null pointer");
+  DMVS_REQUIRE(B >= 1 && B <= 65535 && D >= 2 && h0 >= 1 && w0 >= 1 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE,
+               "hypotheses_next: bad dims");
+  hypotheses_next_kernel<<<pixel_grid(B, h, w), dim3(32, 4), 0, (cudaStream_t)stream>>>(last_depth, interval_pixel, hyp,
+                                                                                      interval_out, D, h0, w0, h, w, inverse);
+  return check_launch("hypotheses_next");
+}

@@ -1,0 +1,107 @@
+// R1 driver: schedules the 2 x 11 layers of CostRegNet / CostRegNet_refine (reference
+// networks/module.py:342-436) on one stream.  Stateless: weights arrive as device pointers in
+// dmvs_regnet_branch, activations live in a caller-provided workspace (owned by torch's allocator).
+#include "common.cuh"
+
+namespace dmvs {
+
+int conv_layer(const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs, float* y,
+               long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
+               cudaStream_t st);
+
+namespace {
+
+struct Level {
+  int D, H, W;
+  long long vox() const { return (long long)D * H * W; }
+};
+
+struct Plan {
+  Level lv[4];
+  // element offsets into the workspace
+  long long c0, u11, c1, c2, c3, c4, c5, c6, total;
+};
+
+Plan make_plan(int refine, int B, int D, int h, int w) {
+  Plan p;
+  p.lv[0] = {D, h, w};
+  for (int k = 1; k < 4; ++k) {
+    const Level& a = p.lv[k - 1];
+    const bool flat = refine && k == 3;  // the refine net's bottleneck is 2-D (module.py:411-414)
+    p.lv[k] = {flat ? a.D : (a.D - 1) / 2 + 1, (a.H - 1) / 2 + 1, (a.W - 1) / 2 + 1};
+  }
+  long long o = 0;
+  auto take = [&](int ch, int lvl) { long long at = o; o += (long long)B * ch * p.lv[lvl].vox(); o = (o + 3) & ~3LL; return at; };
+  p.c0 = take(8, 0); p.u11 = take(8, 0);
+  p.c1 = take(16, 1); p.c2 = take(16, 1);
+  p.c3 = take(32, 2); p.c4 = take(32, 2);
+  p.c5 = take(64, 3); p.c6 = take(64, 3);
+  p.total = o;
+  return p;
+}
+
+}  // namespace
+}  // namespace dmvs
+
+using namespace dmvs;
+
+extern "C" size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, int w) {
+  if (B < 1 || D < 1 || h < 1 || w < 1) return 0;
+  return (size_t)make_plan(refine, B, D, h, w).total * sizeof(float);
+}
+
+extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, float* logits,
+                                       void* workspace, size_t workspace_bytes, int B, int D, int h, int w, void* stream) {
+  DMVS_REQUIRE(branches && cost && logits && workspace, DMVS_ERR_BAD_POINTER, "regnet: null pointer");
+  DMVS_REQUIRE(B >= 1 && h >= 8 && w >= 8 && h % 8 == 0 && w % 8 == 0, DMVS_ERR_BAD_SHAPE,
+               "regnet: h=%d w=%d must be positive multiples of 8", h, w);
+  if (refine)
+    DMVS_REQUIRE(D == 4, DMVS_ERR_BAD_SHAPE, "regnet(refine): D=%d, the refine net squeezes depth 4->2->1", D);
+  else
+    DMVS_REQUIRE(D >= 8 && D % 8 == 0, DMVS_ERR_BAD_SHAPE, "regnet: D=%d must be a positive multiple of 8", D);
+  DMVS_REQUIRE(aligned16(workspace) && aligned16(logits), DMVS_ERR_BAD_POINTER, "regnet: workspace/logits must be 16-byte aligned");
+  const Plan p = make_plan(refine, B, D, h, w);
+  DMVS_REQUIRE(workspace_bytes >= (size_t)p.total * sizeof(float), DMVS_ERR_WORKSPACE, "regnet: workspace %zu < %zu bytes",
+               workspace_bytes, (size_t)p.total * sizeof(float));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  float *c0 = ws + p.c0, *u11 = ws + p.u11, *c1 = ws + p.c1, *c2 = ws + p.c2, *c3 = ws + p.c3, *c4 = ws + p.c4, *c5 = ws + p.c5,
+        *c6 = ws + p.c6;
+  float *u9 = c1, *u7 = c3;  // c1 / c3 are dead once conv2 / conv4 have run
+  const Level *L0 = &p.lv[0], *L1 = &p.lv[1], *L2 = &p.lv[2], *L3 = &p.lv[3];
+  const long long V0 = L0->vox(), V1 = L1->vox(), V2 = L2->vox(), V3 = L3->vox();
+  const int kd_mid = refine ? 1 : 3;
+  for (int br = 0; br < 2; ++br) {
+    const dmvs_conv_layer* L = branches[br].layer;
+    int rc;
+#define RUN(...)                 \
+  rc = conv_layer(__VA_ARGS__);  \
+  if (rc != DMVS_OK) return rc;
+    //   x,  x_bs,    layer, skip, skip_bs, y,   y_bs,   B, Cin, Cout, Di,    Hi,    Wi,    kd, stride, transposed, relu
+    RUN(cost, 2 * V0, L[0], nullptr, 0, c0, 8 * V0, B, 2, 8, L0->D, L0->H, L0->W, 3, 1, 0, 1, st);
+    RUN(c0, 8 * V0, L[1], nullptr, 0, c1, 16 * V1, B, 8, 16, L0->D, L0->H, L0->W, 3, 2, 0, 1, st);
+    RUN(c1, 16 * V1, L[2], nullptr, 0, c2, 16 * V1, B, 16, 16, L1->D, L1->H, L1->W, 3, 1, 0, 1, st);
+    RUN(c2, 16 * V1, L[3], nullptr, 0, c3, 32 * V2, B, 16, 32, L1->D, L1->H, L1->W, 3, 2, 0, 1, st);
+    RUN(c3, 32 * V2, L[4], nullptr, 0, c4, 32 * V2, B, 32, 32, L2->D, L2->H, L2->W, 3, 1, 0, 1, st);
+    RUN(c4, 32 * V2, L[5], nullptr, 0, c5, 64 * V3, B, 32, 64, L2->D, L2->H, L2->W, kd_mid, 2, 0, 1, st);
+    RUN(c5, 64 * V3, L[6], nullptr, 0, c6, 64 * V3, B, 64, 64, L3->D, L3->H, L3->W, kd_mid, 1, 0, 1, st);
+    RUN(c6, 64 * V3, L[7], c4, 32 * V2, u7, 32 * V2, B, 64, 32, L3->D, L3->H, L3->W, kd_mid, 2, 1, 1, st);
+    RUN(u7, 32 * V2, L[8], c2, 16 * V1, u9, 16 * V1, B, 32, 16, L2->D, L2->H, L2->W, 3, 2, 1, 1, st);
+    RUN(u9, 16 * V1, L[9], c0, 8 * V0, u11, 8 * V0, B, 16, 8, L1->D, L1->H, L1->W, 3, 2, 1, 1, st);
+    RUN(u11, 8 * V0, L[10], nullptr, 0, logits + (long long)br * 2 * V0, 4 * V0, B, 8, 2, L0->D, L0->H, L0->W, 3, 1, 0, 0, st);
+#undef RUN
+  }
+  return DMVS_OK;
+}
+
+extern "C" int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* skip, float* y, int B, int Cin,
+                               int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, void* stream) {
+  DMVS_REQUIRE(layer, DMVS_ERR_BAD_POINTER, "conv3d: null layer");
+  DMVS_REQUIRE(Cout >= 1, DMVS_ERR_BAD_SHAPE, "conv3d: Cout=%d", Cout);
+  int Do, Ho, Wo;
+  if (transposed) { Do = (kd == 3) ? 2 * Di : Di; Ho = 2 * Hi; Wo = 2 * Wi; }
+  else if (stride == 2) { Do = (kd == 3) ? (Di - 1) / 2 + 1 : Di; Ho = (Hi - 1) / 2 + 1; Wo = (Wi - 1) / 2 + 1; }
+  else { Do = Di; Ho = Hi; Wo = Wi; }
+  const long long xbs = (long long)Cin * Di * Hi * Wi, ybs = (long long)Cout * Do * Ho * Wo;
+  return conv_layer(x, xbs, *layer, skip, ybs, y, ybs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, (cudaStream_t)stream);
+}

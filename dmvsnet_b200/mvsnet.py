@@ -1,0 +1,152 @@
+"""Host-side mirror of the reference's ``networks/mvsnet.py``: the drop-in boundary.
+
+``MVSNet(ndepths, depth_interval_ratio, ...)`` keeps the reference constructor signature
+(networks/mvsnet.py:157), ``forward(imgs, proj_matrices, depth_values) -> dict`` (mvsnet.py:188), the 787
+``state_dict`` keys and every output key (``depth``, ``photometric_confidence``, ``prob_volume``,
+``depth_sub_plus``, ``depth_values_c``, ``stage1..3`` ...), so ``model.py`` / ``loss.py`` of the reference
+work against it unchanged.  The stage loop runs on hand-written sm_100a kernels:
+
+    per stage:  S1 hypotheses -> W1 warp+corr -> R1 U-Nets -> E1 head -> W1 (D=4, *_c features) -> R1 refine -> E2
+
+Inference only (eval-mode BatchNorm); training raises.  CUDA only; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .module import CostRegNet, CostRegNet_refine, FeatureNet, _require_inference
+
+__all__ = ["MVSNet", "CostAgg", "DepthNet", "Align_Corners_Range"]
+
+Align_Corners_Range = False  # mvsnet.py:8; the fused sampler implements align_corners=False
+
+
+class DepthNet(nn.Module):
+    """Dual-depth heads.  reference networks/mvsnet.py:11-100."""
+
+    def __init__(self, mode="regression"):
+        super().__init__()
+        self.mode = mode
+        self.return_prob_volume = True  # the reference always returns it; turn off to save 4*D*h*w*4 bytes of writes
+
+    def forward(self, cost_reg, depth_values, num_depth, interval, prob_volume_init=None, stage=0):
+        prob, d4, hyp_c, conf = ops.depth_head(cost_reg, depth_values, interval, want_prob=self.return_prob_volume)
+        out = {"photometric_confidence": conf, "depth_sub_plus": d4, "depth_values_c": hyp_c, "depth_values": depth_values,
+               "interval": interval}
+        if prob is not None:
+            out["prob_volume"] = prob
+        return out
+
+    def refine(self, cost_reg, depth_values, num_depth, interval, alpha=5):
+        depth, conf, d4 = ops.refine_head(cost_reg, depth_values, interval, alpha)
+        return {"depth": depth, "photometric_confidence_refine": conf, "depth_sub_plus_refine": d4}
+
+
+class CostAgg(nn.Module):
+    """Group-wise correlation cost volume over the source views.  reference networks/mvsnet.py:102-153."""
+
+    def __init__(self, mode="variance", in_channels=None):
+        super().__init__()
+        assert mode in ("variance", "adaptive"), "Don't support {}!".format(mode)
+        if mode == "adaptive":
+            raise NotImplementedError("agg_mode='adaptive' only adds an unused weight_net in the reference (mvsnet.py:107-108)")
+        self.mode = mode
+
+    def forward(self, features, proj_matrices, depth_values, stage_idx, rt: Optional[torch.Tensor] = None):
+        """features: [ref, src1, ...] each [B,C,h,w]; proj_matrices [B,N,2,4,4]; depth_values [B,D,h,w] -> [B,2,D,h,w].
+
+        ``rt`` lets the cascade pass homographies it has already computed for this stage."""
+        if rt is None:
+            rt = ops.relative_projections(proj_matrices).to(features[0].device, non_blocking=True)
+        return ops.warp_corr(features, rt, depth_values)
+
+
+class MVSNet(nn.Module):
+    def __init__(self, ndepths, depth_interval_ratio, cr_base_chs=None, fea_mode="fpn", agg_mode="variance",
+                 depth_mode="regression", winner_take_all_to_generate_depth=True, inverse_depth=False):
+        super().__init__()
+        if cr_base_chs is None:
+            cr_base_chs = [8] * len(ndepths)
+        assert len(ndepths) == len(depth_interval_ratio)
+        self.ndepths = ndepths
+        self.depth_interval_ratio = depth_interval_ratio
+        self.fea_mode = fea_mode
+        self.cr_base_chs = cr_base_chs
+        self.num_stage = len(ndepths)
+        self.inverse_depth = inverse_depth
+
+        self.feature = FeatureNet(base_channels=8, stride=4, num_stage=self.num_stage, mode=self.fea_mode)
+        self.cost_aggregation = CostAgg(agg_mode, self.feature.out_channels)
+        self.cost_regularization = nn.ModuleList(
+            [CostRegNet(in_channels=2, base_channels=self.cr_base_chs[i], stage=i) for i in range(self.num_stage)])
+        self.cost_regularization_refine = nn.ModuleList(
+            [CostRegNet_refine(in_channels=2, base_channels=self.cr_base_chs[i], stage=i) for i in range(self.num_stage)])
+        self.DepthNet = DepthNet(depth_mode)
+
+    # ------------------------------------------------------------------ the hot path
+    def cascade(self, features: Sequence[Dict[str, torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
+                depth_values: torch.Tensor, image_hw: Sequence[int]) -> Dict[str, object]:
+        """The stage loop (reference mvsnet.py:208-258) on precomputed per-view feature dicts."""
+        _require_inference(self)
+        dev = features[0]["stage1"].device
+        # K1: all homographies up front, on the host, exactly as the reference computes them; one small upload.
+        rts = [ops.relative_projections(proj_matrices["stage%d" % (s + 1)]).to(dev, non_blocking=True)
+               for s in range(self.num_stage)]
+        depth_values = depth_values.to(dev, torch.float32)
+        depth_interval = (depth_values[0, -1] - depth_values[0, 0]) / depth_values.size(1)  # batch 0 only, mvsnet.py:196
+        outputs: Dict[str, object] = {}
+        last_depth = None
+        for s in range(self.num_stage):
+            name = "stage%d" % (s + 1)
+            scale = 2 ** (3 - s - 1)
+            shape = [int(image_hw[0]) // scale, int(image_hw[1]) // scale]
+            if s == 0:
+                hyp, interval = ops.hypotheses_first(depth_values, self.ndepths[s], shape, self.inverse_depth)
+            else:
+                hyp, interval = ops.hypotheses_next(last_depth.detach(), self.ndepths[s],
+                                                    self.depth_interval_ratio[s] * depth_interval, shape, self.inverse_depth)
+            cost = self.cost_aggregation([f[name] for f in features], None, hyp, s, rt=rts[s])
+            logits = self.cost_regularization[s](cost)
+            del cost
+            stage_out = self.DepthNet(logits, hyp, num_depth=self.ndepths[s], interval=interval, stage=s)
+            del logits
+            hyp_c = stage_out["depth_values_c"]
+            cost_c = self.cost_aggregation([f[name + "_c"] for f in features], None, hyp_c, s, rt=rts[s])
+            logits_c = self.cost_regularization_refine[s](cost_c)
+            refine_out = self.DepthNet.refine(logits_c, hyp_c, num_depth=4, interval=interval)
+            stage_out = {**refine_out, **stage_out}
+            last_depth = stage_out["depth"]
+            outputs[name] = stage_out
+            outputs.update(stage_out)
+        return outputs
+
+    def forward(self, imgs, proj_matrices, depth_values):
+        """imgs [B,N,3,H,W], proj_matrices {"stageK": [B,N,2,4,4]}, depth_values [B,Nd] -> dict (mvsnet.py:188-260)."""
+        _require_inference(self)
+        if not imgs.is_cuda:
+            raise RuntimeError("dmvsnet_b200.MVSNet runs on CUDA (sm_100a) only; use MVSNet.infer() for host buffers")
+        features = [self.feature(imgs[:, v]) for v in range(imgs.size(1))]
+        return self.cascade(features, proj_matrices, depth_values, imgs.shape[-2:])
+
+    # ------------------------------------------------------------------ host-buffer entry
+    @torch.no_grad()
+    def infer(self, imgs: torch.Tensor, proj_matrices: Dict[str, torch.Tensor], depth_values: torch.Tensor,
+              keys: Sequence[str] = ("depth", "photometric_confidence")) -> Dict[str, torch.Tensor]:
+        """Host tensors in, host tensors out: H2D of the images, forward, D2H of ``keys`` only.
+
+        What ``Model.test`` does around the network (tools.tocuda model.py:333 / tensor2numpy model.py:347), minus the
+        D2H of the three probability volumes nobody reads at test time."""
+        dev = next(self.parameters()).device
+        imgs_d = (imgs if imgs.is_pinned() else imgs.pin_memory()).to(dev, non_blocking=True) if not imgs.is_cuda else imgs
+        out = self.forward(imgs_d, proj_matrices, depth_values)
+        host = {}
+        for k in keys:
+            buf = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
+            buf.copy_(out[k], non_blocking=True)
+            host[k] = buf
+        torch.cuda.current_stream().synchronize()
+        return host

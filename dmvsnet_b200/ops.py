@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C ABI (include/dmvs_b200.h).
+
+Every function takes/returns CUDA fp32 torch tensors, allocates outputs with ``torch.empty`` (so
+the caching allocator owns all memory) and enqueues kernels on the current torch stream.
+PyTorch is plumbing here: device memory and streams.  There is no fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("dmvsnet_b200: `%s` must be a CUDA tensor - the cost-volume path has no CPU fallback" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("dmvsnet_b200: `%s` must be float32, got %s" % (name, t.dtype))
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------- projections (K1)
+def relative_projections(proj_matrices: torch.Tensor) -> torch.Tensor:
+    """[B,N,2,4,4] -> rt [B,N-1,12] (row-major rot 3x3 then trans) on the CPU, fp32.
+
+    Same operations, same order and same library calls as the reference
+    (networks/mvsnet.py:133-136 composition, networks/module.py:223-225 ``src @ inverse(ref)``) so the
+    homographies are bit-identical to the reference's CPU path.  This is 4x4 host arithmetic on
+    N matrices per stage, done once per forward for all stages; the result is uploaded once.
+    """
+    pm = proj_matrices.detach().to("cpu", torch.float32)
+    b, n = pm.shape[0], pm.shape[1]
+
+    def compose(v):
+        p = pm[:, v, 0].clone()
+        p[:, :3, :4] = torch.matmul(pm[:, v, 1, :3, :3], pm[:, v, 0, :3, :4])
+        return p
+
+    ref_inv = torch.inverse(compose(0))
+    out = torch.empty(b, n - 1, 12)
+    for v in range(1, n):
+        m = torch.matmul(compose(v), ref_inv)
+        out[:, v - 1, :9] = m[:, :3, :3].reshape(b, 9)
+        out[:, v - 1, 9:] = m[:, :3, 3]
+    return out
+
+
+# ----------------------------------------------------------------------------- W1
+def _batch_stride(t: torch.Tensor) -> int:
+    """Accept channel-sliced views of FeatureNet's output ([B,2C,h,w].split): (c,h,w) dense, any batch stride."""
+    b, c, h, w = t.shape
+    if t.stride(3) != 1 or t.stride(2) != w or t.stride(1) != h * w:
+        return -1
+    return t.stride(0) if b > 1 else c * h * w
+
+
+def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor,
+              d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """features: N x [B,C,h,w] (reference view first), rt [B,N-1,12] (device), hyp [B,D,h,w] -> cost [B,2,D,h,w]."""
+    lib = N.load()
+    ref = _req(features[0], "features[0]")
+    b, c, h, w = ref.shape
+    n_src = len(features) - 1
+    if n_src < 1 or n_src > N.MAX_SRC:
+        raise ValueError("need 1..%d source views, got %d" % (N.MAX_SRC, n_src))
+    feats = []
+    strides = []
+    for i, f in enumerate(features):
+        _req(f, "features[%d]" % i)
+        if f.shape != ref.shape:
+            raise ValueError("features[%d] has shape %s, expected %s" % (i, tuple(f.shape), tuple(ref.shape)))
+        bs = _batch_stride(f)
+        if bs < 0:
+            f = f.contiguous()
+            bs = c * h * w
+        feats.append(f)
+        strides.append(bs)
+    if len(set(strides[1:])) != 1:
+        feats = [feats[0]] + [f.contiguous() for f in feats[1:]]
+        strides = [strides[0]] + [c * h * w] * n_src
+    hyp = _req(hyp, "hyp").contiguous()
+    rt = _req(rt, "rt").contiguous()
+    d = hyp.shape[1]
+    if hyp.shape != (b, d, h, w) or rt.shape != (b, n_src, 12):
+        raise ValueError("hyp %s / rt %s do not match features %s" % (tuple(hyp.shape), tuple(rt.shape), tuple(ref.shape)))
+    if out is None:
+        out = torch.empty(b, 2, d, h, w, device=ref.device, dtype=torch.float32)
+    lo, hi = (0, d) if d_range is None else d_range
+    src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in feats[1:]])
+    rc = lib.dmvs_warp_corr_f32(feats[0].data_ptr(), strides[0], src_ptrs, strides[1], n_src, rt.data_ptr(), hyp.data_ptr(),
+                                out.data_ptr(), b, c, d, h, w, lo, hi, _stream())
+    N.check(rc, "dmvs_warp_corr_f32")
+    return out
+
+
+# ----------------------------------------------------------------------------- R1
+class PackedLayer:
+    """Device-side parameters of one conv block in the layout the kernels read."""
+
+    def __init__(self, weight: torch.Tensor, transposed: bool, bn: Optional[Tuple[torch.Tensor, ...]], eps: float = 1e-5):
+        w = weight.detach().to(torch.float32)
+        if w.dim() == 4:  # 2-D conv of the refine bottleneck -> kd = 1
+            w = w.unsqueeze(2)
+        # Conv: [Cout,Cin,kd,kh,kw]; ConvTranspose: [Cin,Cout,kd,kh,kw]  ->  [tap][Cin][Cout]
+        w = w.permute(2, 3, 4, 0, 1) if transposed else w.permute(2, 3, 4, 1, 0)
+        taps = w.shape[0] * w.shape[1] * w.shape[2]
+        cin, cout = w.shape[3], w.shape[4]
+        w = w.reshape(taps, cin, cout)
+        cout_w = (cout + 3) // 4 * 4
+        if cout_w != cout:
+            w = torch.nn.functional.pad(w, (0, cout_w - cout))
+        self.w = w.contiguous()
+        self.kd = 3 if taps == 27 else 1
+        self.cin, self.cout = cin, cout
+        self.transposed = transposed
+        if bn is not None:
+            gamma, beta, mean, var = [t.detach().to(torch.float32) for t in bn]
+            self.scale = (gamma / torch.sqrt(var + eps)).contiguous()
+            self.shift = (beta - mean * self.scale).contiguous()
+        else:
+            self.scale = self.shift = None
+
+    def c_struct(self) -> N.ConvLayer:
+        return N.ConvLayer(self.w.data_ptr(), _ptr(self.scale), _ptr(self.shift))
+
+
+def conv3d(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = True,
+           skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One conv block on a [B,Cin,D,H,W] tensor (kd = 1 layers take D as a batch of planes)."""
+    lib = N.load()
+    x = _req(x, "x").contiguous()
+    b, cin, di, hi, wi = x.shape
+    if cin != layer.cin:
+        raise ValueError("Cin mismatch: input %d, layer %d" % (cin, layer.cin))
+    if layer.transposed:
+        do, ho, wo = (2 * di if layer.kd == 3 else di), 2 * hi, 2 * wi
+    elif stride == 2:
+        do, ho, wo = ((di - 1) // 2 + 1 if layer.kd == 3 else di), (hi - 1) // 2 + 1, (wi - 1) // 2 + 1
+    else:
+        do, ho, wo = di, hi, wi
+    y = torch.empty(b, layer.cout, do, ho, wo, device=x.device, dtype=torch.float32)
+    if skip is not None:
+        skip = _req(skip, "skip").contiguous()
+        if skip.shape != y.shape:
+            raise ValueError("skip shape %s != output shape %s" % (tuple(skip.shape), tuple(y.shape)))
+    cl = layer.c_struct()
+    rc = lib.dmvs_conv3d_f32(x.data_ptr(), ctypes.byref(cl), _ptr(skip), y.data_ptr(), b, cin, layer.cout, di, hi, wi,
+                             layer.kd, 2 if layer.transposed else stride, int(layer.transposed), int(relu), _stream())
+    N.check(rc, "dmvs_conv3d_f32")
+    return y
+
+
+class PackedRegnet:
+    """Both branches of a CostRegNet / CostRegNet_refine, repacked for dmvs_regnet_forward_f32."""
+
+    def __init__(self, branches: Sequence[Sequence[PackedLayer]], refine: bool):
+        assert len(branches) == 2 and all(len(b) == N.REGNET_LAYERS for b in branches)
+        self.layers = branches  # keeps the device tensors alive
+        self.refine = refine
+        self.c_branches = (N.RegnetBranch * 2)()
+        for i, br in enumerate(branches):
+            for j, layer in enumerate(br):
+                self.c_branches[i].layer[j] = layer.c_struct()
+
+
+def regnet_forward(pack: PackedRegnet, cost: torch.Tensor) -> torch.Tensor:
+    """cost [B,2,D,h,w] -> logits [B,4,D,h,w]."""
+    lib = N.load()
+    cost = _req(cost, "cost").contiguous()
+    b, c, d, h, w = cost.shape
+    if c != 2:
+        raise ValueError("cost volume must have 2 channels, got %d" % c)
+    logits = torch.empty(b, 4, d, h, w, device=cost.device, dtype=torch.float32)
+    nbytes = lib.dmvs_regnet_workspace_bytes(int(pack.refine), b, d, h, w)
+    ws = torch.empty((nbytes + 3) // 4, device=cost.device, dtype=torch.float32)
+    rc = lib.dmvs_regnet_forward_f32(pack.c_branches, int(pack.refine), cost.data_ptr(), logits.data_ptr(), ws.data_ptr(),
+                                     ws.numel() * 4, b, d, h, w, _stream())
+    N.check(rc, "dmvs_regnet_forward_f32")
+    return logits
+
+
+# ----------------------------------------------------------------------------- E1 / E2
+def _scalar(v, device) -> torch.Tensor:
+    if isinstance(v, torch.Tensor):
+        return v.detach().to(device=device, dtype=torch.float32).reshape(1)
+    return torch.full((1,), float(v), device=device, dtype=torch.float32)
+
+
+def depth_head(logits: torch.Tensor, hyp: torch.Tensor, interval, want_prob: bool = True):
+    lib = N.load()
+    logits = _req(logits, "logits").contiguous()
+    hyp = _req(hyp, "hyp").contiguous()
+    b, c, d, h, w = logits.shape
+    if c != 4 or hyp.shape != (b, d, h, w):
+        raise ValueError("logits %s / hyp %s mismatch" % (tuple(logits.shape), tuple(hyp.shape)))
+    dev = logits.device
+    prob = torch.empty_like(logits) if want_prob else None
+    d4 = torch.empty(b, 4, h, w, device=dev)
+    hyp_c = torch.empty(b, 4, h, w, device=dev)
+    conf = torch.empty(b, h, w, device=dev)
+    iv = _scalar(interval, dev)
+    rc = lib.dmvs_depth_head_f32(logits.data_ptr(), hyp.data_ptr(), iv.data_ptr(), _ptr(prob), d4.data_ptr(), hyp_c.data_ptr(),
+                                 conf.data_ptr(), b, d, h, w, _stream())
+    N.check(rc, "dmvs_depth_head_f32")
+    return prob, d4, hyp_c, conf
+
+
+def refine_head(logits_c: torch.Tensor, hyp_c: torch.Tensor, interval, alpha: float = 5.0):
+    lib = N.load()
+    logits_c = _req(logits_c, "logits_c").contiguous()
+    hyp_c = _req(hyp_c, "hyp_c").contiguous()
+    b, c, d, h, w = logits_c.shape
+    if c != 4 or d != 4 or hyp_c.shape != (b, 4, h, w):
+        raise ValueError("refine head expects logits [B,4,4,h,w] and hypotheses [B,4,h,w]")
+    dev = logits_c.device
+    depth = torch.empty(b, h, w, device=dev)
+    conf = torch.empty(b, h, w, device=dev)
+    d4 = torch.empty(b, 4, h, w, device=dev)
+    iv = _scalar(interval, dev)
+    rc = lib.dmvs_refine_head_f32(logits_c.data_ptr(), hyp_c.data_ptr(), iv.data_ptr(), float(alpha), depth.data_ptr(),
+                                  conf.data_ptr(), d4.data_ptr(), b, h, w, _stream())
+    N.check(rc, "dmvs_refine_head_f32")
+    return depth, conf, d4
+
+
+# ----------------------------------------------------------------------------- S1
+def hypotheses_first(depth_values: torch.Tensor, ndepth: int, shape: Sequence[int], inverse: bool):
+    lib = N.load()
+    dv = _req(depth_values, "depth_values").contiguous()
+    b, nd = dv.shape
+    h, w = int(shape[0]), int(shape[1])
+    hyp = torch.empty(b, ndepth, h, w, device=dv.device)
+    interval = torch.empty((), device=dv.device)
+    rc = lib.dmvs_hypotheses_first_f32(dv.data_ptr(), nd, hyp.data_ptr(), interval.data_ptr(), b, ndepth, h, w, int(inverse),
+                                       _stream())
+    N.check(rc, "dmvs_hypotheses_first_f32")
+    return hyp, interval
+
+
+def hypotheses_next(last_depth: torch.Tensor, ndepth: int, interval_pixel, shape: Optional[Sequence[int]], inverse: bool):
+    """Per-pixel checkerboard ranges around ``last_depth`` [B,h0,w0], upsampled to ``shape`` (None: no upsample)."""
+    lib = N.load()
+    ld = _req(last_depth, "last_depth").contiguous()
+    b, h0, w0 = ld.shape
+    h, w = (h0, w0) if shape is None else (int(shape[0]), int(shape[1]))
+    hyp = torch.empty(b, ndepth, h, w, device=ld.device)
+    interval = torch.empty((), device=ld.device)
+    ip = _scalar(interval_pixel, ld.device)
+    rc = lib.dmvs_hypotheses_next_f32(ld.data_ptr(), ip.data_ptr(), hyp.data_ptr(), interval.data_ptr(), b, ndepth, h0, w0, h, w,
+                                      int(inverse), _stream())
+    N.check(rc, "dmvs_hypotheses_next_f32")
+    return hyp, interval

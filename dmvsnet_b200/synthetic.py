@@ -1,0 +1,181 @@
+"""Deterministic synthetic inputs for the cost-volume hot path.
+
+No dataset or checkpoint is available offline, so every test, fixture and
+bench line is driven from here.  The generator follows SURVEY.md §8(d):
+
+* DTU-like pinhole intrinsics scaled to the requested image size, mirroring
+  the ``/4`` at reference ``datasets/general_eval.py:69`` and the x2 / x4 per
+  stage at ``datasets/general_eval.py:190-192``;
+* a look-at camera rig (source cameras 100-300 mm off the reference, optical
+  axes through (0, 0, 680)) so that ~90 % of plane-sweep samples land inside
+  the source images;
+* ``depth_values`` in the two forms the reference datasets emit
+  (``datasets/dtu_yao.py:68,167`` linear, ``datasets/general_eval.py:178-181``
+  inverse);
+* a non-degenerate weight recipe: default-initialised
+  weights give an exactly uniform softmax, which would let any warp kernel pass
+  a final-depth parity check.
+
+Everything is generated on the CPU with a seeded ``torch.Generator`` so the
+GPU box (same image, same torch build) regenerates identical tensors and the
+committed golden outputs under ``tests/golden/`` stay valid.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+
+# camera centres of the source views in the reference frame, millimetres
+_RIG_CENTRES = [
+    (100.0, 0.0, 0.0), (-100.0, 0.0, 0.0), (0.0, 100.0, 0.0), (0.0, -100.0, 0.0),
+    (200.0, 0.0, 0.0), (-200.0, 0.0, 0.0), (-200.0, 50.0, 0.0), (200.0, -50.0, 0.0),
+    (150.0, 150.0, 0.0), (-150.0, -150.0, 0.0), (300.0, 0.0, 0.0), (-300.0, 0.0, 0.0),
+]
+_LOOK_AT = (0.0, 0.0, 680.0)
+
+FEATURE_CHANNELS = (32, 16, 8)  # stage1..3, reference networks/module.py:301-311
+
+
+def _normalise(v: torch.Tensor) -> torch.Tensor:
+    return v / v.norm()
+
+
+def look_at_extrinsic(centre: Sequence[float]) -> torch.Tensor:
+    """World(=reference camera)-to-camera 4x4 for a camera at ``centre`` looking at _LOOK_AT."""
+    c = torch.tensor(centre, dtype=torch.float64)
+    z = _normalise(torch.tensor(_LOOK_AT, dtype=torch.float64) - c)
+    x = _normalise(torch.linalg.cross(torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64), z))
+    y = torch.linalg.cross(z, x)
+    rot = torch.stack([x, y, z])
+    ext = torch.eye(4, dtype=torch.float64)
+    ext[:3, :3] = rot
+    ext[:3, 3] = -rot @ c
+    return ext.float()
+
+
+def stage1_intrinsics(height: int, width: int) -> torch.Tensor:
+    k = torch.eye(3, dtype=torch.float32)
+    k[0, 0] = k[1, 1] = 2892.33 * (width / 1600.0) / 4.0
+    k[0, 2] = 823.2 * (width / 1600.0) / 4.0
+    k[1, 2] = 619.07 * (height / 1200.0) / 4.0
+    return k
+
+
+def make_proj_matrices(height: int, width: int, num_views: int, batch: int = 1,
+                       num_stages: int = 3) -> Dict[str, torch.Tensor]:
+    """``{"stageK": [B, N, 2, 4, 4]}``; [:, :, 0] extrinsic, [:, :, 1, :3, :3] intrinsic."""
+    assert num_views - 1 <= len(_RIG_CENTRES), "rig has %d source poses" % len(_RIG_CENTRES)
+    k1 = stage1_intrinsics(height, width)
+    per_view = []
+    for v in range(num_views):
+        pm = torch.zeros(2, 4, 4)
+        pm[0] = torch.eye(4) if v == 0 else look_at_extrinsic(_RIG_CENTRES[v - 1])
+        pm[1, :3, :3] = k1
+        per_view.append(pm)
+    base = torch.stack(per_view)  # [N,2,4,4]
+    out = {}
+    for s in range(num_stages):
+        pm = base.clone()
+        pm[:, 1, :2, :] = base[:, 1, :2, :] * float(2 ** s)
+        pm = pm.unsqueeze(0).repeat(batch, 1, 1, 1, 1).contiguous()
+        if batch > 1:
+            # give later batch entries a slightly different rig so that batching bugs show
+            for b in range(1, batch):
+                pm[b, 1:, 0, :3, 3] *= (1.0 + 0.05 * b)
+        out["stage%d" % (s + 1)] = pm
+    return out
+
+
+def make_depth_values(batch: int = 1, numdepth: int = 192, inverse: bool = False,
+                      depth_min: float = 425.0, depth_interval: float = 2.5 * 1.06) -> torch.Tensor:
+    if inverse:
+        depth_end = depth_interval * numdepth + depth_min
+        inv = torch.linspace(1.0 / depth_min, 1.0 / depth_end, numdepth + 1, dtype=torch.float64)[:-1]
+        dv = (1.0 / inv).float()
+    else:
+        dv = (depth_min + depth_interval * torch.arange(numdepth, dtype=torch.float64)).float()
+    return dv.unsqueeze(0).repeat(batch, 1).contiguous()
+
+
+def make_images(height: int, width: int, num_views: int, batch: int = 1, seed: int = 0) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(batch, num_views, 3, height, width, generator=g)
+
+
+def make_stage_features(height: int, width: int, num_views: int, batch: int = 1, seed: int = 0,
+                        num_stages: int = 3, structured: bool = True) -> List[Dict[str, torch.Tensor]]:
+    """Per-view dicts ``{"stageK": [B,C,h,w], "stageK_c": [B,C,h,w]}`` like FeatureNet's output.
+
+    ``structured=True`` follows the Appendix-D recipe: one smoothed texture,
+    cropped with the disparity that a fronto-parallel plane at z0 = 650 induces
+    for an x-translated camera, plus noise - this gives a peaked cost volume.
+    ``structured=False`` is plain N(0, 1).
+    """
+    g = torch.Generator().manual_seed(seed)
+    feats: List[Dict[str, torch.Tensor]] = [dict() for _ in range(num_views)]
+    for s in range(num_stages):
+        scale = 2 ** (3 - s - 1)  # stage1 is always 1/4 resolution (reference mvsnet.py:214)
+        h, w = height // scale, width // scale
+        c = FEATURE_CHANNELS[s]
+        for suffix in ("", "_c"):
+            key = "stage%d%s" % (s + 1, suffix)
+            if not structured:
+                for v in range(num_views):
+                    feats[v][key] = torch.randn(batch, c, h, w, generator=g)
+                continue
+            pad = max(8, w // 6)
+            base = torch.randn(batch, c, h + 2, w + 2 * pad + 2, generator=g)
+            base = 3.0 * torch.nn.functional.avg_pool2d(base, 3, 1, 0)  # [B,c,h,w+2*pad]
+            f = 2892.33 * (width / 1600.0) / scale
+            for v in range(num_views):
+                tx = 0.0 if v == 0 else _RIG_CENTRES[v - 1][0]
+                # disparity of a plane at z0 = 650 for cameras converging at z = 680
+                off = int(round(f * tx * (1.0 / 650.0 - 1.0 / _LOOK_AT[2])))
+                off = max(-pad, min(pad, off))
+                crop = base[:, :, :, pad + off: pad + off + w]
+                noise = 0.0 if v == 0 else 0.1 * torch.randn(batch, c, h, w, generator=g)
+                feats[v][key] = (crop + noise).contiguous()
+    return feats
+
+
+def randomise_regnet_state(state: Dict[str, torch.Tensor], seed: int = 0, prob_gain: float = 4.0) -> Dict[str, torch.Tensor]:
+    """Non-degenerate parameters for every key of an ``MVSNet.state_dict()``.
+
+    conv weights ~ N(0, 2/fan_in) (stride-2 transposed convs: fan_in / 8 in 3-D, / 4 in 2-D),
+    BN running_mean ~ 0.2 N(0,1), running_var ~ U(0.5,1.5), gamma ~ U(0.8,1.2), beta ~ 0.1 N(0,1),
+    the two ``prob`` convs multiplied by ``prob_gain`` so the softmax over depth is peaked.
+    """
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for key in sorted(state.keys()):
+        t = state[key]
+        if key.endswith("num_batches_tracked"):
+            out[key] = torch.zeros_like(t)
+        elif key.endswith("running_mean"):
+            out[key] = 0.2 * torch.randn(t.shape, generator=g)
+        elif key.endswith("running_var"):
+            out[key] = 0.5 + torch.rand(t.shape, generator=g)
+        elif key.endswith("bn.weight"):
+            out[key] = 0.8 + 0.4 * torch.rand(t.shape, generator=g)
+        elif key.endswith("bn.bias") or key.endswith(".bias"):
+            out[key] = 0.1 * torch.randn(t.shape, generator=g)
+        elif key.endswith("weight") and t.dim() >= 4:
+            ksz = int(torch.tensor(t.shape[2:]).prod())
+            transposed = (".conv7." in key or ".conv9." in key or ".conv11." in key) and "cost_regularization" in key
+            if transposed:  # ConvTranspose weight is [Cin, Cout, k...]; each output sees k^n / 2^n taps
+                fan_in = t.shape[0] * ksz / float(2 ** (t.dim() - 2))
+            else:
+                fan_in = t.shape[1] * ksz
+            w = torch.randn(t.shape, generator=g) * math.sqrt(2.0 / fan_in)
+            if key.endswith("prob.weight"):
+                w = w * prob_gain
+            out[key] = w
+        else:
+            out[key] = t.clone()
+    return out
+
+
+def stage_shapes(height: int, width: int, num_stages: int = 3) -> List[Tuple[int, int]]:
+    return [(height // 2 ** (3 - s - 1), width // 2 ** (3 - s - 1)) for s in range(num_stages)]

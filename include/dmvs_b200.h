@@ -1,0 +1,134 @@
+/*
+ * dmvs_b200.h - C ABI of libdmvs_b200.so: the B200 (sm_100a) implementation of DMVSNet's
+ * per-stage cost-volume hot path.
+ *
+ * The reference (DIVE128/DMVSNet) is pure Python/PyTorch and has no FFI; each entry point below
+ * replaces a group of PyTorch library calls on the reference's forward path and cites them
+ * (paths relative to the reference checkout).  The reference-side binding is a ctypes stub,
+ * shown in INTEGRATION.md; dmvsnet_b200/_native.py is the one this repo ships.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers to contiguous fp32
+ *     in the reference's layouts (NCHW features, [B,D,h,w] hypotheses, [B,C,D,h,w] volumes)
+ *     unless a stride argument says otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it:
+ *     no allocation, no synchronisation, no host<->device copy inside the library;
+ *   - return 0 on success, a negative dmvs_status otherwise; dmvs_last_error() returns a
+ *     thread-local message.  Nothing throws or exits across the ABI;
+ *   - re-entrant per (device, stream); no global mutable state besides the error string.
+ */
+#ifndef DMVS_B200_H_
+#define DMVS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMVS_ABI_VERSION 1
+#define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
+
+typedef enum {
+  DMVS_OK = 0,
+  DMVS_ERR_BAD_SHAPE = -1,   /* unsupported C / D / odd sizes ... */
+  DMVS_ERR_BAD_POINTER = -2, /* null or misaligned pointer */
+  DMVS_ERR_WORKSPACE = -3,   /* workspace too small */
+  DMVS_ERR_CUDA = -4         /* a CUDA runtime call or launch failed */
+} dmvs_status;
+
+int dmvs_abi_version(void);
+const char* dmvs_last_error(void);
+/* number of kernels this library has launched from the calling process (all threads) */
+unsigned long long dmvs_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * W1  fused homography warp + 2-group correlation, summed over source views.
+ * Replaces CostAgg.forward (networks/mvsnet.py:111-153) + homo_warping (networks/module.py:212-251)
+ * i.e. torch meshgrid/matmul/div/stack, F.grid_sample(bilinear, zeros, align_corners=True),
+ * the view*view product, .mean(1) and the += over views.  The [B,C,D,h,w] warped volume and the
+ * sampling grid are never written to memory.
+ *
+ *   ref      [B,C,h,w], batch stride ref_bstride (elements)
+ *   src      host array of n_src device pointers, each [B,C,h,w] with batch stride src_bstride
+ *   rt       [B,n_src,12]: row-major 3x3 `rot` then 3 `trans` of P_src @ inv(P_ref) (module.py:223-225)
+ *   hyp      [B,D,h,w] per-pixel depth hypotheses
+ *   cost     [B,2,D,h,w]; only planes d_begin <= d < d_end are written (depth sharding)
+ *   C in {8,16,32}; group g = channels {2j+g}; cost = (2/C) * sum_j ref[2j+g] * warped[2j+g], summed over views
+ */
+int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* const* src, long long src_bstride,
+                       int n_src, const float* rt, const float* hyp, float* cost, int B, int C, int D, int h, int w,
+                       int d_begin, int d_end, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * R1  3-D regularisation U-Nets.
+ * Replaces CostRegNet / CostRegNet_refine (networks/module.py:342-436): nn.Conv3d / ConvTranspose3d /
+ * Conv2d / ConvTranspose2d + eval-mode BatchNorm + ReLU + skip adds, both branches, concatenated.
+ *
+ * One layer = conv (no bias) -> y*scale[co] + shift[co] (eval BatchNorm) -> ReLU -> (+ skip).
+ *   w      weights repacked as [tap][Cin][Cout] (tap = (kd*3+kh)*3+kw for 3x3x3, kh*3+kw for 1x3x3);
+ *          for transposed convs the tap indexes the ConvTranspose kernel as stored by PyTorch
+ *   scale, shift  [Cout] or NULL (then 1 / 0); relu != 0 applies max(.,0) before the skip add
+ */
+typedef struct {
+  const float* w;
+  const float* scale;
+  const float* shift;
+} dmvs_conv_layer;
+
+/* layers in order: conv0 conv1 conv2 conv3 conv4 conv5 conv6 conv7 conv9 conv11 prob */
+#define DMVS_REGNET_LAYERS 11
+typedef struct {
+  dmvs_conv_layer layer[DMVS_REGNET_LAYERS];
+} dmvs_regnet_branch;
+
+/* bytes of scratch dmvs_regnet_forward_f32 needs for these dimensions */
+size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, int w);
+
+/*   branches   host array of 2 (cosR_small, cosR_huge) descriptors holding device pointers
+ *   refine     0: CostRegNet_part (D % 8 == 0), 1: CostRegNet_part_refine (D == 4, 2-D bottleneck)
+ *   cost       [B,2,D,h,w]   logits [B,4,D,h,w] (channels 0,1 = small branch, 2,3 = huge branch)
+ *   h % 8 == 0 and w % 8 == 0 */
+int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, float* logits,
+                            void* workspace, size_t workspace_bytes, int B, int D, int h, int w, void* stream);
+
+/* single layers (exposed for unit tests and for callers that want their own schedule).
+ *   x [B,Cin,Di,Hi,Wi] -> y [B,Cout,Do,Ho,Wo];  kd in {1,3} (1 = the 2-D convs of the refine net)
+ *   stride in {1,2}; transposed != 0: ConvTranspose(k=3, s=2, p=1, output_padding=1), Do = 2*Di ...
+ *   skip (nullable) has the shape of y and is added after the ReLU (module.py:394-396) */
+int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* skip, float* y, int B, int Cin, int Cout,
+                    int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * E1  dual-depth head.  Replaces DepthNet.forward (networks/mvsnet.py:15-66) + depth_regression
+ * (networks/module.py:454-460): softmax over D, expectation, min/max pairs, 6-value extrapolation
+ * stacks, (row%4, col%2) selection, confidence.
+ *   logits [B,4,D,h,w], hyp [B,D,h,w], interval: device scalar
+ *   prob (nullable) [B,4,D,h,w]; d4 [B,4,h,w]; hyp_c [B,4,h,w]; conf [B,h,w]
+ */
+int dmvs_depth_head_f32(const float* logits, const float* hyp, const float* interval, float* prob, float* d4,
+                        float* hyp_c, float* conf, int B, int D, int h, int w, void* stream);
+
+/* E2  refine head.  Replaces DepthNet.refine (networks/mvsnet.py:67-100).
+ *   logits_c [B,4,4,h,w], hyp_c [B,4,h,w] -> depth [B,h,w], conf [B,h,w], d4 [B,4,h,w] */
+int dmvs_refine_head_f32(const float* logits_c, const float* hyp_c, const float* interval, float alpha, float* depth,
+                         float* conf, float* d4, int B, int h, int w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1  hypothesis sampler.  Replaces get_depth_range_samples (networks/module.py:556-649) and, for
+ * stages > 0, the F.interpolate(bilinear, align_corners=False) that follows it (mvsnet.py:232-233).
+ *
+ * stage 0: depth_values [B,Nd] -> hyp [B,D,h,w], interval_out (device scalar).
+ * stage>0: last_depth [B,h0,w0], interval_pixel (device scalar = ratio * depth_interval) ->
+ *          hyp [B,D,h,w] (sampled at (h0,w0) with the checkerboard n/p ranges, then upsampled), interval_out.
+ */
+int dmvs_hypotheses_first_f32(const float* depth_values, int Nd, float* hyp, float* interval_out, int B, int D, int h,
+                              int w, int inverse, void* stream);
+int dmvs_hypotheses_next_f32(const float* last_depth, const float* interval_pixel, float* hyp, float* interval_out,
+                             int B, int D, int h0, int w0, int h, int w, int inverse, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMVS_B200_H_ */

@@ -1,0 +1,275 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed reference outputs.
+
+Tolerances (fp32 path): cost volume 2e-5 of max|cost| (sum re-association only); single conv layers 1e-5;
+logits 1e-4 of max|logit|; regressed depths / final depth 1e-3 relative (BASELINE.json north_star), measured
+far tighter in practice - the assert message prints the achieved error.
+"""
+import pytest
+import torch
+
+from cases import CASES, case_inputs, case_state
+from conftest import load_golden, rel_linf
+from oracle import dmvs_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(native_lib):
+    return native_lib
+
+
+def cuda(t):
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ W1
+def test_warp_corr_edge_fixture():
+    from dmvsnet_b200 import ops
+    g = load_golden("warp_edge")
+    feats = [cuda(g["feat%d" % i]) for i in range(3)]
+    rt = cuda(ops.relative_projections(g["proj"]))
+    got = ops.warp_corr(feats, rt, cuda(g["hyp"]))
+    assert rel_linf(got, g["cost"]) < 2e-6
+    assert float(got[:, :, 0, :4].abs().max()) == 0.0  # behind-camera rows sample outside -> exact zeros
+
+
+@pytest.mark.parametrize("c,d,n,b,h,w", [(32, 48, 4, 1, 37, 50), (16, 32, 5, 2, 24, 40), (8, 8, 3, 1, 64, 97), (8, 4, 7, 1, 40, 33),
+                                          (32, 4, 2, 2, 16, 24), (16, 5, 3, 1, 9, 130)])
+def test_warp_corr_vs_oracle(c, d, n, b, h, w):
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(c * 1000 + d)
+    feats = [torch.randn(b, c, h, w, generator=g) for _ in range(n)]
+    proj = syn.make_proj_matrices(max(h, 8) * 4, max(w, 8) * 4, n, b, num_stages=1)["stage1"]
+    hyp = 425 + 500 * torch.rand(b, d, h, w, generator=g)
+    want = O.warp_corr(feats, proj, hyp)
+    got = ops.warp_corr([cuda(f) for f in feats], cuda(ops.relative_projections(proj)), cuda(hyp))
+    assert rel_linf(got, want) < 2e-6, rel_linf(got, want)
+
+
+def test_warp_corr_channel_sliced_views_and_plane_sharding():
+    """FeatureNet hands out channel-sliced views ([B,2C,h,w].split); depth shards must tile the full result bit-exactly."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(5)
+    b, c, h, w, d, n = 2, 16, 20, 36, 12, 3
+    both = [cuda(torch.randn(b, 2 * c, h, w, generator=g)) for _ in range(n)]
+    proj = syn.make_proj_matrices(h * 4, w * 4, n, b, num_stages=1)["stage1"]
+    rt = cuda(ops.relative_projections(proj))
+    hyp = cuda(425 + 500 * torch.rand(b, d, h, w, generator=g))
+    for half in (0, 1):
+        views = [t.split([c, c], 1)[half] for t in both]
+        full = ops.warp_corr(views, rt, hyp)
+        dense = ops.warp_corr([v.contiguous() for v in views], rt, hyp)
+        assert torch.equal(full, dense)
+        want = O.warp_corr([v.cpu().contiguous() for v in views], proj, hyp.cpu())
+        assert rel_linf(full, want) < 2e-6
+    sharded = torch.full_like(full, float("nan"))
+    for lo, hi in ((0, 5), (5, 6), (6, 12)):
+        ops.warp_corr(views, rt, hyp, d_range=(lo, hi), out=sharded)
+    assert torch.equal(sharded, full)
+
+
+def test_warp_corr_identity_homography_is_autocorrelation():
+    """src == ref and P_src == P_ref: the warp is the identity for every depth, cost = mean_j ref[2j+g]^2."""
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    b, c, h, w, d = 1, 8, 33, 47, 3
+    ref = cuda(torch.randn(b, c, h, w, generator=g))
+    rt = torch.zeros(b, 1, 12)
+    rt[:, :, 0] = rt[:, :, 4] = rt[:, :, 8] = 1.0
+    hyp = cuda(400 + 300 * torch.rand(b, d, h, w, generator=g))
+    got = ops.warp_corr([ref, ref], cuda(rt), hyp)
+    want = (ref.view(b, c // 2, 2, h, w) ** 2).mean(1).unsqueeze(2).expand(-1, -1, d, -1, -1)
+    assert rel_linf(got, want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ R1 single layers
+def _torch_block(x, w, bn, stride, transposed, relu, skip):
+    import torch.nn.functional as F
+    if w.dim() == 4:
+        xs = x.squeeze(2)
+        y = (F.conv_transpose2d(xs, w, None, stride=2, padding=1, output_padding=1) if transposed
+             else F.conv2d(xs, w, None, stride=stride, padding=1)).unsqueeze(2)
+    else:
+        y = (F.conv_transpose3d(x, w, None, stride=2, padding=1, output_padding=1) if transposed
+             else F.conv3d(x, w, None, stride=stride, padding=1))
+    if bn is not None:
+        y = F.batch_norm(y, bn[2], bn[3], bn[0], bn[1], False, 0.1, 1e-5)
+    if relu:
+        y = F.relu(y)
+    return y if skip is None else y + skip
+
+
+@pytest.mark.parametrize("cin,cout,dims,stride,transposed,two_d", [
+    (2, 8, (8, 16, 24), 1, False, False), (8, 16, (8, 16, 24), 2, False, False), (16, 16, (4, 9, 35), 1, False, False),
+    (16, 32, (4, 8, 12), 2, False, False), (32, 32, (2, 7, 33), 1, False, False), (32, 64, (2, 8, 8), 2, False, False),
+    (64, 64, (1, 5, 6), 1, False, False), (64, 32, (1, 4, 6), 2, True, False), (32, 16, (2, 8, 12), 2, True, False),
+    (16, 8, (4, 6, 37), 2, True, False), (8, 2, (8, 16, 24), 1, False, False), (32, 64, (1, 8, 12), 2, False, True),
+    (64, 64, (1, 6, 7), 1, False, True), (64, 32, (1, 4, 6), 2, True, True), (8, 16, (5, 7, 9), 2, False, False),
+    (16, 16, (3, 5, 70), 1, False, False)])
+def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d):
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    b = 2
+    x = torch.randn(b, cin, *dims, generator=g)
+    ksz = (3, 3) if two_d else (3, 3, 3)
+    w = torch.randn(*((cin, cout) if transposed else (cout, cin)), *ksz, generator=g) * (2.0 / (cin * 9 * (1 if two_d else 3))) ** 0.5
+    has_bn = cout != 2
+    bn = (0.8 + 0.4 * torch.rand(cout, generator=g), 0.1 * torch.randn(cout, generator=g), 0.2 * torch.randn(cout, generator=g),
+          0.5 + torch.rand(cout, generator=g)) if has_bn else None
+    want = _torch_block(x, w, bn, stride, transposed, has_bn, None)
+    skip = torch.randn(want.shape, generator=g) if transposed else None
+    if skip is not None:
+        want = want + skip
+    layer = ops.PackedLayer(cuda(w), transposed, tuple(cuda(t) for t in bn) if bn else None)
+    got = ops.conv3d(cuda(x), layer, stride=stride, relu=has_bn, skip=cuda(skip) if skip is not None else None)
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel_linf(got, want) < 1e-5, rel_linf(got, want)
+
+
+@pytest.mark.parametrize("refine,d,h,w,b", [(False, 8, 16, 24, 1), (False, 16, 8, 40, 2), (True, 4, 16, 24, 2), (True, 4, 40, 8, 1)])
+def test_regnet_vs_oracle(refine, d, h, w, b):
+    from dmvsnet_b200 import MVSNet, ops, synthetic as syn
+    net = MVSNet([8, 8, 8], [4, 2, 1])
+    state = syn.randomise_regnet_state(net.state_dict(), seed=2)
+    net.load_state_dict(state)
+    net = net.to(DEV).eval()
+    mod = (net.cost_regularization_refine if refine else net.cost_regularization)[1]
+    prefix = "cost_regularization%s.1." % ("_refine" if refine else "")
+    g = torch.Generator().manual_seed(d + h)
+    x = torch.randn(b, 2, d, h, w, generator=g)
+    with torch.no_grad():
+        want = O.regnet(x, O._sub(state, prefix), refine=refine)
+        got = mod(cuda(x))
+        # the single-branch layer-by-layer route must agree with the fused driver
+        small = mod.cosR_small(cuda(x))
+    assert rel_linf(got, want) < 1e-4, rel_linf(got, want)
+    assert rel_linf(small, want[:, :2]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ E1 / E2 / S1
+@pytest.mark.parametrize("d,h,w,b", [(48, 9, 37, 1), (8, 16, 33, 2), (5, 7, 5, 1)])
+def test_depth_head_vs_oracle(d, h, w, b):
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    logits = 6 * torch.randn(b, 4, d, h, w, generator=g)
+    hyp = 425 + 500 * torch.rand(b, d, h, w, generator=g).sort(1)[0]
+    interval = torch.tensor(10.77)
+    want = O.depth_head(logits, hyp, interval)
+    prob, d4, hyp_c, conf = ops.depth_head(cuda(logits), cuda(hyp), cuda(interval))
+    assert rel_linf(prob, want["prob_volume"]) < 1e-5
+    assert rel_linf(d4, want["depth_sub_plus"]) < 1e-6
+    assert rel_linf(hyp_c, want["depth_values_c"]) < 1e-5
+    assert float((conf.cpu() - want["photometric_confidence"]).abs().max()) < 1e-4
+    assert ops.depth_head(cuda(logits), cuda(hyp), 10.77, want_prob=False)[0] is None
+
+
+@pytest.mark.parametrize("h,w,b", [(9, 37, 1), (16, 33, 2)])
+def test_refine_head_vs_oracle(h, w, b):
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(h)
+    logits = 3 * torch.randn(b, 4, 4, h, w, generator=g)
+    hyp_c = 425 + 500 * torch.rand(b, 4, h, w, generator=g)
+    want = O.refine_head(logits, hyp_c, torch.tensor(5.0))
+    depth, conf, d4 = ops.refine_head(cuda(logits), cuda(hyp_c), 5.0)
+    assert rel_linf(d4, want["depth_sub_plus_refine"]) < 1e-6
+    assert rel_linf(depth, want["depth"]) < 1e-6
+    assert float((conf.cpu() - want["photometric_confidence_refine"]).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_hypotheses_first_vs_oracle(inverse):
+    from dmvsnet_b200 import ops, synthetic as syn
+    dv = syn.make_depth_values(2, 192, inverse=inverse)
+    dv[1] = dv[1] * 1.1
+    want, wi = O.depth_hypotheses(dv, 48, None, (9, 21), inverse)
+    got, gi = ops.hypotheses_first(cuda(dv), 48, (9, 21), inverse)
+    assert rel_linf(got, want) < 1e-6, rel_linf(got, want)
+    assert abs(float(gi) - float(wi)) < 1e-5 * float(wi)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("d", [32, 8])
+def test_hypotheses_next_vs_oracle(inverse, d):
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    last = 450 + 400 * torch.rand(2, 11, 14, generator=g)
+    ip = torch.tensor(2.65 * 2)
+    lo_res, wi = O.depth_hypotheses(last, d, ip, None, inverse)
+    want = O.upsample_hypotheses(lo_res, (22, 28))
+    got, gi = ops.hypotheses_next(cuda(last), d, cuda(ip), (22, 28), inverse)
+    assert rel_linf(got, want) < 1e-6, rel_linf(got, want)
+    assert abs(float(gi) - float(wi)) < 1e-6 * float(wi)
+    same, _ = ops.hypotheses_next(cuda(last), d, cuda(ip), None, inverse)
+    assert rel_linf(same, lo_res) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ whole cascade vs reference fixtures
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cascade_against_reference_fixture(name):
+    from dmvsnet_b200 import MVSNet
+    case = CASES[name]
+    gold = load_golden(name)
+    inp = case_inputs(case)
+    net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
+    net.load_state_dict(case_state(case))
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        if "features" in inp:
+            feats = [{k: cuda(v) for k, v in f.items()} for f in inp["features"]]
+            out = net.cascade(feats, inp["proj"], cuda(inp["depth_values"]), (case["H"], case["W"]))
+        else:
+            out = net(cuda(inp["imgs"]), {k: cuda(v) for k, v in inp["proj"].items()}, cuda(inp["depth_values"]))
+    report = []
+    for s in range(len(case["ndepths"])):
+        st = out["stage%d" % (s + 1)]
+        for seam, tol in (("depth_values", 1e-5), ("depth_sub_plus", 1e-3), ("depth_values_c", 1e-3), ("depth", 1e-3),
+                          ("depth_sub_plus_refine", 1e-3)):
+            want = gold["s%d_%s" % (s + 1, seam)]
+            err = float(((st[seam].cpu() - want).abs() / want.abs().clamp_min(1.0)).max())  # relative, per element
+            report.append((s + 1, seam, err))
+            assert err < tol, "stage %d %s: max relative error %.3e (tol %.0e)" % (s + 1, seam, err, tol)
+        for seam in ("photometric_confidence", "photometric_confidence_refine"):
+            err = float((st[seam].cpu() - gold["s%d_%s" % (s + 1, seam)]).abs().max())
+            assert err < 2e-3, (s + 1, seam, err)
+    for k in ("depth", "photometric_confidence", "prob_volume", "depth_values_c", "stage1"):
+        assert k in out
+    print("\n".join("stage%d %-24s max rel err %.2e" % r for r in report))
+
+
+def test_infer_from_host_buffers():
+    from dmvsnet_b200 import MVSNet
+    case = CASES["cfg1_full"]
+    gold = load_golden("cfg1_full")
+    inp = case_inputs(case)
+    net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
+    net.load_state_dict(case_state(case))
+    net = net.to(DEV).eval()
+    host = net.infer(inp["imgs"], inp["proj"], inp["depth_values"])
+    assert not host["depth"].is_cuda
+    err = float(((host["depth"] - gold["s1_depth"]).abs() / gold["s1_depth"].abs().clamp_min(1.0)).max())
+    assert err < 1e-3, err
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_dtu_stage3_properties():
+    """BASELINE config 2 at full stage-3 size (1184x1600, C=8, N=5): size-independent properties instead of the oracle."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    h, w, c, n, d = 1184, 1600, 8, 5, 8
+    g = torch.Generator().manual_seed(0)
+    feats = [cuda(torch.randn(1, c, h, w, generator=g)) for _ in range(n)]
+    proj = syn.make_proj_matrices(h, w, n, 1)["stage3"]
+    rt = cuda(ops.relative_projections(proj))
+    hyp = cuda(425 + 500 * torch.rand(1, d, h, w, generator=g))
+    full = ops.warp_corr(feats, rt, hyp)
+    assert torch.isfinite(full).all()
+    # linear in the reference features, additive over source views, plane shards tile exactly
+    scaled = ops.warp_corr([2.0 * feats[0]] + feats[1:], rt, hyp)
+    assert torch.equal(scaled, 2.0 * full)
+    parts = sum(ops.warp_corr([feats[0], feats[i + 1]], rt[:, i:i + 1].contiguous(), hyp) for i in range(n - 1))
+    assert rel_linf(parts, full) < 1e-6
+    shard = torch.empty_like(full)
+    for r in range(8):
+        ops.warp_corr(feats, rt, hyp, d_range=(r, r + 1), out=shard)
+    assert torch.equal(shard, full)

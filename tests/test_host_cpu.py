@@ -1,0 +1,170 @@
+"""Host-side logic and the C-ABI surface, without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "dmvs_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(dmvs_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    from dmvsnet_b200 import _native
+    declared = _declared_symbols()
+    assert len(declared) >= 11
+    for name in declared:
+        assert hasattr(native_lib, name), "libdmvs_b200.so does not export %s" % name
+    assert sorted(_native.SIGNATURES) == declared, "ctypes binding and header disagree"
+    assert native_lib.dmvs_abi_version() == 1
+    assert native_lib.dmvs_launch_count() == 0
+
+
+def test_library_is_sm100a_only(native_lib):
+    import subprocess
+    from dmvsnet_b200 import _native
+    out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_bad_arguments_return_errors_not_crashes(native_lib):
+    # argument validation happens before any CUDA call, so it is testable without a device
+    rc = native_lib.dmvs_warp_corr_f32(None, 0, None, 0, 1, None, None, None, 1, 32, 4, 8, 8, 0, 4, None)
+    assert rc == -2 and b"null" in native_lib.dmvs_last_error()
+    assert native_lib.dmvs_regnet_workspace_bytes(0, 1, 8, 16, 16) > 0
+    assert native_lib.dmvs_regnet_workspace_bytes(0, 0, 8, 16, 16) == 0
+
+
+def test_workspace_formula(native_lib):
+    # main net, B=1, D=8, 16x16: levels (8,16,16) (4,8,8) (2,4,4) (1,2,2)
+    v = [8 * 16 * 16, 4 * 8 * 8, 2 * 4 * 4, 1 * 2 * 2]
+    want = 4 * (2 * 8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3])
+    assert native_lib.dmvs_regnet_workspace_bytes(0, 1, 8, 16, 16) == want
+    # refine net: D 4 -> 2 -> 1, then a 2-D level
+    v = [4 * 16 * 16, 2 * 8 * 8, 1 * 4 * 4, 1 * 2 * 2]
+    want = 4 * (2 * 8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3])
+    assert native_lib.dmvs_regnet_workspace_bytes(1, 1, 4, 16, 16) == want
+
+
+def test_state_dict_contract():
+    from dmvsnet_b200 import MVSNet
+    net = MVSNet([48, 32, 8], [4, 2, 1], inverse_depth=True)
+    sd = net.state_dict()
+    assert len(sd) == 787
+    assert sum(p.numel() for p in net.parameters()) == 2673048
+    assert tuple(sd["cost_regularization.0.cosR_small.conv0.conv.weight"].shape) == (8, 2, 3, 3, 3)
+    assert tuple(sd["cost_regularization_refine.2.cosR_huge.conv5.conv.weight"].shape) == (64, 32, 3, 3)
+    assert tuple(sd["cost_regularization.1.cosR_huge.prob.weight"].shape) == (2, 8, 3, 3, 3)
+    assert tuple(sd["cost_regularization.2.cosR_small.conv7.conv.weight"].shape) == (64, 32, 3, 3, 3)
+    assert "cost_regularization.0.cosR_small.conv0.bn.num_batches_tracked" in sd
+    assert tuple(sd["feature.out1.weight"].shape) == (64, 32, 1, 1)
+
+
+@pytest.mark.reference
+def test_state_dict_identical_to_reference():
+    import contextlib
+    import io
+    import sys
+    sys.path.insert(0, "/root/reference")
+    with contextlib.redirect_stdout(io.StringIO()):
+        from networks import mvsnet as MV
+        ref = MV.MVSNet([48, 32, 8], [4, 2, 1])
+    from dmvsnet_b200 import MVSNet
+    mine = MVSNet([48, 32, 8], [4, 2, 1])
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    mine.load_state_dict(a)  # strict
+    x = torch.rand(1, 3, 64, 96)
+    ref.eval(), mine.eval()
+    with torch.no_grad():
+        fa, fb = ref.feature(x), mine.feature(x)
+    assert all(torch.equal(fa[k], fb[k]) for k in fa)
+
+
+def test_weight_packing_and_cache():
+    from dmvsnet_b200 import MVSNet, synthetic as syn
+    net = MVSNet([8, 8, 8], [4, 2, 1])
+    net.load_state_dict(syn.randomise_regnet_state(net.state_dict()))
+    net.eval()
+    reg = net.cost_regularization[1]
+    pk = reg.packed()
+    assert reg.packed() is pk  # cached
+    br = reg.cosR_huge
+    # conv2: [Cout=16,Cin=16,3,3,3] -> [27][16][16]
+    w = br.conv2.conv.weight
+    assert torch.equal(pk.layers[1][2].w[5, 3, 7], w[7, 3, 0, 1, 2])
+    # conv7 is transposed: [Cin=64,Cout=32,3,3,3] -> [27][64][32]
+    w = br.conv7.conv.weight
+    assert torch.equal(pk.layers[1][7].w[26, 60, 30], w[60, 30, 2, 2, 2])
+    # prob: Cout=2 padded to 4
+    assert tuple(pk.layers[1][10].w.shape) == (27, 8, 4) and float(pk.layers[1][10].w[:, :, 2:].abs().max()) == 0
+    bn = br.conv2.bn
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    assert torch.allclose(pk.layers[1][2].scale, scale) and torch.allclose(pk.layers[1][2].shift, bn.bias - bn.running_mean * scale)
+    # writing a parameter invalidates the cache (load_state_dict copies in place)
+    net.load_state_dict(syn.randomise_regnet_state(net.state_dict(), seed=3))
+    assert reg.packed() is not pk
+    rf = net.cost_regularization_refine[0].packed()
+    assert rf.refine and rf.layers[0][5].kd == 1 and rf.layers[0][7].kd == 1 and rf.layers[0][7].transposed
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from dmvsnet_b200 import MVSNet, ops
+    net = MVSNet([8], [4]).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.rand(1, 2, 3, 32, 32), {"stage1": torch.zeros(1, 2, 2, 4, 4)}, torch.rand(1, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.warp_corr([torch.zeros(1, 8, 8, 8)] * 2, torch.zeros(1, 1, 12), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(NotImplementedError, match="eval"):
+        MVSNet([8], [4]).train().cost_regularization[0](torch.zeros(1, 2, 8, 8, 8))
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dmvsnet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("dmvs_oracle_unused", ""), "%s mentions the oracle" % f
+
+
+def test_shim_resolves_reference_import_path():
+    import importlib
+    import sys
+    shim = os.path.join(ROOT, "dmvsnet_b200", "shim")
+    sys.path.insert(0, shim)
+    for m in [k for k in sys.modules if k == "networks" or k.startswith("networks.")]:
+        del sys.modules[m]
+    try:
+        mv = importlib.import_module("networks.mvsnet")
+        from dmvsnet_b200 import MVSNet
+        assert mv.MVSNet is MVSNet and hasattr(mv, "homo_warping") and hasattr(mv, "get_depth_range_samples")
+        md = importlib.import_module("networks.module")
+        assert hasattr(md, "CostRegNet") and hasattr(md, "FeatureNet") and hasattr(md, "CostRegNet_part_refine")
+    finally:
+        sys.path.remove(shim)
+        for m in [k for k in sys.modules if k == "networks" or k.startswith("networks.")]:
+            del sys.modules[m]
+
+
+def test_synthetic_rig_is_in_frustum():
+    """the look-at rig keeps most plane-sweep samples inside the source images."""
+    from dmvsnet_b200 import synthetic as syn
+    from oracle import dmvs_oracle as O
+    h, w = 74, 100  # DTU stage-1 grid / 4
+    proj = syn.make_proj_matrices(h * 4, w * 4, 5)["stage1"]
+    hyp, _ = O.depth_hypotheses(syn.make_depth_values(), 48, None, (h, w))
+    ref_p = O.compose_projection(proj[:, 0])
+    fr = []
+    for v in range(1, 5):
+        rot, tr = O.relative_projection(O.compose_projection(proj[:, v]), ref_p)
+        g = O.sampling_grid(rot, tr, hyp)
+        fr.append(float(((g.abs() <= 1).all(-1)).float().mean()))
+    assert min(fr) > 0.8, fr
