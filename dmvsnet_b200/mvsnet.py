@@ -89,8 +89,11 @@ class MVSNet(nn.Module):
 
     # ------------------------------------------------------------------ the hot path
     def cascade(self, features: Sequence[Dict[str, torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
-                depth_values: torch.Tensor, image_hw: Sequence[int]) -> Dict[str, object]:
-        """The stage loop (reference mvsnet.py:208-258) on precomputed per-view feature dicts."""
+                depth_values: torch.Tensor, image_hw: Sequence[int], keep_seams: bool = False) -> Dict[str, object]:
+        """The stage loop (reference mvsnet.py:208-258) on precomputed per-view feature dicts.
+
+        ``keep_seams`` additionally returns the cost volumes and logits (``_cost``, ``_logits``, ``_cost_c``,
+        ``_logits_c``) per stage, for the parity tests."""
         _require_inference(self)
         dev = features[0]["stage1"].device
         # K1: all homographies up front, on the host, exactly as the reference computes them; one small upload.
@@ -111,14 +114,16 @@ class MVSNet(nn.Module):
                                                     self.depth_interval_ratio[s] * depth_interval, shape, self.inverse_depth)
             cost = self.cost_aggregation([f[name] for f in features], None, hyp, s, rt=rts[s])
             logits = self.cost_regularization[s](cost)
-            del cost
             stage_out = self.DepthNet(logits, hyp, num_depth=self.ndepths[s], interval=interval, stage=s)
-            del logits
+            seams = {"_cost": cost, "_logits": logits} if keep_seams else {}
+            del cost, logits
             hyp_c = stage_out["depth_values_c"]
             cost_c = self.cost_aggregation([f[name + "_c"] for f in features], None, hyp_c, s, rt=rts[s])
             logits_c = self.cost_regularization_refine[s](cost_c)
             refine_out = self.DepthNet.refine(logits_c, hyp_c, num_depth=4, interval=interval)
-            stage_out = {**refine_out, **stage_out}
+            if keep_seams:
+                seams.update({"_cost_c": cost_c, "_logits_c": logits_c})
+            stage_out = {**refine_out, **stage_out, **seams}
             last_depth = stage_out["depth"]
             outputs[name] = stage_out
             outputs.update(stage_out)

@@ -14,6 +14,30 @@ import torch
 from . import _native as N
 
 
+# Optional instrumentation for bench.py: when PROFILE is a list, every op appends (tag, start_event, end_event,
+# algorithmic_bytes) recorded on the launching stream; when CAPTURE is a list, warp_corr appends (rt, hyp).
+PROFILE = None
+CAPTURE = None
+
+
+class _timed:
+    def __init__(self, tag: str, nbytes: int = 0):
+        self.tag, self.nbytes = tag, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.tag, self.e0, self.e1, self.nbytes))
+        return False
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -98,8 +122,13 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         out = torch.empty(b, 2, d, h, w, device=ref.device, dtype=torch.float32)
     lo, hi = (0, d) if d_range is None else d_range
     src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in feats[1:]])
-    rc = lib.dmvs_warp_corr_f32(feats[0].data_ptr(), strides[0], src_ptrs, strides[1], n_src, rt.data_ptr(), hyp.data_ptr(),
-                                out.data_ptr(), b, c, d, h, w, lo, hi, _stream())
+    if CAPTURE is not None:
+        CAPTURE.append((rt, hyp))
+    # algorithmic bytes: every feature map, the hypotheses and the cost volume cross HBM exactly once
+    nbytes = 4 * b * h * w * ((n_src + 1) * c + 3 * (hi - lo))
+    with _timed("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), nbytes):
+        rc = lib.dmvs_warp_corr_f32(feats[0].data_ptr(), strides[0], src_ptrs, strides[1], n_src, rt.data_ptr(), hyp.data_ptr(),
+                                    out.data_ptr(), b, c, d, h, w, lo, hi, _stream())
     N.check(rc, "dmvs_warp_corr_f32")
     return out
 
@@ -184,8 +213,9 @@ def regnet_forward(pack: PackedRegnet, cost: torch.Tensor) -> torch.Tensor:
     logits = torch.empty(b, 4, d, h, w, device=cost.device, dtype=torch.float32)
     nbytes = lib.dmvs_regnet_workspace_bytes(int(pack.refine), b, d, h, w)
     ws = torch.empty((nbytes + 3) // 4, device=cost.device, dtype=torch.float32)
-    rc = lib.dmvs_regnet_forward_f32(pack.c_branches, int(pack.refine), cost.data_ptr(), logits.data_ptr(), ws.data_ptr(),
-                                     ws.numel() * 4, b, d, h, w, _stream())
+    with _timed("regnet%s:D%d_%dx%d" % ("_refine" if pack.refine else "", d, h, w), 4 * b * 6 * d * h * w):
+        rc = lib.dmvs_regnet_forward_f32(pack.c_branches, int(pack.refine), cost.data_ptr(), logits.data_ptr(), ws.data_ptr(),
+                                         ws.numel() * 4, b, d, h, w, _stream())
     N.check(rc, "dmvs_regnet_forward_f32")
     return logits
 
@@ -210,8 +240,9 @@ def depth_head(logits: torch.Tensor, hyp: torch.Tensor, interval, want_prob: boo
     hyp_c = torch.empty(b, 4, h, w, device=dev)
     conf = torch.empty(b, h, w, device=dev)
     iv = _scalar(interval, dev)
-    rc = lib.dmvs_depth_head_f32(logits.data_ptr(), hyp.data_ptr(), iv.data_ptr(), _ptr(prob), d4.data_ptr(), hyp_c.data_ptr(),
-                                 conf.data_ptr(), b, d, h, w, _stream())
+    with _timed("head:D%d_%dx%d" % (d, h, w), 4 * b * h * w * ((9 if want_prob else 5) * d + 9)):
+        rc = lib.dmvs_depth_head_f32(logits.data_ptr(), hyp.data_ptr(), iv.data_ptr(), _ptr(prob), d4.data_ptr(), hyp_c.data_ptr(),
+                                     conf.data_ptr(), b, d, h, w, _stream())
     N.check(rc, "dmvs_depth_head_f32")
     return prob, d4, hyp_c, conf
 
@@ -228,8 +259,9 @@ def refine_head(logits_c: torch.Tensor, hyp_c: torch.Tensor, interval, alpha: fl
     conf = torch.empty(b, h, w, device=dev)
     d4 = torch.empty(b, 4, h, w, device=dev)
     iv = _scalar(interval, dev)
-    rc = lib.dmvs_refine_head_f32(logits_c.data_ptr(), hyp_c.data_ptr(), iv.data_ptr(), float(alpha), depth.data_ptr(),
-                                  conf.data_ptr(), d4.data_ptr(), b, h, w, _stream())
+    with _timed("head_refine:%dx%d" % (h, w), 4 * b * h * w * 26):
+        rc = lib.dmvs_refine_head_f32(logits_c.data_ptr(), hyp_c.data_ptr(), iv.data_ptr(), float(alpha), depth.data_ptr(),
+                                      conf.data_ptr(), d4.data_ptr(), b, h, w, _stream())
     N.check(rc, "dmvs_refine_head_f32")
     return depth, conf, d4
 
@@ -242,8 +274,9 @@ def hypotheses_first(depth_values: torch.Tensor, ndepth: int, shape: Sequence[in
     h, w = int(shape[0]), int(shape[1])
     hyp = torch.empty(b, ndepth, h, w, device=dv.device)
     interval = torch.empty((), device=dv.device)
-    rc = lib.dmvs_hypotheses_first_f32(dv.data_ptr(), nd, hyp.data_ptr(), interval.data_ptr(), b, ndepth, h, w, int(inverse),
-                                       _stream())
+    with _timed("sampler:D%d_%dx%d" % (ndepth, h, w), 4 * b * ndepth * h * w):
+        rc = lib.dmvs_hypotheses_first_f32(dv.data_ptr(), nd, hyp.data_ptr(), interval.data_ptr(), b, ndepth, h, w, int(inverse),
+                                           _stream())
     N.check(rc, "dmvs_hypotheses_first_f32")
     return hyp, interval
 
@@ -257,7 +290,8 @@ def hypotheses_next(last_depth: torch.Tensor, ndepth: int, interval_pixel, shape
     hyp = torch.empty(b, ndepth, h, w, device=ld.device)
     interval = torch.empty((), device=ld.device)
     ip = _scalar(interval_pixel, ld.device)
-    rc = lib.dmvs_hypotheses_next_f32(ld.data_ptr(), ip.data_ptr(), hyp.data_ptr(), interval.data_ptr(), b, ndepth, h0, w0, h, w,
-                                      int(inverse), _stream())
+    with _timed("sampler:D%d_%dx%d" % (ndepth, h, w), 4 * b * (ndepth * h * w + h0 * w0)):
+        rc = lib.dmvs_hypotheses_next_f32(ld.data_ptr(), ip.data_ptr(), hyp.data_ptr(), interval.data_ptr(), b, ndepth, h0, w0, h, w,
+                                          int(inverse), _stream())
     N.check(rc, "dmvs_hypotheses_next_f32")
     return hyp, interval

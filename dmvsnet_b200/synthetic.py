@@ -140,12 +140,19 @@ def make_stage_features(height: int, width: int, num_views: int, batch: int = 1,
     return feats
 
 
-def randomise_regnet_state(state: Dict[str, torch.Tensor], seed: int = 0, prob_gain: float = 4.0) -> Dict[str, torch.Tensor]:
+def randomise_regnet_state(state: Dict[str, torch.Tensor], seed: int = 0, prob_gain: float = 4.0,
+                           branch_jitter: float = 0.03) -> Dict[str, torch.Tensor]:
     """Non-degenerate parameters for every key of an ``MVSNet.state_dict()``.
 
     conv weights ~ N(0, 2/fan_in) (stride-2 transposed convs: fan_in / 8 in 3-D, / 4 in 2-D),
     BN running_mean ~ 0.2 N(0,1), running_var ~ U(0.5,1.5), gamma ~ U(0.8,1.2), beta ~ 0.1 N(0,1),
-    the two ``prob`` convs multiplied by ``prob_gain`` so the softmax over depth is peaked.
+    the ``prob`` convs multiplied by ``prob_gain`` so the softmax over depth is peaked.
+
+    A trained DMVSNet regresses four *nearby* depths per pixel (the dual-depth pairs bracket the surface);
+    four independent random nets would disagree by hundreds of millimetres and the (3a-2b ...) extrapolation
+    of networks/mvsnet.py:42-45 would throw the refine hypotheses behind the camera, which makes every
+    later seam ill-conditioned.  So, like a trained net, the four heads are made similar: ``cosR_huge`` is
+    ``cosR_small`` with a relative jitter, and output channel 1 of each ``prob`` is channel 0 with a jitter.
     """
     g = torch.Generator().manual_seed(seed)
     out = {}
@@ -171,9 +178,15 @@ def randomise_regnet_state(state: Dict[str, torch.Tensor], seed: int = 0, prob_g
             w = torch.randn(t.shape, generator=g) * math.sqrt(2.0 / fan_in)
             if key.endswith("prob.weight"):
                 w = w * prob_gain
+                w[1] = w[0] * (1.0 + 2.0 * branch_jitter * torch.randn(w[0].shape, generator=g))
             out[key] = w
         else:
             out[key] = t.clone()
+    if branch_jitter is not None:
+        for key in sorted(out.keys()):
+            if ".cosR_huge." in key and not key.endswith("num_batches_tracked"):
+                twin = out[key.replace(".cosR_huge.", ".cosR_small.")]
+                out[key] = twin * (1.0 + branch_jitter * torch.randn(twin.shape, generator=g))
     return out
 
 

@@ -27,12 +27,9 @@ REF = os.environ.get("DMVS_REFERENCE", "/root/reference")
 from dmvsnet_b200 import synthetic as syn  # noqa: E402
 from oracle import dmvs_oracle as O  # noqa: E402
 
-CASES = {
-    # name: dict(H, W, views, ndepths, ratios, inverse, batch, mode)
-    "cascade_lin": dict(H=64, W=96, views=3, ndepths=[16, 8, 8], ratios=[4, 2, 1], inverse=False, batch=1, mode="features"),
-    "cascade_inv_b2": dict(H=32, W=64, views=4, ndepths=[8, 8, 8], ratios=[4, 2, 1], inverse=True, batch=2, mode="features"),
-    "cfg1_full": dict(H=128, W=160, views=4, ndepths=[48], ratios=[4], inverse=False, batch=1, mode="images"),
-}
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cases import CASES  # noqa: E402  (shared with the tests)
+
 SEAM_KEYS = ["depth_values", "depth_sub_plus", "depth_values_c", "photometric_confidence", "depth",
              "photometric_confidence_refine", "depth_sub_plus_refine", "interval"]
 
@@ -178,7 +175,10 @@ def main():
         # softmax peakedness: confirms the weights are non-degenerate
         for s in range(len(case["ndepths"])):
             p = torch.softmax(ref["s%d_logits" % (s + 1)], 2).max(2)[0].mean()
-            print("  stage%d mean max-prob %.3f (uniform %.3f)" % (s + 1, float(p), 1.0 / case["ndepths"][s]))
+            hc = ref["s%d_depth_values_c" % (s + 1)]
+            print("  stage%d mean max-prob %.3f (uniform %.3f); refine hypotheses in [%.1f, %.1f], final depth in [%.1f, %.1f]" % (
+                s + 1, float(p), 1.0 / case["ndepths"][s], float(hc.min()), float(hc.max()),
+                float(ref["s%d_depth" % (s + 1)].min()), float(ref["s%d_depth" % (s + 1)].max())))
     np.savez(os.path.join(outdir, "warp_edge.npz"), **edge_case_warp(MV))
     print("worst oracle-vs-reference rel-Linf per seam:")
     for k, v in sorted(worst.items()):
