@@ -236,6 +236,13 @@ def run_gpu_arm(args, cfg_name):
         out = hot_step()
     del out
     barrier()
+    if args.profile_step:
+        # exactly one hot-path step between cudaProfilerStart/Stop, for `ncu --profile-from-start off`
+        torch.cuda.cudart().cudaProfilerStart()
+        hot_step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return 0
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -370,6 +377,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="dtu", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-step", action="store_true", help="run one hot-path step inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args, args.config)

@@ -89,16 +89,20 @@ class MVSNet(nn.Module):
 
     # ------------------------------------------------------------------ the hot path
     def cascade(self, features: Sequence[Dict[str, torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
-                depth_values: torch.Tensor, image_hw: Sequence[int], keep_seams: bool = False) -> Dict[str, object]:
+                depth_values: torch.Tensor, image_hw: Sequence[int], keep_seams: bool = False,
+                rts: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, object]:
         """The stage loop (reference mvsnet.py:208-258) on precomputed per-view feature dicts.
 
         ``keep_seams`` additionally returns the cost volumes and logits (``_cost``, ``_logits``, ``_cost_c``,
-        ``_logits_c``) per stage, for the parity tests."""
+        ``_logits_c``) per stage, for the parity tests.  ``rts`` overrides the per-stage homographies
+        ([B,N-1,12] each, see ops.relative_projections): fp32 ``inverse(P_ref)`` is ill-conditioned (entries ~1e5),
+        two hosts' LAPACKs differ by ~1e-4 relative in H, so cross-machine fixtures carry the reference's own H."""
         _require_inference(self)
         dev = features[0]["stage1"].device
         # K1: all homographies up front, on the host, exactly as the reference computes them; one small upload.
-        rts = [ops.relative_projections(proj_matrices["stage%d" % (s + 1)]).to(dev, non_blocking=True)
-               for s in range(self.num_stage)]
+        if rts is None:
+            rts = [ops.relative_projections(proj_matrices["stage%d" % (s + 1)]) for s in range(self.num_stage)]
+        rts = [r.to(dev, torch.float32, non_blocking=True) for r in rts]
         depth_values = depth_values.to(dev, torch.float32)
         depth_interval = (depth_values[0, -1] - depth_values[0, 0]) / depth_values.size(1)  # batch 0 only, mvsnet.py:196
         outputs: Dict[str, object] = {}

@@ -230,8 +230,14 @@ def test_cascade_against_reference_fixture(name):
         else:
             imgs = cuda(inp["imgs"])
             feats = [net.feature(imgs[:, v]) for v in range(imgs.shape[1])]
-        out = net.cascade(feats, inp["proj"], cuda(inp["depth_values"]), (case["H"], case["W"]), keep_seams=True)
-    report, bad = [], []
+        rts = [gold["s%d_rt" % (s + 1)] for s in range(len(case["ndepths"]))]
+        out = net.cascade(feats, inp["proj"], cuda(inp["depth_values"]), (case["H"], case["W"]), keep_seams=True, rts=rts)
+        # second pass with the homographies recomputed on this host: only the 1e-3 depth contract is asserted
+        own = net.cascade(feats, inp["proj"], cuda(inp["depth_values"]), (case["H"], case["W"]))
+    last = "s%d_depth" % len(case["ndepths"])
+    own_err = float(((own["depth"].cpu() - gold[last]).abs() / gold[last].abs().clamp_min(1.0)).max())
+    assert own_err < 1e-3, "host-computed homographies: final depth rel err %.2e" % own_err
+    report, bad = ["final depth with host-computed H: rel err %.2e" % own_err], []
     for s in range(len(case["ndepths"])):
         st = out["stage%d" % (s + 1)]
         for seam, tol, how in CASCADE_SEAMS:
