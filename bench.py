@@ -93,7 +93,7 @@ def cpu_band_step(state, ndepths, ratios, views, width, rows, seed=0):
     import torch
     from dmvsnet_b200 import synthetic as syn
     from oracle import dmvs_oracle as O
-    imgs = syn.make_images(rows, width, views, 1, seed=seed)
+    imgs = syn.make_images(rows, width, views, 1, seed=seed, natural=True)
     proj = syn.make_proj_matrices(rows, width, views, 1, num_stages=len(ndepths))
     dv = syn.make_depth_values(1, 192, inverse=True)
 
@@ -209,7 +209,7 @@ def run_gpu_arm(args, cfg_name):
     net.DepthNet.return_prob_volume = True  # reference default: the probability volumes are part of the output
 
     # every rank works on its own view set (independent replicas)
-    imgs_host = syn.make_images(H, W, views, 1, seed=rank).pin_memory()
+    imgs_host = syn.make_images(H, W, views, 1, seed=rank, natural=True).pin_memory()
     proj = syn.make_proj_matrices(H, W, views, 1, num_stages=len(ndepths))
     dv_host = syn.make_depth_values(1, 192, inverse=True)
     dv = dv_host.to(dev)

@@ -45,11 +45,15 @@ __device__ __forceinline__ void route_axis(float pos, int n, int& base, float& c
 
 template <int C, int DP>
 __global__ void __launch_bounds__(128, 4) warp_corr_kernel(const __grid_constant__ WarpCorrParams p) {
-  const int x = blockIdx.x * 32 + threadIdx.x;
+  // plane chunks are the fastest-varying block index: the blocks that share a pixel tile (same reference
+  // features, neighbouring source footprints) are co-resident, so the features cross L2->L1 while hot
+  // instead of being re-streamed once per chunk sweep.
+  const int tile_x = blockIdx.x / p.n_chunks;
+  const int chunk = blockIdx.x - tile_x * p.n_chunks;
+  const int x = tile_x * 32 + threadIdx.x;
   const int y = blockIdx.y * 4 + threadIdx.y;
   if (x >= p.w || y >= p.h) return;
-  const int b = blockIdx.z / p.n_chunks;
-  const int chunk = blockIdx.z - b * p.n_chunks;
+  const int b = blockIdx.z;
   const int d0 = p.d_begin + chunk * DP;
   const int hw = p.h * p.w;
   const int pix = y * p.w + x;
@@ -125,9 +129,8 @@ static int launch_warp_corr(const WarpCorrParams& p0, cudaStream_t st) {
   int dp = 4;
   while (dp > 1 && pixels * ceil_div(nd, dp) < 4LL * kNumSMs * 2048) dp >>= 1;
   p.n_chunks = ceil_div(nd, dp);
-  dim3 block(32, 4, 1), grid(ceil_div(p.w, 32), ceil_div(p.h, 4), p.B * p.n_chunks);
-  DMVS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, DMVS_ERR_BAD_SHAPE, "warp_corr: grid too large (h=%d, B*chunks=%d)", p.h,
-               (int)grid.z);
+  dim3 block(32, 4, 1), grid(ceil_div(p.w, 32) * p.n_chunks, ceil_div(p.h, 4), p.B);
+  DMVS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, DMVS_ERR_BAD_SHAPE, "warp_corr: grid too large (h=%d, B=%d)", p.h, p.B);
   if (dp == 4)
     warp_corr_kernel<C, 4><<<grid, block, 0, st>>>(p);
   else if (dp == 2)

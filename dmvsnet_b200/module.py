@@ -99,7 +99,17 @@ class FeatureNet(nn.Module):
         self.out3 = nn.Conv2d(4 * c, 2 * c, 3, padding=1, bias=False)
         self.out_channels = [4 * c, 2 * c, c]
 
+    # cuDNN may run fp32 convolutions on TF32 tensor cores (torch default); that alone moves the stage-1 cost volume by
+    # ~1e-3 relative, i.e. the whole parity budget, so it is off unless the caller opts in.
+    allow_tf32 = False
+
     def forward(self, x):
+        if x.is_cuda:
+            with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=self.allow_tf32):
+                return self._forward(x)
+        return self._forward(x)
+
+    def _forward(self, x):
         c0 = self.conv0(x)
         c1 = self.conv1(c0)
         c2 = self.conv2(c1)

@@ -99,9 +99,23 @@ def make_depth_values(batch: int = 1, numdepth: int = 192, inverse: bool = False
     return dv.unsqueeze(0).repeat(batch, 1).contiguous()
 
 
-def make_images(height: int, width: int, num_views: int, batch: int = 1, seed: int = 0) -> torch.Tensor:
+def make_images(height: int, width: int, num_views: int, batch: int = 1, seed: int = 0, natural: bool = False) -> torch.Tensor:
+    """``natural=False``: iid U[0,1) pixels (the parity fixtures).  ``natural=True``: a 1/f-like multi-octave texture shared by
+    all views plus 2 % pixel noise - photographs are spatially smooth, and so are the depth maps (hence the gather
+    locality of the stage-2/3 warps) that a network regresses from them; white noise would misrepresent both."""
     g = torch.Generator().manual_seed(seed)
-    return torch.rand(batch, num_views, 3, height, width, generator=g)
+    if not natural:
+        return torch.rand(batch, num_views, 3, height, width, generator=g)
+    tex = torch.zeros(batch, 3, height, width)
+    amp, octave = 1.0, 0
+    while (height >> octave) >= 4 and octave < 8:
+        hh, ww = max(2, height >> octave), max(2, width >> octave)
+        layer = torch.randn(batch, 3, hh, ww, generator=g)
+        tex = tex + amp * torch.nn.functional.interpolate(layer, size=(height, width), mode="bilinear", align_corners=False)
+        amp, octave = amp * 1.6, octave + 1
+    tex = (tex - tex.mean()) / (4.0 * tex.std()) + 0.5
+    views = [tex + 0.02 * torch.randn(batch, 3, height, width, generator=g) for _ in range(num_views)]
+    return torch.stack(views, 1).clamp_(0.0, 1.0).contiguous()
 
 
 def make_stage_features(height: int, width: int, num_views: int, batch: int = 1, seed: int = 0,

@@ -36,7 +36,7 @@ def test_oracle_matches_reference_fixture(name):
             # same ATen calls in the same order: bit-exact on the machine that made the fixture; other hosts may pick
             # different conv/BLAS code paths, hence a small tolerance on the float seams.
             err = rel_linf(got, want)
-            tol = 0.0 if seam in ("depth_values", "interval") and s == 0 else 2e-4
+            tol = 0.0 if seam in ("depth_values", "interval") and s == 0 else (2e-3 if "confidence" in seam else 2e-4)
             assert err <= tol, "stage %d %s: rel-Linf %.3e" % (s + 1, seam, err)
 
 
