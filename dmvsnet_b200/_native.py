@@ -12,6 +12,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ul
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
+ABI_VERSION = 2
+ENGINE_FP32, ENGINE_TENSOR = 0, 1
 MAX_SRC = 16
 REGNET_LAYERS = 11
 LAYER_NAMES = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11", "prob")
@@ -22,7 +24,7 @@ class NativeLibraryError(RuntimeError):
 
 
 class ConvLayer(ctypes.Structure):
-    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p)]
+    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("w_tc", c_void_p)]
 
 
 class RegnetBranch(ctypes.Structure):
@@ -38,9 +40,9 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_regnet_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "dmvs_regnet_forward_f32": (c_int, [POINTER(RegnetBranch), c_int, c_void_p, c_void_p, c_void_p, c_size_t,
-                                        c_int, c_int, c_int, c_int, c_void_p]),
+                                        c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_conv3d_f32": (c_int, [c_void_p, POINTER(ConvLayer), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_int, c_int, c_int, c_int, c_void_p]),
+                                c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_depth_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_refine_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
@@ -73,8 +75,8 @@ def load() -> ctypes.CDLL:
             raise NativeLibraryError("%s does not export %s (stale build?)" % (LIB_PATH, name)) from e
         fn.restype = res
         fn.argtypes = args
-    if lib.dmvs_abi_version() != 1:
-        raise NativeLibraryError("ABI version mismatch: library %d, binding 1" % lib.dmvs_abi_version())
+    if lib.dmvs_abi_version() != ABI_VERSION:
+        raise NativeLibraryError("ABI version mismatch: library %d, binding %d" % (lib.dmvs_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

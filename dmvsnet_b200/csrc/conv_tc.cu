@@ -1,0 +1,299 @@
+// R1 on 5th-generation tensor cores: implicit-GEMM 3-D convolution with tcgen05.mma (sm_100a).
+//
+// Replaces the same reference blocks as conv3d.cu (networks/module.py:120-208 inside CostRegNet_part,
+// module.py:358-436) - this is the fast path, conv3d.cu the exact-fp32 one.
+//
+// GEMM view (per CTA):  D[M = 128 voxels, N = 2*Cout] += A[M, K = 16] * B[K, N]   for every (plane, tap, channel chunk)
+//   * M: a 16(h) x 8(w) patch of one output depth plane.  UMMA row r = 8*hl + wl.
+//   * A: the input halo tile staged ONCE in shared memory in the UMMA canonical no-swizzle K-major layout
+//        "[16-byte channel chunk][voxel]": 8 consecutive voxels along w are 8 contiguous 16-byte rows (one core
+//        matrix), the 16 h-rows of the patch are SBO = (row pitch) apart, the two K chunks LBO apart.  Because rows are
+//        plain voxels, the A operand of tap (kd,kh,kw) is the SAME buffer behind a descriptor whose start address is
+//        shifted by ((kd*SH + kh)*SW + kw) voxels: im2col happens in the descriptor, no data is moved per tap.
+//   * precision: fp32 activations / weights are split x = hi + lo (two fp16).  One K = 16 step carries 8 channels as
+//        [A_hi | A_lo] against B = [[W_hi | W_lo], [W_hi | 0]], i.e. hi*hi + lo*hi in columns [0,Cout) and hi*lo in
+//        [Cout, 2*Cout); the epilogue adds the two halves.  Only lo*lo (2^-22 relative) is dropped: fp32-class accuracy
+//        at fp16 tensor rate (single-pass TF32 / BF16 breaks the 1e-3 depth contract).
+//   * D: fp32 accumulators in TMEM, one [128 x N] block per output plane of the tile; read back with tcgen05.ld
+//        for the fused eval-BatchNorm + ReLU + skip epilogue, stored straight to NCDHW.
+//
+// One elected thread issues all MMAs of a pass and commits them to an mbarrier; the CTA's other threads fill /
+// drain.  Two to four CTAs are co-resident per SM, so one CTA's fill and epilogue overlap another's MMAs.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace dmvs {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns -> 8 registers per thread (thread i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__device__ __forceinline__ void split_pack8(const float (&v)[8], uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
+    h[i] = __halves2half2(a, b);
+    l[i] = __halves2half2(__float2half_rn(v[2 * i] - __half2float(a)), __float2half_rn(v[2 * i + 1] - __half2float(b)));
+  }
+  hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]), *reinterpret_cast<uint32_t*>(&h[2]),
+                  *reinterpret_cast<uint32_t*>(&h[3]));
+  lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]), *reinterpret_cast<uint32_t*>(&l[2]),
+                  *reinterpret_cast<uint32_t*>(&l[3]));
+}
+
+// ------------------------------------------------------------------------------------------------ parameters
+struct TcParams {
+  const float* x;
+  const uint4* wtc;  // packed fp16 weights: [chunk j][tap][kc][n][8 halfs]
+  const float* scale;
+  const float* shift;
+  const float* skip;
+  float* y;
+  long long x_bs, y_bs, skip_bs;
+  int B, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo;
+  int relu;
+  int tiles_x, tiles_y, tiles_z;
+};
+
+constexpr int TC_THREADS = 256;
+constexpr int TILE_H = 16, TILE_W = 8;
+
+// ------------------------------------------------------------------------------------------------ stride-1 conv
+// CIN_P: input channels per pass (multiple of 8); NB: UMMA N = 2 * Cout_p; TD: output planes per CTA; KD in {1,3}
+template <int CIN_P, int NB, int TD, int KD>
+struct S1Cfg {
+  static constexpr int SD = (KD == 3) ? TD + 2 : TD, SH = TILE_H + 2, SW = TILE_W + 2;
+  static constexpr int SV = SD * SH * SW;        // staged voxels
+  static constexpr int CJ = CIN_P / 8;           // channel chunks per pass
+  static constexpr int TAPS = KD * 9;
+  static constexpr int A_PITCH = SV * 16;        // bytes per 16-byte-chunk plane
+  static constexpr int A_BYTES = 2 * CJ * A_PITCH;
+  static constexpr int B_TILE = 2 * NB * 16;     // bytes per (chunk, tap): [kc][n][16B]
+  static constexpr int B_BYTES = CJ * TAPS * B_TILE;
+  static constexpr int SMEM = A_BYTES + B_BYTES + 64;
+  static constexpr int TMEM_COLS = (TD * NB <= 32) ? 32 : (TD * NB <= 64) ? 64 : (TD * NB <= 128) ? 128 : (TD * NB <= 256) ? 256 : 512;
+  static_assert(TD * NB <= 512, "accumulators exceed TMEM");
+};
+
+template <int CIN_P, int NB, int TD, int KD>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_s1_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = S1Cfg<CIN_P, NB, TD, KD>;
+  constexpr int COUT_P = NB / 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::A_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + Cfg::B_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+  const int zb = blockIdx.z % p.tiles_z, b = blockIdx.z / p.tiles_z;
+  const int z0 = zb * TD;
+
+  if (warp == 0) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (tid == 32) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long iplane = (long long)p.Hi * p.Wi;
+  const int n_pass = p.Cin / CIN_P;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    if (pass > 0) mbar_wait(bar, (pass - 1) & 1);  // previous pass' MMAs have finished reading smem
+    // ---- stage the halo tile: fp32 NCDHW -> [chunk][voxel][8 x fp16], hi chunk 2j, lo chunk 2j+1
+    for (int item = tid; item < Cfg::SV * Cfg::CJ; item += TC_THREADS) {
+      const int j = item / Cfg::SV, sv = item - j * Cfg::SV;
+      const int sx = sv % Cfg::SW, sy = (sv / Cfg::SW) % Cfg::SH, sz = sv / (Cfg::SW * Cfg::SH);
+      const int ix = x0 + sx - 1, iy = y0 + sy - 1, iz = (KD == 3) ? z0 + sz - 1 : z0 + sz;
+      float v[8];
+      if (ix >= 0 && ix < p.Wi && iy >= 0 && iy < p.Hi && iz >= 0 && iz < p.Di) {
+        const float* src = p.x + (long long)b * p.x_bs + ((long long)(pass * CIN_P + j * 8) * p.Di + iz) * iplane +
+                           (long long)iy * p.Wi + ix;
+        const long long cs = (long long)p.Di * iplane;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c * cs);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = 0.f;
+      }
+      uint4 hi, lo;
+      split_pack8(v, hi, lo);
+      *reinterpret_cast<uint4*>(sA + (2 * j) * Cfg::A_PITCH + sv * 16) = hi;
+      *reinterpret_cast<uint4*>(sA + (2 * j + 1) * Cfg::A_PITCH + sv * 16) = lo;
+    }
+    // ---- weights of this pass: a contiguous byte range of the packed image
+    {
+      const uint4* wsrc = p.wtc + (size_t)pass * (Cfg::B_BYTES / 16);
+      uint4* wdst = reinterpret_cast<uint4*>(sB);
+      for (int i = tid; i < Cfg::B_BYTES / 16; i += TC_THREADS) wdst[i] = __ldg(wsrc + i);
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc(NB);
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll 1
+      for (int t = 0; t < TD; ++t) {
+#pragma unroll 1
+        for (int tap = 0; tap < Cfg::TAPS; ++tap) {
+          const int kd = (KD == 3) ? tap / 9 : 0, kh = (tap % 9) / 3, kw = tap % 3;
+          const uint32_t voff = (uint32_t)(((t + kd) * Cfg::SH + kh) * Cfg::SW + kw) * 16u;
+#pragma unroll
+          for (int j = 0; j < Cfg::CJ; ++j) {
+            const uint64_t ad = make_desc(a0 + (2 * j) * Cfg::A_PITCH + voff, Cfg::A_PITCH, Cfg::SW * 16);
+            const uint64_t bd = make_desc(b0 + (j * Cfg::TAPS + tap) * Cfg::B_TILE, NB * 16, 128);
+            umma_f16(tmem_base + t * NB, ad, bd, idesc, (pass > 0 || tap > 0 || j > 0) ? 1u : 0u);
+          }
+        }
+      }
+      umma_commit(bar);
+    }
+  }
+  mbar_wait(bar, (n_pass - 1) & 1);
+  tc_fence_after();
+
+  // ---- epilogue: TMEM -> registers -> BN / ReLU / skip -> NCDHW.  Warp w reads TMEM lanes 32*(w%4)..+31.
+  const int q = warp & 3;
+  const int hl = q * 4 + (lane >> 3), wl = lane & 7;
+  const int oy = y0 + hl, ox = x0 + wl;
+  const bool in_img = (oy < p.Ho) && (ox < p.Wo);
+  const long long oplane = (long long)p.Ho * p.Wo;
+  for (int t = (warp >> 2); t < TD; t += 2) {
+    const int oz = z0 + t;
+    if (oz >= p.Do) break;  // warp-uniform
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + t * NB;
+#pragma unroll 1
+    for (int c0 = 0; c0 < COUT_P; c0 += 8) {
+      float hi8[8], lo8[8];
+      tmem_ld8(taddr + c0, hi8);
+      tmem_ld8(taddr + COUT_P + c0, lo8);
+      if (!in_img) continue;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int co = c0 + c;
+        if (co >= p.Cout) break;
+        float v = hi8[c] + lo8[c];
+        if (p.scale) v = fmaf(v, __ldg(p.scale + co), __ldg(p.shift + co));
+        if (p.relu) v = fmaxf(v, 0.f);
+        const long long off = ((long long)co * p.Do + oz) * oplane + (long long)oy * p.Wo + ox;
+        if (p.skip) v += __ldg(p.skip + (long long)b * p.skip_bs + off);
+        p.y[(long long)b * p.y_bs + off] = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int CIN_P, int NB, int TD, int KD>
+static int launch_s1(TcParams p, cudaStream_t st) {
+  using Cfg = S1Cfg<CIN_P, NB, TD, KD>;
+  p.tiles_x = ceil_div(p.Wo, TILE_W);
+  p.tiles_y = ceil_div(p.Ho, TILE_H);
+  p.tiles_z = ceil_div(p.Do, TD);
+  dim3 grid(p.tiles_x, p.tiles_y, p.tiles_z * p.B);
+  DMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DMVS_ERR_BAD_SHAPE, "conv_tc: grid too large");
+  auto kern = conv_tc_s1_kernel<CIN_P, NB, TD, KD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      set_error("conv_tc: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+      return DMVS_ERR_CUDA;
+    }
+    configured = true;
+  }
+  kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(p);
+  return check_launch("conv_tc_s1");
+}
+
+// returns DMVS_OK, an error, or +1 when this layer shape has no tensor-core specialisation (caller falls back to conv3d.cu)
+int conv_layer_tc(const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs, float* y,
+                  long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
+                  cudaStream_t st) {
+  if (!L.w_tc || transposed || stride != 1 || kd != 3) return 1;
+  DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc: null pointer");
+  DMVS_REQUIRE(aligned16(L.w_tc), DMVS_ERR_BAD_POINTER, "conv_tc: packed weights must be 16-byte aligned");
+  TcParams p;
+  p.x = x; p.wtc = reinterpret_cast<const uint4*>(L.w_tc); p.scale = L.scale; p.shift = L.shift; p.skip = skip; p.y = y;
+  p.x_bs = x_bs; p.y_bs = y_bs; p.skip_bs = skip_bs;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.Do = Di; p.Ho = Hi; p.Wo = Wi; p.relu = relu;
+  p.tiles_x = p.tiles_y = p.tiles_z = 1;
+  if (Cin == 8 && Cout <= 8) return launch_s1<8, 16, 4, 3>(p, st);      // prob (8 -> 2)
+  if (Cin == 16 && Cout == 16) return launch_s1<16, 32, 2, 3>(p, st);   // conv2
+  if (Cin == 32 && Cout == 32) return launch_s1<16, 64, 2, 3>(p, st);   // conv4, two channel passes
+  if (Cin == 64 && Cout == 64) return launch_s1<8, 128, 1, 3>(p, st);   // conv6, eight channel passes
+  return 1;
+}
+
+}  // namespace dmvs

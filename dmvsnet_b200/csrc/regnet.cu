@@ -8,6 +8,20 @@ namespace dmvs {
 int conv_layer(const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs, float* y,
                long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
                cudaStream_t st);
+int conv_layer_tc(const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs, float* y,
+                  long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
+                  cudaStream_t st);
+
+// engine dispatch: tensor path where a specialisation exists (returns +1 otherwise), fp32 kernels as the exact path
+static int run_layer(int engine, const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs,
+                     float* y, long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed,
+                     int relu, cudaStream_t st) {
+  if (engine == DMVS_ENGINE_TENSOR) {
+    const int rc = conv_layer_tc(x, x_bs, L, skip, skip_bs, y, y_bs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, st);
+    if (rc <= 0) return rc;
+  }
+  return conv_layer(x, x_bs, L, skip, skip_bs, y, y_bs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, st);
+}
 
 namespace {
 
@@ -51,7 +65,8 @@ extern "C" size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, i
 }
 
 extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, float* logits,
-                                       void* workspace, size_t workspace_bytes, int B, int D, int h, int w, void* stream) {
+                                       void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine, void* stream) {
+  DMVS_REQUIRE(engine == DMVS_ENGINE_FP32 || engine == DMVS_ENGINE_TENSOR, DMVS_ERR_BAD_SHAPE, "regnet: unknown engine %d", engine);
   DMVS_REQUIRE(branches && cost && logits && workspace, DMVS_ERR_BAD_POINTER, "regnet: null pointer");
   DMVS_REQUIRE(B >= 1 && h >= 8 && w >= 8 && h % 8 == 0 && w % 8 == 0, DMVS_ERR_BAD_SHAPE,
                "regnet: h=%d w=%d must be positive multiples of 8", h, w);
@@ -75,7 +90,7 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
     const dmvs_conv_layer* L = branches[br].layer;
     int rc;
 #define RUN(...)                 \
-  rc = conv_layer(__VA_ARGS__);  \
+  rc = run_layer(engine, __VA_ARGS__);  \
   if (rc != DMVS_OK) return rc;
     //   x,  x_bs,    layer, skip, skip_bs, y,   y_bs,   B, Cin, Cout, Di,    Hi,    Wi,    kd, stride, transposed, relu
     RUN(cost, 2 * V0, L[0], nullptr, 0, c0, 8 * V0, B, 2, 8, L0->D, L0->H, L0->W, 3, 1, 0, 1, st);
@@ -95,13 +110,16 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
 }
 
 extern "C" int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* skip, float* y, int B, int Cin,
-                               int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, void* stream) {
+                               int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int engine,
+                               void* stream) {
   DMVS_REQUIRE(layer, DMVS_ERR_BAD_POINTER, "conv3d: null layer");
+  DMVS_REQUIRE(engine == DMVS_ENGINE_FP32 || engine == DMVS_ENGINE_TENSOR, DMVS_ERR_BAD_SHAPE, "conv3d: unknown engine %d", engine);
   DMVS_REQUIRE(Cout >= 1, DMVS_ERR_BAD_SHAPE, "conv3d: Cout=%d", Cout);
   int Do, Ho, Wo;
   if (transposed) { Do = (kd == 3) ? 2 * Di : Di; Ho = 2 * Hi; Wo = 2 * Wi; }
   else if (stride == 2) { Do = (kd == 3) ? (Di - 1) / 2 + 1 : Di; Ho = (Hi - 1) / 2 + 1; Wo = (Wi - 1) / 2 + 1; }
   else { Do = Di; Ho = Hi; Wo = Wi; }
   const long long xbs = (long long)Cin * Di * Hi * Wi, ybs = (long long)Cout * Do * Ho * Wo;
-  return conv_layer(x, xbs, *layer, skip, ybs, y, ybs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, (cudaStream_t)stream);
+  return run_layer(engine, x, xbs, *layer, skip, ybs, y, ybs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu,
+                   (cudaStream_t)stream);
 }

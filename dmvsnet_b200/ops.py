@@ -150,6 +150,7 @@ class PackedLayer:
         if cout_w != cout:
             w = torch.nn.functional.pad(w, (0, cout_w - cout))
         self.w = w.contiguous()
+        self.w_tc = _pack_tensor_core(w[:, :, :cout]) if (cin % 8 == 0) else None
         self.kd = 3 if taps == 27 else 1
         self.cin, self.cout = cin, cout
         self.transposed = transposed
@@ -161,11 +162,34 @@ class PackedLayer:
             self.scale = self.shift = None
 
     def c_struct(self) -> N.ConvLayer:
-        return N.ConvLayer(self.w.data_ptr(), _ptr(self.scale), _ptr(self.shift))
+        return N.ConvLayer(self.w.data_ptr(), _ptr(self.scale), _ptr(self.shift), _ptr(self.w_tc))
+
+
+def _pack_tensor_core(w: torch.Tensor) -> torch.Tensor:
+    """[tap][Cin][Cout] fp32 -> the fp16 hi/lo image of include/dmvs_b200.h (dmvs_conv_layer.w_tc):
+    [chunk j][tap][kc][n = 2*Cout_p][8 halfs]; columns [0,Cout_p) hold hi(W) for both K halves (they multiply A_hi and
+    A_lo), columns [Cout_p, 2*Cout_p) hold lo(W) for the A_hi half only."""
+    taps, cin, cout = w.shape
+    cout_p = max(8, (cout + 7) // 8 * 8)
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    img = torch.zeros(cin // 8, taps, 2, 2 * cout_p, 8, dtype=torch.float16, device=w.device)
+    hi_r = hi.reshape(taps, cin // 8, 8, cout).permute(1, 0, 3, 2)  # [j][tap][n][k]
+    lo_r = lo.reshape(taps, cin // 8, 8, cout).permute(1, 0, 3, 2)
+    img[:, :, 0, :cout] = hi_r
+    img[:, :, 1, :cout] = hi_r
+    img[:, :, 0, cout_p:cout_p + cout] = lo_r
+    return img.contiguous()
+
+
+# engine used by conv3d / regnet_forward unless the caller says otherwise: "tensor" = tcgen05 split-fp16 where a
+# specialisation exists (fp32 kernels elsewhere), "fp32" = CUDA-core fp32 everywhere.
+DEFAULT_ENGINE = "tensor"
+_ENGINES = {"fp32": N.ENGINE_FP32, "tensor": N.ENGINE_TENSOR}
 
 
 def conv3d(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = True,
-           skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+           skip: Optional[torch.Tensor] = None, engine: Optional[str] = None) -> torch.Tensor:
     """One conv block on a [B,Cin,D,H,W] tensor (kd = 1 layers take D as a batch of planes)."""
     lib = N.load()
     x = _req(x, "x").contiguous()
@@ -185,7 +209,8 @@ def conv3d(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = Tr
             raise ValueError("skip shape %s != output shape %s" % (tuple(skip.shape), tuple(y.shape)))
     cl = layer.c_struct()
     rc = lib.dmvs_conv3d_f32(x.data_ptr(), ctypes.byref(cl), _ptr(skip), y.data_ptr(), b, cin, layer.cout, di, hi, wi,
-                             layer.kd, 2 if layer.transposed else stride, int(layer.transposed), int(relu), _stream())
+                             layer.kd, 2 if layer.transposed else stride, int(layer.transposed), int(relu),
+                             _ENGINES[engine or DEFAULT_ENGINE], _stream())
     N.check(rc, "dmvs_conv3d_f32")
     return y
 
@@ -203,7 +228,7 @@ class PackedRegnet:
                 self.c_branches[i].layer[j] = layer.c_struct()
 
 
-def regnet_forward(pack: PackedRegnet, cost: torch.Tensor) -> torch.Tensor:
+def regnet_forward(pack: PackedRegnet, cost: torch.Tensor, engine: Optional[str] = None) -> torch.Tensor:
     """cost [B,2,D,h,w] -> logits [B,4,D,h,w]."""
     lib = N.load()
     cost = _req(cost, "cost").contiguous()
@@ -215,7 +240,7 @@ def regnet_forward(pack: PackedRegnet, cost: torch.Tensor) -> torch.Tensor:
     ws = torch.empty((nbytes + 3) // 4, device=cost.device, dtype=torch.float32)
     with _timed("regnet%s:D%d_%dx%d" % ("_refine" if pack.refine else "", d, h, w), 4 * b * 6 * d * h * w):
         rc = lib.dmvs_regnet_forward_f32(pack.c_branches, int(pack.refine), cost.data_ptr(), logits.data_ptr(), ws.data_ptr(),
-                                         ws.numel() * 4, b, d, h, w, _stream())
+                                         ws.numel() * 4, b, d, h, w, _ENGINES[engine or DEFAULT_ENGINE], _stream())
     N.check(rc, "dmvs_regnet_forward_f32")
     return logits
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 1
+#define DMVS_ABI_VERSION 2
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -75,7 +75,17 @@ typedef struct {
   const float* w;
   const float* scale;
   const float* shift;
+  /* optional: the same weights packed for the tcgen05 path (engine = DMVS_ENGINE_TENSOR), fp16 hi/lo split:
+   * [chunk j = Cin/8][tap][kc = 2][n = 2*Cout_p][8 halfs], Cout_p = max(8, Cout rounded up to 8);
+   * n < Cout_p: hi(W[tap][8j+k][n]) for kc = 0 and 1;  n >= Cout_p: lo(W[tap][8j+k][n-Cout_p]) for kc = 0, zero for kc = 1.
+   * NULL: the layer always runs on the fp32 path. */
+  const void* w_tc;
 } dmvs_conv_layer;
+
+/* which arithmetic a convolution call uses */
+#define DMVS_ENGINE_FP32 0   /* CUDA-core fp32 FMA, bit-level faithful accumulation order aside */
+#define DMVS_ENGINE_TENSOR 1 /* tcgen05 tensor cores on split fp16 operands (hi*hi + hi*lo + lo*hi, fp32 accumulate); layers
+                                without a tensor specialisation silently use the fp32 kernels */
 
 /* layers in order: conv0 conv1 conv2 conv3 conv4 conv5 conv6 conv7 conv9 conv11 prob */
 #define DMVS_REGNET_LAYERS 11
@@ -91,14 +101,14 @@ size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, int w);
  *   cost       [B,2,D,h,w]   logits [B,4,D,h,w] (channels 0,1 = small branch, 2,3 = huge branch)
  *   h % 8 == 0 and w % 8 == 0 */
 int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, float* logits,
-                            void* workspace, size_t workspace_bytes, int B, int D, int h, int w, void* stream);
+                            void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine, void* stream);
 
 /* single layers (exposed for unit tests and for callers that want their own schedule).
  *   x [B,Cin,Di,Hi,Wi] -> y [B,Cout,Do,Ho,Wo];  kd in {1,3} (1 = the 2-D convs of the refine net)
  *   stride in {1,2}; transposed != 0: ConvTranspose(k=3, s=2, p=1, output_padding=1), Do = 2*Di ...
  *   skip (nullable) has the shape of y and is added after the ReLU (module.py:394-396) */
 int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* skip, float* y, int B, int Cin, int Cout,
-                    int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, void* stream);
+                    int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int engine, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * E1  dual-depth head.  Replaces DepthNet.forward (networks/mvsnet.py:15-66) + depth_regression

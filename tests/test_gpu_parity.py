@@ -107,8 +107,10 @@ def _torch_block(x, w, bn, stride, transposed, relu, skip):
     (64, 64, (1, 5, 6), 1, False, False), (64, 32, (1, 4, 6), 2, True, False), (32, 16, (2, 8, 12), 2, True, False),
     (16, 8, (4, 6, 37), 2, True, False), (8, 2, (8, 16, 24), 1, False, False), (32, 64, (1, 8, 12), 2, False, True),
     (64, 64, (1, 6, 7), 1, False, True), (64, 32, (1, 4, 6), 2, True, True), (8, 16, (5, 7, 9), 2, False, False),
-    (16, 16, (3, 5, 70), 1, False, False)])
-def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d):
+    (16, 16, (3, 5, 70), 1, False, False), (16, 16, (5, 37, 50), 1, False, False), (32, 32, (3, 19, 27), 1, False, False),
+    (64, 64, (2, 17, 9), 1, False, False), (8, 2, (7, 33, 41), 1, False, False)])
+@pytest.mark.parametrize("engine", ["fp32", "tensor"])
+def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d, engine):
     from dmvsnet_b200 import ops
     g = torch.Generator().manual_seed(cin * 100 + cout)
     b = 2
@@ -123,13 +125,15 @@ def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d):
     if skip is not None:
         want = want + skip
     layer = ops.PackedLayer(cuda(w), transposed, tuple(cuda(t) for t in bn) if bn else None)
-    got = ops.conv3d(cuda(x), layer, stride=stride, relu=has_bn, skip=cuda(skip) if skip is not None else None)
+    got = ops.conv3d(cuda(x), layer, stride=stride, relu=has_bn, skip=cuda(skip) if skip is not None else None, engine=engine)
     assert tuple(got.shape) == tuple(want.shape)
+    # tensor engine: fp16 hi/lo split operands, only lo*lo (2^-22 relative) is dropped
     assert rel_linf(got, want) < 1e-5, rel_linf(got, want)
 
 
+@pytest.mark.parametrize("engine", ["fp32", "tensor"])
 @pytest.mark.parametrize("refine,d,h,w,b", [(False, 8, 16, 24, 1), (False, 16, 8, 40, 2), (True, 4, 16, 24, 2), (True, 4, 40, 8, 1)])
-def test_regnet_vs_oracle(refine, d, h, w, b):
+def test_regnet_vs_oracle(refine, d, h, w, b, engine):
     from dmvsnet_b200 import MVSNet, ops, synthetic as syn
     net = MVSNet([8, 8, 8], [4, 2, 1])
     state = syn.randomise_regnet_state(net.state_dict(), seed=2)
@@ -141,7 +145,11 @@ def test_regnet_vs_oracle(refine, d, h, w, b):
     x = torch.randn(b, 2, d, h, w, generator=g)
     with torch.no_grad():
         want = O.regnet(x, O._sub(state, prefix), refine=refine)
-        got = mod(cuda(x))
+        ops.DEFAULT_ENGINE, saved = engine, ops.DEFAULT_ENGINE
+        try:
+            got = mod(cuda(x))
+        finally:
+            ops.DEFAULT_ENGINE = saved
         # the single-branch layer-by-layer route must agree with the fused driver
         small = mod.cosR_small(cuda(x))
     assert rel_linf(got, want) < 1e-4, rel_linf(got, want)
