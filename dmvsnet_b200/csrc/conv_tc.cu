@@ -19,6 +19,15 @@
 //
 // One elected thread issues all MMAs of a pass and commits them to an mbarrier; the CTA's other threads fill /
 // drain.  Two to four CTAs are co-resident per SM, so one CTA's fill and epilogue overlap another's MMAs.
+//
+// Four staging modes share the issue / epilogue machinery:
+//   S1  3x3x3 stride 1            halo box [TD+2][18][10], tap = descriptor shifted by (kd,kh,kw) voxels
+//   S2  3x3x3 stride 2            box [2TD+1][33][17]; columns de-interleaved (8 even, 9 odd) so the 8 voxels of a core
+//                                 matrix stay contiguous, rows 2 apart (SBO = 2 row pitches)
+//   TR  ConvTranspose k3 s2 p1 op1 input box [TD+1][17][9]; the 8 output parity classes are 8 accumulators, each tap of the
+//                                 transposed kernel belongs to exactly one class (even: k=1; odd: k=0 at +1, k=2 at 0)
+//   C0  conv0 (Cin = 2)           K is packed along kw: a 16-byte chunk holds (hi,lo) x 2 channels of voxel x and x+1, the
+//                                 K=16 step reads the chunks at x-1 and x+1 (LBO = 2 voxels) = taps kw 0,1,2 (+ a zero column)
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -116,32 +125,40 @@ struct TcParams {
   long long x_bs, y_bs, skip_bs;
   int B, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo;
   int relu;
-  int tiles_x, tiles_y, tiles_z;
+  int tiles_z;
 };
 
 constexpr int TC_THREADS = 256;
 constexpr int TILE_H = 16, TILE_W = 8;
+enum { MODE_S1 = 0, MODE_S2 = 1, MODE_TR = 2, MODE_C0 = 3 };
 
-// ------------------------------------------------------------------------------------------------ stride-1 conv
-// CIN_P: input channels per pass (multiple of 8); NB: UMMA N = 2 * Cout_p; TD: output planes per CTA; KD in {1,3}
-template <int CIN_P, int NB, int TD, int KD>
-struct S1Cfg {
-  static constexpr int SD = (KD == 3) ? TD + 2 : TD, SH = TILE_H + 2, SW = TILE_W + 2;
-  static constexpr int SV = SD * SH * SW;        // staged voxels
-  static constexpr int CJ = CIN_P / 8;           // channel chunks per pass
-  static constexpr int TAPS = KD * 9;
-  static constexpr int A_PITCH = SV * 16;        // bytes per 16-byte-chunk plane
-  static constexpr int A_BYTES = 2 * CJ * A_PITCH;
-  static constexpr int B_TILE = 2 * NB * 16;     // bytes per (chunk, tap): [kc][n][16B]
+// CIN_P: input channels per pass; NB: UMMA N = 2 * Cout_p; TD: planes per CTA (output planes; input planes for TR)
+template <int MODE, int CIN_P, int NB, int TD>
+struct TcCfg {
+  static constexpr int SD = (MODE == MODE_S2) ? 2 * TD + 1 : (MODE == MODE_TR) ? TD + 1 : TD + 2;
+  static constexpr int SH = (MODE == MODE_S2) ? 2 * TILE_H + 1 : (MODE == MODE_TR) ? TILE_H + 1 : TILE_H + 2;
+  static constexpr int SW = (MODE == MODE_S2) ? 2 * TILE_W + 1 : (MODE == MODE_TR) ? TILE_W + 1 : TILE_W + 2;
+  static constexpr int SV = SD * SH * SW;  // staged voxels (16-byte rows per chunk plane)
+  static constexpr int CJ = (MODE == MODE_C0) ? 1 : CIN_P / 8;
+  static constexpr int NPLANE = (MODE == MODE_C0) ? 1 : 2 * CJ;  // 16-byte chunk planes per pass
+  static constexpr int TAPS = (MODE == MODE_C0) ? 9 : 27;
+  static constexpr int A_PITCH = SV * 16;
+  static constexpr int A_BYTES = NPLANE * A_PITCH;
+  static constexpr int A_LBO = (MODE == MODE_C0) ? 32 : A_PITCH;
+  static constexpr int A_SBO = (MODE == MODE_S2) ? 2 * SW * 16 : SW * 16;
+  static constexpr int B_TILE = 2 * NB * 16;  // bytes per (chunk, tap): [kc][n][16B]
   static constexpr int B_BYTES = CJ * TAPS * B_TILE;
   static constexpr int SMEM = A_BYTES + B_BYTES + 64;
-  static constexpr int TMEM_COLS = (TD * NB <= 32) ? 32 : (TD * NB <= 64) ? 64 : (TD * NB <= 128) ? 128 : (TD * NB <= 256) ? 256 : 512;
-  static_assert(TD * NB <= 512, "accumulators exceed TMEM");
+  static constexpr int NACC = (MODE == MODE_TR) ? 8 * TD : TD;
+  static constexpr int COLS = NACC * NB;
+  static constexpr int TMEM_COLS = (COLS <= 32) ? 32 : (COLS <= 64) ? 64 : (COLS <= 128) ? 128 : (COLS <= 256) ? 256 : 512;
+  static_assert(COLS <= 512, "accumulators exceed TMEM");
+  static_assert(SMEM <= 227 * 1024, "tile does not fit shared memory");
 };
 
-template <int CIN_P, int NB, int TD, int KD>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_s1_kernel(const __grid_constant__ TcParams p) {
-  using Cfg = S1Cfg<CIN_P, NB, TD, KD>;
+template <int MODE, int CIN_P, int NB, int TD>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<MODE, CIN_P, NB, TD>;
   constexpr int COUT_P = NB / 2;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
@@ -150,6 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_s1_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // tile origin: output coordinates for S1 / S2 / C0, input coordinates for TR
   const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
   const int zb = blockIdx.z % p.tiles_z, b = blockIdx.z / p.tiles_z;
   const int z0 = zb * TD;
@@ -165,29 +183,60 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_s1_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   const long long iplane = (long long)p.Hi * p.Wi;
-  const int n_pass = p.Cin / CIN_P;
+  const long long cs = (long long)p.Di * iplane;  // channel stride
+  const int n_pass = (MODE == MODE_C0) ? 1 : p.Cin / CIN_P;
   for (int pass = 0; pass < n_pass; ++pass) {
     if (pass > 0) mbar_wait(bar, (pass - 1) & 1);  // previous pass' MMAs have finished reading smem
-    // ---- stage the halo tile: fp32 NCDHW -> [chunk][voxel][8 x fp16], hi chunk 2j, lo chunk 2j+1
+    // ---- stage the input box: fp32 NCDHW -> [chunk plane][voxel][8 x fp16]
     for (int item = tid; item < Cfg::SV * Cfg::CJ; item += TC_THREADS) {
       const int j = item / Cfg::SV, sv = item - j * Cfg::SV;
       const int sx = sv % Cfg::SW, sy = (sv / Cfg::SW) % Cfg::SH, sz = sv / (Cfg::SW * Cfg::SH);
-      const int ix = x0 + sx - 1, iy = y0 + sy - 1, iz = (KD == 3) ? z0 + sz - 1 : z0 + sz;
-      float v[8];
-      if (ix >= 0 && ix < p.Wi && iy >= 0 && iy < p.Hi && iz >= 0 && iz < p.Di) {
-        const float* src = p.x + (long long)b * p.x_bs + ((long long)(pass * CIN_P + j * 8) * p.Di + iz) * iplane +
-                           (long long)iy * p.Wi + ix;
-        const long long cs = (long long)p.Di * iplane;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c * cs);
+      int ix, iy, iz;
+      if (MODE == MODE_S2) {
+        ix = (sx < TILE_W) ? 2 * (x0 + sx) : 2 * (x0 + sx - TILE_W) - 1;
+        iy = 2 * y0 - 1 + sy;
+        iz = 2 * z0 - 1 + sz;
+      } else if (MODE == MODE_TR) {
+        ix = x0 + sx; iy = y0 + sy; iz = z0 + sz;
       } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = 0.f;
+        ix = x0 + sx - 1; iy = y0 + sy - 1; iz = z0 + sz - 1;
       }
-      uint4 hi, lo;
-      split_pack8(v, hi, lo);
-      *reinterpret_cast<uint4*>(sA + (2 * j) * Cfg::A_PITCH + sv * 16) = hi;
-      *reinterpret_cast<uint4*>(sA + (2 * j + 1) * Cfg::A_PITCH + sv * 16) = lo;
+      const bool vyz = (iy >= 0 && iy < p.Hi && iz >= 0 && iz < p.Di);
+      if (MODE == MODE_C0) {
+        // chunk = [hi c0, hi c1, lo c0, lo c1] of voxel ix, then the same of voxel ix + 1
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vyz) {
+          const float* src = p.x + (long long)b * p.x_bs + (long long)iz * iplane + (long long)iy * p.Wi;
+          if (ix >= 0 && ix < p.Wi) { v[0] = __ldg(src + ix); v[1] = __ldg(src + cs + ix); }
+          if (ix + 1 >= 0 && ix + 1 < p.Wi) { v[2] = __ldg(src + ix + 1); v[3] = __ldg(src + cs + ix + 1); }
+        }
+        __half h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          h[i] = __float2half_rn(v[i]);
+          l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+        }
+        const __half2 w0 = __halves2half2(h[0], h[1]), w1 = __halves2half2(l[0], l[1]);
+        const __half2 w2 = __halves2half2(h[2], h[3]), w3 = __halves2half2(l[2], l[3]);
+        *reinterpret_cast<uint4*>(sA + sv * 16) =
+            make_uint4(*reinterpret_cast<const uint32_t*>(&w0), *reinterpret_cast<const uint32_t*>(&w1),
+                       *reinterpret_cast<const uint32_t*>(&w2), *reinterpret_cast<const uint32_t*>(&w3));
+      } else {
+        float v[8];
+        if (vyz && ix >= 0 && ix < p.Wi) {
+          const float* src = p.x + (long long)b * p.x_bs + ((long long)(pass * CIN_P + j * 8) * p.Di + iz) * iplane +
+                             (long long)iy * p.Wi + ix;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c * cs);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = 0.f;
+        }
+        uint4 hi, lo;
+        split_pack8(v, hi, lo);
+        *reinterpret_cast<uint4*>(sA + (2 * j) * Cfg::A_PITCH + sv * 16) = hi;
+        *reinterpret_cast<uint4*>(sA + (2 * j + 1) * Cfg::A_PITCH + sv * 16) = lo;
+      }
     }
     // ---- weights of this pass: a contiguous byte range of the packed image
     {
@@ -201,19 +250,50 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_s1_kernel(const __grid_con
       tc_fence_after();
       constexpr uint32_t idesc = make_idesc(NB);
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll 1
-      for (int t = 0; t < TD; ++t) {
-#pragma unroll 1
-        for (int tap = 0; tap < Cfg::TAPS; ++tap) {
-          const int kd = (KD == 3) ? tap / 9 : 0, kh = (tap % 9) / 3, kw = tap % 3;
-          const uint32_t voff = (uint32_t)(((t + kd) * Cfg::SH + kh) * Cfg::SW + kw) * 16u;
+      auto issue = [&](int acc, int tap, uint32_t voxel, bool first) {
 #pragma unroll
-          for (int j = 0; j < Cfg::CJ; ++j) {
-            const uint64_t ad = make_desc(a0 + (2 * j) * Cfg::A_PITCH + voff, Cfg::A_PITCH, Cfg::SW * 16);
-            const uint64_t bd = make_desc(b0 + (j * Cfg::TAPS + tap) * Cfg::B_TILE, NB * 16, 128);
-            umma_f16(tmem_base + t * NB, ad, bd, idesc, (pass > 0 || tap > 0 || j > 0) ? 1u : 0u);
-          }
+        for (int j = 0; j < Cfg::CJ; ++j) {
+          const uint64_t ad = make_desc(a0 + (MODE == MODE_C0 ? 0 : (2 * j) * Cfg::A_PITCH) + voxel * 16u, Cfg::A_LBO, Cfg::A_SBO);
+          const uint64_t bd = make_desc(b0 + (j * Cfg::TAPS + tap) * Cfg::B_TILE, NB * 16, 128);
+          umma_f16(tmem_base + acc * NB, ad, bd, idesc, (pass > 0 || !first || j > 0) ? 1u : 0u);
         }
+      };
+      if (MODE == MODE_TR) {
+#pragma unroll 1
+        for (int t = 0; t < TD; ++t)
+#pragma unroll 1
+          for (int cls = 0; cls < 8; ++cls) {
+            const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+            bool first = true;
+            // per dimension: even output -> (k=1, offset 0); odd output -> (k=0, offset +1) and (k=2, offset 0)
+            for (int a = 0; a <= pz; ++a)
+              for (int bq = 0; bq <= py; ++bq)
+                for (int c = 0; c <= px; ++c) {
+                  const int kz = pz ? (a ? 2 : 0) : 1, oz = pz ? (a ? 0 : 1) : 0;
+                  const int ky = py ? (bq ? 2 : 0) : 1, oy = py ? (bq ? 0 : 1) : 0;
+                  const int kx = px ? (c ? 2 : 0) : 1, ox = px ? (c ? 0 : 1) : 0;
+                  issue(t * 8 + cls, (kz * 3 + ky) * 3 + kx, (uint32_t)(((t + oz) * Cfg::SH + oy) * Cfg::SW + ox), first);
+                  first = false;
+                }
+          }
+      } else {
+#pragma unroll 1
+        for (int t = 0; t < TD; ++t)
+#pragma unroll 1
+          for (int tap = 0; tap < Cfg::TAPS; ++tap) {
+            uint32_t voxel;
+            if (MODE == MODE_C0) {
+              const int kd = tap / 3, kh = tap % 3;
+              voxel = (uint32_t)(((t + kd) * Cfg::SH + kh) * Cfg::SW);
+            } else {
+              const int kd = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
+              if (MODE == MODE_S2)
+                voxel = (uint32_t)(((2 * t + kd) * Cfg::SH + kh) * Cfg::SW + (kw == 1 ? 0 : (kw == 0 ? TILE_W : TILE_W + 1)));
+              else
+                voxel = (uint32_t)(((t + kd) * Cfg::SH + kh) * Cfg::SW + kw);
+            }
+            issue(t, tap, voxel, tap == 0);
+          }
       }
       umma_commit(bar);
     }
@@ -221,32 +301,74 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_s1_kernel(const __grid_con
   mbar_wait(bar, (n_pass - 1) & 1);
   tc_fence_after();
 
-  // ---- epilogue: TMEM -> registers -> BN / ReLU / skip -> NCDHW.  Warp w reads TMEM lanes 32*(w%4)..+31.
+  // ---- epilogue: TMEM -> registers -> BN / ReLU / skip -> NCDHW.  Warp w reads TMEM lanes 32*(w%4)..+31,
+  //      lane l of quadrant q is UMMA row 32q + l = patch position (hl = 4q + l/8, wl = l%8).
   const int q = warp & 3;
   const int hl = q * 4 + (lane >> 3), wl = lane & 7;
-  const int oy = y0 + hl, ox = x0 + wl;
-  const bool in_img = (oy < p.Ho) && (ox < p.Wo);
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
   const long long oplane = (long long)p.Ho * p.Wo;
-  for (int t = (warp >> 2); t < TD; t += 2) {
-    const int oz = z0 + t;
-    if (oz >= p.Do) break;  // warp-uniform
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + t * NB;
+  if (MODE == MODE_TR) {
+    const int iy = y0 + hl, ix = x0 + wl;
+    const bool in_img = (iy < p.Hi) && (ix < p.Wi);
+    for (int t = (warp >> 2); t < TD; t += 2) {
+      if (z0 + t >= p.Di) break;  // warp-uniform
 #pragma unroll 1
-    for (int c0 = 0; c0 < COUT_P; c0 += 8) {
-      float hi8[8], lo8[8];
-      tmem_ld8(taddr + c0, hi8);
-      tmem_ld8(taddr + COUT_P + c0, lo8);
-      if (!in_img) continue;
+      for (int pzy = 0; pzy < 4; ++pzy) {
+        const int oz = 2 * (z0 + t) + (pzy >> 1), oy = 2 * iy + (pzy & 1);
+        const uint32_t te = lane_addr + (t * 8 + pzy * 2) * NB, to = te + NB;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT_P; c0 += 8) {
+          float he[8], le[8], ho[8], lo8[8];
+          tmem_ld8(te + c0, he);
+          tmem_ld8(te + COUT_P + c0, le);
+          tmem_ld8(to + c0, ho);
+          tmem_ld8(to + COUT_P + c0, lo8);
+          if (!in_img) continue;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int co = c0 + c;
-        if (co >= p.Cout) break;
-        float v = hi8[c] + lo8[c];
-        if (p.scale) v = fmaf(v, __ldg(p.scale + co), __ldg(p.shift + co));
-        if (p.relu) v = fmaxf(v, 0.f);
-        const long long off = ((long long)co * p.Do + oz) * oplane + (long long)oy * p.Wo + ox;
-        if (p.skip) v += __ldg(p.skip + (long long)b * p.skip_bs + off);
-        p.y[(long long)b * p.y_bs + off] = v;
+          for (int c = 0; c < 8; ++c) {
+            const int co = c0 + c;
+            if (co >= p.Cout) break;
+            float e = he[c] + le[c], o = ho[c] + lo8[c];
+            if (p.scale) {
+              const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
+              e = fmaf(e, sc, sh);
+              o = fmaf(o, sc, sh);
+            }
+            if (p.relu) { e = fmaxf(e, 0.f); o = fmaxf(o, 0.f); }
+            const long long off = ((long long)co * p.Do + oz) * oplane + (long long)oy * p.Wo + 2 * ix;
+            if (p.skip) {
+              const float2 sk = __ldg(reinterpret_cast<const float2*>(p.skip + (long long)b * p.skip_bs + off));
+              e += sk.x; o += sk.y;
+            }
+            *reinterpret_cast<float2*>(p.y + (long long)b * p.y_bs + off) = make_float2(e, o);
+          }
+        }
+      }
+    }
+  } else {
+    const int oy = y0 + hl, ox = x0 + wl;
+    const bool in_img = (oy < p.Ho) && (ox < p.Wo);
+    for (int t = (warp >> 2); t < TD; t += 2) {
+      const int oz = z0 + t;
+      if (oz >= p.Do) break;  // warp-uniform
+      const uint32_t taddr = lane_addr + t * NB;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT_P; c0 += 8) {
+        float hi8[8], lo8[8];
+        tmem_ld8(taddr + c0, hi8);
+        tmem_ld8(taddr + COUT_P + c0, lo8);
+        if (!in_img) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int co = c0 + c;
+          if (co >= p.Cout) break;
+          float v = hi8[c] + lo8[c];
+          if (p.scale) v = fmaf(v, __ldg(p.scale + co), __ldg(p.shift + co));
+          if (p.relu) v = fmaxf(v, 0.f);
+          const long long off = ((long long)co * p.Do + oz) * oplane + (long long)oy * p.Wo + ox;
+          if (p.skip) v += __ldg(p.skip + (long long)b * p.skip_bs + off);
+          p.y[(long long)b * p.y_bs + off] = v;
+        }
       }
     }
   }
@@ -255,15 +377,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_s1_kernel(const __grid_con
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int CIN_P, int NB, int TD, int KD>
-static int launch_s1(TcParams p, cudaStream_t st) {
-  using Cfg = S1Cfg<CIN_P, NB, TD, KD>;
-  p.tiles_x = ceil_div(p.Wo, TILE_W);
-  p.tiles_y = ceil_div(p.Ho, TILE_H);
-  p.tiles_z = ceil_div(p.Do, TD);
-  dim3 grid(p.tiles_x, p.tiles_y, p.tiles_z * p.B);
+template <int MODE, int CIN_P, int NB, int TD>
+static int launch_tc(TcParams p, cudaStream_t st) {
+  using Cfg = TcCfg<MODE, CIN_P, NB, TD>;
+  // tiles cover the output grid, except TR where they cover the input grid (each input voxel owns a 2x2x2 output block)
+  const int gw = (MODE == MODE_TR) ? p.Wi : p.Wo, gh = (MODE == MODE_TR) ? p.Hi : p.Ho, gd = (MODE == MODE_TR) ? p.Di : p.Do;
+  p.tiles_z = ceil_div(gd, TD);
+  dim3 grid(ceil_div(gw, TILE_W), ceil_div(gh, TILE_H), p.tiles_z * p.B);
   DMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DMVS_ERR_BAD_SHAPE, "conv_tc: grid too large");
-  auto kern = conv_tc_s1_kernel<CIN_P, NB, TD, KD>;
+  auto kern = conv_tc_kernel<MODE, CIN_P, NB, TD>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -274,25 +396,42 @@ static int launch_s1(TcParams p, cudaStream_t st) {
     configured = true;
   }
   kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(p);
-  return check_launch("conv_tc_s1");
+  return check_launch("conv_tc");
 }
 
 // returns DMVS_OK, an error, or +1 when this layer shape has no tensor-core specialisation (caller falls back to conv3d.cu)
 int conv_layer_tc(const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs, float* y,
                   long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
                   cudaStream_t st) {
-  if (!L.w_tc || transposed || stride != 1 || kd != 3) return 1;
+  if (!L.w_tc || kd != 3) return 1;
   DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc: null pointer");
   DMVS_REQUIRE(aligned16(L.w_tc), DMVS_ERR_BAD_POINTER, "conv_tc: packed weights must be 16-byte aligned");
   TcParams p;
   p.x = x; p.wtc = reinterpret_cast<const uint4*>(L.w_tc); p.scale = L.scale; p.shift = L.shift; p.skip = skip; p.y = y;
   p.x_bs = x_bs; p.y_bs = y_bs; p.skip_bs = skip_bs;
-  p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.Do = Di; p.Ho = Hi; p.Wo = Wi; p.relu = relu;
-  p.tiles_x = p.tiles_y = p.tiles_z = 1;
-  if (Cin == 8 && Cout <= 8) return launch_s1<8, 16, 4, 3>(p, st);      // prob (8 -> 2)
-  if (Cin == 16 && Cout == 16) return launch_s1<16, 32, 2, 3>(p, st);   // conv2
-  if (Cin == 32 && Cout == 32) return launch_s1<16, 64, 2, 3>(p, st);   // conv4, two channel passes
-  if (Cin == 64 && Cout == 64) return launch_s1<8, 128, 1, 3>(p, st);   // conv6, eight channel passes
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.relu = relu; p.tiles_z = 1;
+  if (transposed) {
+    p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
+    DMVS_REQUIRE(aligned16(y) && (y_bs % 2 == 0) && (!skip || (aligned16(skip) && skip_bs % 2 == 0)), DMVS_ERR_BAD_POINTER,
+                 "conv_tc: y/skip must be 16-byte aligned for the transposed conv");
+    if (Cin == 16 && Cout == 8) return launch_tc<MODE_TR, 16, 16, 2>(p, st);   // conv11
+    if (Cin == 32 && Cout == 16) return launch_tc<MODE_TR, 16, 32, 1>(p, st);  // conv9, two channel passes
+    if (Cin == 64 && Cout == 32) return launch_tc<MODE_TR, 16, 64, 1>(p, st);  // conv7, four channel passes
+    return 1;
+  }
+  if (stride == 2) {
+    p.Do = (Di - 1) / 2 + 1; p.Ho = (Hi - 1) / 2 + 1; p.Wo = (Wi - 1) / 2 + 1;
+    if (Cin == 8 && Cout == 16) return launch_tc<MODE_S2, 8, 32, 1>(p, st);    // conv1
+    if (Cin == 16 && Cout == 32) return launch_tc<MODE_S2, 8, 64, 1>(p, st);   // conv3, two passes
+    if (Cin == 32 && Cout == 64) return launch_tc<MODE_S2, 8, 128, 1>(p, st);  // conv5, four passes
+    return 1;
+  }
+  p.Do = Di; p.Ho = Hi; p.Wo = Wi;
+  if (Cin == 2 && Cout == 8) return launch_tc<MODE_C0, 2, 16, 4>(p, st);       // conv0, K packed along kw
+  if (Cin == 8 && Cout <= 8) return launch_tc<MODE_S1, 8, 16, 4>(p, st);       // prob (8 -> 2)
+  if (Cin == 16 && Cout == 16) return launch_tc<MODE_S1, 16, 32, 2>(p, st);    // conv2
+  if (Cin == 32 && Cout == 32) return launch_tc<MODE_S1, 16, 64, 2>(p, st);    // conv4, two channel passes
+  if (Cin == 64 && Cout == 64) return launch_tc<MODE_S1, 8, 128, 1>(p, st);    // conv6, eight channel passes
   return 1;
 }
 

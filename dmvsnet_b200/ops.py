@@ -150,7 +150,12 @@ class PackedLayer:
         if cout_w != cout:
             w = torch.nn.functional.pad(w, (0, cout_w - cout))
         self.w = w.contiguous()
-        self.w_tc = _pack_tensor_core(w[:, :, :cout]) if (cin % 8 == 0) else None
+        if cin % 8 == 0:
+            self.w_tc = _pack_tensor_core(w[:, :, :cout])
+        elif cin == 2 and taps == 27 and not transposed:
+            self.w_tc = _pack_tensor_core_kw(w[:, :, :cout])
+        else:
+            self.w_tc = None
         self.kd = 3 if taps == 27 else 1
         self.cin, self.cout = cin, cout
         self.transposed = transposed
@@ -179,6 +184,27 @@ def _pack_tensor_core(w: torch.Tensor) -> torch.Tensor:
     img[:, :, 0, :cout] = hi_r
     img[:, :, 1, :cout] = hi_r
     img[:, :, 0, cout_p:cout_p + cout] = lo_r
+    return img.contiguous()
+
+
+def _pack_tensor_core_kw(w: torch.Tensor) -> torch.Tensor:
+    """conv0 (Cin = 2): K packed along kw.  [27][2][Cout] -> [1][9 taps (kd,kh)][kc][n][8 halfs]; the 16 K entries of a tap
+    are 4 voxels (x-1, x | x+1, x+2) x [hi c0, hi c1, lo c0, lo c1]; voxel x+2 is outside the 3-wide kernel -> zeros."""
+    taps, cin, cout = w.shape
+    assert taps == 27 and cin == 2
+    cout_p = max(8, (cout + 7) // 8 * 8)
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    hi = hi.reshape(9, 3, 2, cout)  # [(kd,kh)][kw][c][n]
+    lo = lo.reshape(9, 3, 2, cout)
+    img = torch.zeros(1, 9, 2, 2 * cout_p, 8, dtype=torch.float16, device=w.device)
+    for v in range(3):                      # voxel slot v <-> kw = v
+        kc, base = divmod(v, 2)
+        base *= 4
+        for c in range(2):
+            img[0, :, kc, :cout, base + c] = hi[:, v, c]                    # A_hi * W_hi
+            img[0, :, kc, :cout, base + 2 + c] = hi[:, v, c]                # A_lo * W_hi
+            img[0, :, kc, cout_p:cout_p + cout, base + c] = lo[:, v, c]     # A_hi * W_lo
     return img.contiguous()
 
 

@@ -108,7 +108,9 @@ def _torch_block(x, w, bn, stride, transposed, relu, skip):
     (16, 8, (4, 6, 37), 2, True, False), (8, 2, (8, 16, 24), 1, False, False), (32, 64, (1, 8, 12), 2, False, True),
     (64, 64, (1, 6, 7), 1, False, True), (64, 32, (1, 4, 6), 2, True, True), (8, 16, (5, 7, 9), 2, False, False),
     (16, 16, (3, 5, 70), 1, False, False), (16, 16, (5, 37, 50), 1, False, False), (32, 32, (3, 19, 27), 1, False, False),
-    (64, 64, (2, 17, 9), 1, False, False), (8, 2, (7, 33, 41), 1, False, False)])
+    (64, 64, (2, 17, 9), 1, False, False), (8, 2, (7, 33, 41), 1, False, False), (2, 8, (6, 35, 29), 1, False, False),
+    (8, 16, (8, 34, 50), 2, False, False), (16, 32, (4, 37, 21), 2, False, False), (32, 64, (3, 18, 25), 2, False, False),
+    (16, 8, (3, 19, 13), 2, True, False), (32, 16, (2, 17, 11), 2, True, False), (64, 32, (1, 9, 10), 2, True, False)])
 @pytest.mark.parametrize("engine", ["fp32", "tensor"])
 def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d, engine):
     from dmvsnet_b200 import ops
