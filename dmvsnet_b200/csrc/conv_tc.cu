@@ -575,22 +575,22 @@ int conv_layer_tc(const float* x, long long x_bs, const dmvs_conv_layer& L, cons
     p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
     DMVS_REQUIRE(aligned16(y) && (y_bs % 2 == 0) && (!skip || (aligned16(skip) && skip_bs % 2 == 0)), DMVS_ERR_BAD_POINTER,
                  "conv_tc: y/skip must be 16-byte aligned for the transposed conv");
-    if (Cin == 16 && Cout == 8) return launch_tcp<MODE_TR, 16, 16, 2, 4>(p, st);  // conv11
+    if (Cin == 16 && Cout == 8) return launch_tc<MODE_TR, 16, 16, 2>(p, st);      // conv11
     if (Cin == 32 && Cout == 16) return launch_tc<MODE_TR, 16, 32, 1>(p, st);     // conv9, two channel passes
     if (Cin == 64 && Cout == 32) return launch_tc<MODE_TR, 16, 64, 1>(p, st);     // conv7, four channel passes
     return 1;
   }
   if (stride == 2) {
     p.Do = (Di - 1) / 2 + 1; p.Ho = (Hi - 1) / 2 + 1; p.Wo = (Wi - 1) / 2 + 1;
-    if (Cin == 8 && Cout == 16) return launch_tcp<MODE_S2, 8, 32, 1, 3>(p, st);  // conv1
+    if (Cin == 8 && Cout == 16) return launch_tc<MODE_S2, 8, 32, 1>(p, st);     // conv1
     if (Cin == 16 && Cout == 32) return launch_tc<MODE_S2, 8, 64, 1>(p, st);     // conv3, two passes
     if (Cin == 32 && Cout == 64) return launch_tc<MODE_S2, 8, 128, 1>(p, st);    // conv5, four passes
     return 1;
   }
   p.Do = Di; p.Ho = Hi; p.Wo = Wi;
-  if (Cin == 2 && Cout == 8) return launch_tcp<MODE_C0, 2, 16, 4, 4>(p, st);    // conv0, K packed along kw
-  if (Cin == 8 && Cout <= 8) return launch_tcp<MODE_S1, 8, 16, 4, 4>(p, st);    // prob (8 -> 2)
-  if (Cin == 16 && Cout == 16) return launch_tcp<MODE_S1, 16, 32, 2, 3>(p, st); // conv2
+  if (Cin == 2 && Cout == 8) return launch_tc<MODE_C0, 2, 16, 4>(p, st);       // conv0, K packed along kw
+  if (Cin == 8 && Cout <= 8) return launch_tc<MODE_S1, 8, 16, 4>(p, st);       // prob (8 -> 2)
+  if (Cin == 16 && Cout == 16) return launch_tc<MODE_S1, 16, 32, 2>(p, st);    // conv2
   if (Cin == 32 && Cout == 32) return launch_tc<MODE_S1, 16, 64, 2>(p, st);     // conv4, two channel passes
   if (Cin == 64 && Cout == 64) return launch_tc<MODE_S1, 8, 128, 1>(p, st);     // conv6, eight channel passes
   return 1;

@@ -251,7 +251,7 @@ def test_cascade_against_reference_fixture(name):
     for s in range(len(case["ndepths"])):
         st = out["stage%d" % (s + 1)]
         for seam, tol, how in CASCADE_SEAMS:
-            if s > 0 and seam == "cost":
+            if s > 0 and seam in ("cost", "depth_values"):
                 tol = 2e-4  # later stages inherit ~1e-5 relative differences in the regressed depth through the hypotheses
             got = (st["_" + seam] if "_" + seam in st else st[seam]).cpu()
             want = gold["s%d_%s" % (s + 1, seam)]
