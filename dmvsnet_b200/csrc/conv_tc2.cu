@@ -1,0 +1,594 @@
+// R1 tensor-core path, second generation: TMA-fed, persistent, warp-specialised implicit-GEMM convolutions (sm_100a).
+//
+// Same arithmetic as conv_tc.cu (fp16 hi/lo split operands, UMMA M = 128 voxels x N = 2*Cout, shifted-descriptor im2col,
+// fp32 accumulators in TMEM) - what changes is how operands get to shared memory:
+//
+//   * Activations between tensor layers live in HBM in the layout the tensor core consumes ("CH16"): 16-byte cells of 8 fp16,
+//     [B][plane][D][H][W] with plane 2j = hi(channels 8j..8j+7), plane 2j+1 = lo.  Same bytes as fp32.  Tensors that feed a
+//     stride-2 conv are written column-parity split ("CH16P": [..][H][parity][W/2]) so that the even and odd input columns
+//     of a stride-2 tap are contiguous cells again.
+//   * One thread per CTA issues TMA box loads (cp.async.bulk.tensor, OOB zero fill = the conv padding) straight into the
+//     UMMA canonical no-swizzle layout; weights of multi-pass layers ride along as 1-D bulk copies.  A ring of STAGES
+//     smem stages is handed between producer and MMA issuer by full/empty mbarriers (expect_tx / tcgen05.commit).
+//   * Two TMEM accumulator sets ping-pong between the MMA issuer and 8 epilogue warps (accfull / accempty mbarriers);
+//     the epilogue applies eval-BatchNorm + ReLU (+ skip), splits to hi/lo fp16 and stores CH16 / CH16P cells (or fp32
+//     NCDHW for the last layer).
+//   * conv0 (Cin = 2, fp32 cost volume in) keeps a thread-filled producer (12 warps) in the same pipeline.
+#include <cuda.h>
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace dmvs {
+
+enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2 };
+enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3 };
+constexpr int T_H = 16, T_W = 8;
+
+struct Tc2Params {
+  const float* x_f32;  // C0 only
+  const uint4* wtc;
+  const float* scale;
+  const float* shift;
+  const uint4* skip;  // CH16P, TR only
+  void* y;
+  long long x_bs;     // C0 only (elements)
+  long long y_bs;     // fp32 output only: batch stride in elements (the logits tensor interleaves two branches)
+  int B, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo;
+  int relu, out_fmt;
+  int tiles_x, tiles_y, tiles_z, n_tiles;
+};
+
+__host__ __device__ constexpr int pad128(int v) { return (v + 127) / 128 * 128; }
+__host__ __device__ constexpr int pow2c(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
+struct C2 {
+  static constexpr int SD = (MODE == M2_S2) ? 2 * TD + 1 : (MODE == M2_TR) ? TD + 1 : TD + 2;
+  static constexpr int SH = (MODE == M2_S2) ? 2 * T_H + 1 : (MODE == M2_TR) ? T_H + 1 : T_H + 2;
+  static constexpr int BW = (MODE == M2_S1 || MODE == M2_C0) ? T_W + 2 : T_W + 1;  // cells per staged row (S2: per parity block)
+  static constexpr int ROWS = SD * SH;
+  static constexpr int BLK_BYTES = ROWS * BW * 16;  // bytes one TMA box writes
+  static constexpr int BLK_PITCH = pad128(BLK_BYTES);
+  static constexpr int NBLK = (MODE == M2_S2) ? 2 : 1;
+  static constexpr int PLANE = NBLK * BLK_PITCH;
+  static constexpr int CJ = (MODE == M2_C0) ? 1 : CIN_P / 8;
+  static constexpr int NPLANE = (MODE == M2_C0) ? 1 : 2 * CJ;
+  static constexpr int NPASS = (MODE == M2_C0) ? 1 : CIN / CIN_P;
+  static constexpr bool RESIDENT = NPASS == 1;
+  static constexpr int TAPS = (MODE == M2_C0) ? 9 : 27;
+  static constexpr int A_BYTES = NPLANE * PLANE;
+  static constexpr int A_LBO = (MODE == M2_C0) ? 32 : PLANE;
+  static constexpr int A_SBO = (MODE == M2_S2) ? 2 * BW * 16 : BW * 16;
+  static constexpr int B_TILE = 2 * NB * 16;
+  static constexpr int B_BYTES = CJ * TAPS * B_TILE;
+  static constexpr int TX_BYTES = NPLANE * NBLK * BLK_BYTES + (RESIDENT ? 0 : B_BYTES);
+  static constexpr int STAGE_BYTES = A_BYTES + (RESIDENT ? 0 : pad128(B_BYTES));
+  static constexpr int OFF_B = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_B + (RESIDENT ? pad128(B_BYTES) : 0);
+  static constexpr int SMEM = OFF_BAR + 8 * (2 * STAGES + 4) + 16 + 128;  // + slack for manual 128-byte alignment
+  static constexpr int NACC = (MODE == M2_TR) ? 8 * TD : TD;
+  static constexpr int COLS = NACC * NB;
+  static constexpr int ACC_SETS = (2 * COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = pow2c(ACC_SETS * COLS);
+  static constexpr int PROD_WARPS = (MODE == M2_C0) ? 12 : 1;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
+  static_assert(COLS <= 512, "accumulators exceed TMEM");
+  static_assert(SMEM <= 227 * 1024, "pipeline does not fit shared memory");
+  static_assert(CIN % CIN_P == 0 || MODE == M2_C0, "channel passes");
+};
+
+struct Tile2 {
+  int x0, y0, z0, b;
+};
+__device__ __forceinline__ Tile2 decode2(const Tc2Params& p, int lt, int td) {
+  Tile2 t;
+  t.x0 = (lt % p.tiles_x) * T_W;
+  lt /= p.tiles_x;
+  t.y0 = (lt % p.tiles_y) * T_H;
+  lt /= p.tiles_y;
+  t.z0 = (lt % p.tiles_z) * td;
+  t.b = lt / p.tiles_z;
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------ cell helpers
+__device__ __forceinline__ void unpack_cell(const uint4& c, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+// cell index of voxel (z, y, x) of plane `pl` in a CH16 / CH16P tensor with dims (D, H, W) and NP planes per batch entry
+__device__ __forceinline__ long long cell_index(int fmt, int b, int np, int pl, int D, int H, int W, int z, int y, int x) {
+  const long long row = ((long long)(b * np + pl) * D + z) * H + y;
+  if (fmt == FMT_CH16P) {
+    const int we = (W + 1) >> 1;
+    return (row * 2 + (x & 1)) * we + (x >> 1);
+  }
+  return row * W + x;
+}
+
+// ------------------------------------------------------------------------------------------------ MMA issue (one thread)
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
+__device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_base, bool fresh) {
+  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  constexpr uint32_t idesc = make_idesc(NB);
+  auto issue = [&](int acc, int tap, uint32_t byte_off, bool first) {
+#pragma unroll
+    for (int j = 0; j < Cfg::CJ; ++j) {
+      const uint64_t ad = make_desc(a0 + (MODE == M2_C0 ? 0 : (2 * j) * Cfg::PLANE) + byte_off, Cfg::A_LBO, Cfg::A_SBO);
+      const uint64_t bd = make_desc(b0 + (j * Cfg::TAPS + tap) * Cfg::B_TILE, NB * 16, 128);
+      umma_f16(acc_base + acc * NB, ad, bd, idesc, (!fresh || !first || j > 0) ? 1u : 0u);
+    }
+  };
+  if (MODE == M2_TR) {
+#pragma unroll 1
+    for (int t = 0; t < TD; ++t)
+#pragma unroll 1
+      for (int cls = 0; cls < 8; ++cls) {
+        const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+        bool first = true;
+        for (int a = 0; a <= pz; ++a)
+          for (int bq = 0; bq <= py; ++bq)
+            for (int c = 0; c <= px; ++c) {
+              const int kz = pz ? (a ? 2 : 0) : 1, oz = pz ? (a ? 0 : 1) : 0;
+              const int ky = py ? (bq ? 2 : 0) : 1, oy = py ? (bq ? 0 : 1) : 0;
+              const int kx = px ? (c ? 2 : 0) : 1, ox = px ? (c ? 0 : 1) : 0;
+              issue(t * 8 + cls, (kz * 3 + ky) * 3 + kx, (uint32_t)((((t + oz) * Cfg::SH + oy) * Cfg::BW + ox) * 16), first);
+              first = false;
+            }
+      }
+  } else {
+#pragma unroll 1
+    for (int t = 0; t < TD; ++t)
+#pragma unroll 1
+      for (int tap = 0; tap < Cfg::TAPS; ++tap) {
+        uint32_t off;
+        if (MODE == M2_C0) {
+          const int kd = tap / 3, kh = tap % 3;
+          off = (uint32_t)((((t + kd) * Cfg::SH + kh) * Cfg::BW) * 16);
+        } else {
+          const int kd = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
+          if (MODE == M2_S2) {
+            const int row = (2 * t + kd) * Cfg::SH + kh;  // even block: kw = 1; odd block: kw = 0 at column 0, kw = 2 at column 1
+            off = (uint32_t)((kw == 1 ? 0 : Cfg::BLK_PITCH) + (row * Cfg::BW + (kw == 2 ? 1 : 0)) * 16);
+          } else {
+            off = (uint32_t)((((t + kd) * Cfg::SH + kh) * Cfg::BW + kw) * 16);
+          }
+        }
+        issue(t, tap, off, tap == 0);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue
+// One warp: TMEM lanes 32*(warp%4)..+31; `part` in {0,1} splits the planes (or plane x parity units for TR) between
+// the two warps that share a quadrant.
+template <int MODE, int NB, int TD>
+__device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, uint32_t acc_base, int q, int lane, int part) {
+  constexpr int COUT_P = NB / 2;
+  const int hl = q * 4 + (lane >> 3), wl = lane & 7;
+  const uint32_t lane_addr = acc_base + ((uint32_t)(q * 32) << 16);
+  const int npo = p.Cout / 4;  // planes per batch entry of a CH16 output with Cout channels
+  if (MODE == M2_TR) {
+    const int iy = tc.y0 + hl, ix = tc.x0 + wl;
+    const bool in_img = (iy < p.Hi) && (ix < p.Wi);
+    uint4* yc = reinterpret_cast<uint4*>(p.y);
+    for (int u = part; u < TD * 4; u += 2) {
+      const int t = u >> 2, pzy = u & 3;
+      if (tc.z0 + t >= p.Di) break;  // warp-uniform
+      const int oz = 2 * (tc.z0 + t) + (pzy >> 1), oy = 2 * iy + (pzy & 1);
+      const uint32_t te = lane_addr + (t * 8 + pzy * 2) * NB, to = te + NB;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT_P; c0 += 8) {
+        float e[8], o[8], le[8], lo8[8];
+        tmem_ld8(te + c0, e);
+        tmem_ld8(te + COUT_P + c0, le);
+        tmem_ld8(to + c0, o);
+        tmem_ld8(to + COUT_P + c0, lo8);
+        if (!in_img || c0 >= p.Cout) continue;
+        const int ph = (c0 >> 3) * 2;
+        float se[8], so[8];
+        if (p.skip) {  // CH16P tensor: even output column 2ix -> parity 0 cell ix, odd column -> parity 1 cell ix
+          const long long ce = cell_index(FMT_CH16P, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, 2 * ix);
+          const long long co_ = cell_index(FMT_CH16P, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, 2 * ix + 1);
+          const long long pstride = (long long)p.Do * p.Ho * (2 * ((p.Wo + 1) >> 1));
+          const uint4 he = __ldg(p.skip + ce), hle = __ldg(p.skip + ce + pstride);
+          const uint4 ho = __ldg(p.skip + co_), hlo = __ldg(p.skip + co_ + pstride);
+          float a[8], b2[8];
+          unpack_cell(he, a); unpack_cell(hle, b2);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) se[c] = a[c] + b2[c];
+          unpack_cell(ho, a); unpack_cell(hlo, b2);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) so[c] = a[c] + b2[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float ve = e[c] + le[c], vo = o[c] + lo8[c];
+          if (p.scale) {
+            const float sc = __ldg(p.scale + c0 + c), sh = __ldg(p.shift + c0 + c);
+            ve = fmaf(ve, sc, sh);
+            vo = fmaf(vo, sc, sh);
+          }
+          if (p.relu) { ve = fmaxf(ve, 0.f); vo = fmaxf(vo, 0.f); }
+          if (p.skip) { ve += se[c]; vo += so[c]; }
+          e[c] = ve; o[c] = vo;
+        }
+        uint4 ehi, elo, ohi, olo;
+        split_pack8(e, ehi, elo);
+        split_pack8(o, ohi, olo);
+        const long long cell = cell_index(FMT_CH16, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, 2 * ix);
+        const long long pstride = (long long)p.Do * p.Ho * p.Wo;
+        yc[cell] = ehi; yc[cell + 1] = ohi;
+        yc[cell + pstride] = elo; yc[cell + pstride + 1] = olo;
+      }
+    }
+  } else {
+    const int oy = tc.y0 + hl, ox = tc.x0 + wl;
+    const bool in_img = (oy < p.Ho) && (ox < p.Wo);
+    for (int t = part; t < TD; t += 2) {
+      const int oz = tc.z0 + t;
+      if (oz >= p.Do) break;  // warp-uniform
+      const uint32_t taddr = lane_addr + t * NB;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT_P; c0 += 8) {
+        float v[8], l8[8];
+        tmem_ld8(taddr + c0, v);
+        tmem_ld8(taddr + COUT_P + c0, l8);
+        if (!in_img || c0 >= p.Cout) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float a = v[c] + l8[c];
+          if (p.scale && c0 + c < p.Cout) a = fmaf(a, __ldg(p.scale + c0 + c), __ldg(p.shift + c0 + c));
+          if (p.relu) a = fmaxf(a, 0.f);
+          v[c] = a;
+        }
+        if (p.out_fmt == FMT_F32) {
+          float* yf = reinterpret_cast<float*>(p.y);
+          const long long oplane = (long long)p.Ho * p.Wo;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c0 + c < p.Cout)
+              yf[(long long)tc.b * p.y_bs + ((long long)(c0 + c) * p.Do + oz) * oplane + (long long)oy * p.Wo + ox] = v[c];
+        } else {
+          uint4 hi, lo;
+          split_pack8(v, hi, lo);
+          const int ph = (c0 >> 3) * 2;
+          const long long cell = cell_index(p.out_fmt, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, ox);
+          const long long pstride = (p.out_fmt == FMT_CH16P) ? (long long)p.Do * p.Ho * (2 * ((p.Wo + 1) >> 1))
+                                                             : (long long)p.Do * p.Ho * p.Wo;
+          uint4* yc = reinterpret_cast<uint4*>(p.y);
+          yc[cell] = hi;
+          yc[cell + pstride] = lo;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
+__global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS, 1)
+    conv_tc2_kernel(const __grid_constant__ Tc2Params p, const __grid_constant__ CUtensorMap tmap) {
+  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* sB = smem + Cfg::OFF_B;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accfull = empty + STAGES;
+  uint64_t* accempty = accfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int MMA_WARP = Cfg::PROD_WARPS;
+
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, (MODE == M2_C0) ? Cfg::PROD_WARPS * 32 : 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(accfull + a, 1);
+      mbar_init(accempty + a, Cfg::EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (Cfg::RESIDENT) {  // the layer's weights stay in smem for the life of the CTA
+    uint4* wdst = reinterpret_cast<uint4*>(sB);
+    for (int i = tid; i < Cfg::B_BYTES / 16; i += Cfg::THREADS) wdst[i] = __ldg(p.wtc + i);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < Cfg::PROD_WARPS) {
+    // ---------------------------------------------------------------- producer
+    if (MODE == M2_C0) {
+      // fp32 cost volume (2 channels) -> cells [hi c0, hi c1, lo c0, lo c1](x) ++ the same of x+1, filled by 12 warps
+      const long long iplane = (long long)p.Hi * p.Wi, cs = (long long)p.Di * iplane;
+      int k = 0;
+      for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++k) {
+        const int s = k % STAGES, u = k / STAGES;
+        const Tile2 tc = decode2(p, lt, TD);
+        mbar_wait(empty + s, (u & 1) ^ 1);
+        uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+        for (int sv = tid; sv < Cfg::ROWS * Cfg::BW; sv += Cfg::PROD_WARPS * 32) {
+          const int sx = sv % Cfg::BW, sy = (sv / Cfg::BW) % Cfg::SH, sz = sv / (Cfg::BW * Cfg::SH);
+          const int ix = tc.x0 + sx - 1, iy = tc.y0 + sy - 1, iz = tc.z0 + sz - 1;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (iy >= 0 && iy < p.Hi && iz >= 0 && iz < p.Di) {
+            const float* src = p.x_f32 + (long long)tc.b * p.x_bs + (long long)iz * iplane + (long long)iy * p.Wi;
+            if (ix >= 0 && ix < p.Wi) { v[0] = __ldg(src + ix); v[1] = __ldg(src + cs + ix); }
+            if (ix + 1 >= 0 && ix + 1 < p.Wi) { v[2] = __ldg(src + ix + 1); v[3] = __ldg(src + cs + ix + 1); }
+          }
+          __half h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            h[i] = __float2half_rn(v[i]);
+            l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+          }
+          const __half2 w0 = __halves2half2(h[0], h[1]), w1 = __halves2half2(l[0], l[1]);
+          const __half2 w2 = __halves2half2(h[2], h[3]), w3 = __halves2half2(l[2], l[3]);
+          *reinterpret_cast<uint4*>(sA + sv * 16) =
+              make_uint4(*reinterpret_cast<const uint32_t*>(&w0), *reinterpret_cast<const uint32_t*>(&w1),
+                         *reinterpret_cast<const uint32_t*>(&w2), *reinterpret_cast<const uint32_t*>(&w3));
+        }
+        fence_proxy_async();
+        mbar_arrive(full + s);
+      }
+    } else if (lane == 0) {
+      // one thread: TMA box loads into the UMMA layout; OOB zero fill is the convolution's padding
+      prefetch_tmap(&tmap);
+      const int planes_per_b = 2 * CIN / 8;
+      int k = 0;
+      for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x) {
+        const Tile2 tc = decode2(p, lt, TD);
+        for (int pass = 0; pass < Cfg::NPASS; ++pass, ++k) {
+          const int s = k % STAGES, u = k / STAGES;
+          mbar_wait(empty + s, (u & 1) ^ 1);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(full + s, Cfg::TX_BYTES);
+#pragma unroll 1
+          for (int pl = 0; pl < Cfg::NPLANE; ++pl) {
+            const int gpl = tc.b * planes_per_b + pass * Cfg::NPLANE + pl;
+            uint8_t* dst = st + pl * Cfg::PLANE;
+            if (MODE == M2_S1) {
+              tma_load_4d(dst, &tmap, full + s, 8 * (tc.x0 - 1), tc.y0 - 1, tc.z0 - 1, gpl);
+            } else if (MODE == M2_TR) {
+              tma_load_4d(dst, &tmap, full + s, 8 * tc.x0, tc.y0, tc.z0, gpl);
+            } else {  // S2 on a CH16P tensor: even columns 2*(x0+i) = even cell x0+i; odd columns 2*(x0+i)-1 = odd cell x0+i-1
+              tma_load_5d(dst, &tmap, full + s, 8 * tc.x0, 0, 2 * tc.y0 - 1, 2 * tc.z0 - 1, gpl);
+              tma_load_5d(dst + Cfg::BLK_PITCH, &tmap, full + s, 8 * (tc.x0 - 1), 1, 2 * tc.y0 - 1, 2 * tc.z0 - 1, gpl);
+            }
+          }
+          if (!Cfg::RESIDENT)
+            bulk_load(st + Cfg::A_BYTES, p.wtc + (size_t)pass * (Cfg::B_BYTES / 16), Cfg::B_BYTES, full + s);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ---------------------------------------------------------------- MMA issuer
+    int k = 0, tile_k = 0;
+    for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
+      if (lane == 0) {
+        const int a = (Cfg::ACC_SETS == 2) ? (tile_k & 1) : 0, v = (Cfg::ACC_SETS == 2) ? (tile_k >> 1) : tile_k;
+        mbar_wait(accempty + a, (v & 1) ^ 1);
+        for (int pass = 0; pass < Cfg::NPASS; ++pass, ++k) {
+          const int s = k % STAGES, u = k / STAGES;
+          mbar_wait(full + s, u & 1);
+          tc_fence_after();
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          issue2<MODE, CIN, CIN_P, NB, TD, STAGES>(smem_u32(st), Cfg::RESIDENT ? smem_u32(sB) : smem_u32(st + Cfg::A_BYTES),
+                                                   tmem_base + a * Cfg::COLS, pass == 0);
+          umma_commit(empty + s);
+        }
+        umma_commit(accfull + a);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (8 warps)
+    const int ew = warp - MMA_WARP - 1;
+    const int q = warp & 3, part = ew >> 2;
+    int tile_k = 0;
+    for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
+      const int a = (Cfg::ACC_SETS == 2) ? (tile_k & 1) : 0, v = (Cfg::ACC_SETS == 2) ? (tile_k >> 1) : tile_k;
+      mbar_wait(accfull + a, v & 1);
+      tc_fence_after();
+      epilogue2<MODE, NB, TD>(p, decode2(p, lt, TD), tmem_base + a * Cfg::COLS, q, lane, part);
+      tc_fence_before();
+      mbar_arrive(accempty + a);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ layout converters
+__global__ void __launch_bounds__(256) f32_to_ch16_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, int D, int H,
+                                                          int W, int fmt, long long n_cells) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;  // one thread per (b, chunk j, z, y, x)
+  if (i >= n_cells) return;
+  const int xx = (int)(i % W);
+  long long r = i / W;
+  const int yy = (int)(r % H); r /= H;
+  const int zz = (int)(r % D); r /= D;
+  const int j = (int)(r % (C / 8));
+  const int b = (int)(r / (C / 8));
+  const long long vol = (long long)D * H * W;
+  const float* src = x + ((long long)b * C + j * 8) * vol + ((long long)zz * H + yy) * W + xx;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c * vol);
+  uint4 hi, lo;
+  split_pack8(v, hi, lo);
+  const long long cell = cell_index(fmt, b, C / 4, 2 * j, D, H, W, zz, yy, xx);
+  const long long pstride = (fmt == FMT_CH16P) ? (long long)D * H * (2 * ((W + 1) >> 1)) : vol;
+  y[cell] = hi;
+  y[cell + pstride] = lo;
+}
+
+__global__ void __launch_bounds__(256) ch16_to_f32_kernel(const uint4* __restrict__ x, float* __restrict__ y, int C, int D, int H,
+                                                          int W, int fmt, long long n_cells) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_cells) return;
+  const int xx = (int)(i % W);
+  long long r = i / W;
+  const int yy = (int)(r % H); r /= H;
+  const int zz = (int)(r % D); r /= D;
+  const int j = (int)(r % (C / 8));
+  const int b = (int)(r / (C / 8));
+  const long long vol = (long long)D * H * W;
+  const long long cell = cell_index(fmt, b, C / 4, 2 * j, D, H, W, zz, yy, xx);
+  const long long pstride = (fmt == FMT_CH16P) ? (long long)D * H * (2 * ((W + 1) >> 1)) : vol;
+  float a[8], l[8];
+  unpack_cell(__ldg(x + cell), a);
+  unpack_cell(__ldg(x + cell + pstride), l);
+  float* dst = y + ((long long)b * C + j * 8) * vol + ((long long)zz * H + yy) * W + xx;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) dst[c * vol] = a[c] + l[c];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// tensor map over a CH16 (rank 4: {W*8 halfs, H, D, planes}) or CH16P (rank 5: {We*8, 2, H, D, planes}) tensor
+static int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int D, int H, int W, int box_cells, int box_h, int box_d) {
+  EncodeTiledFn enc = encode_fn();
+  DMVS_REQUIRE(enc != nullptr, DMVS_ERR_CUDA, "conv_tc2: cuTensorMapEncodeTiled is not available from the driver");
+  CUresult r;
+  if (fmt == FMT_CH16) {
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)box_cells * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t we = (cuuint64_t)(W + 1) / 2;
+    const cuuint64_t dims[5] = {we * 8, 2, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
+    const cuuint64_t strides[4] = {we * 16, 2 * we * 16, (cuuint64_t)H * 2 * we * 16, (cuuint64_t)D * H * 2 * we * 16};
+    const cuuint32_t box[5] = {(cuuint32_t)box_cells * 8, 1, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  DMVS_REQUIRE(r == CUDA_SUCCESS, DMVS_ERR_CUDA, "conv_tc2: cuTensorMapEncodeTiled failed (%d) for dims D=%d H=%d W=%d planes=%d", (int)r,
+               D, H, W, planes);
+  return DMVS_OK;
+}
+
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
+static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
+  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  const int gw = (MODE == M2_TR) ? p.Wi : p.Wo, gh = (MODE == M2_TR) ? p.Hi : p.Ho, gd = (MODE == M2_TR) ? p.Di : p.Do;
+  p.tiles_x = ceil_div(gw, T_W);
+  p.tiles_y = ceil_div(gh, T_H);
+  p.tiles_z = ceil_div(gd, TD);
+  p.n_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.B;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (MODE == M2_C0) {
+    p.x_f32 = reinterpret_cast<const float*>(x);
+    p.x_bs = 2LL * p.Di * p.Hi * p.Wi;
+  } else {
+    const int rc = make_tmap(&tmap, x, MODE == M2_S2 ? FMT_CH16P : FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, Cfg::SD);
+    if (rc != DMVS_OK) return rc;
+  }
+  auto kern = conv_tc2_kernel<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      set_error("conv_tc2: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+      return DMVS_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;  // one persistent CTA per SM
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, tmap);
+  return check_launch("conv_tc2");
+}
+
+// One conv block on CH16 activations.  x: CH16 (stride 1 / transposed), CH16P (stride 2) or fp32 NCDHW (Cin == 2);
+// skip: CH16P (transposed only); y: out_fmt.  Returns +1 if the shape has no specialisation.
+int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, void* y, long long y_bs_f32, int B, int Cin, int Cout, int Di,
+                   int Hi, int Wi, int stride, int transposed, int relu, int out_fmt, cudaStream_t st) {
+  if (!L.w_tc) return 1;
+  DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc2: null pointer");
+  DMVS_REQUIRE(aligned16(L.w_tc) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
+               "conv_tc2: pointers must be 16-byte aligned");
+  DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P, DMVS_ERR_BAD_SHAPE, "conv_tc2: bad out_fmt %d", out_fmt);
+  Tc2Params p;
+  memset(&p, 0, sizeof(p));
+  p.wtc = reinterpret_cast<const uint4*>(L.w_tc); p.scale = L.scale; p.shift = L.shift;
+  p.skip = reinterpret_cast<const uint4*>(skip); p.y = y;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.relu = relu; p.out_fmt = out_fmt;
+  p.y_bs = y_bs_f32;
+  if (transposed) {
+    p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
+    DMVS_REQUIRE(out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE, "conv_tc2: transposed convs write CH16");
+    if (Cin == 16 && Cout == 8) return launch2<M2_TR, 16, 16, 16, 2, 4>(p, x, st);   // conv11
+    if (Cin == 32 && Cout == 16) return launch2<M2_TR, 32, 16, 32, 1, 2>(p, x, st);  // conv9, 2 passes, weights streamed
+    if (Cin == 64 && Cout == 32) return launch2<M2_TR, 64, 8, 64, 1, 3>(p, x, st);   // conv7, 8 passes
+    return 1;
+  }
+  DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");
+  if (stride == 2) {
+    p.Do = (Di - 1) / 2 + 1; p.Ho = (Hi - 1) / 2 + 1; p.Wo = (Wi - 1) / 2 + 1;
+    DMVS_REQUIRE(Wi % 2 == 0, DMVS_ERR_BAD_SHAPE, "conv_tc2: stride-2 input width must be even");
+    if (Cin == 8 && Cout == 16) return launch2<M2_S2, 8, 8, 32, 1, 3>(p, x, st);     // conv1
+    if (Cin == 16 && Cout == 32) return launch2<M2_S2, 16, 8, 64, 1, 2>(p, x, st);   // conv3, 2 passes
+    if (Cin == 32 && Cout == 64) return launch2<M2_S2, 32, 8, 128, 1, 1>(p, x, st);  // conv5, 4 passes
+    return 1;
+  }
+  p.Do = Di; p.Ho = Hi; p.Wo = Wi;
+  if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
+  if (Cin == 2 && Cout == 8) return launch2<M2_C0, 2, 2, 16, 4, 4>(p, x, st);        // conv0
+  if (Cin == 8 && Cout <= 8) {                                                       // prob (8 -> 2)
+    DMVS_REQUIRE(out_fmt == FMT_F32 || Cout == 8, DMVS_ERR_BAD_SHAPE, "conv_tc2: Cout < 8 needs an fp32 output");
+    return launch2<M2_S1, 8, 8, 16, 4, 4>(p, x, st);
+  }
+  if (Cin == 16 && Cout == 16) return launch2<M2_S1, 16, 16, 32, 2, 3>(p, x, st);    // conv2
+  if (Cin == 32 && Cout == 32) return launch2<M2_S1, 32, 8, 64, 2, 2>(p, x, st);     // conv4, 4 passes
+  if (Cin == 64 && Cout == 64) return launch2<M2_S1, 64, 8, 128, 1, 1>(p, x, st);    // conv6, 8 passes
+  return 1;
+}
+
+int convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, cudaStream_t st) {
+  DMVS_REQUIRE(x && y && aligned16(x) && aligned16(y), DMVS_ERR_BAD_POINTER, "convert_layout: null or misaligned pointer");
+  DMVS_REQUIRE(C % 8 == 0 && (fmt == FMT_CH16 || fmt == FMT_CH16P), DMVS_ERR_BAD_SHAPE, "convert_layout: C=%d fmt=%d", C, fmt);
+  DMVS_REQUIRE(fmt != FMT_CH16P || W % 2 == 0, DMVS_ERR_BAD_SHAPE, "convert_layout: CH16P needs an even width");
+  const long long n = (long long)B * (C / 8) * D * H * W;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (to_ch16)
+    f32_to_ch16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<uint4*>(y), C, D, H, W, fmt, n);
+  else
+    ch16_to_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<float*>(y), C, D, H, W, fmt, n);
+  return check_launch("convert_layout");
+}
+
+}  // namespace dmvs

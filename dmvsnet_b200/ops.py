@@ -241,6 +241,57 @@ def conv3d(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = Tr
     return y
 
 
+_FMT = {"f32": N.FMT_F32, "ch16": N.FMT_CH16, "ch16p": N.FMT_CH16P}
+
+
+def to_ch16(x: torch.Tensor, parity_split: bool = False) -> torch.Tensor:
+    """fp32 [B,C,D,H,W] -> the tensor path's cell layout (include/dmvs_b200.h DMVS_FMT_CH16 / CH16P), as a flat byte-equal
+    fp32-sized buffer viewed as int32 [B, C/4 planes, D, H, W, 4]."""
+    lib = N.load()
+    x = _req(x, "x").contiguous()
+    b, c, d, h, w = x.shape
+    y = torch.empty(b, c // 4, d, h, w, 4, device=x.device, dtype=torch.int32)
+    rc = lib.dmvs_convert_layout(x.data_ptr(), y.data_ptr(), b, c, d, h, w, N.FMT_CH16P if parity_split else N.FMT_CH16, 1, _stream())
+    N.check(rc, "dmvs_convert_layout")
+    return y
+
+
+def from_ch16(y: torch.Tensor, channels: int, parity_split: bool = False) -> torch.Tensor:
+    lib = N.load()
+    b, planes, d, h, w, _ = y.shape
+    x = torch.empty(b, channels, d, h, w, device=y.device, dtype=torch.float32)
+    rc = lib.dmvs_convert_layout(y.data_ptr(), x.data_ptr(), b, channels, d, h, w, N.FMT_CH16P if parity_split else N.FMT_CH16, 0, _stream())
+    N.check(rc, "dmvs_convert_layout")
+    return x
+
+
+def conv3d_ch16(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = True, skip: Optional[torch.Tensor] = None,
+                out_fmt: str = "ch16") -> torch.Tensor:
+    """One block of the tensor path.  x: cells from ``to_ch16`` (parity split for stride 2) or fp32 [B,2,D,H,W] for conv0;
+    skip: parity-split cells; returns cells (or fp32 when out_fmt == "f32")."""
+    lib = N.load()
+    if layer.cin == 2:
+        x = _req(x, "x").contiguous()
+        b, _, di, hi, wi = x.shape
+    else:
+        b, _, di, hi, wi, _ = x.shape
+    if layer.transposed:
+        do, ho, wo = 2 * di, 2 * hi, 2 * wi
+    elif stride == 2:
+        do, ho, wo = (di - 1) // 2 + 1, (hi - 1) // 2 + 1, (wi - 1) // 2 + 1
+    else:
+        do, ho, wo = di, hi, wi
+    if out_fmt == "f32":
+        y = torch.empty(b, layer.cout, do, ho, wo, device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty(b, layer.cout // 4, do, ho, wo, 4, device=x.device, dtype=torch.int32)
+    cl = layer.c_struct()
+    rc = lib.dmvs_conv3d_ch16(x.data_ptr(), ctypes.byref(cl), _ptr(skip), y.data_ptr(), b, layer.cin, layer.cout, di, hi, wi,
+                              2 if layer.transposed else stride, int(layer.transposed), int(relu), _FMT[out_fmt], _stream())
+    N.check(rc, "dmvs_conv3d_ch16")
+    return y
+
+
 class PackedRegnet:
     """Both branches of a CostRegNet / CostRegNet_refine, repacked for dmvs_regnet_forward_f32."""
 

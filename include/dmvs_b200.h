@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 2
+#define DMVS_ABI_VERSION 3
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -109,6 +109,24 @@ int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, cons
  *   skip (nullable) has the shape of y and is added after the ReLU (module.py:394-396) */
 int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* skip, float* y, int B, int Cin, int Cout,
                     int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int engine, void* stream);
+
+/* Activation layouts of the tensor path.  CH16: 16-byte cells of 8 fp16, [B][plane][D][H][W], plane 2j = hi and plane
+ * 2j+1 = lo of channels 8j..8j+7 (x = hi + lo, same bytes as fp32) - the layout the UMMA descriptors and TMA boxes consume.
+ * CH16P: the same with every row stored column-parity split, [..][H][parity][ceil(W/2)] (inputs of stride-2 convs). */
+#define DMVS_FMT_F32 0
+#define DMVS_FMT_CH16 1
+#define DMVS_FMT_CH16P 2
+
+/* fp32 NCDHW <-> CH16 / CH16P (C % 8 == 0; CH16P: W even).  to_ch16 != 0: x fp32 -> y cells; else x cells -> y fp32. */
+int dmvs_convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, void* stream);
+
+/* One conv block of the tensor path on CH16 activations (TMA-fed persistent tcgen05 kernel, kernel 3x3x3 only).
+ *   x     CH16 (stride 1, transposed), CH16P (stride 2), or fp32 [B,2,D,H,W] when Cin == 2 (conv0)
+ *   skip  CH16P with the output's shape, transposed convs only (nullable)
+ *   y     out_fmt: DMVS_FMT_CH16 / DMVS_FMT_CH16P, or DMVS_FMT_F32 (needed when Cout < 8); transposed convs write CH16
+ * Returns DMVS_ERR_BAD_SHAPE for (Cin, Cout, stride) combinations outside the U-Net's. layer->w_tc must be set. */
+int dmvs_conv3d_ch16(const void* x, const dmvs_conv_layer* layer, const void* skip, void* y, int B, int Cin, int Cout, int Di,
+                     int Hi, int Wi, int stride, int transposed, int relu, int out_fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * E1  dual-depth head.  Replaces DepthNet.forward (networks/mvsnet.py:15-66) + depth_regression

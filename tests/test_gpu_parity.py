@@ -133,6 +133,44 @@ def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d, engine)
     assert rel_linf(got, want) < 1e-5, rel_linf(got, want)
 
 
+@pytest.mark.parametrize("cin,cout,dims,stride,transposed", [
+    (2, 8, (6, 35, 24), 1, False), (8, 16, (8, 34, 48), 2, False), (16, 16, (5, 37, 50), 1, False), (16, 32, (4, 37, 22), 2, False),
+    (32, 32, (3, 19, 27), 1, False), (32, 64, (3, 18, 26), 2, False), (64, 64, (2, 17, 9), 1, False), (64, 32, (1, 9, 10), 2, True),
+    (32, 16, (2, 17, 11), 2, True), (16, 8, (3, 19, 13), 2, True), (8, 2, (7, 33, 41), 1, False), (8, 16, (1, 8, 8), 2, False),
+    (16, 8, (1, 40, 100), 2, True)])
+def test_conv_layer_ch16_vs_torch(cin, cout, dims, stride, transposed):
+    """The TMA-fed persistent tcgen05 kernels on the CH16 / CH16P cell layouts, one layer at a time, vs torch fp32."""
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(cin * 100 + cout + 7)
+    b = 2
+    x = torch.randn(b, cin, *dims, generator=g)
+    w = torch.randn(*((cin, cout) if transposed else (cout, cin)), 3, 3, 3, generator=g) * (2.0 / (cin * 27)) ** 0.5
+    has_bn = cout != 2
+    bn = (0.8 + 0.4 * torch.rand(cout, generator=g), 0.1 * torch.randn(cout, generator=g), 0.2 * torch.randn(cout, generator=g),
+          0.5 + torch.rand(cout, generator=g)) if has_bn else None
+    want = _torch_block(x, w, bn, stride, transposed, has_bn, None)
+    skip = torch.randn(want.shape, generator=g) if transposed else None
+    if skip is not None:
+        want = want + skip
+    layer = ops.PackedLayer(cuda(w), transposed, tuple(cuda(t) for t in bn) if bn else None)
+    xin = cuda(x) if cin == 2 else ops.to_ch16(cuda(x), parity_split=(stride == 2 and not transposed))
+    if cin != 2:  # the converters round-trip to 2^-22
+        back = ops.from_ch16(xin, cin, parity_split=(stride == 2 and not transposed))
+        assert rel_linf(back, x) < 1e-6
+    sk = ops.to_ch16(cuda(skip), parity_split=True) if skip is not None else None
+    if cout == 2:
+        got = ops.conv3d_ch16(xin, layer, stride=stride, relu=False, out_fmt="f32")
+    else:
+        for fmt in (["ch16"] if transposed else ["ch16", "ch16p"]):
+            if fmt == "ch16p" and want.shape[-1] % 2:
+                continue
+            cells = ops.conv3d_ch16(xin, layer, stride=stride, relu=True, skip=sk, out_fmt=fmt)
+            got = ops.from_ch16(cells, cout, parity_split=(fmt == "ch16p"))
+            assert rel_linf(got, want) < 1e-5, (fmt, rel_linf(got, want))
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel_linf(got, want) < 1e-5, rel_linf(got, want)
+
+
 @pytest.mark.parametrize("engine", ["fp32", "tensor"])
 @pytest.mark.parametrize("refine,d,h,w,b", [(False, 8, 16, 24, 1), (False, 16, 8, 40, 2), (True, 4, 16, 24, 2), (True, 4, 40, 8, 1)])
 def test_regnet_vs_oracle(refine, d, h, w, b, engine):
