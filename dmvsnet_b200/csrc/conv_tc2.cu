@@ -114,55 +114,52 @@ __device__ __forceinline__ long long cell_index(int fmt, int b, int np, int pl, 
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issue (one thread)
+// The issuing thread is the serial resource of a persistent CTA, so the whole tap / plane / chunk nest is unrolled at
+// compile time: every descriptor is "base descriptor + constant" (the 14-bit address field never carries: smem < 256 KB),
+// i.e. one 64-bit add per operand and the tcgen05.mma itself.
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
 __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_base, bool fresh) {
   using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES>;
   constexpr uint32_t idesc = make_idesc(NB);
-  auto issue = [&](int acc, int tap, uint32_t byte_off, bool first) {
+  const uint64_t adesc0 = make_desc(a0, Cfg::A_LBO, Cfg::A_SBO);
+  const uint64_t bdesc0 = make_desc(b0, NB * 16, 128);
+  const uint32_t fresh_acc = fresh ? 0u : 1u;
 #pragma unroll
-    for (int j = 0; j < Cfg::CJ; ++j) {
-      const uint64_t ad = make_desc(a0 + (MODE == M2_C0 ? 0 : (2 * j) * Cfg::PLANE) + byte_off, Cfg::A_LBO, Cfg::A_SBO);
-      const uint64_t bd = make_desc(b0 + (j * Cfg::TAPS + tap) * Cfg::B_TILE, NB * 16, 128);
-      umma_f16(acc_base + acc * NB, ad, bd, idesc, (!fresh || !first || j > 0) ? 1u : 0u);
-    }
-  };
-  if (MODE == M2_TR) {
-#pragma unroll 1
-    for (int t = 0; t < TD; ++t)
-#pragma unroll 1
-      for (int cls = 0; cls < 8; ++cls) {
-        const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
-        bool first = true;
-        for (int a = 0; a <= pz; ++a)
-          for (int bq = 0; bq <= py; ++bq)
-            for (int c = 0; c <= px; ++c) {
-              const int kz = pz ? (a ? 2 : 0) : 1, oz = pz ? (a ? 0 : 1) : 0;
-              const int ky = py ? (bq ? 2 : 0) : 1, oy = py ? (bq ? 0 : 1) : 0;
-              const int kx = px ? (c ? 2 : 0) : 1, ox = px ? (c ? 0 : 1) : 0;
-              issue(t * 8 + cls, (kz * 3 + ky) * 3 + kx, (uint32_t)((((t + oz) * Cfg::SH + oy) * Cfg::BW + ox) * 16), first);
-              first = false;
-            }
-      }
-  } else {
-#pragma unroll 1
-    for (int t = 0; t < TD; ++t)
-#pragma unroll 1
-      for (int tap = 0; tap < Cfg::TAPS; ++tap) {
-        uint32_t off;
-        if (MODE == M2_C0) {
-          const int kd = tap / 3, kh = tap % 3;
-          off = (uint32_t)((((t + kd) * Cfg::SH + kh) * Cfg::BW) * 16);
+  for (int t = 0; t < TD; ++t) {
+#pragma unroll
+    for (int tap = 0; tap < Cfg::TAPS; ++tap) {
+      int acc, off;
+      bool first;
+      if (MODE == M2_TR) {
+        // tap (kz,ky,kx) of the transposed kernel feeds output parity class (kz!=1, ky!=1, kx!=1); k = 0 reads input +1
+        const int kz = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
+        const int pz = kz != 1, py = ky != 1, px = kx != 1;
+        acc = t * 8 + pz * 4 + py * 2 + px;
+        off = (((t + (kz == 0)) * Cfg::SH + (ky == 0)) * Cfg::BW + (kx == 0)) * 16;
+        first = (kz == (pz ? 0 : 1)) && (ky == (py ? 0 : 1)) && (kx == (px ? 0 : 1));
+      } else if (MODE == M2_C0) {
+        const int kd = tap / 3, kh = tap % 3;
+        acc = t;
+        off = (((t + kd) * Cfg::SH + kh) * Cfg::BW) * 16;
+        first = tap == 0;
+      } else {
+        const int kd = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
+        acc = t;
+        first = tap == 0;
+        if (MODE == M2_S2) {
+          const int row = (2 * t + kd) * Cfg::SH + kh;  // even block: kw = 1; odd block: kw = 0 at column 0, kw = 2 at column 1
+          off = (kw == 1 ? 0 : Cfg::BLK_PITCH) + (row * Cfg::BW + (kw == 2 ? 1 : 0)) * 16;
         } else {
-          const int kd = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
-          if (MODE == M2_S2) {
-            const int row = (2 * t + kd) * Cfg::SH + kh;  // even block: kw = 1; odd block: kw = 0 at column 0, kw = 2 at column 1
-            off = (uint32_t)((kw == 1 ? 0 : Cfg::BLK_PITCH) + (row * Cfg::BW + (kw == 2 ? 1 : 0)) * 16);
-          } else {
-            off = (uint32_t)((((t + kd) * Cfg::SH + kh) * Cfg::BW + kw) * 16);
-          }
+          off = (((t + kd) * Cfg::SH + kh) * Cfg::BW + kw) * 16;
         }
-        issue(t, tap, off, tap == 0);
       }
+#pragma unroll
+      for (int j = 0; j < Cfg::CJ; ++j) {
+        const uint64_t ad = adesc0 + (uint64_t)(((MODE == M2_C0 ? 0 : (2 * j) * Cfg::PLANE) + off) >> 4);
+        const uint64_t bd = bdesc0 + (uint64_t)(((j * Cfg::TAPS + tap) * Cfg::B_TILE) >> 4);
+        umma_f16(acc_base + acc * NB, ad, bd, idesc, (first && j == 0) ? fresh_acc : 1u);
+      }
+    }
   }
 }
 
@@ -322,26 +319,40 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS,
         const Tile2 tc = decode2(p, lt, TD);
         mbar_wait(empty + s, (u & 1) ^ 1);
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
-        for (int sv = tid; sv < Cfg::ROWS * Cfg::BW; sv += Cfg::PROD_WARPS * 32) {
-          const int sx = sv % Cfg::BW, sy = (sv / Cfg::BW) % Cfg::SH, sz = sv / (Cfg::BW * Cfg::SH);
-          const int ix = tc.x0 + sx - 1, iy = tc.y0 + sy - 1, iz = tc.z0 + sz - 1;
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (iy >= 0 && iy < p.Hi && iz >= 0 && iz < p.Di) {
-            const float* src = p.x_f32 + (long long)tc.b * p.x_bs + (long long)iz * iplane + (long long)iy * p.Wi;
-            if (ix >= 0 && ix < p.Wi) { v[0] = __ldg(src + ix); v[1] = __ldg(src + cs + ix); }
-            if (ix + 1 >= 0 && ix + 1 < p.Wi) { v[2] = __ldg(src + ix + 1); v[3] = __ldg(src + cs + ix + 1); }
-          }
-          __half h[4], l[4];
+        // three cells per thread per trip, all 12 loads issued before any conversion (the fill is latency bound)
+        constexpr int NCELL = Cfg::ROWS * Cfg::BW, PT = Cfg::PROD_WARPS * 32, UNR = 3;
+        for (int base = tid; base < NCELL; base += UNR * PT) {
+          float v[UNR][4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            h[i] = __float2half_rn(v[i]);
-            l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+          for (int r = 0; r < UNR; ++r) {
+            const int sv = base + r * PT;
+            v[r][0] = v[r][1] = v[r][2] = v[r][3] = 0.f;
+            if (sv < NCELL) {
+              const int sx = sv % Cfg::BW, sy = (sv / Cfg::BW) % Cfg::SH, sz = sv / (Cfg::BW * Cfg::SH);
+              const int ix = tc.x0 + sx - 1, iy = tc.y0 + sy - 1, iz = tc.z0 + sz - 1;
+              if (iy >= 0 && iy < p.Hi && iz >= 0 && iz < p.Di) {
+                const float* src = p.x_f32 + (long long)tc.b * p.x_bs + (long long)iz * iplane + (long long)iy * p.Wi;
+                if (ix >= 0 && ix < p.Wi) { v[r][0] = __ldg(src + ix); v[r][1] = __ldg(src + cs + ix); }
+                if (ix + 1 >= 0 && ix + 1 < p.Wi) { v[r][2] = __ldg(src + ix + 1); v[r][3] = __ldg(src + cs + ix + 1); }
+              }
+            }
           }
-          const __half2 w0 = __halves2half2(h[0], h[1]), w1 = __halves2half2(l[0], l[1]);
-          const __half2 w2 = __halves2half2(h[2], h[3]), w3 = __halves2half2(l[2], l[3]);
-          *reinterpret_cast<uint4*>(sA + sv * 16) =
-              make_uint4(*reinterpret_cast<const uint32_t*>(&w0), *reinterpret_cast<const uint32_t*>(&w1),
-                         *reinterpret_cast<const uint32_t*>(&w2), *reinterpret_cast<const uint32_t*>(&w3));
+#pragma unroll
+          for (int r = 0; r < UNR; ++r) {
+            const int sv = base + r * PT;
+            if (sv >= NCELL) break;
+            __half h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              h[i] = __float2half_rn(v[r][i]);
+              l[i] = __float2half_rn(v[r][i] - __half2float(h[i]));
+            }
+            const __half2 w0 = __halves2half2(h[0], h[1]), w1 = __halves2half2(l[0], l[1]);
+            const __half2 w2 = __halves2half2(h[2], h[3]), w3 = __halves2half2(l[2], l[3]);
+            *reinterpret_cast<uint4*>(sA + sv * 16) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&w0), *reinterpret_cast<const uint32_t*>(&w1),
+                           *reinterpret_cast<const uint32_t*>(&w2), *reinterpret_cast<const uint32_t*>(&w3));
+          }
         }
         fence_proxy_async();
         mbar_arrive(full + s);
