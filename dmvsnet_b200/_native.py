@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ul
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 5
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 ENGINE_FP32, ENGINE_TENSOR = 0, 1
 MAX_SRC = 16
@@ -25,7 +25,7 @@ class NativeLibraryError(RuntimeError):
 
 
 class ConvLayer(ctypes.Structure):
-    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("w_tc", c_void_p)]
+    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("w_tc", c_void_p), ("w_tc_kd", c_void_p)]
 
 
 class RegnetBranch(ctypes.Structure):
@@ -46,7 +46,7 @@ SIGNATURES = {
                                 c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_convert_layout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_conv3d_ch16": (c_int, [c_void_p, POINTER(ConvLayer), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                 c_int, c_int, c_int, c_int, c_void_p]),
+                                 c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_depth_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_refine_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,

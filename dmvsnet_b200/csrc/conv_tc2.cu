@@ -14,6 +14,9 @@
 //     the epilogue applies eval-BatchNorm + ReLU (+ skip), splits to hi/lo fp16 and stores CH16 / CH16P cells (or fp32
 //     NCDHW for the last layer).
 //   * conv0 (Cin = 2, fp32 cost volume in) keeps a thread-filled producer (12 warps) in the same pipeline.
+//   * prob (8 -> 2, mode PB): the depth tap kd is folded into N.  Cout = 2 uses only 4 of the 16 UMMA columns, so the
+//     columns carry [kd][hi0 hi1 lo0 lo1]: one accumulator per INPUT plane holds the three kd partial sums, the
+//     epilogue adds P[t+kd][kd] - (TD+2)*9 MMAs per tile instead of TD*27 at the same cost each.
 #include <cuda.h>
 #include <string.h>
 
@@ -22,7 +25,7 @@
 namespace dmvs {
 
 enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2 };
-enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3 };
+enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4 };
 constexpr int T_H = 16, T_W = 8;
 
 struct Tc2Params {
@@ -42,11 +45,12 @@ struct Tc2Params {
 __host__ __device__ constexpr int pad128(int v) { return (v + 127) / 128 * 128; }
 __host__ __device__ constexpr int pow2c(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
 struct C2 {
-  static constexpr int SD = (MODE == M2_S2) ? 2 * TD + 1 : (MODE == M2_TR) ? TD + 1 : TD + 2;
+  // KD = 1: the 2-D convolutions of the refine net's bottleneck (no taps, halo or stride along depth)
+  static constexpr int SD = (KD == 1) ? TD : (MODE == M2_S2) ? 2 * TD + 1 : (MODE == M2_TR) ? TD + 1 : TD + 2;
   static constexpr int SH = (MODE == M2_S2) ? 2 * T_H + 1 : (MODE == M2_TR) ? T_H + 1 : T_H + 2;
-  static constexpr int BW = (MODE == M2_S1 || MODE == M2_C0) ? T_W + 2 : T_W + 1;  // cells per staged row (S2: per parity block)
+  static constexpr int BW = (MODE == M2_S1 || MODE == M2_C0 || MODE == M2_PB) ? T_W + 2 : T_W + 1;  // cells per staged row (S2: per parity block)
   static constexpr int ROWS = SD * SH;
   static constexpr int BLK_BYTES = ROWS * BW * 16;  // bytes one TMA box writes
   static constexpr int BLK_PITCH = pad128(BLK_BYTES);
@@ -56,7 +60,7 @@ struct C2 {
   static constexpr int NPLANE = (MODE == M2_C0) ? 1 : 2 * CJ;
   static constexpr int NPASS = (MODE == M2_C0) ? 1 : CIN / CIN_P;
   static constexpr bool RESIDENT = NPASS == 1;
-  static constexpr int TAPS = (MODE == M2_C0) ? 9 : 27;
+  static constexpr int TAPS = (MODE == M2_C0 || MODE == M2_PB || KD == 1) ? 9 : 27;
   static constexpr int A_BYTES = NPLANE * PLANE;
   static constexpr int A_LBO = (MODE == M2_C0) ? 32 : PLANE;
   static constexpr int A_SBO = (MODE == M2_S2) ? 2 * BW * 16 : BW * 16;
@@ -67,13 +71,19 @@ struct C2 {
   static constexpr int OFF_B = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_B + (RESIDENT ? pad128(B_BYTES) : 0);
   static constexpr int SMEM = OFF_BAR + 8 * (2 * STAGES + 4) + 16 + 128;  // + slack for manual 128-byte alignment
-  static constexpr int NACC = (MODE == M2_TR) ? 8 * TD : TD;
+  static constexpr int NACC = (MODE == M2_TR) ? (KD == 1 ? 4 : 8) * TD : (MODE == M2_PB) ? TD + 2 : TD;
   static constexpr int COLS = NACC * NB;
   static constexpr int ACC_SETS = (2 * COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = pow2c(ACC_SETS * COLS);
   static constexpr int PROD_WARPS = (MODE == M2_C0) ? 12 : 1;
   static constexpr int EPI_WARPS = 8;
-  static constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
+  // one MMA-issuing warp per accumulator set: tile k is issued by warp k % MMA_WARPS into set k % 2, so the (serial,
+  // single-thread) descriptor arithmetic of consecutive tiles overlaps
+  // Each issuing warp owns a private slice of the stage ring (stage = MMA_WARPS*(j % HS) + warp, j = its own item count):
+  // a full/empty mbarrier is then always consumed by one warp in order - parity waits cannot alias a phase two uses away.
+  static constexpr int MMA_WARPS = (ACC_SETS == 2 && STAGES % 2 == 0) ? 2 : 1;
+  static constexpr int HS = STAGES / MMA_WARPS;
+  static constexpr int THREADS = (PROD_WARPS + MMA_WARPS + EPI_WARPS) * 32;
   static_assert(COLS <= 512, "accumulators exceed TMEM");
   static_assert(SMEM <= 227 * 1024, "pipeline does not fit shared memory");
   static_assert(CIN % CIN_P == 0 || MODE == M2_C0, "channel passes");
@@ -117,24 +127,30 @@ __device__ __forceinline__ long long cell_index(int fmt, int b, int np, int pl, 
 // The issuing thread is the serial resource of a persistent CTA, so the whole tap / plane / chunk nest is unrolled at
 // compile time: every descriptor is "base descriptor + constant" (the 14-bit address field never carries: smem < 256 KB),
 // i.e. one 64-bit add per operand and the tcgen05.mma itself.
-template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD>
 __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_base, bool fresh) {
-  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
   constexpr uint32_t idesc = make_idesc(NB);
   const uint64_t adesc0 = make_desc(a0, Cfg::A_LBO, Cfg::A_SBO);
   const uint64_t bdesc0 = make_desc(b0, NB * 16, 128);
   const uint32_t fresh_acc = fresh ? 0u : 1u;
 #pragma unroll
-  for (int t = 0; t < TD; ++t) {
+  for (int t = 0; t < ((MODE == M2_PB) ? TD + 2 : TD); ++t) {
 #pragma unroll
     for (int tap = 0; tap < Cfg::TAPS; ++tap) {
       int acc, off;
       bool first;
-      if (MODE == M2_TR) {
+      if (MODE == M2_PB) {
+        // t is the staged INPUT plane; its accumulator collects the (kh,kw) taps for all three kd at once
+        const int kh = tap / 3, kw = tap % 3;
+        acc = t;
+        off = ((t * Cfg::SH + kh) * Cfg::BW + kw) * 16;
+        first = tap == 0;
+      } else if (MODE == M2_TR) {
         // tap (kz,ky,kx) of the transposed kernel feeds output parity class (kz!=1, ky!=1, kx!=1); k = 0 reads input +1
-        const int kz = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
+        const int kz = (KD == 3) ? tap / 9 : 1, ky = (tap % 9) / 3, kx = tap % 3;
         const int pz = kz != 1, py = ky != 1, px = kx != 1;
-        acc = t * 8 + pz * 4 + py * 2 + px;
+        acc = (KD == 3) ? t * 8 + pz * 4 + py * 2 + px : t * 4 + py * 2 + px;
         off = (((t + (kz == 0)) * Cfg::SH + (ky == 0)) * Cfg::BW + (kx == 0)) * 16;
         first = (kz == (pz ? 0 : 1)) && (ky == (py ? 0 : 1)) && (kx == (px ? 0 : 1));
       } else if (MODE == M2_C0) {
@@ -143,11 +159,11 @@ __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_ba
         off = (((t + kd) * Cfg::SH + kh) * Cfg::BW) * 16;
         first = tap == 0;
       } else {
-        const int kd = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
+        const int kd = (KD == 3) ? tap / 9 : 0, kh = (tap % 9) / 3, kw = tap % 3;
         acc = t;
         first = tap == 0;
         if (MODE == M2_S2) {
-          const int row = (2 * t + kd) * Cfg::SH + kh;  // even block: kw = 1; odd block: kw = 0 at column 0, kw = 2 at column 1
+          const int row = ((KD == 3 ? 2 * t : t) + kd) * Cfg::SH + kh;  // even block: kw = 1; odd block: kw = 0 at column 0, kw = 2 at column 1
           off = (kw == 1 ? 0 : Cfg::BLK_PITCH) + (row * Cfg::BW + (kw == 2 ? 1 : 0)) * 16;
         } else {
           off = (((t + kd) * Cfg::SH + kh) * Cfg::BW + kw) * 16;
@@ -166,7 +182,7 @@ __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_ba
 // ------------------------------------------------------------------------------------------------ epilogue
 // One warp: TMEM lanes 32*(warp%4)..+31; `part` in {0,1} splits the planes (or plane x parity units for TR) between
 // the two warps that share a quadrant.
-template <int MODE, int NB, int TD>
+template <int MODE, int NB, int TD, int KD>
 __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, uint32_t acc_base, int q, int lane, int part) {
   constexpr int COUT_P = NB / 2;
   const int hl = q * 4 + (lane >> 3), wl = lane & 7;
@@ -176,11 +192,12 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
     const int iy = tc.y0 + hl, ix = tc.x0 + wl;
     const bool in_img = (iy < p.Hi) && (ix < p.Wi);
     uint4* yc = reinterpret_cast<uint4*>(p.y);
-    for (int u = part; u < TD * 4; u += 2) {
-      const int t = u >> 2, pzy = u & 3;
+    constexpr int NZY = (KD == 3) ? 4 : 2;  // (pz, py) output parity classes per input plane
+    for (int u = part; u < TD * NZY; u += 2) {
+      const int t = u / NZY, pzy = u % NZY;
       if (tc.z0 + t >= p.Di) break;  // warp-uniform
-      const int oz = 2 * (tc.z0 + t) + (pzy >> 1), oy = 2 * iy + (pzy & 1);
-      const uint32_t te = lane_addr + (t * 8 + pzy * 2) * NB, to = te + NB;
+      const int oz = (KD == 3) ? 2 * (tc.z0 + t) + (pzy >> 1) : tc.z0 + t, oy = 2 * iy + (pzy & 1);
+      const uint32_t te = lane_addr + (t * 2 * NZY + pzy * 2) * NB, to = te + NB;
 #pragma unroll 1
       for (int c0 = 0; c0 < COUT_P; c0 += 8) {
         float e[8], o[8], le[8], lo8[8];
@@ -224,6 +241,29 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
         const long long pstride = (long long)p.Do * p.Ho * p.Wo;
         yc[cell] = ehi; yc[cell + 1] = ohi;
         yc[cell + pstride] = elo; yc[cell + pstride + 1] = olo;
+      }
+    }
+  } else if (MODE == M2_PB) {
+    // columns of accumulator s (input plane z0 - 1 + s): [kd][hi co0, hi co1, lo co0, lo co1]; out[t] = sum_kd P[t + kd][kd]
+    const int oy = tc.y0 + hl, ox = tc.x0 + wl;
+    const bool in_img = (oy < p.Ho) && (ox < p.Wo);
+    float* yf = reinterpret_cast<float*>(p.y);
+    const long long oplane = (long long)p.Ho * p.Wo;
+    for (int t = part; t < TD; t += 2) {
+      const int oz = tc.z0 + t;
+      if (oz >= p.Do) break;  // warp-uniform
+      float a0[8], a1[8], b2[8];
+      tmem_ld8(lane_addr + (t + 0) * NB, a0);
+      tmem_ld8(lane_addr + (t + 1) * NB, a1);
+      tmem_ld8(lane_addr + (t + 2) * NB + 8, b2);
+      if (!in_img) continue;
+      // kd = 0 -> columns 0..3 of plane t; kd = 1 -> columns 4..7 of plane t+1; kd = 2 -> columns 8..11 (= b2[0..3]) of plane t+2
+#pragma unroll
+      for (int co = 0; co < 2; ++co) {
+        float v = (a0[co] + a0[2 + co]) + (a1[4 + co] + a1[6 + co]) + (b2[co] + b2[2 + co]);
+        if (p.scale) v = fmaf(v, __ldg(p.scale + co), __ldg(p.shift + co));
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (co < p.Cout) yf[(long long)tc.b * p.y_bs + ((long long)co * p.Do + oz) * oplane + (long long)oy * p.Wo + ox] = v;
       }
     }
   } else {
@@ -270,10 +310,10 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
-__global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS, 1)
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD>
+__global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THREADS, 1)
     conv_tc2_kernel(const __grid_constant__ Tc2Params p, const __grid_constant__ CUtensorMap tmap) {
-  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* sB = smem + Cfg::OFF_B;
@@ -315,7 +355,8 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS,
       const long long iplane = (long long)p.Hi * p.Wi, cs = (long long)p.Di * iplane;
       int k = 0;
       for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++k) {
-        const int s = k % STAGES, u = k / STAGES;
+        const int m = k % Cfg::MMA_WARPS, j = k / Cfg::MMA_WARPS;
+        const int s = Cfg::MMA_WARPS * (j % Cfg::HS) + m, u = j / Cfg::HS;
         const Tile2 tc = decode2(p, lt, TD);
         mbar_wait(empty + s, (u & 1) ^ 1);
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
@@ -361,11 +402,12 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS,
       // one thread: TMA box loads into the UMMA layout; OOB zero fill is the convolution's padding
       prefetch_tmap(&tmap);
       const int planes_per_b = 2 * CIN / 8;
-      int k = 0;
-      for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x) {
+      int tile_k = 0;
+      for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
         const Tile2 tc = decode2(p, lt, TD);
-        for (int pass = 0; pass < Cfg::NPASS; ++pass, ++k) {
-          const int s = k % STAGES, u = k / STAGES;
+        for (int pass = 0; pass < Cfg::NPASS; ++pass) {
+          const int m = tile_k % Cfg::MMA_WARPS, j = (tile_k / Cfg::MMA_WARPS) * Cfg::NPASS + pass;
+          const int s = Cfg::MMA_WARPS * (j % Cfg::HS) + m, u = j / Cfg::HS;
           mbar_wait(empty + s, (u & 1) ^ 1);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           mbar_expect_tx(full + s, Cfg::TX_BYTES);
@@ -373,13 +415,14 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS,
           for (int pl = 0; pl < Cfg::NPLANE; ++pl) {
             const int gpl = tc.b * planes_per_b + pass * Cfg::NPLANE + pl;
             uint8_t* dst = st + pl * Cfg::PLANE;
-            if (MODE == M2_S1) {
-              tma_load_4d(dst, &tmap, full + s, 8 * (tc.x0 - 1), tc.y0 - 1, tc.z0 - 1, gpl);
+            if (MODE == M2_S1 || MODE == M2_PB) {
+              tma_load_4d(dst, &tmap, full + s, 8 * (tc.x0 - 1), tc.y0 - 1, (KD == 3) ? tc.z0 - 1 : tc.z0, gpl);
             } else if (MODE == M2_TR) {
               tma_load_4d(dst, &tmap, full + s, 8 * tc.x0, tc.y0, tc.z0, gpl);
             } else {  // S2 on a CH16P tensor: even columns 2*(x0+i) = even cell x0+i; odd columns 2*(x0+i)-1 = odd cell x0+i-1
-              tma_load_5d(dst, &tmap, full + s, 8 * tc.x0, 0, 2 * tc.y0 - 1, 2 * tc.z0 - 1, gpl);
-              tma_load_5d(dst + Cfg::BLK_PITCH, &tmap, full + s, 8 * (tc.x0 - 1), 1, 2 * tc.y0 - 1, 2 * tc.z0 - 1, gpl);
+              const int zc = (KD == 3) ? 2 * tc.z0 - 1 : tc.z0;
+              tma_load_5d(dst, &tmap, full + s, 8 * tc.x0, 0, 2 * tc.y0 - 1, zc, gpl);
+              tma_load_5d(dst + Cfg::BLK_PITCH, &tmap, full + s, 8 * (tc.x0 - 1), 1, 2 * tc.y0 - 1, zc, gpl);
             }
           }
           if (!Cfg::RESIDENT)
@@ -387,19 +430,21 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS,
         }
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ---------------------------------------------------------------- MMA issuer
-    int k = 0, tile_k = 0;
+  } else if (warp < MMA_WARP + Cfg::MMA_WARPS) {
+    // ---------------------------------------------------------------- MMA issuers (one thread each)
+    const int me = warp - MMA_WARP;
+    int tile_k = 0;
     for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
-      if (lane == 0) {
+      if (lane == 0 && (tile_k % Cfg::MMA_WARPS) == me) {
         const int a = (Cfg::ACC_SETS == 2) ? (tile_k & 1) : 0, v = (Cfg::ACC_SETS == 2) ? (tile_k >> 1) : tile_k;
         mbar_wait(accempty + a, (v & 1) ^ 1);
-        for (int pass = 0; pass < Cfg::NPASS; ++pass, ++k) {
-          const int s = k % STAGES, u = k / STAGES;
+        for (int pass = 0; pass < Cfg::NPASS; ++pass) {
+          const int j = (tile_k / Cfg::MMA_WARPS) * Cfg::NPASS + pass;
+          const int s = Cfg::MMA_WARPS * (j % Cfg::HS) + me, u = j / Cfg::HS;
           mbar_wait(full + s, u & 1);
           tc_fence_after();
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          issue2<MODE, CIN, CIN_P, NB, TD, STAGES>(smem_u32(st), Cfg::RESIDENT ? smem_u32(sB) : smem_u32(st + Cfg::A_BYTES),
+          issue2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>(smem_u32(st), Cfg::RESIDENT ? smem_u32(sB) : smem_u32(st + Cfg::A_BYTES),
                                                    tmem_base + a * Cfg::COLS, pass == 0);
           umma_commit(empty + s);
         }
@@ -409,14 +454,14 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES>::THREADS,
     }
   } else {
     // ---------------------------------------------------------------- epilogue (8 warps)
-    const int ew = warp - MMA_WARP - 1;
+    const int ew = warp - MMA_WARP - Cfg::MMA_WARPS;
     const int q = warp & 3, part = ew >> 2;
     int tile_k = 0;
     for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
       const int a = (Cfg::ACC_SETS == 2) ? (tile_k & 1) : 0, v = (Cfg::ACC_SETS == 2) ? (tile_k >> 1) : tile_k;
       mbar_wait(accfull + a, v & 1);
       tc_fence_after();
-      epilogue2<MODE, NB, TD>(p, decode2(p, lt, TD), tmem_base + a * Cfg::COLS, q, lane, part);
+      epilogue2<MODE, NB, TD, KD>(p, decode2(p, lt, TD), tmem_base + a * Cfg::COLS, q, lane, part);
       tc_fence_before();
       mbar_arrive(accempty + a);
     }
@@ -512,9 +557,9 @@ static int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int 
   return DMVS_OK;
 }
 
-template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES>
+template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
 static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
-  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
   const int gw = (MODE == M2_TR) ? p.Wi : p.Wo, gh = (MODE == M2_TR) ? p.Hi : p.Ho, gd = (MODE == M2_TR) ? p.Di : p.Do;
   p.tiles_x = ceil_div(gw, T_W);
   p.tiles_y = ceil_div(gh, T_H);
@@ -529,7 +574,7 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
     const int rc = make_tmap(&tmap, x, MODE == M2_S2 ? FMT_CH16P : FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, Cfg::SD);
     if (rc != DMVS_OK) return rc;
   }
-  auto kern = conv_tc2_kernel<MODE, CIN, CIN_P, NB, TD, STAGES>;
+  auto kern = conv_tc2_kernel<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -541,14 +586,16 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
   }
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;  // one persistent CTA per SM
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, tmap);
-  return check_launch("conv_tc2");
+  static char what[96];
+  snprintf(what, sizeof(what), "conv_tc2<mode %d, Cin %d/%d, N %d, TD %d, stages %d, kd %d> tiles %d", MODE, CIN, CIN_P, NB, TD, STAGES, KD, p.n_tiles);
+  return check_launch(what);
 }
 
 // One conv block on CH16 activations.  x: CH16 (stride 1 / transposed), CH16P (stride 2) or fp32 NCDHW (Cin == 2);
 // skip: CH16P (transposed only); y: out_fmt.  Returns +1 if the shape has no specialisation.
 int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, void* y, long long y_bs_f32, int B, int Cin, int Cout, int Di,
-                   int Hi, int Wi, int stride, int transposed, int relu, int out_fmt, cudaStream_t st) {
-  if (!L.w_tc) return 1;
+                   int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, cudaStream_t st) {
+  if (!L.w_tc || (kd != 1 && kd != 3)) return 1;
   DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc2: null pointer");
   DMVS_REQUIRE(aligned16(L.w_tc) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
                "conv_tc2: pointers must be 16-byte aligned");
@@ -559,6 +606,25 @@ int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, vo
   p.skip = reinterpret_cast<const uint4*>(skip); p.y = y;
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.relu = relu; p.out_fmt = out_fmt;
   p.y_bs = y_bs_f32;
+  if (kd == 1) {  // the refine net's 2-D bottleneck: depth is a batch of planes
+    DMVS_REQUIRE(out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE, "conv_tc2: the 2-D layers write CH16");
+    p.Do = Di;
+    if (transposed) {
+      p.Ho = 2 * Hi; p.Wo = 2 * Wi;
+      if (Cin == 64 && Cout == 32) return launch2<M2_TR, 64, 8, 64, 1, 4, 1>(p, x, st);  // conv7 (2-D)
+      return 1;
+    }
+    DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");
+    if (stride == 2) {
+      p.Ho = (Hi - 1) / 2 + 1; p.Wo = (Wi - 1) / 2 + 1;
+      DMVS_REQUIRE(Wi % 2 == 0, DMVS_ERR_BAD_SHAPE, "conv_tc2: stride-2 input width must be even");
+      if (Cin == 32 && Cout == 64) return launch2<M2_S2, 32, 8, 128, 1, 2, 1>(p, x, st);  // conv5 (2-D)
+      return 1;
+    }
+    p.Ho = Hi; p.Wo = Wi;
+    if (Cin == 64 && Cout == 64) return launch2<M2_S1, 64, 8, 128, 1, 4, 1>(p, x, st);    // conv6 (2-D)
+    return 1;
+  }
   if (transposed) {
     p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
     DMVS_REQUIRE(out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE, "conv_tc2: transposed convs write CH16");
@@ -571,7 +637,7 @@ int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, vo
   if (stride == 2) {
     p.Do = (Di - 1) / 2 + 1; p.Ho = (Hi - 1) / 2 + 1; p.Wo = (Wi - 1) / 2 + 1;
     DMVS_REQUIRE(Wi % 2 == 0, DMVS_ERR_BAD_SHAPE, "conv_tc2: stride-2 input width must be even");
-    if (Cin == 8 && Cout == 16) return launch2<M2_S2, 8, 8, 32, 1, 3>(p, x, st);     // conv1
+    if (Cin == 8 && Cout == 16) return launch2<M2_S2, 8, 8, 32, 1, 2>(p, x, st);     // conv1
     if (Cin == 16 && Cout == 32) return launch2<M2_S2, 16, 8, 64, 1, 2>(p, x, st);   // conv3, 2 passes
     if (Cin == 32 && Cout == 64) return launch2<M2_S2, 32, 8, 128, 1, 1>(p, x, st);  // conv5, 4 passes
     return 1;
@@ -581,9 +647,13 @@ int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, vo
   if (Cin == 2 && Cout == 8) return launch2<M2_C0, 2, 2, 16, 4, 4>(p, x, st);        // conv0
   if (Cin == 8 && Cout <= 8) {                                                       // prob (8 -> 2)
     DMVS_REQUIRE(out_fmt == FMT_F32 || Cout == 8, DMVS_ERR_BAD_SHAPE, "conv_tc2: Cout < 8 needs an fp32 output");
+    if (Cout == 2 && L.w_tc_kd) {  // prob with kd folded into N
+      p.wtc = reinterpret_cast<const uint4*>(L.w_tc_kd);
+      return launch2<M2_PB, 8, 8, 16, 4, 4>(p, x, st);
+    }
     return launch2<M2_S1, 8, 8, 16, 4, 4>(p, x, st);
   }
-  if (Cin == 16 && Cout == 16) return launch2<M2_S1, 16, 16, 32, 2, 3>(p, x, st);    // conv2
+  if (Cin == 16 && Cout == 16) return launch2<M2_S1, 16, 16, 32, 2, 2>(p, x, st);    // conv2
   if (Cin == 32 && Cout == 32) return launch2<M2_S1, 32, 8, 64, 2, 2>(p, x, st);     // conv4, 4 passes
   if (Cin == 64 && Cout == 64) return launch2<M2_S1, 64, 8, 128, 1, 1>(p, x, st);    // conv6, 8 passes
   return 1;

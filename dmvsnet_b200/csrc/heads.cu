@@ -23,9 +23,72 @@ __device__ __forceinline__ float confidence_of(const float d[4], float interval)
 }
 
 // ------------------------------------------------------------------------------------------ E1
-// Softmax over D for each of the 4 logit channels, expectation against the per-pixel hypotheses,
-// then the dual-depth bookkeeping.  Logits are streamed three times (max, sum, normalise); the
-// second and third pass hit L2 (a block's working set is 128 px x 4 x D floats).
+// Softmax over D for each of the 4 logit channels, expectation against the per-pixel hypotheses, then the dual-depth
+// bookkeeping (row class, extrapolation stack, window selection, confidence).
+__device__ __forceinline__ void dual_depth_tail(const float (&d4)[4], int x, int y, int b, long long hw, long long pix,
+                                                float* __restrict__ hyp_c, float* __restrict__ conf, float interval) {
+  // row class: 0 small, 1 huge, 2 small with doubled range, 3 huge with doubled range   mvsnet.py:25-28,33-56
+  const int r = y & 3;
+  float lo = (r & 1) ? fminf(d4[2], d4[3]) : fminf(d4[0], d4[1]);
+  float hi = (r & 1) ? fmaxf(d4[2], d4[3]) : fmaxf(d4[0], d4[1]);
+  if (r & 2) {
+    const float lo2 = 2.f * lo - hi, hi2 = 2.f * hi - lo;
+    lo = lo2;
+    hi = hi2;
+  }
+  const float s6[6] = {3.f * lo - 2.f * hi, 2.f * lo - hi, lo, hi, 2.f * hi - lo, 3.f * hi - 2.f * lo};
+  const bool low_window = ((x & 1) == 0) == ((r & 1) == 0);
+  const int off = low_window ? 0 : 2;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) hyp_c[(long long)(b * 4 + j) * hw + pix] = s6[off + j];
+  conf[(long long)b * hw + pix] = confidence_of(d4, interval);
+}
+
+// D known at compile time: the D logits of one channel live in registers, so every logit is read from memory exactly once
+// (D independent loads in flight), exponentiated once, and the probability volume is written in the same pass.
+template <int D>
+__global__ void __launch_bounds__(128) depth_head_reg_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
+                                                             const float* __restrict__ interval_p, float* __restrict__ prob,
+                                                             float* __restrict__ d4o, float* __restrict__ hyp_c,
+                                                             float* __restrict__ conf, int h, int w) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int b = blockIdx.z;
+  const long long hw = (long long)h * w;
+  const long long pix = (long long)y * w + x;
+  const float* hp = hyp + (long long)b * D * hw + pix;
+  float d4[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float* lp = logits + ((long long)(b * 4 + c) * D) * hw + pix;
+    float v[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v[k] = __ldg(lp + k * hw);
+    float mx = v[0];
+#pragma unroll
+    for (int k = 1; k < D; ++k) mx = fmaxf(mx, v[k]);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      v[k] = expf(v[k] - mx);
+      sum += v[k];
+    }
+    float acc = 0.f;
+    float* pp = prob ? prob + ((long long)(b * 4 + c) * D) * hw + pix : nullptr;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float pr = v[k] / sum;
+      if (pp) pp[k * hw] = pr;
+      acc += pr * __ldg(hp + k * hw);
+    }
+    d4[c] = acc;
+    d4o[(long long)(b * 4 + c) * hw + pix] = acc;
+  }
+  dual_depth_tail(d4, x, y, b, hw, pix, hyp_c, conf, __ldg(interval_p));
+}
+
+// any D: three streaming passes per channel (max, sum, normalise); the 2nd and 3rd hit L2
 __global__ void __launch_bounds__(128) depth_head_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
                                                          const float* __restrict__ interval_p, float* __restrict__ prob,
                                                          float* __restrict__ d4o, float* __restrict__ hyp_c,
@@ -55,21 +118,7 @@ __global__ void __launch_bounds__(128) depth_head_kernel(const float* __restrict
     d4[c] = acc;
     d4o[(long long)(b * 4 + c) * hw + pix] = acc;
   }
-  // row class: 0 small, 1 huge, 2 small with doubled range, 3 huge with doubled range   mvsnet.py:25-28,33-56
-  const int r = y & 3;
-  float lo = (r & 1) ? fminf(d4[2], d4[3]) : fminf(d4[0], d4[1]);
-  float hi = (r & 1) ? fmaxf(d4[2], d4[3]) : fmaxf(d4[0], d4[1]);
-  if (r & 2) {
-    const float lo2 = 2.f * lo - hi, hi2 = 2.f * hi - lo;
-    lo = lo2;
-    hi = hi2;
-  }
-  const float s6[6] = {3.f * lo - 2.f * hi, 2.f * lo - hi, lo, hi, 2.f * hi - lo, 3.f * hi - 2.f * lo};
-  const bool low_window = ((x & 1) == 0) == ((r & 1) == 0);
-  const int off = low_window ? 0 : 2;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) hyp_c[(long long)(b * 4 + j) * hw + pix] = s6[off + j];
-  conf[(long long)b * hw + pix] = confidence_of(d4, __ldg(interval_p));
+  dual_depth_tail(d4, x, y, b, hw, pix, hyp_c, conf, __ldg(interval_p));
 }
 
 // ------------------------------------------------------------------------------------------ E2
@@ -227,8 +276,19 @@ extern "C" int dmvs_depth_head_f32(const float* logits, const float* hyp, const 
                                    float* hyp_c, float* conf, int B, int D, int h, int w, void* stream) {
   DMVS_REQUIRE(logits && hyp && interval && d4 && hyp_c && conf, DMVS_ERR_BAD_POINTER, "depth_head: null pointer");
   DMVS_REQUIRE(B >= 1 && B <= 65535 && D >= 1 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE, "depth_head: bad dims");
-  depth_head_kernel<<<pixel_grid(B, h, w), dim3(32, 4), 0, (cudaStream_t)stream>>>(logits, hyp, interval, prob, d4, hyp_c,
-                                                                                 conf, D, h, w);
+  const dim3 grid = pixel_grid(B, h, w), block(32, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (D) {
+#define DMVS_HEAD_CASE(N) \
+  case N: depth_head_reg_kernel<N><<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, h, w); break;
+    DMVS_HEAD_CASE(8)
+    DMVS_HEAD_CASE(16)
+    DMVS_HEAD_CASE(32)
+    DMVS_HEAD_CASE(48)
+    DMVS_HEAD_CASE(64)
+#undef DMVS_HEAD_CASE
+    default: depth_head_kernel<<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, D, h, w);
+  }
   return check_launch("depth_head");
 }
 

@@ -156,6 +156,7 @@ class PackedLayer:
             self.w_tc = _pack_tensor_core_kw(w[:, :, :cout])
         else:
             self.w_tc = None
+        self.w_tc_kd = _pack_tensor_core_prob(w[:, :, :cout]) if (cin == 8 and cout == 2 and taps == 27 and not transposed) else None
         self.kd = 3 if taps == 27 else 1
         self.cin, self.cout = cin, cout
         self.transposed = transposed
@@ -167,7 +168,7 @@ class PackedLayer:
             self.scale = self.shift = None
 
     def c_struct(self) -> N.ConvLayer:
-        return N.ConvLayer(self.w.data_ptr(), _ptr(self.scale), _ptr(self.shift), _ptr(self.w_tc))
+        return N.ConvLayer(self.w.data_ptr(), _ptr(self.scale), _ptr(self.shift), _ptr(self.w_tc), _ptr(self.w_tc_kd))
 
 
 def _pack_tensor_core(w: torch.Tensor) -> torch.Tensor:
@@ -184,6 +185,24 @@ def _pack_tensor_core(w: torch.Tensor) -> torch.Tensor:
     img[:, :, 0, :cout] = hi_r
     img[:, :, 1, :cout] = hi_r
     img[:, :, 0, cout_p:cout_p + cout] = lo_r
+    return img.contiguous()
+
+
+def _pack_tensor_core_prob(w: torch.Tensor) -> torch.Tensor:
+    """`prob` (8 -> 2): depth tap folded into N.  [27][8][2] -> [1][9 (kh,kw)][kc][n = 16][8 halfs]; column n = 4*kd + co holds
+    hi(W) (both K halves), n = 4*kd + 2 + co holds lo(W) (A_hi half only); columns 12..15 stay zero."""
+    taps, cin, cout = w.shape
+    assert taps == 27 and cin == 8 and cout == 2
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    hi = hi.reshape(3, 9, 8, 2)  # [kd][(kh,kw)][k][co]
+    lo = lo.reshape(3, 9, 8, 2)
+    img = torch.zeros(1, 9, 2, 16, 8, dtype=torch.float16, device=w.device)
+    for kd in range(3):
+        for co in range(2):
+            img[0, :, 0, 4 * kd + co] = hi[kd, :, :, co]
+            img[0, :, 1, 4 * kd + co] = hi[kd, :, :, co]
+            img[0, :, 0, 4 * kd + 2 + co] = lo[kd, :, :, co]
     return img.contiguous()
 
 
@@ -276,9 +295,9 @@ def conv3d_ch16(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool
     else:
         b, _, di, hi, wi, _ = x.shape
     if layer.transposed:
-        do, ho, wo = 2 * di, 2 * hi, 2 * wi
+        do, ho, wo = (2 * di if layer.kd == 3 else di), 2 * hi, 2 * wi
     elif stride == 2:
-        do, ho, wo = (di - 1) // 2 + 1, (hi - 1) // 2 + 1, (wi - 1) // 2 + 1
+        do, ho, wo = ((di - 1) // 2 + 1 if layer.kd == 3 else di), (hi - 1) // 2 + 1, (wi - 1) // 2 + 1
     else:
         do, ho, wo = di, hi, wi
     if out_fmt == "f32":
@@ -287,7 +306,7 @@ def conv3d_ch16(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool
         y = torch.empty(b, layer.cout // 4, do, ho, wo, 4, device=x.device, dtype=torch.int32)
     cl = layer.c_struct()
     rc = lib.dmvs_conv3d_ch16(x.data_ptr(), ctypes.byref(cl), _ptr(skip), y.data_ptr(), b, layer.cin, layer.cout, di, hi, wi,
-                              2 if layer.transposed else stride, int(layer.transposed), int(relu), _FMT[out_fmt], _stream())
+                              layer.kd, 2 if layer.transposed else stride, int(layer.transposed), int(relu), _FMT[out_fmt], _stream())
     N.check(rc, "dmvs_conv3d_ch16")
     return y
 

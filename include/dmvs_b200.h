@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 3
+#define DMVS_ABI_VERSION 5
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -80,6 +80,9 @@ typedef struct {
    * n < Cout_p: hi(W[tap][8j+k][n]) for kc = 0 and 1;  n >= Cout_p: lo(W[tap][8j+k][n-Cout_p]) for kc = 0, zero for kc = 1.
    * NULL: the layer always runs on the fp32 path. */
   const void* w_tc;
+  /* optional, Cin = 8 / Cout = 2 (`prob`) only: the depth tap folded into the UMMA N dimension,
+   * [1][9 taps (kh,kw)][kc = 2][n = 16][8 halfs] with n = 4*kd + co (hi, both kc) and n = 4*kd + 2 + co (lo, kc = 0). */
+  const void* w_tc_kd;
 } dmvs_conv_layer;
 
 /* which arithmetic a convolution call uses */
@@ -120,13 +123,14 @@ int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* s
 /* fp32 NCDHW <-> CH16 / CH16P (C % 8 == 0; CH16P: W even).  to_ch16 != 0: x fp32 -> y cells; else x cells -> y fp32. */
 int dmvs_convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, void* stream);
 
-/* One conv block of the tensor path on CH16 activations (TMA-fed persistent tcgen05 kernel, kernel 3x3x3 only).
+/* One conv block of the tensor path on CH16 activations (TMA-fed persistent tcgen05 kernel; kd = 3: 3x3x3,
+ * kd = 1: the 1x3x3 layers of the refine net's bottleneck, depth treated as a batch of planes).
  *   x     CH16 (stride 1, transposed), CH16P (stride 2), or fp32 [B,2,D,H,W] when Cin == 2 (conv0)
  *   skip  CH16P with the output's shape, transposed convs only (nullable)
  *   y     out_fmt: DMVS_FMT_CH16 / DMVS_FMT_CH16P, or DMVS_FMT_F32 (needed when Cout < 8); transposed convs write CH16
  * Returns DMVS_ERR_BAD_SHAPE for (Cin, Cout, stride) combinations outside the U-Net's. layer->w_tc must be set. */
 int dmvs_conv3d_ch16(const void* x, const dmvs_conv_layer* layer, const void* skip, void* y, int B, int Cin, int Cout, int Di,
-                     int Hi, int Wi, int stride, int transposed, int relu, int out_fmt, void* stream);
+                     int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * E1  dual-depth head.  Replaces DepthNet.forward (networks/mvsnet.py:15-66) + depth_regression

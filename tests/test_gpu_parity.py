@@ -133,18 +133,28 @@ def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d, engine)
     assert rel_linf(got, want) < 1e-5, rel_linf(got, want)
 
 
-@pytest.mark.parametrize("cin,cout,dims,stride,transposed", [
+@pytest.mark.parametrize("cfg", [
     (2, 8, (6, 35, 24), 1, False), (8, 16, (8, 34, 48), 2, False), (16, 16, (5, 37, 50), 1, False), (16, 32, (4, 37, 22), 2, False),
     (32, 32, (3, 19, 27), 1, False), (32, 64, (3, 18, 26), 2, False), (64, 64, (2, 17, 9), 1, False), (64, 32, (1, 9, 10), 2, True),
     (32, 16, (2, 17, 11), 2, True), (16, 8, (3, 19, 13), 2, True), (8, 2, (7, 33, 41), 1, False), (8, 16, (1, 8, 8), 2, False),
-    (16, 8, (1, 40, 100), 2, True)])
-def test_conv_layer_ch16_vs_torch(cin, cout, dims, stride, transposed):
+    (16, 8, (1, 40, 100), 2, True),
+    # many tiles per persistent CTA: the stage ring and both accumulator sets wrap several times
+    (8, 2, (24, 160, 200), 1, False), (2, 8, (16, 160, 200), 1, False), (16, 16, (12, 160, 200), 1, False),
+    (8, 16, (12, 160, 200), 2, False), (16, 8, (6, 80, 100), 2, True), (32, 32, (8, 80, 104), 1, False),
+    (32, 64, (4, 80, 104), 2, False), (64, 64, (3, 40, 56), 1, False), (64, 32, (2, 40, 56), 2, True), (32, 16, (4, 40, 56), 2, True),
+    # the refine net's 2-D bottleneck (kd = 1)
+    (32, 64, (1, 18, 26), 2, False, True), (64, 64, (1, 17, 9), 1, False, True), (64, 32, (1, 9, 10), 2, True, True),
+    (32, 64, (1, 148, 200), 2, False, True), (64, 64, (1, 74, 100), 1, False, True), (64, 32, (1, 74, 100), 2, True, True)])
+def test_conv_layer_ch16_vs_torch(cfg):
     """The TMA-fed persistent tcgen05 kernels on the CH16 / CH16P cell layouts, one layer at a time, vs torch fp32."""
     from dmvsnet_b200 import ops
+    cin, cout, dims, stride, transposed = cfg[:5]
+    two_d = len(cfg) > 5 and cfg[5]
     g = torch.Generator().manual_seed(cin * 100 + cout + 7)
-    b = 2
+    b = 2 if dims[1] < 80 else 1
     x = torch.randn(b, cin, *dims, generator=g)
-    w = torch.randn(*((cin, cout) if transposed else (cout, cin)), 3, 3, 3, generator=g) * (2.0 / (cin * 27)) ** 0.5
+    ksz = (3, 3) if two_d else (3, 3, 3)
+    w = torch.randn(*((cin, cout) if transposed else (cout, cin)), *ksz, generator=g) * (2.0 / (cin * 9 * (1 if two_d else 3))) ** 0.5
     has_bn = cout != 2
     bn = (0.8 + 0.4 * torch.rand(cout, generator=g), 0.1 * torch.randn(cout, generator=g), 0.2 * torch.randn(cout, generator=g),
           0.5 + torch.rand(cout, generator=g)) if has_bn else None
@@ -161,7 +171,7 @@ def test_conv_layer_ch16_vs_torch(cin, cout, dims, stride, transposed):
     if cout == 2:
         got = ops.conv3d_ch16(xin, layer, stride=stride, relu=False, out_fmt="f32")
     else:
-        for fmt in (["ch16"] if transposed else ["ch16", "ch16p"]):
+        for fmt in (["ch16"] if (transposed or two_d) else ["ch16", "ch16p"]):
             if fmt == "ch16p" and want.shape[-1] % 2:
                 continue
             cells = ops.conv3d_ch16(xin, layer, stride=stride, relu=True, skip=sk, out_fmt=fmt)

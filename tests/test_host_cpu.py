@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for name in declared:
         assert hasattr(native_lib, name), "libdmvs_b200.so does not export %s" % name
     assert sorted(_native.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert native_lib.dmvs_abi_version() == 3
+    assert native_lib.dmvs_abi_version() == 5
     assert native_lib.dmvs_launch_count() == 0
 
 
@@ -48,8 +48,7 @@ def test_workspace_formula(native_lib):
     assert native_lib.dmvs_regnet_workspace_bytes(0, 1, 8, 16, 16) == want
     # refine net: D 4 -> 2 -> 1, then a 2-D level
     v = [4 * 16 * 16, 2 * 8 * 8, 1 * 4 * 4, 1 * 2 * 2]
-    # + two fp32 staging buffers (32 ch at level 2) around the 2-D bottleneck for the tensor path
-    want = 4 * (2 * 8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3] + 2 * 32 * v[2])
+    want = 4 * (2 * 8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3])
     assert native_lib.dmvs_regnet_workspace_bytes(1, 1, 4, 16, 16) == want
 
 
