@@ -44,81 +44,76 @@ __device__ __forceinline__ void dual_depth_tail(const float (&d4)[4], int x, int
   conf[(long long)b * hw + pix] = confidence_of(d4, interval);
 }
 
-// D known at compile time: the D logits of one channel live in registers, so every logit is read from memory exactly once
-// (D independent loads in flight), exponentiated once, and the probability volume is written in the same pass.
-template <int D>
-__global__ void __launch_bounds__(128) depth_head_reg_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
-                                                             const float* __restrict__ interval_p, float* __restrict__ prob,
-                                                             float* __restrict__ d4o, float* __restrict__ hyp_c,
-                                                             float* __restrict__ conf, int h, int w) {
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 4 + threadIdx.y;
-  if (x >= w || y >= h) return;
-  const int b = blockIdx.z;
-  const long long hw = (long long)h * w;
-  const long long pix = (long long)y * w + x;
-  const float* hp = hyp + (long long)b * D * hw + pix;
-  float d4[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float* lp = logits + ((long long)(b * 4 + c) * D) * hw + pix;
-    float v[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) v[k] = __ldg(lp + k * hw);
-    float mx = v[0];
-#pragma unroll
-    for (int k = 1; k < D; ++k) mx = fmaxf(mx, v[k]);
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      v[k] = expf(v[k] - mx);
-      sum += v[k];
-    }
-    float acc = 0.f;
-    float* pp = prob ? prob + ((long long)(b * 4 + c) * D) * hw + pix : nullptr;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      const float pr = v[k] / sum;
-      if (pp) pp[k * hw] = pr;
-      acc += pr * __ldg(hp + k * hw);
-    }
-    d4[c] = acc;
-    d4o[(long long)(b * 4 + c) * hw + pix] = acc;
-  }
-  dual_depth_tail(d4, x, y, b, hw, pix, hyp_c, conf, __ldg(interval_p));
-}
-
-// any D: three streaming passes per channel (max, sum, normalise); the 2nd and 3rd hit L2
-__global__ void __launch_bounds__(128) depth_head_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
+// Block = 32 pixels of one row x the 4 logit channels (threadIdx.y = channel): each thread owns one (pixel, channel)
+// softmax column.  With D known at compile time the D logits live in registers - read from memory exactly once with D
+// independent loads in flight, exponentiated once, probability volume written in the same pass.  The four regressed
+// depths of a pixel meet in shared memory for the dual-depth tail.
+template <int DT>  // DT > 0: compile-time D (registers); DT == 0: any D, three streaming passes (2nd / 3rd hit L2)
+__global__ void __launch_bounds__(128, 4) depth_head_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
                                                          const float* __restrict__ interval_p, float* __restrict__ prob,
                                                          float* __restrict__ d4o, float* __restrict__ hyp_c,
-                                                         float* __restrict__ conf, int D, int h, int w) {
+                                                         float* __restrict__ conf, int Drt, int h, int w) {
+  __shared__ float d4s[4][32];
+  const int D = (DT > 0) ? DT : Drt;
   const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 4 + threadIdx.y;
-  if (x >= w || y >= h) return;
+  const int y = blockIdx.y;
+  const int c = threadIdx.y;
   const int b = blockIdx.z;
   const long long hw = (long long)h * w;
   const long long pix = (long long)y * w + x;
-  const float* hp = hyp + (long long)b * D * hw + pix;
-  float d4[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  if (x < w) {
+    const float* hp = hyp + (long long)b * D * hw + pix;
     const float* lp = logits + ((long long)(b * 4 + c) * D) * hw + pix;
-    float mx = -INFINITY;
-    for (int k = 0; k < D; ++k) mx = fmaxf(mx, __ldg(lp + k * hw));
-    float sum = 0.f;
-    for (int k = 0; k < D; ++k) sum += expf(__ldg(lp + k * hw) - mx);
-    float acc = 0.f;
     float* pp = prob ? prob + ((long long)(b * 4 + c) * D) * hw + pix : nullptr;
-    for (int k = 0; k < D; ++k) {
-      const float pr = expf(__ldg(lp + k * hw) - mx) / sum;
-      if (pp) pp[k * hw] = pr;
-      acc += pr * __ldg(hp + k * hw);
+    float acc = 0.f;
+    if (DT > 0) {
+      constexpr int DN = DT > 0 ? DT : 1;
+      float v[DN];
+#pragma unroll
+      for (int k = 0; k < DN; ++k) v[k] = __ldg(lp + k * hw);
+      float mx = v[0];
+#pragma unroll
+      for (int k = 1; k < DN; ++k) mx = fmaxf(mx, v[k]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < DN; ++k) {
+        v[k] = expf(v[k] - mx);
+        sum += v[k];
+      }
+      // hypotheses in batches of 8 independent loads (a load -> fma -> load chain would pay D memory latencies in a row)
+#pragma unroll
+      for (int k0 = 0; k0 < DN; k0 += 8) {
+        float hh[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hh[i] = (k0 + i < DN) ? __ldg(hp + (k0 + i) * hw) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (k0 + i < DN) {
+            const float pr = v[k0 + i] / sum;
+            if (pp) pp[(k0 + i) * hw] = pr;
+            acc += pr * hh[i];
+          }
+        }
+      }
+    } else {
+      float mx = -INFINITY;
+      for (int k = 0; k < D; ++k) mx = fmaxf(mx, __ldg(lp + k * hw));
+      float sum = 0.f;
+      for (int k = 0; k < D; ++k) sum += expf(__ldg(lp + k * hw) - mx);
+      for (int k = 0; k < D; ++k) {
+        const float pr = expf(__ldg(lp + k * hw) - mx) / sum;
+        if (pp) pp[k * hw] = pr;
+        acc += pr * __ldg(hp + k * hw);
+      }
     }
-    d4[c] = acc;
     d4o[(long long)(b * 4 + c) * hw + pix] = acc;
+    d4s[c][threadIdx.x] = acc;
   }
-  dual_depth_tail(d4, x, y, b, hw, pix, hyp_c, conf, __ldg(interval_p));
+  __syncthreads();
+  if (c == 0 && x < w) {
+    const float d4[4] = {d4s[0][threadIdx.x], d4s[1][threadIdx.x], d4s[2][threadIdx.x], d4s[3][threadIdx.x]};
+    dual_depth_tail(d4, x, y, b, hw, pix, hyp_c, conf, __ldg(interval_p));
+  }
 }
 
 // ------------------------------------------------------------------------------------------ E2
@@ -276,18 +271,19 @@ extern "C" int dmvs_depth_head_f32(const float* logits, const float* hyp, const 
                                    float* hyp_c, float* conf, int B, int D, int h, int w, void* stream) {
   DMVS_REQUIRE(logits && hyp && interval && d4 && hyp_c && conf, DMVS_ERR_BAD_POINTER, "depth_head: null pointer");
   DMVS_REQUIRE(B >= 1 && B <= 65535 && D >= 1 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE, "depth_head: bad dims");
-  const dim3 grid = pixel_grid(B, h, w), block(32, 4);
+  DMVS_REQUIRE(h <= 65535, DMVS_ERR_BAD_SHAPE, "depth_head: h=%d too large", h);
+  const dim3 grid(ceil_div(w, 32), h, B), block(32, 4);
   cudaStream_t st = (cudaStream_t)stream;
   switch (D) {
 #define DMVS_HEAD_CASE(N) \
-  case N: depth_head_reg_kernel<N><<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, h, w); break;
+  case N: depth_head_kernel<N><<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, D, h, w); break;
     DMVS_HEAD_CASE(8)
     DMVS_HEAD_CASE(16)
     DMVS_HEAD_CASE(32)
     DMVS_HEAD_CASE(48)
     DMVS_HEAD_CASE(64)
 #undef DMVS_HEAD_CASE
-    default: depth_head_kernel<<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, D, h, w);
+    default: depth_head_kernel<0><<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, D, h, w);
   }
   return check_launch("depth_head");
 }
