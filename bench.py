@@ -217,7 +217,7 @@ def run_gpu_arm(args, cfg_name):
 
     with torch.no_grad():
         imgs_dev = imgs_host.to(dev)
-        feats = [net.feature(imgs_dev[:, v]) for v in range(views)]
+        feats = net.extract_features(imgs_dev)
         feats = [{k: t.contiguous() for k, t in f.items()} for f in feats]
         del imgs_dev
     torch.cuda.synchronize()
@@ -334,7 +334,10 @@ def run_gpu_arm(args, cfg_name):
             "metric": "views/sec", "value": world * args.steps / (ms * 1e-3), "unit": "views/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg_name), "scope_value": "hot path (stage loop mvsnet.py:208-258), features resident in HBM",
+            "config": {"workload": workload_name(cfg_name),
+                       "arithmetic": "W1 / heads / sampler fp32; regularisation nets on tcgen05 kind::f16 with hi/lo-split fp16 operands "
+                                     "(hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) = fp32-class accuracy; FeatureNet cuDNN fp32 (TF32 off)",
+                       "scope_value": "hot path (stage loop mvsnet.py:208-258), features resident in HBM",
                        "scope_e2e": "MVSNet.infer: pinned host imgs -> H2D -> FeatureNet (torch/cuDNN) -> hot path -> D2H depth+confidence",
                        "l2": "inputs (1.06 GB of features + >1 GB of activations per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": "replicas x%d (one view set per GPU, no collective)" % world, "weights": "random (SURVEY App. D recipe)",

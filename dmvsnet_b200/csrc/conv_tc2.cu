@@ -13,7 +13,9 @@
 //   * Two TMEM accumulator sets ping-pong between the MMA issuer and 8 epilogue warps (accfull / accempty mbarriers);
 //     the epilogue applies eval-BatchNorm + ReLU (+ skip), splits to hi/lo fp16 and stores CH16 / CH16P cells (or fp32
 //     NCDHW for the last layer).
-//   * conv0 (Cin = 2, fp32 cost volume in) keeps a thread-filled producer (12 warps) in the same pipeline.
+//   * conv0 (Cin = 2): K packed along kw.  Mode C0T reads the cost volume in the cell layout the W1 kernel emits for it
+//     (DMVS_FMT_COST2) by TMA like every other layer; mode C0 takes the plain fp32 cost volume through a thread-filled
+//     producer (12 warps) in the same pipeline.
 //   * prob (8 -> 2, mode PB): the depth tap kd is folded into N.  Cout = 2 uses only 4 of the 16 UMMA columns, so the
 //     columns carry [kd][hi0 hi1 lo0 lo1]: one accumulator per INPUT plane holds the three kd partial sums, the
 //     epilogue adds P[t+kd][kd] - (TD+2)*9 MMAs per tile instead of TD*27 at the same cost each.
@@ -25,7 +27,8 @@
 namespace dmvs {
 
 enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2 };
-enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4 };
+enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4, M2_C0T = 5 };
+__host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mode == M2_C0T; }
 constexpr int T_H = 16, T_W = 8;
 
 struct Tc2Params {
@@ -50,19 +53,19 @@ struct C2 {
   // KD = 1: the 2-D convolutions of the refine net's bottleneck (no taps, halo or stride along depth)
   static constexpr int SD = (KD == 1) ? TD : (MODE == M2_S2) ? 2 * TD + 1 : (MODE == M2_TR) ? TD + 1 : TD + 2;
   static constexpr int SH = (MODE == M2_S2) ? 2 * T_H + 1 : (MODE == M2_TR) ? T_H + 1 : T_H + 2;
-  static constexpr int BW = (MODE == M2_S1 || MODE == M2_C0 || MODE == M2_PB) ? T_W + 2 : T_W + 1;  // cells per staged row (S2: per parity block)
+  static constexpr int BW = (MODE == M2_S1 || is_c0(MODE) || MODE == M2_PB) ? T_W + 2 : T_W + 1;  // cells per staged row (S2: per parity block)
   static constexpr int ROWS = SD * SH;
   static constexpr int BLK_BYTES = ROWS * BW * 16;  // bytes one TMA box writes
   static constexpr int BLK_PITCH = pad128(BLK_BYTES);
   static constexpr int NBLK = (MODE == M2_S2) ? 2 : 1;
   static constexpr int PLANE = NBLK * BLK_PITCH;
-  static constexpr int CJ = (MODE == M2_C0) ? 1 : CIN_P / 8;
-  static constexpr int NPLANE = (MODE == M2_C0) ? 1 : 2 * CJ;
-  static constexpr int NPASS = (MODE == M2_C0) ? 1 : CIN / CIN_P;
+  static constexpr int CJ = is_c0(MODE) ? 1 : CIN_P / 8;
+  static constexpr int NPLANE = is_c0(MODE) ? 1 : 2 * CJ;
+  static constexpr int NPASS = is_c0(MODE) ? 1 : CIN / CIN_P;
   static constexpr bool RESIDENT = NPASS == 1;
-  static constexpr int TAPS = (MODE == M2_C0 || MODE == M2_PB || KD == 1) ? 9 : 27;
+  static constexpr int TAPS = (is_c0(MODE) || MODE == M2_PB || KD == 1) ? 9 : 27;
   static constexpr int A_BYTES = NPLANE * PLANE;
-  static constexpr int A_LBO = (MODE == M2_C0) ? 32 : PLANE;
+  static constexpr int A_LBO = is_c0(MODE) ? 32 : PLANE;
   static constexpr int A_SBO = (MODE == M2_S2) ? 2 * BW * 16 : BW * 16;
   static constexpr int B_TILE = 2 * NB * 16;
   static constexpr int B_BYTES = CJ * TAPS * B_TILE;
@@ -86,7 +89,7 @@ struct C2 {
   static constexpr int THREADS = (PROD_WARPS + MMA_WARPS + EPI_WARPS) * 32;
   static_assert(COLS <= 512, "accumulators exceed TMEM");
   static_assert(SMEM <= 227 * 1024, "pipeline does not fit shared memory");
-  static_assert(CIN % CIN_P == 0 || MODE == M2_C0, "channel passes");
+  static_assert(CIN % CIN_P == 0 || is_c0(MODE), "channel passes");
 };
 
 struct Tile2 {
@@ -153,7 +156,7 @@ __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_ba
         acc = (KD == 3) ? t * 8 + pz * 4 + py * 2 + px : t * 4 + py * 2 + px;
         off = (((t + (kz == 0)) * Cfg::SH + (ky == 0)) * Cfg::BW + (kx == 0)) * 16;
         first = (kz == (pz ? 0 : 1)) && (ky == (py ? 0 : 1)) && (kx == (px ? 0 : 1));
-      } else if (MODE == M2_C0) {
+      } else if (is_c0(MODE)) {
         const int kd = tap / 3, kh = tap % 3;
         acc = t;
         off = (((t + kd) * Cfg::SH + kh) * Cfg::BW) * 16;
@@ -171,7 +174,7 @@ __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_ba
       }
 #pragma unroll
       for (int j = 0; j < Cfg::CJ; ++j) {
-        const uint64_t ad = adesc0 + (uint64_t)(((MODE == M2_C0 ? 0 : (2 * j) * Cfg::PLANE) + off) >> 4);
+        const uint64_t ad = adesc0 + (uint64_t)(((is_c0(MODE) ? 0 : (2 * j) * Cfg::PLANE) + off) >> 4);
         const uint64_t bd = bdesc0 + (uint64_t)(((j * Cfg::TAPS + tap) * Cfg::B_TILE) >> 4);
         umma_f16(acc_base + acc * NB, ad, bd, idesc, (first && j == 0) ? fresh_acc : 1u);
       }
@@ -415,7 +418,9 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
           for (int pl = 0; pl < Cfg::NPLANE; ++pl) {
             const int gpl = tc.b * planes_per_b + pass * Cfg::NPLANE + pl;
             uint8_t* dst = st + pl * Cfg::PLANE;
-            if (MODE == M2_S1 || MODE == M2_PB) {
+            if (MODE == M2_C0T) {  // cost cells: cell x = [voxel x-1 | voxel x], one plane per batch entry
+              tma_load_4d(dst, &tmap, full + s, 8 * tc.x0, tc.y0 - 1, tc.z0 - 1, tc.b);
+            } else if (MODE == M2_S1 || MODE == M2_PB) {
               tma_load_4d(dst, &tmap, full + s, 8 * (tc.x0 - 1), tc.y0 - 1, (KD == 3) ? tc.z0 - 1 : tc.z0, gpl);
             } else if (MODE == M2_TR) {
               tma_load_4d(dst, &tmap, full + s, 8 * tc.x0, tc.y0, tc.z0, gpl);
@@ -570,6 +575,9 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
   if (MODE == M2_C0) {
     p.x_f32 = reinterpret_cast<const float*>(x);
     p.x_bs = 2LL * p.Di * p.Hi * p.Wi;
+  } else if (MODE == M2_C0T) {  // [B][D][H][W+1] cells viewed as a CH16 tensor of width W+1 with one plane per batch entry
+    const int rc = make_tmap(&tmap, x, FMT_CH16, p.B, p.Di, p.Hi, p.Wi + 1, Cfg::BW, Cfg::SH, Cfg::SD);
+    if (rc != DMVS_OK) return rc;
   } else {
     const int rc = make_tmap(&tmap, x, MODE == M2_S2 ? FMT_CH16P : FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, Cfg::SD);
     if (rc != DMVS_OK) return rc;
@@ -593,8 +601,8 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
 
 // One conv block on CH16 activations.  x: CH16 (stride 1 / transposed), CH16P (stride 2) or fp32 NCDHW (Cin == 2);
 // skip: CH16P (transposed only); y: out_fmt.  Returns +1 if the shape has no specialisation.
-int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, void* y, long long y_bs_f32, int B, int Cin, int Cout, int Di,
-                   int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, cudaStream_t st) {
+int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const void* skip, void* y, long long y_bs_f32, int B, int Cin,
+                   int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, cudaStream_t st) {
   if (!L.w_tc || (kd != 1 && kd != 3)) return 1;
   DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc2: null pointer");
   DMVS_REQUIRE(aligned16(L.w_tc) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
@@ -644,7 +652,10 @@ int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, vo
   }
   p.Do = Di; p.Ho = Hi; p.Wo = Wi;
   if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
-  if (Cin == 2 && Cout == 8) return launch2<M2_C0, 2, 2, 16, 4, 4>(p, x, st);        // conv0
+  if (Cin == 2 && Cout == 8) {                                                       // conv0
+    if (in_cells) return launch2<M2_C0T, 2, 2, 16, 4, 4>(p, x, st);
+    return launch2<M2_C0, 2, 2, 16, 4, 4>(p, x, st);
+  }
   if (Cin == 8 && Cout <= 8) {                                                       // prob (8 -> 2)
     DMVS_REQUIRE(out_fmt == FMT_F32 || Cout == 8, DMVS_ERR_BAD_SHAPE, "conv_tc2: Cout < 8 needs an fp32 output");
     if (Cout == 2 && L.w_tc_kd) {  // prob with kd folded into N

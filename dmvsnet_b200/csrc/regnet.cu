@@ -12,8 +12,8 @@ int conv_layer_tc(const float* x, long long x_bs, const dmvs_conv_layer& L, cons
                   long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
                   cudaStream_t st);
 
-int conv_layer_tc2(const void* x, const dmvs_conv_layer& L, const void* skip, void* y, long long y_bs_f32, int B, int Cin, int Cout, int Di,
-                   int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, cudaStream_t st);
+int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const void* skip, void* y, long long y_bs_f32, int B, int Cin,
+                   int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, cudaStream_t st);
 int convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, cudaStream_t st);
 
 // engine dispatch: tensor path where a specialisation exists (returns +1 otherwise), fp32 kernels as the exact path
@@ -69,10 +69,11 @@ extern "C" size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, i
   return (size_t)make_plan(refine, B, D, h, w).total * sizeof(float);
 }
 
-extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, float* logits,
-                                       void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine, void* stream) {
+extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
+                                       float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
+                                       void* stream) {
   DMVS_REQUIRE(engine == DMVS_ENGINE_FP32 || engine == DMVS_ENGINE_TENSOR, DMVS_ERR_BAD_SHAPE, "regnet: unknown engine %d", engine);
-  DMVS_REQUIRE(branches && cost && logits && workspace, DMVS_ERR_BAD_POINTER, "regnet: null pointer");
+  DMVS_REQUIRE(branches && (cost || cost_cells) && logits && workspace, DMVS_ERR_BAD_POINTER, "regnet: null pointer");
   DMVS_REQUIRE(B >= 1 && h >= 8 && w >= 8 && h % 8 == 0 && w % 8 == 0, DMVS_ERR_BAD_SHAPE,
                "regnet: h=%d w=%d must be positive multiples of 8", h, w);
   if (refine)
@@ -95,6 +96,7 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
   for (int br = 0; br < 2 && tensor_ok; ++br)
     for (int i = 0; i < DMVS_REGNET_LAYERS; ++i)
       if (!branches[br].layer[i].w_tc) tensor_ok = false;
+  DMVS_REQUIRE(cost || tensor_ok, DMVS_ERR_BAD_POINTER, "regnet: the fp32 engine needs the fp32 cost volume");
   if (tensor_ok) {
     // ---- tensor path: activations in CH16 / CH16P cells between layers, every 3x3x3 layer a TMA-fed tcgen05 kernel
     enum { F32 = DMVS_FMT_F32, CH = DMVS_FMT_CH16, CHP = DMVS_FMT_CH16P };
@@ -109,23 +111,23 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
   rc = conv_layer(__VA_ARGS__);  \
   if (rc != DMVS_OK) return rc;
       //  x,   layer, skip,    y,  y_bs, B, Cin, Cout, Di,    Hi,    Wi,   stride, transposed, relu, out_fmt
-      TC2(cost, L[0], nullptr, c0, 0, B, 2, 8, L0->D, L0->H, L0->W, 3, 1, 0, 1, CHP, st);
-      TC2(c0, L[1], nullptr, c1, 0, B, 8, 16, L0->D, L0->H, L0->W, 3, 2, 0, 1, CH, st);
-      TC2(c1, L[2], nullptr, c2, 0, B, 16, 16, L1->D, L1->H, L1->W, 3, 1, 0, 1, CHP, st);
-      TC2(c2, L[3], nullptr, c3, 0, B, 16, 32, L1->D, L1->H, L1->W, 3, 2, 0, 1, CH, st);
-      TC2(c3, L[4], nullptr, c4, 0, B, 32, 32, L2->D, L2->H, L2->W, 3, 1, 0, 1, CHP, st);
+      TC2(cost_cells ? cost_cells : (const void*)cost, cost_cells ? 1 : 0, L[0], nullptr, c0, 0, B, 2, 8, L0->D, L0->H, L0->W, 3, 1, 0, 1, CHP, st);
+      TC2(c0, 0, L[1], nullptr, c1, 0, B, 8, 16, L0->D, L0->H, L0->W, 3, 2, 0, 1, CH, st);
+      TC2(c1, 0, L[2], nullptr, c2, 0, B, 16, 16, L1->D, L1->H, L1->W, 3, 1, 0, 1, CHP, st);
+      TC2(c2, 0, L[3], nullptr, c3, 0, B, 16, 32, L1->D, L1->H, L1->W, 3, 2, 0, 1, CH, st);
+      TC2(c3, 0, L[4], nullptr, c4, 0, B, 32, 32, L2->D, L2->H, L2->W, 3, 1, 0, 1, CHP, st);
       if (!refine) {
-        TC2(c4, L[5], nullptr, c5, 0, B, 32, 64, L2->D, L2->H, L2->W, 3, 2, 0, 1, CH, st);
-        TC2(c5, L[6], nullptr, c6, 0, B, 64, 64, L3->D, L3->H, L3->W, 3, 1, 0, 1, CH, st);
-        TC2(c6, L[7], c4, u7, 0, B, 64, 32, L3->D, L3->H, L3->W, 3, 2, 1, 1, CH, st);
+        TC2(c4, 0, L[5], nullptr, c5, 0, B, 32, 64, L2->D, L2->H, L2->W, 3, 2, 0, 1, CH, st);
+        TC2(c5, 0, L[6], nullptr, c6, 0, B, 64, 64, L3->D, L3->H, L3->W, 3, 1, 0, 1, CH, st);
+        TC2(c6, 0, L[7], c4, u7, 0, B, 64, 32, L3->D, L3->H, L3->W, 3, 2, 1, 1, CH, st);
       } else {  // 2-D bottleneck (module.py:411-414): depth has been squeezed to one plane
-        TC2(c4, L[5], nullptr, c5, 0, B, 32, 64, L2->D, L2->H, L2->W, 1, 2, 0, 1, CH, st);
-        TC2(c5, L[6], nullptr, c6, 0, B, 64, 64, L3->D, L3->H, L3->W, 1, 1, 0, 1, CH, st);
-        TC2(c6, L[7], c4, u7, 0, B, 64, 32, L3->D, L3->H, L3->W, 1, 2, 1, 1, CH, st);
+        TC2(c4, 0, L[5], nullptr, c5, 0, B, 32, 64, L2->D, L2->H, L2->W, 1, 2, 0, 1, CH, st);
+        TC2(c5, 0, L[6], nullptr, c6, 0, B, 64, 64, L3->D, L3->H, L3->W, 1, 1, 0, 1, CH, st);
+        TC2(c6, 0, L[7], c4, u7, 0, B, 64, 32, L3->D, L3->H, L3->W, 1, 2, 1, 1, CH, st);
       }
-      TC2(u7, L[8], c2, u9, 0, B, 32, 16, L2->D, L2->H, L2->W, 3, 2, 1, 1, CH, st);
-      TC2(u9, L[9], c0, u11, 0, B, 16, 8, L1->D, L1->H, L1->W, 3, 2, 1, 1, CH, st);
-      TC2(u11, L[10], nullptr, logits + (long long)br * 2 * V0, 4 * V0, B, 8, 2, L0->D, L0->H, L0->W, 3, 1, 0, 0, F32, st);
+      TC2(u7, 0, L[8], c2, u9, 0, B, 32, 16, L2->D, L2->H, L2->W, 3, 2, 1, 1, CH, st);
+      TC2(u9, 0, L[9], c0, u11, 0, B, 16, 8, L1->D, L1->H, L1->W, 3, 2, 1, 1, CH, st);
+      TC2(u11, 0, L[10], nullptr, logits + (long long)br * 2 * V0, 4 * V0, B, 8, 2, L0->D, L0->H, L0->W, 3, 1, 0, 0, F32, st);
 #undef TC2
 #undef F32L
     }
@@ -159,11 +161,12 @@ extern "C" int dmvs_convert_layout(const void* x, void* y, int B, int C, int D, 
   return convert_layout(x, y, B, C, D, H, W, fmt, to_ch16, (cudaStream_t)stream);
 }
 
-extern "C" int dmvs_conv3d_ch16(const void* x, const dmvs_conv_layer* layer, const void* skip, void* y, int B, int Cin, int Cout, int Di,
-                                int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, void* stream) {
+extern "C" int dmvs_conv3d_ch16(const void* x, int in_cells, const dmvs_conv_layer* layer, const void* skip, void* y, int B, int Cin,
+                                int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, void* stream) {
   DMVS_REQUIRE(layer && layer->w_tc, DMVS_ERR_BAD_POINTER, "conv3d_ch16: the layer needs packed tensor-core weights (w_tc)");
   DMVS_REQUIRE(B >= 1 && Di >= 1 && Hi >= 1 && Wi >= 1, DMVS_ERR_BAD_SHAPE, "conv3d_ch16: bad dims");
-  const int rc = conv_layer_tc2(x, *layer, skip, y, 0, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, out_fmt, (cudaStream_t)stream);
+  const int rc = conv_layer_tc2(x, in_cells, *layer, skip, y, 0, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, out_fmt,
+                                (cudaStream_t)stream);
   if (rc > 0) {
     set_error("conv3d_ch16: no tensor specialisation for Cin=%d Cout=%d stride=%d transposed=%d", Cin, Cout, stride, transposed);
     return DMVS_ERR_BAD_SHAPE;

@@ -14,6 +14,8 @@
 // Mapping: one thread = one reference pixel x DP consecutive depth planes.  A warp covers 32
 // consecutive x, so for every channel and corner the 32 lanes read ~32 consecutive floats of one
 // source row (NCHW, coalesced through L1); the reference pixel's C features stay in registers.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dmvs {
@@ -23,7 +25,8 @@ struct WarpCorrParams {
   const float* src[DMVS_MAX_SRC];
   const float* rt;
   const float* hyp;
-  float* cost;
+  float* cost;    // [B,2,D,h,w] fp32, nullable
+  uint2* cells;   // conv0 input cells (DMVS_FMT_COST2), nullable: [B][D][h][w+1] x 16 B, cell x = [voxel x-1 | voxel x]
   long long ref_bs, src_bs;
   int B, D, h, w, n_src, d_begin, d_end, n_chunks;
   float half_w, half_h;  // (w-1)/2, (h-1)/2 rounded to fp32 like the reference's python-float divisor
@@ -114,9 +117,24 @@ __global__ void __launch_bounds__(128, 4) warp_corr_kernel(const __grid_constant
       acc0 += g0 * inv_half;
       acc1 += g1 * inv_half;
     }
-    float* cp = p.cost + ((long long)(b * 2) * p.D + d) * hw + pix;
-    cp[0] = acc0;
-    cp[(long long)p.D * hw] = acc1;
+    if (p.cost) {
+      float* cp = p.cost + ((long long)(b * 2) * p.D + d) * hw + pix;
+      cp[0] = acc0;
+      cp[(long long)p.D * hw] = acc1;
+    }
+    if (p.cells) {
+      // the tensor path's conv0 consumes the two cost channels as hi/lo fp16 pairs, two voxels per 16-byte cell:
+      // this voxel is the second half of cell x and the first half of cell x+1 (16 contiguous bytes at 16x + 8)
+      const __half h0 = __float2half_rn(acc0), h1 = __float2half_rn(acc1);
+      const __half2 hi = __halves2half2(h0, h1);
+      const __half2 lo = __halves2half2(__float2half_rn(acc0 - __half2float(h0)), __float2half_rn(acc1 - __half2float(h1)));
+      const uint2 v = make_uint2(*reinterpret_cast<const uint32_t*>(&hi), *reinterpret_cast<const uint32_t*>(&lo));
+      uint2* row = p.cells + (((long long)(b * p.D + d) * p.h + y) * (p.w + 1)) * 2;  // 2 x uint2 per cell
+      row[2 * x + 1] = v;
+      row[2 * x + 2] = v;
+      if (x == 0) row[0] = make_uint2(0u, 0u);                      // voxel -1
+      if (x == p.w - 1) row[2 * p.w + 1] = make_uint2(0u, 0u);      // voxel w
+    }
   }
 }
 
@@ -143,10 +161,11 @@ static int launch_warp_corr(const WarpCorrParams& p0, cudaStream_t st) {
 }  // namespace dmvs
 
 extern "C" int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* const* src, long long src_bstride,
-                                  int n_src, const float* rt, const float* hyp, float* cost, int B, int C, int D, int h,
-                                  int w, int d_begin, int d_end, void* stream) {
+                                  int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells, int B, int C,
+                                  int D, int h, int w, int d_begin, int d_end, void* stream) {
   using namespace dmvs;
-  DMVS_REQUIRE(ref && src && rt && hyp && cost, DMVS_ERR_BAD_POINTER, "warp_corr: null pointer");
+  DMVS_REQUIRE(ref && src && rt && hyp && (cost || cost_cells), DMVS_ERR_BAD_POINTER, "warp_corr: null pointer");
+  DMVS_REQUIRE(!cost_cells || aligned16(cost_cells), DMVS_ERR_BAD_POINTER, "warp_corr: cost_cells must be 16-byte aligned");
   DMVS_REQUIRE(n_src >= 1 && n_src <= DMVS_MAX_SRC, DMVS_ERR_BAD_SHAPE, "warp_corr: n_src=%d not in [1,%d]", n_src, DMVS_MAX_SRC);
   DMVS_REQUIRE(B >= 1 && D >= 1 && h >= 2 && w >= 2, DMVS_ERR_BAD_SHAPE, "warp_corr: bad dims B=%d D=%d h=%d w=%d", B, D, h, w);
   DMVS_REQUIRE(0 <= d_begin && d_begin <= d_end && d_end <= D, DMVS_ERR_BAD_SHAPE, "warp_corr: bad plane range [%d,%d) of %d",
@@ -160,6 +179,7 @@ extern "C" int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const
   p.rt = rt;
   p.hyp = hyp;
   p.cost = cost;
+  p.cells = reinterpret_cast<uint2*>(cost_cells);
   p.ref_bs = ref_bstride;
   p.src_bs = src_bstride;
   p.B = B; p.D = D; p.h = h; p.w = w; p.n_src = n_src; p.d_begin = d_begin; p.d_end = d_end; p.n_chunks = 1;

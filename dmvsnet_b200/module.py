@@ -213,9 +213,10 @@ class _DualRegNet(nn.Module):
             self._pack_key = key
         return self._pack
 
-    def forward(self, x):
+    def forward(self, x, cost_cells=None):
+        """x: cost volume [B,2,D,h,w] (may be None when ``cost_cells`` - W1's cell-format output - feeds the tensor engine)."""
         _require_inference(self)
-        return ops.regnet_forward(self.packed(), x)
+        return ops.regnet_forward(self.packed(), x, cost_cells=cost_cells)
 
 
 class CostRegNet(_DualRegNet):

@@ -90,8 +90,12 @@ def _batch_stride(t: torch.Tensor) -> int:
 
 
 def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor,
-              d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """features: N x [B,C,h,w] (reference view first), rt [B,N-1,12] (device), hyp [B,D,h,w] -> cost [B,2,D,h,w]."""
+              d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
+              want_f32: bool = True, want_cells: bool = False):
+    """features: N x [B,C,h,w] (reference view first), rt [B,N-1,12] (device), hyp [B,D,h,w] -> cost [B,2,D,h,w].
+
+    ``want_cells``: additionally (or, with ``want_f32=False``, only) emit the cost volume in the cell layout the tensor
+    path's first conv reads by TMA (DMVS_FMT_COST2, int32 [B,D,h,w+1,4]); the call then returns ``(cost_or_None, cells)``."""
     lib = N.load()
     ref = _req(features[0], "features[0]")
     b, c, h, w = ref.shape
@@ -118,8 +122,9 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     d = hyp.shape[1]
     if hyp.shape != (b, d, h, w) or rt.shape != (b, n_src, 12):
         raise ValueError("hyp %s / rt %s do not match features %s" % (tuple(hyp.shape), tuple(rt.shape), tuple(ref.shape)))
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty(b, 2, d, h, w, device=ref.device, dtype=torch.float32)
+    cells = torch.empty(b, d, h, w + 1, 4, device=ref.device, dtype=torch.int32) if want_cells else None
     lo, hi = (0, d) if d_range is None else d_range
     src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in feats[1:]])
     if CAPTURE is not None:
@@ -128,9 +133,9 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     nbytes = 4 * b * h * w * ((n_src + 1) * c + 3 * (hi - lo))
     with _timed("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), nbytes):
         rc = lib.dmvs_warp_corr_f32(feats[0].data_ptr(), strides[0], src_ptrs, strides[1], n_src, rt.data_ptr(), hyp.data_ptr(),
-                                    out.data_ptr(), b, c, d, h, w, lo, hi, _stream())
+                                    _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
     N.check(rc, "dmvs_warp_corr_f32")
-    return out
+    return (out, cells) if want_cells else out
 
 
 # ----------------------------------------------------------------------------- R1
@@ -285,11 +290,13 @@ def from_ch16(y: torch.Tensor, channels: int, parity_split: bool = False) -> tor
 
 
 def conv3d_ch16(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = True, skip: Optional[torch.Tensor] = None,
-                out_fmt: str = "ch16") -> torch.Tensor:
+                out_fmt: str = "ch16", in_cells: bool = False) -> torch.Tensor:
     """One block of the tensor path.  x: cells from ``to_ch16`` (parity split for stride 2) or fp32 [B,2,D,H,W] for conv0;
     skip: parity-split cells; returns cells (or fp32 when out_fmt == "f32")."""
     lib = N.load()
-    if layer.cin == 2:
+    if layer.cin == 2 and in_cells:  # cost cells from warp_corr(want_cells=True): int32 [B, D, H, W+1, 4]
+        b, di, hi, wi = x.shape[0], x.shape[1], x.shape[2], x.shape[3] - 1
+    elif layer.cin == 2:
         x = _req(x, "x").contiguous()
         b, _, di, hi, wi = x.shape
     else:
@@ -305,7 +312,7 @@ def conv3d_ch16(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool
     else:
         y = torch.empty(b, layer.cout // 4, do, ho, wo, 4, device=x.device, dtype=torch.int32)
     cl = layer.c_struct()
-    rc = lib.dmvs_conv3d_ch16(x.data_ptr(), ctypes.byref(cl), _ptr(skip), y.data_ptr(), b, layer.cin, layer.cout, di, hi, wi,
+    rc = lib.dmvs_conv3d_ch16(x.data_ptr(), int(in_cells), ctypes.byref(cl), _ptr(skip), y.data_ptr(), b, layer.cin, layer.cout, di, hi, wi,
                               layer.kd, 2 if layer.transposed else stride, int(layer.transposed), int(relu), _FMT[out_fmt], _stream())
     N.check(rc, "dmvs_conv3d_ch16")
     return y
@@ -324,18 +331,26 @@ class PackedRegnet:
                 self.c_branches[i].layer[j] = layer.c_struct()
 
 
-def regnet_forward(pack: PackedRegnet, cost: torch.Tensor, engine: Optional[str] = None) -> torch.Tensor:
-    """cost [B,2,D,h,w] -> logits [B,4,D,h,w]."""
+def regnet_forward(pack: PackedRegnet, cost: Optional[torch.Tensor], engine: Optional[str] = None,
+                   cost_cells: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cost [B,2,D,h,w] (and / or its cell form from ``warp_corr(want_cells=True)``) -> logits [B,4,D,h,w]."""
     lib = N.load()
-    cost = _req(cost, "cost").contiguous()
-    b, c, d, h, w = cost.shape
-    if c != 2:
-        raise ValueError("cost volume must have 2 channels, got %d" % c)
-    logits = torch.empty(b, 4, d, h, w, device=cost.device, dtype=torch.float32)
+    if cost is not None:
+        cost = _req(cost, "cost").contiguous()
+        b, c, d, h, w = cost.shape
+        if c != 2:
+            raise ValueError("cost volume must have 2 channels, got %d" % c)
+        dev = cost.device
+    else:
+        if cost_cells is None or (engine or DEFAULT_ENGINE) != "tensor":
+            raise ValueError("regnet_forward needs the fp32 cost volume unless the tensor engine gets cost_cells")
+        b, d, h, w = cost_cells.shape[0], cost_cells.shape[1], cost_cells.shape[2], cost_cells.shape[3] - 1
+        dev = cost_cells.device
+    logits = torch.empty(b, 4, d, h, w, device=dev, dtype=torch.float32)
     nbytes = lib.dmvs_regnet_workspace_bytes(int(pack.refine), b, d, h, w)
-    ws = torch.empty((nbytes + 3) // 4, device=cost.device, dtype=torch.float32)
+    ws = torch.empty((nbytes + 3) // 4, device=dev, dtype=torch.float32)
     with _timed("regnet%s:D%d_%dx%d" % ("_refine" if pack.refine else "", d, h, w), 4 * b * 6 * d * h * w):
-        rc = lib.dmvs_regnet_forward_f32(pack.c_branches, int(pack.refine), cost.data_ptr(), logits.data_ptr(), ws.data_ptr(),
+        rc = lib.dmvs_regnet_forward_f32(pack.c_branches, int(pack.refine), _ptr(cost), _ptr(cost_cells), logits.data_ptr(), ws.data_ptr(),
                                          ws.numel() * 4, b, d, h, w, _ENGINES[engine or DEFAULT_ENGINE], _stream())
     N.check(rc, "dmvs_regnet_forward_f32")
     return logits

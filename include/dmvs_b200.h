@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 5
+#define DMVS_ABI_VERSION 6
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -54,12 +54,15 @@ unsigned long long dmvs_launch_count(void);
  *   src      host array of n_src device pointers, each [B,C,h,w] with batch stride src_bstride
  *   rt       [B,n_src,12]: row-major 3x3 `rot` then 3 `trans` of P_src @ inv(P_ref) (module.py:223-225)
  *   hyp      [B,D,h,w] per-pixel depth hypotheses
- *   cost     [B,2,D,h,w]; only planes d_begin <= d < d_end are written (depth sharding)
+ *   cost     [B,2,D,h,w]; only planes d_begin <= d < d_end are written (depth sharding).  Nullable if cost_cells is given.
+ *   cost_cells  nullable: the same cost volume in the layout the tensor path's conv0 consumes (DMVS_FMT_COST2):
+ *            [B][D][h][w+1] 16-byte cells, cell x = [hi g0, hi g1, lo g0, lo g1](voxel x-1) ++ the same of voxel x,
+ *            fp16 hi/lo split (value = hi + lo); cells 0 and w carry the zero padding
  *   C in {8,16,32}; group g = channels {2j+g}; cost = (2/C) * sum_j ref[2j+g] * warped[2j+g], summed over views
  */
 int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* const* src, long long src_bstride,
-                       int n_src, const float* rt, const float* hyp, float* cost, int B, int C, int D, int h, int w,
-                       int d_begin, int d_end, void* stream);
+                       int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells, int B, int C, int D, int h,
+                       int w, int d_begin, int d_end, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * R1  3-D regularisation U-Nets.
@@ -103,8 +106,10 @@ size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, int w);
  *   refine     0: CostRegNet_part (D % 8 == 0), 1: CostRegNet_part_refine (D == 4, 2-D bottleneck)
  *   cost       [B,2,D,h,w]   logits [B,4,D,h,w] (channels 0,1 = small branch, 2,3 = huge branch)
  *   h % 8 == 0 and w % 8 == 0 */
-int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, float* logits,
-                            void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine, void* stream);
+/*   cost_cells  nullable; with engine = DMVS_ENGINE_TENSOR the first layer then reads it by TMA and `cost` may be NULL */
+int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
+                            float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
+                            void* stream);
 
 /* single layers (exposed for unit tests and for callers that want their own schedule).
  *   x [B,Cin,Di,Hi,Wi] -> y [B,Cout,Do,Ho,Wo];  kd in {1,3} (1 = the 2-D convs of the refine net)
@@ -119,18 +124,20 @@ int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* s
 #define DMVS_FMT_F32 0
 #define DMVS_FMT_CH16 1
 #define DMVS_FMT_CH16P 2
+#define DMVS_FMT_COST2 3 /* conv0 input written by dmvs_warp_corr_f32(cost_cells), see there */
 
 /* fp32 NCDHW <-> CH16 / CH16P (C % 8 == 0; CH16P: W even).  to_ch16 != 0: x fp32 -> y cells; else x cells -> y fp32. */
 int dmvs_convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, void* stream);
 
 /* One conv block of the tensor path on CH16 activations (TMA-fed persistent tcgen05 kernel; kd = 3: 3x3x3,
  * kd = 1: the 1x3x3 layers of the refine net's bottleneck, depth treated as a batch of planes).
- *   x     CH16 (stride 1, transposed), CH16P (stride 2), or fp32 [B,2,D,H,W] when Cin == 2 (conv0)
+ *   x     CH16 (stride 1, transposed), CH16P (stride 2); when Cin == 2 (conv0): fp32 [B,2,D,H,W] (in_cells == 0) or
+ *         DMVS_FMT_COST2 cells (in_cells != 0)
  *   skip  CH16P with the output's shape, transposed convs only (nullable)
  *   y     out_fmt: DMVS_FMT_CH16 / DMVS_FMT_CH16P, or DMVS_FMT_F32 (needed when Cout < 8); transposed convs write CH16
  * Returns DMVS_ERR_BAD_SHAPE for (Cin, Cout, stride) combinations outside the U-Net's. layer->w_tc must be set. */
-int dmvs_conv3d_ch16(const void* x, const dmvs_conv_layer* layer, const void* skip, void* y, int B, int Cin, int Cout, int Di,
-                     int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, void* stream);
+int dmvs_conv3d_ch16(const void* x, int in_cells, const dmvs_conv_layer* layer, const void* skip, void* y, int B, int Cin, int Cout,
+                     int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * E1  dual-depth head.  Replaces DepthNet.forward (networks/mvsnet.py:15-66) + depth_regression

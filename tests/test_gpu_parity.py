@@ -70,6 +70,20 @@ def test_warp_corr_channel_sliced_views_and_plane_sharding():
     assert torch.equal(sharded, full)
 
 
+def test_warp_corr_cell_output_matches_fp32_output():
+    """want_cells: the cost volume in the conv0 cell layout must hold exactly the fp16 hi/lo split of the fp32 output."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(21)
+    b, c, h, w, d, n = 2, 8, 19, 45, 5, 3
+    feats = [cuda(torch.randn(b, c, h, w, generator=g)) for _ in range(n)]
+    rt = cuda(ops.relative_projections(syn.make_proj_matrices(h * 4, w * 4, n, b, num_stages=1)["stage1"]))
+    hyp = cuda(425 + 500 * torch.rand(b, d, h, w, generator=g))
+    cost, cells = ops.warp_corr(feats, rt, hyp, want_cells=True)
+    assert torch.equal(cells, _cost_cells_from_volume(cost))
+    only_cells = ops.warp_corr(feats, rt, hyp, want_f32=False, want_cells=True)
+    assert only_cells[0] is None and torch.equal(only_cells[1], cells)
+
+
 def test_warp_corr_identity_homography_is_autocorrelation():
     """src == ref and P_src == P_ref: the warp is the identity for every depth, cost = mean_j ref[2j+g]^2."""
     from dmvsnet_b200 import ops
@@ -133,6 +147,18 @@ def test_conv_layer_vs_torch(cin, cout, dims, stride, transposed, two_d, engine)
     assert rel_linf(got, want) < 1e-5, rel_linf(got, want)
 
 
+def _cost_cells_from_volume(vol):
+    """Pack an fp32 [B,2,D,H,W] volume into DMVS_FMT_COST2 cells with torch (the layout dmvs_warp_corr_f32 emits)."""
+    b, _, d, h, w = vol.shape
+    hi = vol.to(torch.float16)
+    lo = (vol - hi.float()).to(torch.float16)
+    vox = torch.stack((hi[:, 0], hi[:, 1], lo[:, 0], lo[:, 1]), dim=-1)           # [B,D,H,W,4] halfs of one voxel
+    cells = torch.zeros(b, d, h, w + 1, 8, dtype=torch.float16, device=vol.device)
+    cells[:, :, :, 1:, 0:4] = vox       # first half of cell x+1 = voxel x ... i.e. cell x = [voxel x-1 | voxel x]
+    cells[:, :, :, :w, 4:8] = vox
+    return cells.view(torch.int32).reshape(b, d, h, w + 1, 4)
+
+
 @pytest.mark.parametrize("cfg", [
     (2, 8, (6, 35, 24), 1, False), (8, 16, (8, 34, 48), 2, False), (16, 16, (5, 37, 50), 1, False), (16, 32, (4, 37, 22), 2, False),
     (32, 32, (3, 19, 27), 1, False), (32, 64, (3, 18, 26), 2, False), (64, 64, (2, 17, 9), 1, False), (64, 32, (1, 9, 10), 2, True),
@@ -164,6 +190,10 @@ def test_conv_layer_ch16_vs_torch(cfg):
         want = want + skip
     layer = ops.PackedLayer(cuda(w), transposed, tuple(cuda(t) for t in bn) if bn else None)
     xin = cuda(x) if cin == 2 else ops.to_ch16(cuda(x), parity_split=(stride == 2 and not transposed))
+    if cin == 2:  # the same layer fed by W1's cell-format cost volume (identity warp of a 2-channel "feature" = the volume itself)
+        cells = _cost_cells_from_volume(cuda(x))
+        via_cells = ops.from_ch16(ops.conv3d_ch16(cells, layer, relu=True, out_fmt="ch16", in_cells=True), cout)
+        assert rel_linf(via_cells, want) < 1e-5, rel_linf(via_cells, want)
     if cin != 2:  # the converters round-trip to 2^-22
         back = ops.from_ch16(xin, cin, parity_split=(stride == 2 and not transposed))
         assert rel_linf(back, x) < 1e-6
@@ -286,8 +316,7 @@ def test_cascade_against_reference_fixture(name):
         if "features" in inp:
             feats = [{k: cuda(v) for k, v in f.items()} for f in inp["features"]]
         else:
-            imgs = cuda(inp["imgs"])
-            feats = [net.feature(imgs[:, v]) for v in range(imgs.shape[1])]
+            feats = net.extract_features(cuda(inp["imgs"]))
         rts = [gold["s%d_rt" % (s + 1)] for s in range(len(case["ndepths"]))]
         out = net.cascade(feats, inp["proj"], cuda(inp["depth_values"]), (case["H"], case["W"]), keep_seams=True, rts=rts)
         # second pass with the homographies recomputed on this host: only the 1e-3 depth contract is asserted
