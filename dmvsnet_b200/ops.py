@@ -89,34 +89,80 @@ def _batch_stride(t: torch.Tensor) -> int:
     return t.stride(0) if b > 1 else c * h * w
 
 
+# which W1 kernel ops.warp_corr uses: "nhwc" = channel-last sources (dmvs_warp_corr_nhwc_f32, sources repacked on the fly
+# unless they already are channel-last), "nchw" = the original kernel on the reference's layout (dmvs_warp_corr_f32)
+W1_LAYOUT = "nhwc"
+
+
+def _nhwc_strides(t: torch.Tensor):
+    """(pixel stride, batch stride) if ``t`` [B,C,h,w] is physically channel-last (torch channels_last, possibly a channel
+    slice of a wider map), else None."""
+    b, c, h, w = t.shape
+    ps = t.stride(3)
+    if t.stride(1) != 1 or ps < c or ps % 4 or t.stride(2) != w * ps or t.data_ptr() % 16:
+        return None
+    bs = t.stride(0) if b > 1 else h * w * ps
+    return (ps, bs) if bs % 4 == 0 else None
+
+
+def features_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """[B,C,h,w] fp32 (dense (c,h,w), any batch stride) -> the same map physically channel-last, returned as a
+    [B,C,h,w] view of a dense [B,h,w,C] buffer (torch channels_last strides), so it can be passed wherever the NCHW
+    tensor went."""
+    lib = N.load()
+    _req(t, "features")
+    b, c, h, w = t.shape
+    bs = _batch_stride(t)
+    if bs < 0:
+        t = t.contiguous()
+        bs = c * h * w
+    y = torch.empty(b, h, w, c, device=t.device, dtype=torch.float32)
+    with _timed("w1_layout:C%d_%dx%d" % (c, h, w), 8 * b * c * h * w):
+        rc = lib.dmvs_features_nhwc_f32(t.data_ptr(), bs, y.data_ptr(), b, c, h, w, _stream())
+    N.check(rc, "dmvs_features_nhwc_f32")
+    return y.permute(0, 3, 1, 2)
+
+
 def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor,
               d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
-              want_f32: bool = True, want_cells: bool = False):
+              want_f32: bool = True, want_cells: bool = False, layout: Optional[str] = None):
     """features: N x [B,C,h,w] (reference view first), rt [B,N-1,12] (device), hyp [B,D,h,w] -> cost [B,2,D,h,w].
 
     ``want_cells``: additionally (or, with ``want_f32=False``, only) emit the cost volume in the cell layout the tensor
-    path's first conv reads by TMA (DMVS_FMT_COST2, int32 [B,D,h,w+1,4]); the call then returns ``(cost_or_None, cells)``."""
+    path's first conv reads by TMA (DMVS_FMT_COST2, int32 [B,D,h,w+1,4]); the call then returns ``(cost_or_None, cells)``.
+    ``layout`` (default ``W1_LAYOUT``): "nhwc" gathers from channel-last source maps - sources that are not already
+    channel-last in memory are repacked first (one read + one write of the map) - "nchw" uses the kernel on the
+    reference's layout."""
     lib = N.load()
+    layout = layout or W1_LAYOUT
+    if layout not in ("nhwc", "nchw"):
+        raise ValueError("layout must be 'nhwc' or 'nchw'")
     ref = _req(features[0], "features[0]")
     b, c, h, w = ref.shape
     n_src = len(features) - 1
     if n_src < 1 or n_src > N.MAX_SRC:
         raise ValueError("need 1..%d source views, got %d" % (N.MAX_SRC, n_src))
-    feats = []
-    strides = []
     for i, f in enumerate(features):
         _req(f, "features[%d]" % i)
         if f.shape != ref.shape:
             raise ValueError("features[%d] has shape %s, expected %s" % (i, tuple(f.shape), tuple(ref.shape)))
-        bs = _batch_stride(f)
-        if bs < 0:
-            f = f.contiguous()
-            bs = c * h * w
-        feats.append(f)
-        strides.append(bs)
-    if len(set(strides[1:])) != 1:
-        feats = [feats[0]] + [f.contiguous() for f in feats[1:]]
-        strides = [strides[0]] + [c * h * w] * n_src
+    ref_bs = _batch_stride(ref)
+    if ref_bs < 0:
+        ref = ref.contiguous()
+        ref_bs = c * h * w
+    srcs = list(features[1:])
+    if layout == "nchw":
+        strides = [_batch_stride(f) for f in srcs]
+        if min(strides) < 0 or len(set(strides)) != 1:
+            srcs = [f.contiguous() for f in srcs]
+            strides = [c * h * w] * n_src
+        src_ps, src_bs = 0, strides[0]
+    else:
+        st = [_nhwc_strides(f) for f in srcs]
+        if any(x is None for x in st) or len(set(st)) != 1:
+            srcs = [f if x == (c, h * w * c) else features_nhwc(f) for f, x in zip(srcs, st)]
+            st = [(c, h * w * c)] * n_src
+        src_ps, src_bs = st[0]
     hyp = _req(hyp, "hyp").contiguous()
     rt = _req(rt, "rt").contiguous()
     d = hyp.shape[1]
@@ -126,15 +172,19 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         out = torch.empty(b, 2, d, h, w, device=ref.device, dtype=torch.float32)
     cells = torch.empty(b, d, h, w + 1, 4, device=ref.device, dtype=torch.int32) if want_cells else None
     lo, hi = (0, d) if d_range is None else d_range
-    src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in feats[1:]])
+    src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in srcs])
     if CAPTURE is not None:
         CAPTURE.append((rt, hyp))
     # algorithmic bytes: every feature map, the hypotheses and the cost volume cross HBM exactly once
     nbytes = 4 * b * h * w * ((n_src + 1) * c + 3 * (hi - lo))
     with _timed("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), nbytes):
-        rc = lib.dmvs_warp_corr_f32(feats[0].data_ptr(), strides[0], src_ptrs, strides[1], n_src, rt.data_ptr(), hyp.data_ptr(),
-                                    _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
-    N.check(rc, "dmvs_warp_corr_f32")
+        if layout == "nchw":
+            rc = lib.dmvs_warp_corr_f32(ref.data_ptr(), ref_bs, src_ptrs, src_bs, n_src, rt.data_ptr(), hyp.data_ptr(),
+                                        _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
+        else:
+            rc = lib.dmvs_warp_corr_nhwc_f32(ref.data_ptr(), ref_bs, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(), hyp.data_ptr(),
+                                             _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
+    N.check(rc, "dmvs_warp_corr_%sf32" % ("nhwc_" if layout == "nhwc" else ""))
     return (out, cells) if want_cells else out
 
 

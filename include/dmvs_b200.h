@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 6
+#define DMVS_ABI_VERSION 7
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -63,6 +63,21 @@ unsigned long long dmvs_launch_count(void);
 int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* const* src, long long src_bstride,
                        int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells, int B, int C, int D, int h,
                        int w, int d_begin, int d_end, void* stream);
+
+/* W1, channel-last sources.  Same result as dmvs_warp_corr_f32, but every SOURCE feature map is given channel-last,
+ * [B,h,w,C] with `src_pixstride` floats between pixels (>= C, multiple of 4; FeatureNet's [B,2C,h,w] output in
+ * channels_last memory format has stride 2C and its channel slices are consumed in place) and `src_bstride` between
+ * batches; pointers 16-byte aligned.  The reference view stays NCHW.  A bilinear footprint row is then one contiguous
+ * run of 2*C floats that C/2 lanes fetch with one 16-byte load each, which is what makes the gather cheap when the
+ * per-pixel hypotheses are rough (see csrc/warp_corr_nhwc.cu).  All other arguments as above. */
+int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, const float* const* src, long long src_bstride,
+                            int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
+                            int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
+
+/* NCHW -> channel-last repack of one feature map for the call above: x [B,C,h,w] (batch stride x_bstride) -> y [B,h,w,C]
+ * dense.  Replaces nothing in the reference (it is `tensor.permute(0,2,3,1).contiguous()`); callers whose FeatureNet
+ * already runs in channels_last skip it.  C in {8,16,32}. */
+int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float* y, int B, int C, int h, int w, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * R1  3-D regularisation U-Nets.

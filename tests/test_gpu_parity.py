@@ -25,7 +25,16 @@ def cuda(t):
 
 
 # ------------------------------------------------------------------------------------------ W1
-def test_warp_corr_edge_fixture():
+@pytest.fixture(params=["nhwc", "nchw"])
+def w1_layout(request):
+    """Both W1 kernels (channel-last sources = default, reference layout) go through every W1 test."""
+    from dmvsnet_b200 import ops
+    old, ops.W1_LAYOUT = ops.W1_LAYOUT, request.param
+    yield request.param
+    ops.W1_LAYOUT = old
+
+
+def test_warp_corr_edge_fixture(w1_layout):
     from dmvsnet_b200 import ops
     g = load_golden("warp_edge")
     feats = [cuda(g["feat%d" % i]) for i in range(3)]
@@ -37,7 +46,7 @@ def test_warp_corr_edge_fixture():
 
 @pytest.mark.parametrize("c,d,n,b,h,w", [(32, 48, 4, 1, 37, 50), (16, 32, 5, 2, 24, 40), (8, 8, 3, 1, 64, 97), (8, 4, 7, 1, 40, 33),
                                           (32, 4, 2, 2, 16, 24), (16, 5, 3, 1, 9, 130)])
-def test_warp_corr_vs_oracle(c, d, n, b, h, w):
+def test_warp_corr_vs_oracle(c, d, n, b, h, w, w1_layout):
     from dmvsnet_b200 import ops, synthetic as syn
     g = torch.Generator().manual_seed(c * 1000 + d)
     feats = [torch.randn(b, c, h, w, generator=g) for _ in range(n)]
@@ -48,7 +57,7 @@ def test_warp_corr_vs_oracle(c, d, n, b, h, w):
     assert rel_linf(got, want) < 2e-6, rel_linf(got, want)
 
 
-def test_warp_corr_channel_sliced_views_and_plane_sharding():
+def test_warp_corr_channel_sliced_views_and_plane_sharding(w1_layout):
     """FeatureNet hands out channel-sliced views ([B,2C,h,w].split); depth shards must tile the full result bit-exactly."""
     from dmvsnet_b200 import ops, synthetic as syn
     g = torch.Generator().manual_seed(5)
@@ -70,7 +79,7 @@ def test_warp_corr_channel_sliced_views_and_plane_sharding():
     assert torch.equal(sharded, full)
 
 
-def test_warp_corr_cell_output_matches_fp32_output():
+def test_warp_corr_cell_output_matches_fp32_output(w1_layout):
     """want_cells: the cost volume in the conv0 cell layout must hold exactly the fp16 hi/lo split of the fp32 output."""
     from dmvsnet_b200 import ops, synthetic as syn
     g = torch.Generator().manual_seed(21)
@@ -84,7 +93,7 @@ def test_warp_corr_cell_output_matches_fp32_output():
     assert only_cells[0] is None and torch.equal(only_cells[1], cells)
 
 
-def test_warp_corr_identity_homography_is_autocorrelation():
+def test_warp_corr_identity_homography_is_autocorrelation(w1_layout):
     """src == ref and P_src == P_ref: the warp is the identity for every depth, cost = mean_j ref[2j+g]^2."""
     from dmvsnet_b200 import ops
     g = torch.Generator().manual_seed(11)
@@ -96,6 +105,36 @@ def test_warp_corr_identity_homography_is_autocorrelation():
     got = ops.warp_corr([ref, ref], cuda(rt), hyp)
     want = (ref.view(b, c // 2, 2, h, w) ** 2).mean(1).unsqueeze(2).expand(-1, -1, d, -1, -1)
     assert rel_linf(got, want) < 1e-5
+
+
+def test_warp_corr_channels_last_sources_in_place():
+    """Sources that already are channel-last in memory (torch channels_last, incl. channel slices of a [B,2C,h,w] map,
+    pixel stride 2C) are gathered in place: same bits as after the library's own repack, and as the dense NHWC copy."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(9)
+    b, c, h, w, d, n = 2, 8, 21, 52, 8, 4
+    both = [cuda(torch.randn(b, 2 * c, h, w, generator=g)) for _ in range(n)]
+    proj = syn.make_proj_matrices(h * 4, w * 4, n, b, num_stages=1)["stage1"]
+    rt = cuda(ops.relative_projections(proj))
+    hyp = cuda(425 + 500 * torch.rand(b, d, h, w, generator=g))
+    both_cl = [t.contiguous(memory_format=torch.channels_last) for t in both]
+    for half in (0, 1):
+        views = [t.split([c, c], 1)[half] for t in both]
+        views_cl = [t.split([c, c], 1)[half] for t in both_cl]
+        assert ops._nhwc_strides(views_cl[1]) == (2 * c, h * w * 2 * c)
+        want = O.warp_corr([v.cpu().contiguous() for v in views], proj, hyp.cpu())
+        launches = _lib_launches()
+        got = ops.warp_corr(views_cl, rt, hyp, layout="nhwc")
+        assert _lib_launches() - launches == 1  # no repack kernels
+        assert rel_linf(got, want) < 2e-6
+        assert torch.equal(got, ops.warp_corr(views, rt, hyp, layout="nhwc"))
+        repacked = ops.features_nhwc(views[1])
+        assert torch.equal(repacked, views[1]) and ops._nhwc_strides(repacked) == (c, h * w * c)
+
+
+def _lib_launches():
+    from dmvsnet_b200 import _native
+    return _native.launch_count()
 
 
 # ------------------------------------------------------------------------------------------ R1 single layers
@@ -373,7 +412,7 @@ def test_infer_from_host_buffers():
 
 
 # ------------------------------------------------------------------------------------------ full-size properties
-def test_full_size_dtu_stage3_properties():
+def test_full_size_dtu_stage3_properties(w1_layout):
     """BASELINE config 2 at full stage-3 size (1184x1600, C=8, N=5): size-independent properties instead of the oracle."""
     from dmvsnet_b200 import ops, synthetic as syn
     h, w, c, n, d = 1184, 1600, 8, 5, 8
