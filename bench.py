@@ -262,11 +262,11 @@ def run_gpu_arm(args, cfg_name):
     depth_mean = float(out["depth"].mean())
 
     # in-bounds fraction of the six W1 launches (one extra untimed step, recorded hypotheses)
-    inb = []
+    inb = {}
     ops.CAPTURE = []
     hot_step()
-    for rt_t, hyp_t in ops.CAPTURE:
-        inb.append(in_bounds_fraction(rt_t, hyp_t))
+    for tag, rt_t, hyp_t in ops.CAPTURE:
+        inb[tag] = in_bounds_fraction(rt_t, hyp_t)
     ops.CAPTURE = None
     del out
 
@@ -311,23 +311,24 @@ def run_gpu_arm(args, cfg_name):
     for (tag, ev0, ev1, nbytes) in prof:
         d = per_launch.setdefault(tag, [0.0, 0, nbytes])
         d[0] += ev0.elapsed_time(ev1); d[1] += 1
-    w1 = {k: v for k, v in per_launch.items() if k.startswith("w1")}
-    w1_ms = sum(v[0] / v[1] for v in w1.values())
-    w1_bytes_total = sum(v[2] for v in w1.values())
+    n_steps = float(args.steps)
+    w1 = {k: v for k, v in per_launch.items() if k.startswith("w1:")}
+    w1_ms = sum(v[0] for v in w1.values()) / n_steps
+    w1_bytes_total = sum(v[2] * v[1] for v in w1.values()) / n_steps
     roof_rows = []
     for i, (k, v) in enumerate(sorted(w1.items())):
         gbs = v[2] / (v[0] / v[1] * 1e-3) / 1e9
         roof_rows.append({"launch": k, "ms": v[0] / v[1], "alg_MB": v[2] / 1e6, "GBps": gbs, "frac": gbs / peak,
-                          "in_bounds": inb[i] if i < len(inb) else None})
+                          "in_bounds": inb.get(k)})
     achieved = w1_bytes_total / (w1_ms * 1e-3) / 1e9 if w1_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "w1_traffic.json")
     if os.path.exists(tp) and cfg_name == "dtu":
         traffic = json.load(open(tp)).get("dram_bytes_per_step")
-    other = {k: v[0] / v[1] for k, v in per_launch.items() if not k.startswith("w1")}
     groups = {}
-    for k, v in other.items():
-        groups[k.split(":")[0]] = groups.get(k.split(":")[0], 0.0) + v
+    for k, v in per_launch.items():
+        if not k.startswith("w1:"):
+            groups[k.split(":")[0]] = groups.get(k.split(":")[0], 0.0) + v[0] / n_steps
 
     if rank == 0:
         line = {
@@ -346,7 +347,7 @@ def run_gpu_arm(args, cfg_name):
             "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "warp_corr_kernel (W1, 6 launches/step pooled)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "warp_corr_kernel / warp_corr_nhwc_kernel (W1, 6 launches/step pooled; source repack reported as w1_layout in the breakdown)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": w1_bytes_total, "ms_per_step": w1_ms},
             "roofline_per_launch": roof_rows,

@@ -15,7 +15,7 @@ from . import _native as N
 
 
 # Optional instrumentation for bench.py: when PROFILE is a list, every op appends (tag, start_event, end_event,
-# algorithmic_bytes) recorded on the launching stream; when CAPTURE is a list, warp_corr appends (rt, hyp).
+# algorithmic_bytes) recorded on the launching stream; when CAPTURE is a list, warp_corr appends (tag, rt, hyp).
 PROFILE = None
 CAPTURE = None
 
@@ -174,7 +174,7 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     lo, hi = (0, d) if d_range is None else d_range
     src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in srcs])
     if CAPTURE is not None:
-        CAPTURE.append((rt, hyp))
+        CAPTURE.append(("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), rt, hyp))
     # algorithmic bytes: every feature map, the hypotheses and the cost volume cross HBM exactly once
     nbytes = 4 * b * h * w * ((n_src + 1) * c + 3 * (hi - lo))
     with _timed("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), nbytes):

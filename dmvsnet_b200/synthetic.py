@@ -118,6 +118,72 @@ def make_images(height: int, width: int, num_views: int, batch: int = 1, seed: i
     return torch.stack(views, 1).clamp_(0.0, 1.0).contiguous()
 
 
+def _fractal_texture(height: int, width: int, g: torch.Generator, channels: int = 3) -> torch.Tensor:
+    """1/f-like multi-octave texture [channels, height, width], roughly zero mean / unit variance."""
+    tex = torch.zeros(1, channels, height, width)
+    amp, octave = 1.0, 0
+    while (min(height, width) >> octave) >= 4 and octave < 9:
+        hh, ww = max(2, height >> octave), max(2, width >> octave)
+        layer = torch.randn(1, channels, hh, ww, generator=g)
+        tex = tex + amp * torch.nn.functional.interpolate(layer, size=(height, width), mode="bilinear", align_corners=False)
+        amp, octave = amp * 1.5, octave + 1
+    return ((tex - tex.mean()) / tex.std())[0]
+
+
+def scene_depth(height: int, width: int, proj_full: torch.Tensor) -> torch.Tensor:
+    """Depth map [height, width] (reference view, millimetres) of the surface ``make_scene_images`` renders: the plane
+    n . X = c through (0, 0, 640) tilted about both axes, in the reference camera frame (extrinsic = identity)."""
+    k = proj_full[0, 0, 1, :3, :3].double()
+    n, c = _scene_plane()
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float64), torch.arange(width, dtype=torch.float64), indexing="ij")
+    rays = torch.linalg.solve(k, torch.stack([xs, ys, torch.ones_like(xs)], 0).reshape(3, -1))
+    lam = c / (n[:, None] * rays).sum(0)
+    return (lam * rays[2]).reshape(height, width).float()
+
+
+def _scene_plane():
+    n = torch.tensor([0.22, -0.12, 1.0], dtype=torch.float64)
+    n = n / n.norm()
+    return n, float(n[2] * 640.0)
+
+
+def make_scene_images(height: int, width: int, num_views: int, proj_full: torch.Tensor, seed: int = 0,
+                      noise: float = 0.01) -> torch.Tensor:
+    """[1, N, 3, H, W] renderings of ONE textured plane seen by the rig's cameras (``proj_full`` = the full-resolution
+    ``proj_matrices["stage3"]``, [1,N,2,4,4]), plus ``noise`` per-view pixel noise.
+
+    Unlike ``make_images`` the views are photo-consistent with the cameras, as photographs of a scene are: the cost
+    volume then has a ridge at the true depth, the regularisation nets regress a piecewise-smooth depth map even with
+    random weights, and the per-pixel hypotheses of stages 2/3 (hence the gather pattern of the warp) look like those a
+    trained network produces on DTU instead of white noise over the whole depth range."""
+    g = torch.Generator().manual_seed(seed)
+    n, c = _scene_plane()
+    # texture parametrised by the world (x, y) of the surface point, 4 texels per millimetre-ish at DTU scale
+    fx = float(proj_full[0, 0, 1, 0, 0])
+    mm_per_px = 680.0 / fx
+    ext_mm = (width * mm_per_px + 700.0, height * mm_per_px + 700.0)
+    tw, th = int(ext_mm[0] / mm_per_px * 0.75), int(ext_mm[1] / mm_per_px * 0.75)
+    tex = _fractal_texture(th, tw, g)
+    tex = (tex / 4.0 + 0.5).clamp_(0.0, 1.0)
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float64), torch.arange(width, dtype=torch.float64), indexing="ij")
+    pix = torch.stack([xs, ys, torch.ones_like(xs)], 0).reshape(3, -1)
+    views = []
+    for v in range(num_views):
+        k = proj_full[0, v, 1, :3, :3].double()
+        e = proj_full[0, v, 0].double()
+        rot, t = e[:3, :3], e[:3, 3]
+        dirs = rot.T @ torch.linalg.solve(k, pix)          # ray directions in the world frame
+        centre = -(rot.T @ t)
+        lam = (c - float(n @ centre)) / (n[:, None] * dirs).sum(0)
+        pts = centre[:, None] + lam * dirs                 # [3, H*W] surface points
+        gx = (pts[0] / (ext_mm[0] / 2.0)).reshape(1, height, width)
+        gy = (pts[1] / (ext_mm[1] / 2.0)).reshape(1, height, width)
+        grid = torch.stack([gx, gy], -1).float()
+        img = torch.nn.functional.grid_sample(tex[None], grid, mode="bilinear", padding_mode="border", align_corners=False)[0]
+        views.append(img + noise * torch.randn(3, height, width, generator=g))
+    return torch.stack(views, 0)[None].clamp_(0.0, 1.0).contiguous()
+
+
 def make_stage_features(height: int, width: int, num_views: int, batch: int = 1, seed: int = 0,
                         num_stages: int = 3, structured: bool = True) -> List[Dict[str, torch.Tensor]]:
     """Per-view dicts ``{"stageK": [B,C,h,w], "stageK_c": [B,C,h,w]}`` like FeatureNet's output.
