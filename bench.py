@@ -218,7 +218,6 @@ def run_gpu_arm(args, cfg_name):
     with torch.no_grad():
         imgs_dev = imgs_host.to(dev)
         feats = net.extract_features(imgs_dev)
-        feats = [{k: t.contiguous() for k, t in f.items()} for f in feats]
         del imgs_dev
     torch.cuda.synchronize()
 

@@ -1,0 +1,226 @@
+// N1: FeatureNet's 2-D convolutions (reference networks/module.py:274-340, Conv2d wrapper :28-69) as fp32 direct
+// convolutions for small channel counts (3..32 in, 8..64 out), sm_100a.
+//
+// The FPN runs on N full-resolution views per reference view (230 GFLOP at DTU size, a third of the regularisation
+// nets) and is FMA-bound once written for these shapes: cuDNN's fp32 kernels reach ~10 TFLOP/s on them.
+// One kernel template covers every layer:
+//   * block = 32x32 output pixels x CT output channels, 256 threads; thread = 4 x-consecutive pixels x CT channels
+//     (64 / 32 accumulators), lanes 8 (x) x 4 (y) so a quarter warp reads 128 contiguous bytes of an input row;
+//   * the input halo tile is staged through shared memory CC input channels at a time (zero padding applied while
+//     staging), the weights of the chunk as [ci][kh][kw][co] so four output channels arrive with one broadcast
+//     LDS.128: per (ci, kh) a thread issues 2-3 input loads + K*CT/4 weight loads for K*4*CT FMAs (>= 12 FMA per load);
+//   * epilogue: eval BatchNorm as scale/shift (or the conv bias as shift), ReLU, optional "+ nearest-x2-upsampled
+//     coarser map" (the FPN top-down add, module.py:329,334), and stores in NCHW and/or channel-last split into the
+//     two feature sets (`stageK` / `stageK_c` = the channel halves, module.py:326-336) so the W1 gather kernel reads
+//     them in place.
+// Arithmetic is plain fp32 FMA in (ci, kh, kw) order: differences to cuDNN are summation order only.
+#include "common.cuh"
+
+namespace dmvs {
+
+struct FeatConvParams {
+  const float* x;       // [B,CIN,Hi,Wi]
+  const float* w;       // [CIN][K][K][COUT]
+  const float* scale;   // [COUT] or null
+  const float* shift;   // [COUT] or null
+  const float* up_add;  // [B,COUT,Ho/2,Wo/2] or null: added after the affine (no ReLU in that case in the FPN)
+  float* y_nchw;        // [B,COUT,Ho,Wo] or null
+  float* y_nhwc0;       // [B,Ho,Wo,COUT/2] channels [0,COUT/2) or null
+  float* y_nhwc1;       // [B,Ho,Wo,COUT/2] channels [COUT/2,COUT) or null
+  int B, Hi, Wi, Ho, Wo, relu;
+};
+
+template <int K, int S, int CIN, int COUT>
+struct FeatCfg {
+  static constexpr int CT = COUT < 16 ? COUT : 16;               // output channels per thread / block
+  static constexpr int NZ = COUT / CT;                           // channel groups -> blockIdx.z
+  static constexpr int TILE = 32;                                // output tile edge
+  static constexpr int IN = (TILE - 1) * S + K;                  // input tile edge
+  static constexpr int PITCH = ((IN + 3) / 4) * 4 + (S == 2 ? 0 : 0);
+  static constexpr int CC_MAX = (40 * 1024) / (IN * PITCH * 4);  // input channels per chunk (about 40 KB of tile)
+  static constexpr int CC = CIN < (CC_MAX < 1 ? 1 : CC_MAX) ? CIN : (CC_MAX < 1 ? 1 : (CC_MAX >= 8 ? 8 : (CC_MAX >= 4 ? 4 : (CC_MAX >= 2 ? 2 : 1))));
+  static constexpr int NIN = 3 * S + K;                          // input columns one thread touches per row
+  static constexpr int NLD = (NIN + 3) / 4;                      // as 16-byte loads
+  static constexpr size_t kSmem = (size_t)(CC * IN * PITCH + CC * K * K * CT) * 4;
+  static_assert(CIN % CC == 0, "chunking must divide CIN");
+};
+
+template <int K, int S, int CIN, int COUT>
+__global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant__ FeatConvParams p) {
+  using Cfg = FeatCfg<K, S, CIN, COUT>;
+  constexpr int CT = Cfg::CT, NZ = Cfg::NZ, IN = Cfg::IN, PITCH = Cfg::PITCH, CC = Cfg::CC, NLD = Cfg::NLD;
+  constexpr int PAD = K / 2;
+  extern __shared__ __align__(16) float fsm[];
+  float* s_in = fsm;                    // [CC][IN][PITCH]
+  float* s_w = fsm + CC * IN * PITCH;   // [CC][K][K][CT]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = lane & 7, ly = lane >> 3;
+  const int b = blockIdx.z / NZ, cz = blockIdx.z - b * NZ;
+  const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+  const int ox = X0 + 4 * lx, oy = Y0 + 4 * warp + ly;        // this thread's first output pixel
+  const int ix0 = X0 * S - PAD, iy0 = Y0 * S - PAD;           // input coordinates of the tile origin
+
+  float acc[4][CT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) acc[i][j] = 0.0f;
+
+  const float* xb = p.x + (long long)b * CIN * p.Hi * p.Wi;
+#pragma unroll 1
+  for (int c0 = 0; c0 < CIN; c0 += CC) {
+    __syncthreads();
+    // ---- stage CC input channels of the halo tile (zero padding) and their weights
+    for (int e = threadIdx.x; e < CC * IN * PITCH; e += 256) {
+      const int col = e % PITCH, row = (e / PITCH) % IN, ci = e / (PITCH * IN);
+      const int gx = ix0 + col, gy = iy0 + row;
+      float v = 0.0f;
+      if (col < IN && gx >= 0 && gx < p.Wi && gy >= 0 && gy < p.Hi) v = __ldg(xb + ((long long)(c0 + ci) * p.Hi + gy) * p.Wi + gx);
+      s_in[e] = v;
+    }
+    for (int e = threadIdx.x; e < CC * K * K * CT; e += 256) {
+      const int co = e % CT, t = e / CT;  // t = ci*K*K + tap
+      s_w[e] = __ldg(p.w + (long long)(c0 * K * K + t) * COUT + cz * CT + co);
+    }
+    __syncthreads();
+    // ---- FMA loop
+#pragma unroll
+    for (int ci = 0; ci < CC; ++ci) {
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        float in[NLD * 4];
+        const float* rp = s_in + (ci * IN + (4 * warp + ly) * S + kh) * PITCH + 4 * lx * S;
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(rp + 4 * q);
+          in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const float* wp = s_w + ((ci * K + kh) * K + kw) * CT;
+#pragma unroll
+          for (int j4 = 0; j4 < CT / 4; ++j4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wp + 4 * j4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float xv = in[i * S + kw];
+              acc[i][4 * j4] = fmaf(xv, wv.x, acc[i][4 * j4]);
+              acc[i][4 * j4 + 1] = fmaf(xv, wv.y, acc[i][4 * j4 + 1]);
+              acc[i][4 * j4 + 2] = fmaf(xv, wv.z, acc[i][4 * j4 + 2]);
+              acc[i][4 * j4 + 3] = fmaf(xv, wv.w, acc[i][4 * j4 + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue
+  if (oy >= p.Ho || ox >= p.Wo) return;
+  const int nvalid = min(4, p.Wo - ox);
+#pragma unroll
+  for (int j = 0; j < CT; ++j) {
+    const int co = cz * CT + j;
+    const float sc = p.scale ? __ldg(p.scale + co) : 1.0f, sh = p.shift ? __ldg(p.shift + co) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = fmaf(acc[i][j], sc, sh);
+      if (p.relu) v = fmaxf(v, 0.0f);
+      acc[i][j] = v;
+    }
+    if (p.up_add) {
+      const int hw2 = (p.Ho >> 1) * (p.Wo >> 1);
+      const float* up = p.up_add + ((long long)b * COUT + co) * hw2 + (oy >> 1) * (p.Wo >> 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nvalid) acc[i][j] += __ldg(up + ((ox + i) >> 1));
+    }
+  }
+  if (p.y_nchw) {
+    const long long hw = (long long)p.Ho * p.Wo;
+    float* yp = p.y_nchw + ((long long)b * COUT + cz * CT) * hw + (long long)oy * p.Wo + ox;
+    const bool vec = nvalid == 4 && ((p.Wo & 3) == 0);
+#pragma unroll
+    for (int j = 0; j < CT; ++j) {
+      if (vec) {
+        *reinterpret_cast<float4*>(yp + j * hw) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nvalid) yp[j * hw + i] = acc[i][j];
+      }
+    }
+  }
+  if (p.y_nhwc0) {
+    constexpr int HALF = COUT / 2;
+#pragma unroll
+    for (int j4 = 0; j4 < CT / 4; ++j4) {
+      const int co = cz * CT + 4 * j4;
+      float* base = (co < HALF) ? p.y_nhwc0 : p.y_nhwc1;
+      const int cc = (co < HALF) ? co : co - HALF;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nvalid)
+          *reinterpret_cast<float4*>(base + (((long long)b * p.Ho + oy) * p.Wo + ox + i) * HALF + cc) =
+              make_float4(acc[i][4 * j4], acc[i][4 * j4 + 1], acc[i][4 * j4 + 2], acc[i][4 * j4 + 3]);
+    }
+  }
+}
+
+template <int K, int S, int CIN, int COUT>
+static int launch_feat(const FeatConvParams& p, cudaStream_t st) {
+  using Cfg = FeatCfg<K, S, CIN, COUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(feat_conv_kernel<K, S, CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) {
+      set_error("conv2d: cannot reserve %zu bytes of shared memory: %s", Cfg::kSmem, cudaGetErrorString(e));
+      return DMVS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.Wo, 32), ceil_div(p.Ho, 32), p.B * Cfg::NZ);
+  DMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DMVS_ERR_BAD_SHAPE, "conv2d: grid too large");
+  feat_conv_kernel<K, S, CIN, COUT><<<grid, 256, Cfg::kSmem, st>>>(p);
+  return check_launch("conv2d");
+}
+
+}  // namespace dmvs
+
+extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
+                               float* y_nchw, float* y_nhwc0, float* y_nhwc1, int B, int Cin, int Cout, int Hi, int Wi, int K,
+                               int stride, int relu, void* stream) {
+  using namespace dmvs;
+  DMVS_REQUIRE(x && w && (y_nchw || (y_nhwc0 && y_nhwc1)), DMVS_ERR_BAD_POINTER, "conv2d: null pointer");
+  DMVS_REQUIRE((y_nhwc0 == nullptr) == (y_nhwc1 == nullptr), DMVS_ERR_BAD_POINTER, "conv2d: both channel-last outputs or none");
+  DMVS_REQUIRE((!y_nhwc0 || aligned16(y_nhwc0)) && (!y_nhwc1 || aligned16(y_nhwc1)) && (!y_nchw || aligned16(y_nchw)),
+               DMVS_ERR_BAD_POINTER, "conv2d: outputs must be 16-byte aligned");
+  DMVS_REQUIRE(B >= 1 && Hi >= 1 && Wi >= 1, DMVS_ERR_BAD_SHAPE, "conv2d: bad dims B=%d Hi=%d Wi=%d", B, Hi, Wi);
+  DMVS_REQUIRE((K == 1 || K == 3 || K == 5) && (stride == 1 || stride == 2), DMVS_ERR_BAD_SHAPE, "conv2d: K=%d stride=%d unsupported", K, stride);
+  FeatConvParams p;
+  p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.up_add = up_add;
+  p.y_nchw = y_nchw; p.y_nhwc0 = y_nhwc0; p.y_nhwc1 = y_nhwc1;
+  p.B = B; p.Hi = Hi; p.Wi = Wi; p.relu = relu;
+  const int pad = K / 2;
+  p.Ho = (Hi + 2 * pad - K) / stride + 1;
+  p.Wo = (Wi + 2 * pad - K) / stride + 1;
+  DMVS_REQUIRE(!up_add || ((p.Ho % 2) == 0 && (p.Wo % 2) == 0), DMVS_ERR_BAD_SHAPE, "conv2d: up_add needs even output size, got %dx%d", p.Ho, p.Wo);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int key = ((K * 10 + stride) * 100 + Cin) * 100 + Cout;
+  switch (key) {
+    case 310308: return launch_feat<3, 1, 3, 8>(p, st);     // conv0.0
+    case 310808: return launch_feat<3, 1, 8, 8>(p, st);     // conv0.1
+    case 520816: return launch_feat<5, 2, 8, 16>(p, st);    // conv1.0
+    case 311616: return launch_feat<3, 1, 16, 16>(p, st);   // conv1.1, conv1.2
+    case 521632: return launch_feat<5, 2, 16, 32>(p, st);   // conv2.0
+    case 313232: return launch_feat<3, 1, 32, 32>(p, st);   // conv2.1, conv2.2, out2
+    case 313216: return launch_feat<3, 1, 32, 16>(p, st);   // out3
+    case 113264: return launch_feat<1, 1, 32, 64>(p, st);   // out1
+    case 111632: return launch_feat<1, 1, 16, 32>(p, st);   // inner1
+    case 110832: return launch_feat<1, 1, 8, 32>(p, st);    // inner2
+    default:
+      set_error("conv2d: (K=%d, stride=%d, Cin=%d, Cout=%d) is not a FeatureNet layer shape", K, stride, Cin, Cout);
+      return DMVS_ERR_BAD_SHAPE;
+  }
+}

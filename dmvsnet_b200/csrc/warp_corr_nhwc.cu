@@ -29,14 +29,14 @@
 namespace dmvs {
 
 struct W1cParams {
-  const float* ref;                // [B,C,h,w] (NCHW, batch stride ref_bs)
+  const float* ref;                // [B,C,h,w] NCHW (ref_ps == 0) or channel-last with pixel stride ref_ps; batch stride ref_bs
   const float* src[DMVS_MAX_SRC];  // [B,h,w,C] channel-last, pixel stride src_ps, batch stride src_bs
   const float* rt;
   const float* hyp;
   float* cost;   // [B,2,D,h,w] fp32, nullable
   uint2* cells;  // conv0 input cells (DMVS_FMT_COST2), nullable
   long long ref_bs, src_bs;
-  int src_ps;
+  int src_ps, ref_ps;
   int B, D, h, w, n_src, d_begin, d_end, n_chunks;
   float half_w, half_h;
 };
@@ -116,9 +116,14 @@ __global__ void __launch_bounds__(kW1Warps * 32) warp_corr_nhwc_kernel(const __g
     float r[4];
     {
       const int pix = min(Y0 + zy, p.h - 1) * p.w + min(X0 + zx, p.w - 1);
-      const float* rp = p.ref + (long long)b * p.ref_bs + (long long)(4 * k) * hw + pix;
+      if (p.ref_ps > 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.ref + (long long)b * p.ref_bs + (long long)pix * p.ref_ps + 4 * k));
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+      } else {
+        const float* rp = p.ref + (long long)b * p.ref_bs + (long long)(4 * k) * hw + pix;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = __ldg(rp + (long long)i * hw);
+        for (int i = 0; i < 4; ++i) r[i] = __ldg(rp + (long long)i * hw);
+      }
     }
     float acc[V];
 #pragma unroll
@@ -320,8 +325,8 @@ extern "C" int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float
   return check_launch("features_nhwc");
 }
 
-extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, const float* const* src, long long src_bstride,
-                                       int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost,
+extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
+                                       long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost,
                                        void* cost_cells, int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream) {
   using namespace dmvs;
   DMVS_REQUIRE(ref && src && rt && hyp && (cost || cost_cells), DMVS_ERR_BAD_POINTER, "warp_corr_nhwc: null pointer");
@@ -332,6 +337,9 @@ extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, 
                d_begin, d_end, D);
   DMVS_REQUIRE(src_pixstride >= C && src_pixstride % 4 == 0 && src_bstride % 4 == 0, DMVS_ERR_BAD_SHAPE,
                "warp_corr_nhwc: pixel stride %d / batch stride %lld must be multiples of 4 floats and >= C", src_pixstride, src_bstride);
+  DMVS_REQUIRE(ref_pixstride == 0 || (ref_pixstride >= C && ref_pixstride % 4 == 0 && ref_bstride % 4 == 0 && aligned16(ref)),
+               DMVS_ERR_BAD_SHAPE, "warp_corr_nhwc: channel-last reference needs pixel stride %d >= C, strides multiples of 4 floats, 16-byte alignment",
+               ref_pixstride);
   DMVS_REQUIRE((long long)src_pixstride * h * w < (1LL << 31) && (long long)C * h * w < (1LL << 31), DMVS_ERR_BAD_SHAPE,
                "warp_corr_nhwc: feature map too large for 32-bit offsets");
   if (d_begin == d_end) return DMVS_OK;
@@ -348,6 +356,7 @@ extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, 
   p.ref_bs = ref_bstride;
   p.src_bs = src_bstride;
   p.src_ps = src_pixstride;
+  p.ref_ps = ref_pixstride;
   p.B = B; p.D = D; p.h = h; p.w = w; p.n_src = n_src; p.d_begin = d_begin; p.d_end = d_end; p.n_chunks = 1;
   p.half_w = (float)((double)(w - 1) / 2.0);
   p.half_h = (float)((double)(h - 1) / 2.0);

@@ -102,8 +102,15 @@ class FeatureNet(nn.Module):
     # cuDNN may run fp32 convolutions on TF32 tensor cores (torch default); that alone moves the stage-1 cost volume by
     # ~1e-3 relative, i.e. the whole parity budget, so it is off unless the caller opts in.
     allow_tf32 = False
+    # "native": this library's fp32 direct-convolution kernels (dmvs_conv2d_f32), features emitted channel-last for the
+    # W1 gather (stage-1 main set additionally NCHW); "cudnn": torch/cuDNN, the reference's own path.  CPU tensors always
+    # take the torch path (FeatureNet is above the hot path and keeps a plain PyTorch definition), and so do
+    # configurations other than the reference's (fpn, 3 stages).
+    engine = "native"
 
     def forward(self, x):
+        if x.is_cuda and self.engine == "native" and not self.training and self.mode == "fpn" and self.num_stage == 3:
+            return self._forward_native(x)
         if x.is_cuda:
             with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=self.allow_tf32):
                 return self._forward(x)
@@ -124,6 +131,48 @@ class FeatureNet(nn.Module):
         emit("stage2", self.out2(top))
         top = F.interpolate(top, scale_factor=2, mode="nearest") + self.inner2(c0)
         emit("stage3", self.out3(top))
+        return out
+
+    # ------------------------------------------------------------------ native path
+    def _state_key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def packed(self):
+        key = self._state_key()
+        if getattr(self, "_packed_key", None) != key:
+            def block(m):
+                bn = (m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var)
+                return ops.PackedConv2d(m.conv.weight, bn=bn, eps=m.bn.eps, stride=m.stride, relu=m.relu)
+            pk = {"conv0": [block(m) for m in self.conv0], "conv1": [block(m) for m in self.conv1],
+                  "conv2": [block(m) for m in self.conv2],
+                  "out1": ops.PackedConv2d(self.out1.weight), "out2": ops.PackedConv2d(self.out2.weight),
+                  "out3": ops.PackedConv2d(self.out3.weight),
+                  "inner1": ops.PackedConv2d(self.inner1.weight, bias=self.inner1.bias),
+                  "inner2": ops.PackedConv2d(self.inner2.weight, bias=self.inner2.bias)}
+            self._packed, self._packed_key = pk, key
+        return self._packed
+
+    def _forward_native(self, x):
+        """Same graph as ``_forward`` on dmvs_conv2d_f32.  Every returned map is a [B,C,h,w] tensor that is physically
+        channel-last (what the W1 gather reads in place); ``stage1`` (sampler planes -> reference-layout W1 kernel) is NCHW."""
+        pk = self.packed()
+        t = x
+        for layer in pk["conv0"]:
+            t = ops.conv2d(t, layer)
+        c0 = t
+        for layer in pk["conv1"]:
+            t = ops.conv2d(t, layer)
+        c1 = t
+        for layer in pk["conv2"]:
+            t = ops.conv2d(t, layer)
+        c2 = t
+        out = {}
+        y, _, out["stage1_c"] = ops.conv2d(c2, pk["out1"], nchw=True, split_nhwc=True)
+        out["stage1"] = y[:, : y.shape[1] // 2]
+        top = ops.conv2d(c1, pk["inner1"], up_add=c2)
+        _, out["stage2"], out["stage2_c"] = ops.conv2d(top, pk["out2"], nchw=False, split_nhwc=True)
+        top = ops.conv2d(c0, pk["inner2"], up_add=top)
+        _, out["stage3"], out["stage3_c"] = ops.conv2d(top, pk["out3"], nchw=False, split_nhwc=True)
         return out
 
 

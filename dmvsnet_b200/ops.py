@@ -146,8 +146,10 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         _req(f, "features[%d]" % i)
         if f.shape != ref.shape:
             raise ValueError("features[%d] has shape %s, expected %s" % (i, tuple(f.shape), tuple(ref.shape)))
-    ref_bs = _batch_stride(ref)
-    if ref_bs < 0:
+    ref_bs, ref_ps = _batch_stride(ref), 0
+    if ref_bs < 0 and layout == "nhwc" and _nhwc_strides(ref) is not None:
+        ref_ps, ref_bs = _nhwc_strides(ref)  # channel-last reference features are read in place as well
+    elif ref_bs < 0:
         ref = ref.contiguous()
         ref_bs = c * h * w
     srcs = list(features[1:])
@@ -182,10 +184,61 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
             rc = lib.dmvs_warp_corr_f32(ref.data_ptr(), ref_bs, src_ptrs, src_bs, n_src, rt.data_ptr(), hyp.data_ptr(),
                                         _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
         else:
-            rc = lib.dmvs_warp_corr_nhwc_f32(ref.data_ptr(), ref_bs, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(), hyp.data_ptr(),
+            rc = lib.dmvs_warp_corr_nhwc_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(), hyp.data_ptr(),
                                              _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
     N.check(rc, "dmvs_warp_corr_%sf32" % ("nhwc_" if layout == "nhwc" else ""))
     return (out, cells) if want_cells else out
+
+
+# ----------------------------------------------------------------------------- N1 (FeatureNet)
+def _fold_bn(bn, eps: float):
+    gamma, beta, mean, var = [t.detach().to(torch.float32) for t in bn]
+    scale = gamma / torch.sqrt(var + eps)
+    return scale.contiguous(), (beta - mean * scale).contiguous()
+
+
+class PackedConv2d:
+    """One FeatureNet layer for dmvs_conv2d_f32: weights [Cin][K][K][Cout], eval BatchNorm folded to scale/shift (or the
+    conv bias as shift)."""
+
+    def __init__(self, weight: torch.Tensor, bn=None, bias: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                 stride: int = 1, relu: bool = False):
+        w = weight.detach().to(torch.float32)
+        self.cout, self.cin, self.k = w.shape[0], w.shape[1], w.shape[2]
+        self.w = w.permute(1, 2, 3, 0).contiguous()
+        self.scale, self.shift = _fold_bn(bn, eps) if bn is not None else (None, None)
+        if bias is not None:
+            self.shift = bias.detach().to(torch.float32).contiguous()
+        self.stride, self.relu = stride, relu
+
+
+def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] = None, nchw: bool = True, split_nhwc: bool = False):
+    """x [B,Cin,H,W] -> conv (+BN/bias, ReLU, + nearest-x2 ``up_add``).  Returns ``y`` ([B,Cout,Ho,Wo] NCHW) when ``nchw``;
+    with ``split_nhwc`` additionally the two channel halves as channel-last buffers, each returned as a [B,Cout/2,Ho,Wo]
+    view (torch channels_last strides): ``(y_or_None, half0, half1)``."""
+    lib = N.load()
+    x = _req(x, "x").contiguous()
+    b, cin, hi, wi = x.shape
+    if cin != layer.cin:
+        raise ValueError("conv2d: input has %d channels, layer expects %d" % (cin, layer.cin))
+    pad = layer.k // 2
+    ho, wo = (hi + 2 * pad - layer.k) // layer.stride + 1, (wi + 2 * pad - layer.k) // layer.stride + 1
+    y = torch.empty(b, layer.cout, ho, wo, device=x.device, dtype=torch.float32) if nchw else None
+    h0 = h1 = None
+    if split_nhwc:
+        h0 = torch.empty(b, ho, wo, layer.cout // 2, device=x.device, dtype=torch.float32)
+        h1 = torch.empty_like(h0)
+    if up_add is not None:
+        up_add = _req(up_add, "up_add").contiguous()
+        if up_add.shape != (b, layer.cout, ho // 2, wo // 2):
+            raise ValueError("conv2d: up_add has shape %s, expected %s" % (tuple(up_add.shape), (b, layer.cout, ho // 2, wo // 2)))
+    with _timed("featnet:k%ds%d_%dto%d_%dx%d" % (layer.k, layer.stride, cin, layer.cout, ho, wo)):
+        rc = lib.dmvs_conv2d_f32(x.data_ptr(), layer.w.data_ptr(), _ptr(layer.scale), _ptr(layer.shift), _ptr(up_add), _ptr(y),
+                                 _ptr(h0), _ptr(h1), b, cin, layer.cout, hi, wi, layer.k, layer.stride, int(layer.relu), _stream())
+    N.check(rc, "dmvs_conv2d_f32")
+    if split_nhwc:
+        return y, h0.permute(0, 3, 1, 2), h1.permute(0, 3, 1, 2)
+    return y
 
 
 # ----------------------------------------------------------------------------- R1

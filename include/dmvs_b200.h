@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 7
+#define DMVS_ABI_VERSION 8
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -67,17 +67,33 @@ int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* con
 /* W1, channel-last sources.  Same result as dmvs_warp_corr_f32, but every SOURCE feature map is given channel-last,
  * [B,h,w,C] with `src_pixstride` floats between pixels (>= C, multiple of 4; FeatureNet's [B,2C,h,w] output in
  * channels_last memory format has stride 2C and its channel slices are consumed in place) and `src_bstride` between
- * batches; pointers 16-byte aligned.  The reference view stays NCHW.  A bilinear footprint row is then one contiguous
+ * batches; pointers 16-byte aligned.  The reference view is NCHW when `ref_pixstride` == 0, else channel-last too.  A bilinear footprint row is then one contiguous
  * run of 2*C floats that C/2 lanes fetch with one 16-byte load each, which is what makes the gather cheap when the
  * per-pixel hypotheses are rough (see csrc/warp_corr_nhwc.cu).  All other arguments as above. */
-int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, const float* const* src, long long src_bstride,
-                            int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
+int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
+                            long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
                             int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
 
 /* NCHW -> channel-last repack of one feature map for the call above: x [B,C,h,w] (batch stride x_bstride) -> y [B,h,w,C]
  * dense.  Replaces nothing in the reference (it is `tensor.permute(0,2,3,1).contiguous()`); callers whose FeatureNet
  * already runs in channels_last skip it.  C in {8,16,32}. */
 int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float* y, int B, int C, int h, int w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * N1  FeatureNet layers (the caller-side neighbour of the path).
+ * Replaces the Conv2d wrapper (networks/module.py:28-69: nn.Conv2d + eval BatchNorm2d + ReLU) and the bare nn.Conv2d
+ * heads / laterals of FeatureNet (module.py:274-340), fp32 direct convolution, padding = K/2.
+ *   x       [B,Cin,Hi,Wi] NCHW          w  weights repacked [Cin][K][K][Cout]
+ *   scale, shift  [Cout] or NULL (eval BatchNorm folded, or scale = NULL and shift = the conv bias)
+ *   up_add  nullable [B,Cout,Ho/2,Wo/2]: nearest-x2-upsampled and added after the affine (FPN top-down path, module.py:329,334)
+ *   y_nchw  nullable [B,Cout,Ho,Wo];  y_nhwc0 / y_nhwc1 nullable (both or none): channel-last [B,Ho,Wo,Cout/2] buffers that
+ *           receive channels [0,Cout/2) and [Cout/2,Cout) - the `stageK` / `stageK_c` halves (module.py:326-336) in the
+ *           layout dmvs_warp_corr_nhwc_f32 gathers from
+ *   (K, stride, Cin, Cout) must be one of FeatureNet's: (3,1,3,8) (3,1,8,8) (5,2,8,16) (3,1,16,16) (5,2,16,32)
+ *   (3,1,32,32) (3,1,32,16) (1,1,32,64) (1,1,16,32) (1,1,8,32); Ho = (Hi + 2*(K/2) - K)/stride + 1. */
+int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
+                    float* y_nchw, float* y_nhwc0, float* y_nhwc1, int B, int Cin, int Cout, int Hi, int Wi, int K, int stride,
+                    int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * R1  3-D regularisation U-Nets.

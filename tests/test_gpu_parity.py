@@ -137,6 +137,44 @@ def _lib_launches():
     return _native.launch_count()
 
 
+# ------------------------------------------------------------------------------------------ N1 FeatureNet
+@pytest.mark.parametrize("b,n,h,w", [(1, 3, 64, 96), (2, 2, 96, 160)])
+def test_feature_net_native_vs_oracle(b, n, h, w):
+    """dmvs_conv2d_f32 layer chain (fp32 direct convolutions, channel-last outputs) against the oracle's FeatureNet
+    (torch CPU conv2d, module.py:274-340): summation order only -> 1e-5 of max|feature|; the cuDNN engine as well."""
+    from dmvsnet_b200 import MVSNet, synthetic as syn
+    net = MVSNet([8, 8, 8], [4, 2, 1])
+    state = syn.randomise_regnet_state(net.state_dict(), seed=3)
+    net.load_state_dict(state)
+    net = net.to(DEV).eval()
+    imgs = syn.make_images(h, w, n, b, seed=4)
+    fp = O._sub(state, "feature.")
+    want = [O.feature_net(imgs[:, v], fp) for v in range(n)]
+    for engine in ("native", "cudnn"):
+        net.feature.engine = engine
+        launches = _lib_launches()
+        with torch.no_grad():
+            got = net.extract_features(cuda(imgs))
+        assert (_lib_launches() - launches == 13) == (engine == "native")
+        for v in range(n):
+            for key, ref in want[v].items():
+                assert got[v][key].shape == ref.shape
+                assert rel_linf(got[v][key], ref) < 1e-5, (engine, v, key, rel_linf(got[v][key], ref))
+    net.feature.engine = "native"
+    with torch.no_grad():
+        got = net.extract_features(cuda(imgs))
+    from dmvsnet_b200 import ops
+    assert ops._nhwc_strides(got[1]["stage3"]) is not None and ops._nhwc_strides(got[0]["stage2_c"]) is not None
+    assert ops._batch_stride(got[1]["stage1"]) > 0  # stage-1 main set is NCHW (sampler planes -> reference-layout kernel)
+
+
+def test_conv2d_rejects_foreign_shapes():
+    from dmvsnet_b200 import ops
+    layer = ops.PackedConv2d(torch.zeros(8, 4, 3, 3, device=DEV))
+    with pytest.raises(RuntimeError, match="not a FeatureNet layer shape"):
+        ops.conv2d(torch.zeros(1, 4, 8, 8, device=DEV), layer)
+
+
 # ------------------------------------------------------------------------------------------ R1 single layers
 def _torch_block(x, w, bn, stride, transposed, relu, skip):
     import torch.nn.functional as F
