@@ -41,7 +41,9 @@ struct FeatCfg {
   static constexpr int CC = CIN < (CC_MAX < 1 ? 1 : CC_MAX) ? CIN : (CC_MAX < 1 ? 1 : (CC_MAX >= 8 ? 8 : (CC_MAX >= 4 ? 4 : (CC_MAX >= 2 ? 2 : 1))));
   static constexpr int NIN = 3 * S + K;                          // input columns one thread touches per row
   static constexpr int NLD = (NIN + 3) / 4;                      // as 16-byte loads
-  static constexpr size_t kSmem = (size_t)(CC * IN * PITCH + CC * K * K * CT) * 4;
+  static constexpr int NCHUNK = CIN / CC;
+  static constexpr int NBUF = NCHUNK > 1 ? 2 : 1;                // double-buffered staging when there is something to overlap
+  static constexpr size_t kSmem = (size_t)NBUF * (CC * IN * PITCH + CC * K * K * CT) * 4;
   static_assert(CIN % CC == 0, "chunking must divide CIN");
 };
 
@@ -51,8 +53,7 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
   constexpr int CT = Cfg::CT, NZ = Cfg::NZ, IN = Cfg::IN, PITCH = Cfg::PITCH, CC = Cfg::CC, NLD = Cfg::NLD;
   constexpr int PAD = K / 2;
   extern __shared__ __align__(16) float fsm[];
-  float* s_in = fsm;                    // [CC][IN][PITCH]
-  float* s_w = fsm + CC * IN * PITCH;   // [CC][K][K][CT]
+  // fsm: [NBUF][CC][IN][PITCH] input tiles, then [NBUF][CC][K][K][CT] weights
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = lane & 7, ly = lane >> 3;
@@ -68,22 +69,48 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
     for (int j = 0; j < CT; ++j) acc[i][j] = 0.0f;
 
   const float* xb = p.x + (long long)b * CIN * p.Hi * p.Wi;
+  constexpr int NBUF = Cfg::NBUF, IN_FLOATS = CC * IN * PITCH, W_FLOATS = CC * K * K * CT;
+  float* s_wbase = fsm + NBUF * IN_FLOATS;
+
+  // stage chunk c (CC input channels of the halo tile, zero padding via zero-size cp.async, and their weights)
+  auto stage = [&](int c, int buf) {
+    float* din = fsm + buf * IN_FLOATS;
+    const int c0 = c * CC;
+    for (int r = warp; r < CC * IN; r += 8) {
+      const int ci = r / IN, row = r - ci * IN;
+      const int gy = iy0 + row;
+      const bool row_ok = gy >= 0 && gy < p.Hi;
+      const float* src = xb + ((long long)(c0 + ci) * p.Hi + (row_ok ? gy : 0)) * p.Wi;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(din + r * PITCH);
+#pragma unroll
+      for (int col = lane; col < PITCH; col += 32) {
+        const int gx = ix0 + col;
+        const bool ok = row_ok && gx >= 0 && gx < p.Wi && col < IN;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + col * 4), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
+      }
+    }
+    const uint32_t dw = (uint32_t)__cvta_generic_to_shared(s_wbase + buf * W_FLOATS);
+    for (int e = threadIdx.x; e < W_FLOATS / 4; e += 256) {
+      const int co4 = e % (CT / 4), t = e / (CT / 4);  // t = ci*K*K + tap
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dw + e * 16),
+                   "l"(p.w + (long long)(c0 * K * K + t) * COUT + cz * CT + co4 * 4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stage(0, 0);
 #pragma unroll 1
-  for (int c0 = 0; c0 < CIN; c0 += CC) {
-    __syncthreads();
-    // ---- stage CC input channels of the halo tile (zero padding) and their weights
-    for (int e = threadIdx.x; e < CC * IN * PITCH; e += 256) {
-      const int col = e % PITCH, row = (e / PITCH) % IN, ci = e / (PITCH * IN);
-      const int gx = ix0 + col, gy = iy0 + row;
-      float v = 0.0f;
-      if (col < IN && gx >= 0 && gx < p.Wi && gy >= 0 && gy < p.Hi) v = __ldg(xb + ((long long)(c0 + ci) * p.Hi + gy) * p.Wi + gx);
-      s_in[e] = v;
-    }
-    for (int e = threadIdx.x; e < CC * K * K * CT; e += 256) {
-      const int co = e % CT, t = e / CT;  // t = ci*K*K + tap
-      s_w[e] = __ldg(p.w + (long long)(c0 * K * K + t) * COUT + cz * CT + co);
+  for (int c = 0; c < Cfg::NCHUNK; ++c) {
+    const int buf = (NBUF == 2) ? (c & 1) : 0;
+    if (c + 1 < Cfg::NCHUNK) {
+      stage(c + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* s_in = fsm + buf * IN_FLOATS;
+    const float* s_w = s_wbase + buf * W_FLOATS;
     // ---- FMA loop
 #pragma unroll
     for (int ci = 0; ci < CC; ++ci) {
@@ -114,6 +141,7 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
         }
       }
     }
+    __syncthreads();  // the next iteration's cp.async refills the other buffer only; this one is refilled one iteration later
   }
 
   // ---- epilogue
