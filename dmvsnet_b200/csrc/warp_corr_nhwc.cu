@@ -35,6 +35,7 @@ struct W1cParams {
   const float* hyp;
   float* cost;   // [B,2,D,h,w] fp32, nullable
   uint2* cells;  // conv0 input cells (DMVS_FMT_COST2), nullable
+  const unsigned char* flags;  // nullable, [B][tiles_y][tiles_x][D]: compute and write only the flagged (tile, plane) pairs
   long long ref_bs, src_bs;
   int src_ps, ref_ps;
   int B, D, h, w, n_src, d_begin, d_end, n_chunks;
@@ -88,6 +89,16 @@ __global__ void __launch_bounds__(kW1Warps * 32) warp_corr_nhwc_kernel(const __g
   const int Y0 = blockIdx.y * 8 + (warp >> 1) * 2;
   const int hw = p.h * p.w;
 
+  // pass 2 of the staged variant: only the (tile, plane) pairs the staged kernel left behind
+  const unsigned char* tflags = nullptr;
+  if (p.flags) {
+    const int tiles_x = gridDim.x / p.n_chunks;
+    tflags = p.flags + (((long long)b * gridDim.y + blockIdx.y) * tiles_x + tile_x) * p.D;
+    bool any = false;
+    for (int j = 0; j < DP; ++j)
+      if (d0 + j < p.d_end && tflags[d0 + j]) any = true;
+    if (!any) return;  // block-uniform, before any barrier
+  }
   for (int i = threadIdx.x; i < p.n_src * 12; i += blockDim.x) s_rt[i] = p.rt[b * p.n_src * 12 + i];
 
   // natural lane <-> pixel mapping for the coalesced loads / stores: 16 x-consecutive pixels in each of 2 rows
@@ -226,6 +237,7 @@ __global__ void __launch_bounds__(kW1Warps * 32) warp_corr_nhwc_kernel(const __g
   for (int j = 0; j < DP; ++j) {
     const int d = d0 + j;
     if (d >= p.d_end) break;
+    if (tflags && !tflags[d]) continue;
     const float acc0 = s_out[(2 * j) * 32 + lane], acc1 = s_out[(2 * j + 1) * 32 + lane];
     if (p.cost) {
       float* cp = p.cost + ((long long)(b * 2) * p.D + d) * hw + pix;
@@ -306,6 +318,25 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
+// pass 2 of dmvs_warp_corr_staged_f32 (arguments already validated there)
+int launch_w1_pass2(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src, long long src_bstride,
+                    int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
+                    const unsigned char* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, cudaStream_t st) {
+  W1cParams p;
+  p.ref = ref;
+  for (int i = 0; i < DMVS_MAX_SRC; ++i) p.src[i] = (i < n_src) ? src[i] : nullptr;
+  p.rt = rt; p.hyp = hyp; p.cost = cost; p.cells = reinterpret_cast<uint2*>(cost_cells); p.flags = flags;
+  p.ref_bs = ref_bstride; p.src_bs = src_bstride; p.src_ps = src_pixstride; p.ref_ps = ref_pixstride;
+  p.B = B; p.D = D; p.h = h; p.w = w; p.n_src = n_src; p.d_begin = d_begin; p.d_end = d_end; p.n_chunks = 1;
+  p.half_w = (float)((double)(w - 1) / 2.0);
+  p.half_h = (float)((double)(h - 1) / 2.0);
+  switch (C) {
+    case 8: return dispatch_w1c<8>(p, st);
+    case 16: return dispatch_w1c<16>(p, st);
+    default: return dispatch_w1c<32>(p, st);
+  }
+}
+
 }  // namespace dmvs
 
 extern "C" int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float* y, int B, int C, int h, int w, void* stream) {
@@ -353,6 +384,7 @@ extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, 
   p.hyp = hyp;
   p.cost = cost;
   p.cells = reinterpret_cast<uint2*>(cost_cells);
+  p.flags = nullptr;
   p.ref_bs = ref_bstride;
   p.src_bs = src_bstride;
   p.src_ps = src_pixstride;

@@ -169,16 +169,44 @@ class MVSNet(nn.Module):
         return [{k: t.view(b, n, *t.shape[1:])[:, v] for k, t in out.items()} for v in range(n)]
 
     # ------------------------------------------------------------------ host-buffer entry
+    # views per H2D / FeatureNet group in infer(): the copy of group k+1 (side stream) runs under FeatureNet of group k
+    infer_view_groups = 2
+
     @torch.no_grad()
     def infer(self, imgs: torch.Tensor, proj_matrices: Dict[str, torch.Tensor], depth_values: torch.Tensor,
               keys: Sequence[str] = ("depth", "photometric_confidence")) -> Dict[str, torch.Tensor]:
         """Host tensors in, host tensors out: H2D of the images, forward, D2H of ``keys`` only.
 
         What ``Model.test`` does around the network (tools.tocuda model.py:333 / tensor2numpy model.py:347), minus the
-        D2H of the three probability volumes nobody reads at test time."""
+        D2H of the three probability volumes nobody reads at test time.  The views are uploaded in groups on a side
+        stream so that FeatureNet (per-view arithmetic, mvsnet.py:199-202) starts on the first group while the rest is
+        still crossing PCIe."""
+        _require_inference(self)
         dev = next(self.parameters()).device
-        imgs_d = (imgs if imgs.is_pinned() else imgs.pin_memory()).to(dev, non_blocking=True) if not imgs.is_cuda else imgs
-        out = self.forward(imgs_d, proj_matrices, depth_values)
+        if imgs.is_cuda:
+            out = self.forward(imgs, proj_matrices, depth_values)
+        else:
+            src = imgs if imgs.is_pinned() else imgs.pin_memory()
+            b, n = src.shape[0], src.shape[1]
+            main = torch.cuda.current_stream(dev)
+            side = getattr(self, "_copy_stream", None)
+            if side is None or side.device != dev:
+                side = self._copy_stream = torch.cuda.Stream(dev)
+            per = max(1, -(-n // max(1, int(self.infer_view_groups))))
+            side.wait_stream(main)
+            chunks = []
+            for lo in range(0, n, per):
+                with torch.cuda.stream(side):
+                    part = src[:, lo:lo + per].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                chunks.append((lo, part, ev))
+            feats: List[Dict[str, torch.Tensor]] = []
+            for lo, part, ev in chunks:
+                main.wait_event(ev)
+                part.record_stream(main)
+                feats.extend(self.extract_features(part))
+            out = self.cascade(feats, proj_matrices, depth_values, imgs.shape[-2:])
         host = {}
         for k in keys:
             buf = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)

@@ -90,8 +90,11 @@ def _batch_stride(t: torch.Tensor) -> int:
 
 
 # which W1 kernel ops.warp_corr uses: "nhwc" = channel-last sources (dmvs_warp_corr_nhwc_f32, sources repacked on the fly
-# unless they already are channel-last), "nchw" = the original kernel on the reference's layout (dmvs_warp_corr_f32)
+# unless they already are channel-last), "staged" = the same layout, source footprints staged in shared memory by TMA with
+# the "nhwc" kernel as the per-tile fallback (dmvs_warp_corr_staged_f32), "nchw" = the original kernel on the reference's
+# layout (dmvs_warp_corr_f32)
 W1_LAYOUT = "nhwc"
+LAST_W1_FLAGS = None  # "staged": the (tile, plane) flags of the most recent call (1 = computed by the fallback pass), for diagnostics
 
 
 def _nhwc_strides(t: torch.Tensor):
@@ -135,8 +138,8 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     reference's layout."""
     lib = N.load()
     layout = layout or W1_LAYOUT
-    if layout not in ("nhwc", "nchw"):
-        raise ValueError("layout must be 'nhwc' or 'nchw'")
+    if layout not in ("nhwc", "nchw", "staged"):
+        raise ValueError("layout must be 'nhwc', 'nchw' or 'staged'")
     ref = _req(features[0], "features[0]")
     b, c, h, w = ref.shape
     n_src = len(features) - 1
@@ -147,7 +150,7 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         if f.shape != ref.shape:
             raise ValueError("features[%d] has shape %s, expected %s" % (i, tuple(f.shape), tuple(ref.shape)))
     ref_bs, ref_ps = _batch_stride(ref), 0
-    if ref_bs < 0 and layout == "nhwc" and _nhwc_strides(ref) is not None:
+    if ref_bs < 0 and layout != "nchw" and _nhwc_strides(ref) is not None:
         ref_ps, ref_bs = _nhwc_strides(ref)  # channel-last reference features are read in place as well
     elif ref_bs < 0:
         ref = ref.contiguous()
@@ -174,6 +177,7 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         out = torch.empty(b, 2, d, h, w, device=ref.device, dtype=torch.float32)
     cells = torch.empty(b, d, h, w + 1, 4, device=ref.device, dtype=torch.int32) if want_cells else None
     lo, hi = (0, d) if d_range is None else d_range
+    flags = torch.empty(lib.dmvs_warp_corr_flag_bytes(b, d, h, w), device=ref.device, dtype=torch.uint8) if layout == "staged" else None
     src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in srcs])
     if CAPTURE is not None:
         CAPTURE.append(("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), rt, hyp))
@@ -183,10 +187,16 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         if layout == "nchw":
             rc = lib.dmvs_warp_corr_f32(ref.data_ptr(), ref_bs, src_ptrs, src_bs, n_src, rt.data_ptr(), hyp.data_ptr(),
                                         _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
-        else:
+        elif layout == "nhwc":
             rc = lib.dmvs_warp_corr_nhwc_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(), hyp.data_ptr(),
                                              _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
-    N.check(rc, "dmvs_warp_corr_%sf32" % ("nhwc_" if layout == "nhwc" else ""))
+        else:
+            rc = lib.dmvs_warp_corr_staged_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(),
+                                               hyp.data_ptr(), _ptr(out), _ptr(cells), flags.data_ptr(), b, c, d, h, w, lo, hi, _stream())
+    N.check(rc, "dmvs_warp_corr_f32[%s]" % layout)
+    if layout == "staged":
+        global LAST_W1_FLAGS
+        LAST_W1_FLAGS = flags
     return (out, cells) if want_cells else out
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 8
+#define DMVS_ABI_VERSION 9
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -73,6 +73,17 @@ int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* con
 int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
                             long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
                             int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
+
+/* W1, TMA-staged.  Same result and arguments as dmvs_warp_corr_nhwc_f32 plus a scratch byte array `flags` of
+ * dmvs_warp_corr_flag_bytes(B, D, h, w) bytes (device memory, contents irrelevant on entry).  Two launches: (1) per 32x8
+ * pixel tile x plane chunk, the source footprint is fetched into shared memory by one TMA box load per source (zero fill =
+ * zeros padding) and gathered from there with conflict-free 16-byte loads; tiles whose footprint does not fit the box (rough
+ * per-pixel hypotheses, depth discontinuities) are flagged instead; (2) the channel-last gather kernel computes exactly the
+ * flagged (tile, plane) pairs.  Which pairs take which pass depends only on the inputs, not on [d_begin, d_end). */
+int dmvs_warp_corr_staged_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
+                              long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost,
+                              void* cost_cells, void* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
+size_t dmvs_warp_corr_flag_bytes(int B, int D, int h, int w);
 
 /* NCHW -> channel-last repack of one feature map for the call above: x [B,C,h,w] (batch stride x_bstride) -> y [B,h,w,C]
  * dense.  Replaces nothing in the reference (it is `tensor.permute(0,2,3,1).contiguous()`); callers whose FeatureNet

@@ -25,9 +25,9 @@ def cuda(t):
 
 
 # ------------------------------------------------------------------------------------------ W1
-@pytest.fixture(params=["nhwc", "nchw"])
+@pytest.fixture(params=["nhwc", "nchw", "staged"])
 def w1_layout(request):
-    """Both W1 kernels (channel-last sources = default, reference layout) go through every W1 test."""
+    """All W1 kernels (channel-last gather, reference layout, TMA-staged with fallback pass) go through every W1 test."""
     from dmvsnet_b200 import ops
     old, ops.W1_LAYOUT = ops.W1_LAYOUT, request.param
     yield request.param

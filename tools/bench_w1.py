@@ -38,7 +38,7 @@ def depth_map(kind, h, w, g, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="dtu")
-    ap.add_argument("--layouts", default="nhwc,nchw")
+    ap.add_argument("--layouts", default="staged,nhwc,nchw")
     ap.add_argument("--kinds", default="smooth,noise")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--flush", action="store_true")
@@ -81,7 +81,7 @@ def main():
                 d = hy.shape[1]
                 alg = 4 * h * w * (views * c + 3 * d)
                 for layout in args.layouts.split(","):
-                    fs = feats_cl if layout == "nhwc" else feats
+                    fs = feats if layout == "nchw" else feats_cl
                     if args.once:
                         ops.warp_corr(fs, rt, hy, layout=layout)
                         continue
@@ -99,8 +99,11 @@ def main():
                         ms += e0.elapsed_time(e1)
                     ms /= args.iters
                     rows.append((s + 1, name, kind, layout, c, d, h, w, ms, alg / ms / 1e6))
-                    print("stage%d %-6s %-6s %-4s C=%-2d D=%-2d %4dx%-4d  %7.3f ms  %7.1f GB/s  %.3f of HBM peak" %
-                          (s + 1, name, kind, layout, c, d, h, w, ms, alg / ms / 1e6, alg / ms / 1e6 / peak), flush=True)
+                    extra = ""
+                    if layout == "staged":
+                        extra = "  fallback tiles %.1f %%" % (100.0 * float(ops.LAST_W1_FLAGS.float().mean()))
+                    print("stage%d %-6s %-6s %-6s C=%-2d D=%-2d %4dx%-4d  %7.3f ms  %7.1f GB/s  %.3f of HBM peak%s" %
+                          (s + 1, name, kind, layout, c, d, h, w, ms, alg / ms / 1e6, alg / ms / 1e6 / peak, extra), flush=True)
                     del out
         # transposition cost of this stage's source maps (both feature sets)
         if not args.once:
