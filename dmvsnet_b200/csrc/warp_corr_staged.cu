@@ -54,7 +54,7 @@ struct W1sCfg {
   using Box = W1sBox<C>;
   static constexpr int PIX0 = Box::BW0 * Box::BH0, PIX1 = Box::BW1 * Box::BH1;
   static constexpr int BOX_BYTES = (PIX0 > PIX1 ? PIX0 : PIX1) * C * 4;
-  static constexpr size_t kSmem = 1024 /* alignment slack */ + BOX_BYTES + 2 * 8 * 16 /* red */ + 16 /* mbarrier */;
+  static constexpr size_t kSmem = 1024 /* alignment slack */ + BOX_BYTES + 2 * 8 * 16 /* red */ + 16 /* mbarrier */ + DMVS_MAX_SRC * 12 * 4 /* rt */;
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256, (C == 32 ? 2 : 3)) warp_corr_staged_kerne
   uint8_t* aligned = w1s_raw + (box - raw);
   int4* s_red = reinterpret_cast<int4*>(aligned + Cfg::BOX_BYTES);        // [2][8]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(aligned + Cfg::BOX_BYTES + 2 * 8 * 16);
+  float* s_rt = reinterpret_cast<float*>(aligned + Cfg::BOX_BYTES + 2 * 8 * 16 + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_x = blockIdx.x / p.n_chunks;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256, (C == 32 ? 2 : 3)) warp_corr_staged_kerne
   const int xc = min(x, p.w - 1), yc = min(y, p.h - 1);
   const int pix = yc * p.w + xc;
 
+  for (int i = threadIdx.x; i < p.n_src * 12; i += 256) s_rt[i] = __ldg(p.rt + b * p.n_src * 12 + i);
   if (threadIdx.x == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256, (C == 32 ? 2 : 3)) warp_corr_staged_kerne
 
 #pragma unroll 1
   for (int s = 0; s < p.n_src; ++s) {
-    const float* m = p.rt + (b * p.n_src + s) * 12;
+    const float* m = s_rt + s * 12;
     const float rx = __fadd_rn(__fmaf_rn(m[1], fy, __fmul_rn(m[0], fx)), m[2]);
     const float ry = __fadd_rn(__fmaf_rn(m[4], fy, __fmul_rn(m[3], fx)), m[5]);
     const float rz = __fadd_rn(__fmaf_rn(m[7], fy, __fmul_rn(m[6], fx)), m[8]);
@@ -270,9 +272,29 @@ int launch_w1_pass2(const float* ref, long long ref_bstride, int ref_pixstride, 
                     int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
                     const unsigned char* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, cudaStream_t st);
 
+template <int C, int DP>
+static int launch_w1s_dp(W1sParams& p, cudaStream_t st) {
+  using Cfg = W1sCfg<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_corr_staged_kernel<C, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) {
+      set_error("warp_corr_staged: cannot reserve %zu bytes of shared memory: %s", Cfg::kSmem, cudaGetErrorString(e));
+      return DMVS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  p.chunk0 = p.d_begin / DP;
+  p.n_chunks = ceil_div(p.d_end, DP) - p.chunk0;
+  p.tiles_x = ceil_div(p.w, 32);
+  dim3 grid(p.tiles_x * p.n_chunks, ceil_div(p.h, 8), p.B);
+  DMVS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, DMVS_ERR_BAD_SHAPE, "warp_corr_staged: grid too large (h=%d, B=%d)", p.h, p.B);
+  warp_corr_staged_kernel<C, DP><<<grid, 256, Cfg::kSmem, st>>>(p);
+  return check_launch("warp_corr_staged");
+}
+
 template <int C>
 static int launch_w1s(W1sParams& p, const float* const* src, long long src_bs, int src_ps, cudaStream_t st) {
-  using Cfg = W1sCfg<C>;
   using Box = W1sBox<C>;
   EncodeTiledFnW1 enc = encode_fn_w1();
   DMVS_REQUIRE(enc != nullptr, DMVS_ERR_CUDA, "warp_corr_staged: cuTensorMapEncodeTiled is not available from the driver");
@@ -289,22 +311,10 @@ static int launch_w1s(W1sParams& p, const float* const* src, long long src_bs, i
                    C, p.h, p.w, src_ps);
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_corr_staged_kernel<C, Box::DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-    if (e != cudaSuccess) {
-      set_error("warp_corr_staged: cannot reserve %zu bytes of shared memory: %s", Cfg::kSmem, cudaGetErrorString(e));
-      return DMVS_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  p.chunk0 = p.d_begin / Box::DP;
-  p.n_chunks = ceil_div(p.d_end, Box::DP) - p.chunk0;
-  p.tiles_x = ceil_div(p.w, 32);
-  dim3 grid(p.tiles_x * p.n_chunks, ceil_div(p.h, 8), p.B);
-  DMVS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, DMVS_ERR_BAD_SHAPE, "warp_corr_staged: grid too large (h=%d, B=%d)", p.h, p.B);
-  warp_corr_staged_kernel<C, Box::DP><<<grid, 256, Cfg::kSmem, st>>>(p);
-  return check_launch("warp_corr_staged");
+  // planes per thread: the box shapes are sized for Box::DP planes; volumes with few planes (the D = 4 refine passes) use
+  // a smaller chunk so no thread computes positions for planes that do not exist.  The choice depends on D only.
+  if (p.D <= 4 && Box::DP > 4) return launch_w1s_dp<C, (Box::DP > 4 ? 4 : Box::DP)>(p, st);
+  return launch_w1s_dp<C, Box::DP>(p, st);
 }
 
 }  // namespace dmvs

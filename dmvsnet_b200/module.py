@@ -103,7 +103,7 @@ class FeatureNet(nn.Module):
     # ~1e-3 relative, i.e. the whole parity budget, so it is off unless the caller opts in.
     allow_tf32 = False
     # "native": this library's fp32 direct-convolution kernels (dmvs_conv2d_f32), features emitted channel-last for the
-    # W1 gather (stage-1 main set additionally NCHW); "cudnn": torch/cuDNN, the reference's own path.  CPU tensors always
+    # W1 kernels; "cudnn": torch/cuDNN, the reference's own path.  CPU tensors always
     # take the torch path (FeatureNet is above the hot path and keeps a plain PyTorch definition), and so do
     # configurations other than the reference's (fpn, 3 stages).
     engine = "native"
@@ -154,7 +154,7 @@ class FeatureNet(nn.Module):
 
     def _forward_native(self, x):
         """Same graph as ``_forward`` on dmvs_conv2d_f32.  Every returned map is a [B,C,h,w] tensor that is physically
-        channel-last (what the W1 gather reads in place); ``stage1`` (sampler planes -> reference-layout W1 kernel) is NCHW."""
+        channel-last (what the W1 kernels read in place)."""
         pk = self.packed()
         t = x
         for layer in pk["conv0"]:
@@ -167,8 +167,7 @@ class FeatureNet(nn.Module):
             t = ops.conv2d(t, layer)
         c2 = t
         out = {}
-        y, _, out["stage1_c"] = ops.conv2d(c2, pk["out1"], nchw=True, split_nhwc=True)
-        out["stage1"] = y[:, : y.shape[1] // 2]
+        _, out["stage1"], out["stage1_c"] = ops.conv2d(c2, pk["out1"], nchw=False, split_nhwc=True)
         top = ops.conv2d(c1, pk["inner1"], up_add=c2)
         _, out["stage2"], out["stage2_c"] = ops.conv2d(top, pk["out2"], nchw=False, split_nhwc=True)
         top = ops.conv2d(c0, pk["inner2"], up_add=top)

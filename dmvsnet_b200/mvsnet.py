@@ -64,10 +64,10 @@ class CostAgg(nn.Module):
             rt = ops.relative_projections(proj_matrices).to(features[0].device, non_blocking=True)
         return ops.warp_corr(features, rt, depth_values)
 
-    def forward_fused(self, features, depth_values, rt, want_f32=False, layout=None):
+    def forward_fused(self, features, depth_values, rt, want_f32=False, layout=None, coherent=False):
         """Cascade-internal: W1 writes the cost volume directly in the cell layout the tensor engine's first conv reads by
         TMA (no fp32 round trip through HBM unless ``want_f32``).  Returns (cost_or_None, cells)."""
-        return ops.warp_corr(features, rt, depth_values, want_f32=want_f32, want_cells=True, layout=layout)
+        return ops.warp_corr(features, rt, depth_values, want_f32=want_f32, want_cells=True, layout=layout, coherent=coherent)
 
 
 class MVSNet(nn.Module):
@@ -122,16 +122,15 @@ class MVSNet(nn.Module):
                 hyp, interval = ops.hypotheses_next(last_depth.detach(), self.ndepths[s],
                                                     self.depth_interval_ratio[s] * depth_interval, shape, self.inverse_depth)
             fused = ops.DEFAULT_ENGINE == "tensor"
-            # W1 kernel choice: stage-1 planes come from the sampler (two parity classes of fronto-parallel planes), so
-            # neighbouring pixels sample neighbouring source positions and the reference-layout kernel's row-coalesced
-            # gathers win; every later pass has per-pixel hypotheses regressed by the previous pass, where the
-            # channel-last gather is insensitive to their roughness (profiles/, tools/bench_w1.py)
-            main_layout = "nchw" if (s == 0 and ops.W1_LAYOUT == "nhwc") else None
+            # W1 kernel choice (ops.W1_LAYOUT = "auto"): stage-1 planes come from the sampler (two parity classes of
+            # fronto-parallel planes), so a pixel tile's source footprint is a small box -> TMA-staged kernel; every later
+            # pass has per-pixel hypotheses regressed by the previous pass, whose roughness the channel-last gather does
+            # not care about (profiles/, tools/bench_w1.py)
             if fused:
                 cost, cells = self.cost_aggregation.forward_fused([f[name] for f in features], hyp, rts[s], want_f32=keep_seams,
-                                                                  layout=main_layout)
+                                                                  coherent=(s == 0))
             else:
-                cost, cells = ops.warp_corr([f[name] for f in features], rts[s], hyp, layout=main_layout), None
+                cost, cells = ops.warp_corr([f[name] for f in features], rts[s], hyp, coherent=(s == 0)), None
             logits = self.cost_regularization[s](cost, cost_cells=cells)
             stage_out = self.DepthNet(logits, hyp, num_depth=self.ndepths[s], interval=interval, stage=s)
             seams = {"_cost": cost, "_logits": logits} if keep_seams else {}

@@ -93,7 +93,7 @@ def _batch_stride(t: torch.Tensor) -> int:
 # unless they already are channel-last), "staged" = the same layout, source footprints staged in shared memory by TMA with
 # the "nhwc" kernel as the per-tile fallback (dmvs_warp_corr_staged_f32), "nchw" = the original kernel on the reference's
 # layout (dmvs_warp_corr_f32)
-W1_LAYOUT = "nhwc"
+W1_LAYOUT = "auto"  # "auto": staged where the caller says the hypotheses are spatially coherent, else nhwc
 LAST_W1_FLAGS = None  # "staged": the (tile, plane) flags of the most recent call (1 = computed by the fallback pass), for diagnostics
 
 
@@ -128,16 +128,20 @@ def features_nhwc(t: torch.Tensor) -> torch.Tensor:
 
 def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor,
               d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
-              want_f32: bool = True, want_cells: bool = False, layout: Optional[str] = None):
+              want_f32: bool = True, want_cells: bool = False, layout: Optional[str] = None, coherent: bool = False):
     """features: N x [B,C,h,w] (reference view first), rt [B,N-1,12] (device), hyp [B,D,h,w] -> cost [B,2,D,h,w].
 
     ``want_cells``: additionally (or, with ``want_f32=False``, only) emit the cost volume in the cell layout the tensor
     path's first conv reads by TMA (DMVS_FMT_COST2, int32 [B,D,h,w+1,4]); the call then returns ``(cost_or_None, cells)``.
     ``layout`` (default ``W1_LAYOUT``): "nhwc" gathers from channel-last source maps - sources that are not already
-    channel-last in memory are repacked first (one read + one write of the map) - "nchw" uses the kernel on the
-    reference's layout."""
+    channel-last in memory are repacked first (one read + one write of the map) - "staged" the TMA-staged kernel with the
+    "nhwc" kernel as its per-tile fallback, "nchw" the kernel on the reference's layout; "auto" picks "staged" when the caller
+    declares the hypotheses spatially ``coherent`` (neighbouring pixels sample neighbouring source positions: sampler planes),
+    else "nhwc"."""
     lib = N.load()
     layout = layout or W1_LAYOUT
+    if layout == "auto":
+        layout = "staged" if coherent else "nhwc"
     if layout not in ("nhwc", "nchw", "staged"):
         raise ValueError("layout must be 'nhwc', 'nchw' or 'staged'")
     ref = _req(features[0], "features[0]")

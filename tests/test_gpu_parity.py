@@ -25,7 +25,7 @@ def cuda(t):
 
 
 # ------------------------------------------------------------------------------------------ W1
-@pytest.fixture(params=["nhwc", "nchw", "staged"])
+@pytest.fixture(params=["nhwc", "nchw", "staged", "auto"])
 def w1_layout(request):
     """All W1 kernels (channel-last gather, reference layout, TMA-staged with fallback pass) go through every W1 test."""
     from dmvsnet_b200 import ops
@@ -165,7 +165,7 @@ def test_feature_net_native_vs_oracle(b, n, h, w):
         got = net.extract_features(cuda(imgs))
     from dmvsnet_b200 import ops
     assert ops._nhwc_strides(got[1]["stage3"]) is not None and ops._nhwc_strides(got[0]["stage2_c"]) is not None
-    assert ops._batch_stride(got[1]["stage1"]) > 0  # stage-1 main set is NCHW (sampler planes -> reference-layout kernel)
+    assert ops._nhwc_strides(got[1]["stage1"]) is not None
 
 
 def test_conv2d_rejects_foreign_shapes():
