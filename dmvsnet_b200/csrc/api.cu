@@ -1,5 +1,6 @@
 // Library-wide pieces of the C ABI: version, error string, launch counter.
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -15,7 +16,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+extern int g_tc2_max_ctas;
+
 }  // namespace dmvs
+
+// tuning knobs for experiments on the GPU box (not part of the reference-facing surface; values persist per process)
+extern "C" int dmvs_debug_set(const char* key, int value) {
+  if (key && !strcmp(key, "tc2_max_ctas") && value >= 1) {
+    dmvs::g_tc2_max_ctas = value;
+    return DMVS_OK;
+  }
+  dmvs::set_error("dmvs_debug_set: unknown key or bad value");
+  return DMVS_ERR_BAD_SHAPE;
+}
 
 extern "C" int dmvs_abi_version(void) { return DMVS_ABI_VERSION; }
 extern "C" const char* dmvs_last_error(void) { return dmvs::g_err; }

@@ -562,6 +562,8 @@ static int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int 
   return DMVS_OK;
 }
 
+int g_tc2_max_ctas = 1;  // debug knob (dmvs_debug_set("tc2_max_ctas", n))
+
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
 static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
   using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
@@ -592,7 +594,18 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
     }
     configured = true;
   }
-  const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;  // one persistent CTA per SM
+  // persistent CTAs: as many per SM as shared memory, registers AND the 512 TMEM columns allow (the memory-bound
+  // full-resolution layers need the second CTA's loads in flight to cover HBM latency), never more than g_tc2_max_ctas
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM) != cudaSuccess || occ < 1) occ = 1;
+    const int by_tmem = 512 / Cfg::TMEM_COLS;
+    ctas_per_sm = occ < by_tmem ? occ : by_tmem;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const int want = kNumSMs * (ctas_per_sm < g_tc2_max_ctas ? ctas_per_sm : g_tc2_max_ctas);
+  const int grid = p.n_tiles < want ? p.n_tiles : want;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, tmap);
   static char what[96];
   snprintf(what, sizeof(what), "conv_tc2<mode %d, Cin %d/%d, N %d, TD %d, stages %d, kd %d> tiles %d", MODE, CIN, CIN_P, NB, TD, STAGES, KD, p.n_tiles);

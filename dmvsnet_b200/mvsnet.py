@@ -169,7 +169,7 @@ class MVSNet(nn.Module):
 
     # ------------------------------------------------------------------ host-buffer entry
     # views per H2D / FeatureNet group in infer(): the copy of group k+1 (side stream) runs under FeatureNet of group k
-    infer_view_groups = 2
+    infer_view_groups = 3
 
     @torch.no_grad()
     def infer(self, imgs: torch.Tensor, proj_matrices: Dict[str, torch.Tensor], depth_values: torch.Tensor,
@@ -213,3 +213,60 @@ class MVSNet(nn.Module):
             host[k] = buf
         torch.cuda.current_stream().synchronize()
         return host
+
+    @torch.no_grad()
+    def infer_many(self, inputs, keys: Sequence[str] = ("depth", "photometric_confidence")):
+        """Generator over ``(imgs, proj_matrices, depth_values)`` host triples -> host result dicts, in order.
+
+        The production loop of ``Model.test`` (model.py:323-380: one reference view after the other) as a three-stage
+        pipeline: the images of item k+1 cross PCIe on a side stream while item k computes, and the results of item k
+        are copied back while item k+1 computes.  Every item still pays its own H2D and D2H; only their latency is
+        hidden.  Results are yielded one item late (after their D2H has completed)."""
+        _require_inference(self)
+        dev = next(self.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        side = getattr(self, "_copy_stream", None)
+        if side is None or side.device != dev:
+            side = self._copy_stream = torch.cuda.Stream(dev)
+
+        def upload(item):
+            imgs, proj, dv = item
+            src = imgs if imgs.is_pinned() else imgs.pin_memory()
+            with torch.cuda.stream(side):  # side-stream pool; record_stream(main) below keeps recycling safe
+                dimgs = src.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return dimgs, proj, dv, ev
+
+        pending = None  # (host dict, event) of the previous item
+        it = iter(inputs)
+        nxt = next(it, None)
+        cur = upload(nxt) if nxt is not None else None
+        while cur is not None:
+            nxt = next(it, None)
+            dimgs, proj, dv, ev = cur
+            main.wait_event(ev)
+            dimgs.record_stream(main)
+            out = self.forward(dimgs, proj, dv)
+            done = torch.cuda.Event()
+            done.record(main)
+            # queue the next upload and this item's download behind each other on the side stream
+            cur = upload(nxt) if nxt is not None else None
+            host = {}
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                for k in keys:
+                    buf = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
+                    buf.copy_(out[k], non_blocking=True)
+                    out[k].record_stream(side)
+                    host[k] = buf
+                hev = torch.cuda.Event()
+                hev.record(side)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = (host, hev)
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+

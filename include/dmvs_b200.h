@@ -42,6 +42,8 @@ int dmvs_abi_version(void);
 const char* dmvs_last_error(void);
 /* number of kernels this library has launched from the calling process (all threads) */
 unsigned long long dmvs_launch_count(void);
+/* tuning knobs for experiments ("tc2_max_ctas": persistent CTAs per SM of the tensor-core convolutions, default 1; 2 measured no gain) */
+int dmvs_debug_set(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * W1  fused homography warp + 2-group correlation, summed over source views.

@@ -449,6 +449,24 @@ def test_infer_from_host_buffers():
     assert err < 1e-3, err
 
 
+def test_infer_many_pipeline_matches_infer():
+    """The three-stage pipeline (upload k+1 | compute k | download k-1) returns, in order, exactly what infer() returns."""
+    from dmvsnet_b200 import MVSNet
+    case = CASES["cfg1_full"]
+    inp = case_inputs(case)
+    net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
+    net.load_state_dict(case_state(case))
+    net = net.to(DEV).eval()
+    items = [((inp["imgs"] * s).clamp(0, 1), inp["proj"], inp["depth_values"]) for s in (1.0, 0.7, 0.4, 0.9)]
+    want = [net.infer(*it) for it in items]
+    got = list(net.infer_many(items))
+    assert len(got) == len(want)
+    for g, w_ in zip(got, want):
+        assert torch.equal(g["depth"], w_["depth"]) and torch.equal(g["photometric_confidence"], w_["photometric_confidence"])
+    assert not torch.equal(want[0]["depth"], want[2]["depth"])
+    assert list(net.infer_many([])) == []
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_dtu_stage3_properties(w1_layout):
     """BASELINE config 2 at full stage-3 size (1184x1600, C=8, N=5): size-independent properties instead of the oracle."""
