@@ -7,10 +7,11 @@ One step = one pass of the hot path (3-stage cascade: S1 -> W1 -> R1 -> E1 -> W1
 synthetic DTU-shaped view set (1600x1184, N=5, D=[48,32,8]; BASELINE.json configs[1]).
 
   value      views/s, whole job, per-view features already resident in HBM (scope H of SURVEY 8d), CUDA-event timed
-  e2e        views/s through the public API MVSNet.infer(): pinned host images -> H2D -> FeatureNet (torch/cuDNN) ->
-             hot path -> D2H of depth + confidence, every step (scope F + copies)
+  e2e        views/s through the public API MVSNet.infer_many(): per step pinned host images -> H2D -> FeatureNet
+             (dmvs_conv2d_f32) -> hot path -> D2H of depth + confidence (scope F + copies; the copies of neighbouring steps
+             overlap compute on a copy stream); e2e.single_request_ms = one blocking MVSNet.infer() per step
   roofline   the fused warp+corr kernel (W1): algorithmic bytes 4*h*w*(N*C + 3*D) per launch over its CUDA-event time,
-             all six launches of a step pooled; per-launch numbers under "roofline_per_launch"
+             all six passes of a step pooled; per-pass numbers under "roofline_per_launch"
   cpu_baseline / --impl reference
              the oracle port of the reference's PyTorch-CPU path (oracle/dmvs_oracle.py; the reference itself is pure
              Python and cannot travel to the GPU box) on the host cores, on a bounded sample (a 1600x160 band of the

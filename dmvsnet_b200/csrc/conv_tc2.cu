@@ -79,7 +79,10 @@ struct C2 {
   static constexpr int ACC_SETS = (2 * COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = pow2c(ACC_SETS * COLS);
   static constexpr int PROD_WARPS = (MODE == M2_C0) ? 12 : 1;
-  static constexpr int EPI_WARPS = 8;
+  // epilogue warps: TMEM quadrant = warp % 4, so a multiple of 4; the full-resolution layers' epilogues are latency-bound
+  // instruction streams (2 warps per scheduler issue 30-40 % of the cycles), so the cheap-in-registers modes get 16
+  static constexpr int EPI_WARPS = (MODE == M2_PB || MODE == M2_C0T) ? 16 : 8;
+  static constexpr int NPART = EPI_WARPS / 4;
   // one MMA-issuing warp per accumulator set: tile k is issued by warp k % MMA_WARPS into set k % 2, so the (serial,
   // single-thread) descriptor arithmetic of consecutive tiles overlaps
   // Each issuing warp owns a private slice of the stage ring (stage = MMA_WARPS*(j % HS) + warp, j = its own item count):
@@ -183,9 +186,9 @@ __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_ba
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue
-// One warp: TMEM lanes 32*(warp%4)..+31; `part` in {0,1} splits the planes (or plane x parity units for TR) between
+// One warp: TMEM lanes 32*(warp%4)..+31; `part` in [0, NPART) splits the planes (or plane x parity units for TR) between
 // the two warps that share a quadrant.
-template <int MODE, int NB, int TD, int KD>
+template <int MODE, int NB, int TD, int KD, int NPART>
 __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, uint32_t acc_base, int q, int lane, int part) {
   constexpr int COUT_P = NB / 2;
   const int hl = q * 4 + (lane >> 3), wl = lane & 7;
@@ -196,27 +199,40 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
     const bool in_img = (iy < p.Hi) && (ix < p.Wi);
     uint4* yc = reinterpret_cast<uint4*>(p.y);
     constexpr int NZY = (KD == 3) ? 4 : 2;  // (pz, py) output parity classes per input plane
-    for (int u = part; u < TD * NZY; u += 2) {
+    for (int u = part; u < TD * NZY; u += NPART) {
       const int t = u / NZY, pzy = u % NZY;
       if (tc.z0 + t >= p.Di) break;  // warp-uniform
       const int oz = (KD == 3) ? 2 * (tc.z0 + t) + (pzy >> 1) : tc.z0 + t, oy = 2 * iy + (pzy & 1);
       const uint32_t te = lane_addr + (t * 2 * NZY + pzy * 2) * NB, to = te + NB;
 #pragma unroll 1
       for (int c0 = 0; c0 < COUT_P; c0 += 8) {
-        float e[8], o[8], le[8], lo8[8];
-        tmem_ld8(te + c0, e);
-        tmem_ld8(te + COUT_P + c0, le);
-        tmem_ld8(to + c0, o);
-        tmem_ld8(to + COUT_P + c0, lo8);
-        if (!in_img || c0 >= p.Cout) continue;
+        // the skip cells do not depend on the accumulators: their (HBM-latency) loads go out first, then the four TMEM
+        // loads, then ONE wait - the latencies overlap instead of adding up
+        const bool live = in_img && c0 < p.Cout;
         const int ph = (c0 >> 3) * 2;
-        float se[8], so[8];
-        if (p.skip) {  // CH16P tensor: even output column 2ix -> parity 0 cell ix, odd column -> parity 1 cell ix
+        uint4 he = make_uint4(0, 0, 0, 0), hle = he, ho = he, hlo = he;
+        if (p.skip && live) {  // CH16P tensor: even output column 2ix -> parity 0 cell ix, odd column -> parity 1 cell ix
           const long long ce = cell_index(FMT_CH16P, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, 2 * ix);
           const long long co_ = cell_index(FMT_CH16P, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, 2 * ix + 1);
           const long long pstride = (long long)p.Do * p.Ho * (2 * ((p.Wo + 1) >> 1));
-          const uint4 he = __ldg(p.skip + ce), hle = __ldg(p.skip + ce + pstride);
-          const uint4 ho = __ldg(p.skip + co_), hlo = __ldg(p.skip + co_ + pstride);
+          he = __ldg(p.skip + ce); hle = __ldg(p.skip + ce + pstride);
+          ho = __ldg(p.skip + co_); hlo = __ldg(p.skip + co_ + pstride);
+        }
+        uint32_t re[8], rle[8], ro[8], rlo[8];
+        tmem_ld8_issue(te + c0, re);
+        tmem_ld8_issue(te + COUT_P + c0, rle);
+        tmem_ld8_issue(to + c0, ro);
+        tmem_ld8_issue(to + COUT_P + c0, rlo);
+        tmem_wait_ld();
+        if (!live) continue;
+        float e[8], o[8], le[8], lo8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          e[c] = __uint_as_float(re[c]); le[c] = __uint_as_float(rle[c]);
+          o[c] = __uint_as_float(ro[c]); lo8[c] = __uint_as_float(rlo[c]);
+        }
+        float se[8], so[8];
+        if (p.skip) {
           float a[8], b2[8];
           unpack_cell(he, a); unpack_cell(hle, b2);
 #pragma unroll
@@ -252,14 +268,18 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
     const bool in_img = (oy < p.Ho) && (ox < p.Wo);
     float* yf = reinterpret_cast<float*>(p.y);
     const long long oplane = (long long)p.Ho * p.Wo;
-    for (int t = part; t < TD; t += 2) {
+    for (int t = part; t < TD; t += NPART) {
       const int oz = tc.z0 + t;
       if (oz >= p.Do) break;  // warp-uniform
-      float a0[8], a1[8], b2[8];
-      tmem_ld8(lane_addr + (t + 0) * NB, a0);
-      tmem_ld8(lane_addr + (t + 1) * NB, a1);
-      tmem_ld8(lane_addr + (t + 2) * NB + 8, b2);
+      uint32_t r0[8], r1[8], r2[8];
+      tmem_ld8_issue(lane_addr + (t + 0) * NB, r0);
+      tmem_ld8_issue(lane_addr + (t + 1) * NB, r1);
+      tmem_ld8_issue(lane_addr + (t + 2) * NB + 8, r2);
+      tmem_wait_ld();
       if (!in_img) continue;
+      float a0[8], a1[8], b2[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { a0[c] = __uint_as_float(r0[c]); a1[c] = __uint_as_float(r1[c]); b2[c] = __uint_as_float(r2[c]); }
       // kd = 0 -> columns 0..3 of plane t; kd = 1 -> columns 4..7 of plane t+1; kd = 2 -> columns 8..11 (= b2[0..3]) of plane t+2
 #pragma unroll
       for (int co = 0; co < 2; ++co) {
@@ -272,16 +292,20 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
   } else {
     const int oy = tc.y0 + hl, ox = tc.x0 + wl;
     const bool in_img = (oy < p.Ho) && (ox < p.Wo);
-    for (int t = part; t < TD; t += 2) {
+    for (int t = part; t < TD; t += NPART) {
       const int oz = tc.z0 + t;
       if (oz >= p.Do) break;  // warp-uniform
       const uint32_t taddr = lane_addr + t * NB;
 #pragma unroll 1
       for (int c0 = 0; c0 < COUT_P; c0 += 8) {
-        float v[8], l8[8];
-        tmem_ld8(taddr + c0, v);
-        tmem_ld8(taddr + COUT_P + c0, l8);
+        uint32_t rv[8], rl[8];
+        tmem_ld8_issue(taddr + c0, rv);
+        tmem_ld8_issue(taddr + COUT_P + c0, rl);
+        tmem_wait_ld();
         if (!in_img || c0 >= p.Cout) continue;
+        float v[8], l8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { v[c] = __uint_as_float(rv[c]); l8[c] = __uint_as_float(rl[c]); }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float a = v[c] + l8[c];
@@ -466,7 +490,7 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
       const int a = (Cfg::ACC_SETS == 2) ? (tile_k & 1) : 0, v = (Cfg::ACC_SETS == 2) ? (tile_k >> 1) : tile_k;
       mbar_wait(accfull + a, v & 1);
       tc_fence_after();
-      epilogue2<MODE, NB, TD, KD>(p, decode2(p, lt, TD), tmem_base + a * Cfg::COLS, q, lane, part);
+      epilogue2<MODE, NB, TD, KD, Cfg::NPART>(p, decode2(p, lt, TD), tmem_base + a * Cfg::COLS, q, lane, part);
       tc_fence_before();
       mbar_arrive(accempty + a);
     }
