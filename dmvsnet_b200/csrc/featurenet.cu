@@ -6,8 +6,8 @@
 // One kernel template covers every layer:
 //   * block = 32x32 output pixels x CT output channels, 256 threads; thread = 4 x-consecutive pixels x CT channels
 //     (64 / 32 accumulators), lanes 8 (x) x 4 (y) so a quarter warp reads 128 contiguous bytes of an input row;
-//   * the input halo tile is staged through shared memory CC input channels at a time (zero padding applied while
-//     staging), the weights of the chunk as [ci][kh][kw][co] so four output channels arrive with one broadcast
+//   * the input halo tile is staged through shared memory CC input channels at a time by double-buffered 16-byte
+//     cp.async (zero-size copies = zero padding; the tile starts at a 16-byte aligned column left of the halo), the weights of the chunk as [ci][kh][kw][co] so four output channels arrive with one broadcast
 //     LDS.128: per (ci, kh) a thread issues 2-3 input loads + K*CT/4 weight loads for K*4*CT FMAs (>= 12 FMA per load);
 //   * epilogue: eval BatchNorm as scale/shift (or the conv bias as shift), ReLU, optional "+ nearest-x2-upsampled
 //     coarser map" (the FPN top-down add, module.py:329,334), and stores in NCHW and/or channel-last split into the
@@ -35,12 +35,16 @@ struct FeatCfg {
   static constexpr int CT = COUT < 16 ? COUT : 16;               // output channels per thread / block
   static constexpr int NZ = COUT / CT;                           // channel groups -> blockIdx.z
   static constexpr int TILE = 32;                                // output tile edge
-  static constexpr int IN = (TILE - 1) * S + K;                  // input tile edge
-  static constexpr int PITCH = ((IN + 3) / 4) * 4 + (S == 2 ? 0 : 0);
-  static constexpr int CC_MAX = (40 * 1024) / (IN * PITCH * 4);  // input channels per chunk (about 40 KB of tile)
-  static constexpr int CC = CIN < (CC_MAX < 1 ? 1 : CC_MAX) ? CIN : (CC_MAX < 1 ? 1 : (CC_MAX >= 8 ? 8 : (CC_MAX >= 4 ? 4 : (CC_MAX >= 2 ? 2 : 1))));
-  static constexpr int NIN = 3 * S + K;                          // input columns one thread touches per row
+  static constexpr int IN = (TILE - 1) * S + K;                  // input tile edge (rows)
+  static constexpr int PADK = K / 2;
+  // the staged tile starts OFF columns left of the halo so that smem column 0 is a 16-byte aligned global column
+  // (tile origins are multiples of 32): rows are then staged with 16-byte cp.async
+  static constexpr int OFF = (4 - PADK % 4) % 4;
+  static constexpr int NIN = OFF + 3 * S + K;                    // input columns one thread touches per row, from its aligned base
   static constexpr int NLD = (NIN + 3) / 4;                      // as 16-byte loads
+  static constexpr int PITCH = 4 * 7 * S + 4 * NLD;              // last thread's base + its loads
+  static constexpr int CC_MAX = (44 * 1024) / (IN * PITCH * 4);  // input channels per chunk (about 44 KB of tile)
+  static constexpr int CC = CIN < (CC_MAX < 1 ? 1 : CC_MAX) ? CIN : (CC_MAX < 1 ? 1 : (CC_MAX >= 8 ? 8 : (CC_MAX >= 4 ? 4 : (CC_MAX >= 2 ? 2 : 1))));
   static constexpr int NCHUNK = CIN / CC;
   static constexpr int NBUF = NCHUNK > 1 ? 2 : 1;                // double-buffered staging when there is something to overlap
   static constexpr size_t kSmem = (size_t)NBUF * (CC * IN * PITCH + CC * K * K * CT) * 4;
@@ -50,7 +54,7 @@ struct FeatCfg {
 template <int K, int S, int CIN, int COUT>
 __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant__ FeatConvParams p) {
   using Cfg = FeatCfg<K, S, CIN, COUT>;
-  constexpr int CT = Cfg::CT, NZ = Cfg::NZ, IN = Cfg::IN, PITCH = Cfg::PITCH, CC = Cfg::CC, NLD = Cfg::NLD;
+  constexpr int CT = Cfg::CT, NZ = Cfg::NZ, IN = Cfg::IN, PITCH = Cfg::PITCH, CC = Cfg::CC, NLD = Cfg::NLD, OFF = Cfg::OFF;
   constexpr int PAD = K / 2;
   extern __shared__ __align__(16) float fsm[];
   // fsm: [NBUF][CC][IN][PITCH] input tiles, then [NBUF][CC][K][K][CT] weights
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
   const int b = blockIdx.z / NZ, cz = blockIdx.z - b * NZ;
   const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
   const int ox = X0 + 4 * lx, oy = Y0 + 4 * warp + ly;        // this thread's first output pixel
-  const int ix0 = X0 * S - PAD, iy0 = Y0 * S - PAD;           // input coordinates of the tile origin
+  const int ix0 = X0 * S - PAD - OFF, iy0 = Y0 * S - PAD;     // input coordinates of smem (row 0, column 0); ix0 % 4 == 0
 
   float acc[4][CT];
 #pragma unroll
@@ -76,17 +80,31 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
   auto stage = [&](int c, int buf) {
     float* din = fsm + buf * IN_FLOATS;
     const int c0 = c * CC;
-    for (int r = warp; r < CC * IN; r += 8) {
-      const int ci = r / IN, row = r - ci * IN;
-      const int gy = iy0 + row;
-      const bool row_ok = gy >= 0 && gy < p.Hi;
-      const float* src = xb + ((long long)(c0 + ci) * p.Hi + (row_ok ? gy : 0)) * p.Wi;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(din + r * PITCH);
+    if ((p.Wi & 3) == 0) {
+      // 16-byte copies: a group of 4 columns is entirely inside or entirely outside the image (ix0 and Wi are multiples of 4)
+      constexpr int G4 = PITCH / 4;
+      for (int e = threadIdx.x; e < CC * IN * G4; e += 256) {
+        const int g = e % G4, r = e / G4;
+        const int ci = r / IN, row = r - ci * IN;
+        const int gy = iy0 + row, gx = ix0 + 4 * g;
+        const bool ok = gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+        const float* src = xb + ((long long)(c0 + ci) * p.Hi + (ok ? gy : 0)) * p.Wi + (ok ? gx : 0);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(din + r * PITCH + 4 * g);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+      }
+    } else {
+      for (int r = warp; r < CC * IN; r += 8) {
+        const int ci = r / IN, row = r - ci * IN;
+        const int gy = iy0 + row;
+        const bool row_ok = gy >= 0 && gy < p.Hi;
+        const float* src = xb + ((long long)(c0 + ci) * p.Hi + (row_ok ? gy : 0)) * p.Wi;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(din + r * PITCH);
 #pragma unroll
-      for (int col = lane; col < PITCH; col += 32) {
-        const int gx = ix0 + col;
-        const bool ok = row_ok && gx >= 0 && gx < p.Wi && col < IN;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + col * 4), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
+        for (int col = lane; col < PITCH; col += 32) {
+          const int gx = ix0 + col;
+          const bool ok = row_ok && gx >= 0 && gx < p.Wi;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + col * 4), "l"(src + (ok ? gx : 0)), "r"(ok ? 4 : 0) : "memory");
+        }
       }
     }
     const uint32_t dw = (uint32_t)__cvta_generic_to_shared(s_wbase + buf * W_FLOATS);
@@ -131,7 +149,7 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
             const float4 wv = *reinterpret_cast<const float4*>(wp + 4 * j4);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float xv = in[i * S + kw];
+              const float xv = in[OFF + i * S + kw];
               acc[i][4 * j4] = fmaf(xv, wv.x, acc[i][4 * j4]);
               acc[i][4 * j4 + 1] = fmaf(xv, wv.y, acc[i][4 * j4 + 1]);
               acc[i][4 * j4 + 2] = fmaf(xv, wv.z, acc[i][4 * j4 + 2]);
