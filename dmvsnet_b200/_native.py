@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ul
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 ENGINE_FP32, ENGINE_TENSOR = 0, 1
 MAX_SRC = 16
@@ -29,7 +29,7 @@ class ConvLayer(ctypes.Structure):
 
 
 class RegnetBranch(ctypes.Structure):
-    _fields_ = [("layer", ConvLayer * REGNET_LAYERS)]
+    _fields_ = [("layer", ConvLayer * REGNET_LAYERS), ("conv0_pair", ConvLayer)]
 
 
 # name -> (restype, argtypes); mirrors include/dmvs_b200.h one to one

@@ -27,8 +27,12 @@
 namespace dmvs {
 
 enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2 };
-enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4, M2_C0T = 5 };
+enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4, M2_C0T = 5, M2_TRF = 6 };
 __host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mode == M2_C0T; }
+// TRF: transposed conv with the 27 taps folded by input shift: the taps that read the same shifted A view (shift in {0,1}^3,
+// 8 of them) become ONE MMA whose N spans the 8 parity-class accumulators (zero weight columns where a class has no tap for
+// that shift).  Every MMA re-reads its 4 KB A tile from shared memory at 64 B/clk whatever its N, so 8 MMAs instead of 27.
+__host__ __device__ constexpr bool is_tr(int mode) { return mode == M2_TR || mode == M2_TRF; }
 constexpr int T_H = 16, T_W = 8;
 
 struct Tc2Params {
@@ -51,8 +55,8 @@ __host__ __device__ constexpr int pow2c(int c) { return c <= 32 ? 32 : c <= 64 ?
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
 struct C2 {
   // KD = 1: the 2-D convolutions of the refine net's bottleneck (no taps, halo or stride along depth)
-  static constexpr int SD = (KD == 1) ? TD : (MODE == M2_S2) ? 2 * TD + 1 : (MODE == M2_TR) ? TD + 1 : TD + 2;
-  static constexpr int SH = (MODE == M2_S2) ? 2 * T_H + 1 : (MODE == M2_TR) ? T_H + 1 : T_H + 2;
+  static constexpr int SD = (KD == 1) ? TD : (MODE == M2_S2) ? 2 * TD + 1 : is_tr(MODE) ? TD + 1 : TD + 2;
+  static constexpr int SH = (MODE == M2_S2) ? 2 * T_H + 1 : is_tr(MODE) ? T_H + 1 : T_H + 2;
   static constexpr int BW = (MODE == M2_S1 || is_c0(MODE) || MODE == M2_PB) ? T_W + 2 : T_W + 1;  // cells per staged row (S2: per parity block)
   static constexpr int ROWS = SD * SH;
   static constexpr int BLK_BYTES = ROWS * BW * 16;  // bytes one TMA box writes
@@ -63,18 +67,19 @@ struct C2 {
   static constexpr int NPLANE = is_c0(MODE) ? 1 : 2 * CJ;
   static constexpr int NPASS = is_c0(MODE) ? 1 : CIN / CIN_P;
   static constexpr bool RESIDENT = NPASS == 1;
-  static constexpr int TAPS = (is_c0(MODE) || MODE == M2_PB || KD == 1) ? 9 : 27;
+  static constexpr int TAPS = (MODE == M2_TRF) ? 8 : (is_c0(MODE) || MODE == M2_PB || KD == 1) ? 9 : 27;
+  static constexpr int NMMA = (MODE == M2_TRF) ? 8 * NB : NB;  // N of one tcgen05.mma
   static constexpr int A_BYTES = NPLANE * PLANE;
   static constexpr int A_LBO = is_c0(MODE) ? 32 : PLANE;
   static constexpr int A_SBO = (MODE == M2_S2) ? 2 * BW * 16 : BW * 16;
-  static constexpr int B_TILE = 2 * NB * 16;
+  static constexpr int B_TILE = 2 * NMMA * 16;
   static constexpr int B_BYTES = CJ * TAPS * B_TILE;
   static constexpr int TX_BYTES = NPLANE * NBLK * BLK_BYTES + (RESIDENT ? 0 : B_BYTES);
   static constexpr int STAGE_BYTES = A_BYTES + (RESIDENT ? 0 : pad128(B_BYTES));
   static constexpr int OFF_B = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_B + (RESIDENT ? pad128(B_BYTES) : 0);
   static constexpr int SMEM = OFF_BAR + 8 * (2 * STAGES + 4) + 16 + 128;  // + slack for manual 128-byte alignment
-  static constexpr int NACC = (MODE == M2_TR) ? (KD == 1 ? 4 : 8) * TD : (MODE == M2_PB) ? TD + 2 : TD;
+  static constexpr int NACC = is_tr(MODE) ? (KD == 1 ? 4 : 8) * TD : (MODE == M2_PB) ? TD + 2 : TD;
   static constexpr int COLS = NACC * NB;
   static constexpr int ACC_SETS = (2 * COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = pow2c(ACC_SETS * COLS);
@@ -136,9 +141,9 @@ __device__ __forceinline__ long long cell_index(int fmt, int b, int np, int pl, 
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD>
 __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_base, bool fresh) {
   using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
-  constexpr uint32_t idesc = make_idesc(NB);
+  constexpr uint32_t idesc = make_idesc(Cfg::NMMA);
   const uint64_t adesc0 = make_desc(a0, Cfg::A_LBO, Cfg::A_SBO);
-  const uint64_t bdesc0 = make_desc(b0, NB * 16, 128);
+  const uint64_t bdesc0 = make_desc(b0, Cfg::NMMA * 16, 128);
   const uint32_t fresh_acc = fresh ? 0u : 1u;
 #pragma unroll
   for (int t = 0; t < ((MODE == M2_PB) ? TD + 2 : TD); ++t) {
@@ -152,6 +157,12 @@ __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_ba
         acc = t;
         off = ((t * Cfg::SH + kh) * Cfg::BW + kw) * 16;
         first = tap == 0;
+      } else if (MODE == M2_TRF) {
+        // `tap` is the input shift (sz,sy,sx); its MMA covers the 8 class accumulators of plane t in one go
+        const int sz = tap >> 2, sy = (tap >> 1) & 1, sx = tap & 1;
+        acc = t * 8;
+        off = (((t + sz) * Cfg::SH + sy) * Cfg::BW + sx) * 16;
+        first = tap == 0;  // shift 0 has a tap for every class: it initialises all 8 accumulators
       } else if (MODE == M2_TR) {
         // tap (kz,ky,kx) of the transposed kernel feeds output parity class (kz!=1, ky!=1, kx!=1); k = 0 reads input +1
         const int kz = (KD == 3) ? tap / 9 : 1, ky = (tap % 9) / 3, kx = tap % 3;
@@ -194,7 +205,7 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
   const int hl = q * 4 + (lane >> 3), wl = lane & 7;
   const uint32_t lane_addr = acc_base + ((uint32_t)(q * 32) << 16);
   const int npo = p.Cout / 4;  // planes per batch entry of a CH16 output with Cout channels
-  if (MODE == M2_TR) {
+  if (is_tr(MODE)) {
     const int iy = tc.y0 + hl, ix = tc.x0 + wl;
     const bool in_img = (iy < p.Hi) && (ix < p.Wi);
     uint4* yc = reinterpret_cast<uint4*>(p.y);
@@ -446,7 +457,7 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
               tma_load_4d(dst, &tmap, full + s, 8 * tc.x0, tc.y0 - 1, tc.z0 - 1, tc.b);
             } else if (MODE == M2_S1 || MODE == M2_PB) {
               tma_load_4d(dst, &tmap, full + s, 8 * (tc.x0 - 1), tc.y0 - 1, (KD == 3) ? tc.z0 - 1 : tc.z0, gpl);
-            } else if (MODE == M2_TR) {
+            } else if (is_tr(MODE)) {
               tma_load_4d(dst, &tmap, full + s, 8 * tc.x0, tc.y0, tc.z0, gpl);
             } else {  // S2 on a CH16P tensor: even columns 2*(x0+i) = even cell x0+i; odd columns 2*(x0+i)-1 = odd cell x0+i-1
               const int zc = (KD == 3) ? 2 * tc.z0 - 1 : tc.z0;
@@ -591,7 +602,7 @@ int g_tc2_max_ctas = 1;  // debug knob (dmvs_debug_set("tc2_max_ctas", n))
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
 static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
   using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
-  const int gw = (MODE == M2_TR) ? p.Wi : p.Wo, gh = (MODE == M2_TR) ? p.Hi : p.Ho, gd = (MODE == M2_TR) ? p.Di : p.Do;
+  const int gw = is_tr(MODE) ? p.Wi : p.Wo, gh = is_tr(MODE) ? p.Hi : p.Ho, gd = is_tr(MODE) ? p.Di : p.Do;
   p.tiles_x = ceil_div(gw, T_W);
   p.tiles_y = ceil_div(gh, T_H);
   p.tiles_z = ceil_div(gd, TD);
@@ -673,7 +684,13 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   if (transposed) {
     p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
     DMVS_REQUIRE(out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE, "conv_tc2: transposed convs write CH16");
-    if (Cin == 16 && Cout == 8) return launch2<M2_TR, 16, 16, 16, 2, 4>(p, x, st);   // conv11
+    if (Cin == 16 && Cout == 8) {                                                     // conv11
+      if (L.w_tc_kd) {  // taps folded by input shift (8 MMAs per plane and chunk instead of 27)
+        p.wtc = reinterpret_cast<const uint4*>(L.w_tc_kd);
+        return launch2<M2_TRF, 16, 16, 16, 2, 4>(p, x, st);
+      }
+      return launch2<M2_TR, 16, 16, 16, 2, 4>(p, x, st);
+    }
     if (Cin == 32 && Cout == 16) return launch2<M2_TR, 32, 16, 32, 1, 2>(p, x, st);  // conv9, 2 passes, weights streamed
     if (Cin == 64 && Cout == 32) return launch2<M2_TR, 64, 8, 64, 1, 3>(p, x, st);   // conv7, 8 passes
     return 1;
@@ -689,6 +706,7 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   }
   p.Do = Di; p.Ho = Hi; p.Wo = Wi;
   if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
+  if (Cin == 2 && Cout == 16 && in_cells) return launch2<M2_C0T, 2, 2, 32, 4, 4>(p, x, st);  // conv0 of both branches (conv0_pair)
   if (Cin == 2 && Cout == 8) {                                                       // conv0
     if (in_cells) return launch2<M2_C0T, 2, 2, 16, 4, 4>(p, x, st);
     return launch2<M2_C0, 2, 2, 16, 4, 4>(p, x, st);

@@ -50,7 +50,7 @@ Plan make_plan(int refine, int B, int D, int h, int w) {
   }
   long long o = 0;
   auto take = [&](int ch, int lvl) { long long at = o; o += (long long)B * ch * p.lv[lvl].vox(); o = (o + 3) & ~3LL; return at; };
-  p.c0 = take(8, 0); p.u11 = take(8, 0);
+  p.c0 = take(16, 0); p.u11 = take(8, 0);  // c0: room for conv0 of both branches (conv0_pair), 8 channels each
   p.c1 = take(16, 1); p.c2 = take(16, 1);
   p.c3 = take(32, 2); p.c4 = take(32, 2);
   p.c5 = take(64, 3); p.c6 = take(64, 3);
@@ -100,9 +100,19 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
   if (tensor_ok) {
     // ---- tensor path: activations in CH16 / CH16P cells between layers, every 3x3x3 layer a TMA-fed tcgen05 kernel
     enum { F32 = DMVS_FMT_F32, CH = DMVS_FMT_CH16, CHP = DMVS_FMT_CH16P };
+    // conv0 of both branches in one launch: a 2 -> 16 layer whose CH16P output holds branch 0 in planes 0,1 and branch 1
+    // in planes 2,3 (contiguous per branch when B == 1)
+    const bool pair = cost_cells && B == 1 && branches[0].conv0_pair.w_tc != nullptr;
+    if (pair) {
+      const int rc0 = conv_layer_tc2(cost_cells, 1, branches[0].conv0_pair, nullptr, c0, 0, B, 2, 16, L0->D, L0->H, L0->W, 3, 1, 0, 1, CHP, st);
+      if (rc0 > 0) { set_error("regnet: conv0_pair has no tensor specialisation"); return DMVS_ERR_BAD_SHAPE; }
+      if (rc0 != DMVS_OK) return rc0;
+    }
+    float* const c0_base = c0;
     for (int br = 0; br < 2; ++br) {
       const dmvs_conv_layer* L = branches[br].layer;
       int rc;
+      c0 = pair ? c0_base + (long long)br * 8 * V0 : c0_base;
 #define TC2(...)                                                                                         \
   rc = conv_layer_tc2(__VA_ARGS__);                                                                      \
   if (rc > 0) { set_error("regnet: layer has no tensor specialisation"); return DMVS_ERR_BAD_SHAPE; }   \
@@ -111,7 +121,9 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
   rc = conv_layer(__VA_ARGS__);  \
   if (rc != DMVS_OK) return rc;
       //  x,   layer, skip,    y,  y_bs, B, Cin, Cout, Di,    Hi,    Wi,   stride, transposed, relu, out_fmt
-      TC2(cost_cells ? cost_cells : (const void*)cost, cost_cells ? 1 : 0, L[0], nullptr, c0, 0, B, 2, 8, L0->D, L0->H, L0->W, 3, 1, 0, 1, CHP, st);
+      if (!pair) {
+        TC2(cost_cells ? cost_cells : (const void*)cost, cost_cells ? 1 : 0, L[0], nullptr, c0, 0, B, 2, 8, L0->D, L0->H, L0->W, 3, 1, 0, 1, CHP, st);
+      }
       TC2(c0, 0, L[1], nullptr, c1, 0, B, 8, 16, L0->D, L0->H, L0->W, 3, 2, 0, 1, CH, st);
       TC2(c1, 0, L[2], nullptr, c2, 0, B, 16, 16, L1->D, L1->H, L1->W, 3, 1, 0, 1, CHP, st);
       TC2(c2, 0, L[3], nullptr, c3, 0, B, 16, 32, L1->D, L1->H, L1->W, 3, 2, 0, 1, CH, st);

@@ -278,7 +278,11 @@ class PackedLayer:
             self.w_tc = _pack_tensor_core_kw(w[:, :, :cout])
         else:
             self.w_tc = None
-        self.w_tc_kd = _pack_tensor_core_prob(w[:, :, :cout]) if (cin == 8 and cout == 2 and taps == 27 and not transposed) else None
+        self.w_tc_kd = None
+        if cin == 8 and cout == 2 and taps == 27 and not transposed:
+            self.w_tc_kd = _pack_tensor_core_prob(w[:, :, :cout])
+        elif cin == 16 and cout == 8 and taps == 27 and transposed:
+            self.w_tc_kd = _pack_tensor_core_tr_fold(w[:, :, :cout])
         self.kd = 3 if taps == 27 else 1
         self.cin, self.cout = cin, cout
         self.transposed = transposed
@@ -328,6 +332,36 @@ def _pack_tensor_core_prob(w: torch.Tensor) -> torch.Tensor:
     return img.contiguous()
 
 
+def _pack_tensor_core_tr_fold(w: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose3d(k3, s2, p1, op1) with the taps folded by input shift.  [27][Cin][Cout] -> [chunk j][shift s = (sz,sy,sx)]
+    [kc][n = 8 classes x 2*Cout_p][8 halfs].  Output parity class c = (pz,py,px) along an axis: even outputs (p = 0) only see
+    tap k = 1 of the unshifted input; odd outputs (p = 1) see tap k = 2 of the unshifted and tap k = 0 of the +1-shifted input.
+    The MMA of shift s therefore carries, in class block c, the weights of tap (k_z,k_y,k_x) with k = 1 (p = 0, s = 0),
+    k = 2 (p = 1, s = 0), k = 0 (p = 1, s = 1), and zeros where p = 0 meets s = 1.  Inside a class block the columns are
+    those of ``_pack_tensor_core``: [hi | lo]."""
+    taps, cin, cout = w.shape
+    assert taps == 27 and cin % 8 == 0
+    cout_p = max(8, (cout + 7) // 8 * 8)
+    nb = 2 * cout_p
+    per_tap = _pack_tensor_core(w)  # [j][27][kc][nb][8]
+    img = torch.zeros(cin // 8, 8, 2, 8 * nb, 8, dtype=torch.float16, device=w.device)
+    for s in range(8):
+        sh = ((s >> 2) & 1, (s >> 1) & 1, s & 1)
+        for c in range(8):
+            par = ((c >> 2) & 1, (c >> 1) & 1, c & 1)
+            k = []
+            for p_, s_ in zip(par, sh):
+                if p_ == 0 and s_ == 1:
+                    k = None
+                    break
+                k.append(1 if p_ == 0 else (0 if s_ == 1 else 2))
+            if k is None:
+                continue
+            tap = (k[0] * 3 + k[1]) * 3 + k[2]
+            img[:, s, :, c * nb:(c + 1) * nb] = per_tap[:, tap]
+    return img.contiguous()
+
+
 def _pack_tensor_core_kw(w: torch.Tensor) -> torch.Tensor:
     """conv0 (Cin = 2): K packed along kw.  [27][2][Cout] -> [1][9 taps (kd,kh)][kc][n][8 halfs]; the 16 K entries of a tap
     are 4 voxels (x-1, x | x+1, x+2) x [hi c0, hi c1, lo c0, lo c1]; voxel x+2 is outside the 3-wide kernel -> zeros."""
@@ -352,6 +386,7 @@ def _pack_tensor_core_kw(w: torch.Tensor) -> torch.Tensor:
 # engine used by conv3d / regnet_forward unless the caller says otherwise: "tensor" = tcgen05 split-fp16 where a
 # specialisation exists (fp32 kernels elsewhere), "fp32" = CUDA-core fp32 everywhere.
 DEFAULT_ENGINE = "tensor"
+PAIR_CONV0 = True  # run conv0 of both regularisation branches as one launch (N = 32); False = one launch per branch
 _ENGINES = {"fp32": N.ENGINE_FP32, "tensor": N.ENGINE_TENSOR}
 
 
@@ -446,6 +481,14 @@ class PackedRegnet:
         for i, br in enumerate(branches):
             for j, layer in enumerate(br):
                 self.c_branches[i].layer[j] = layer.c_struct()
+        # conv0 of both branches as one 2 -> 16 layer (they read the same cost volume; include/dmvs_b200.h: conv0_pair)
+        a, b = branches[0][0], branches[1][0]
+        self.pair = None
+        if (PAIR_CONV0 and a.cin == 2 and a.cout == 8 and b.cin == 2 and b.cout == 8 and a.kd == 3 and not a.transposed
+                and a.scale is not None and b.scale is not None):
+            w = torch.cat([a.w[:, :, :8], b.w[:, :, :8]], 2)
+            self.pair = (_pack_tensor_core_kw(w), torch.cat([a.scale, b.scale]).contiguous(), torch.cat([a.shift, b.shift]).contiguous())
+            self.c_branches[0].conv0_pair = N.ConvLayer(None, self.pair[1].data_ptr(), self.pair[2].data_ptr(), self.pair[0].data_ptr(), None)
 
 
 def regnet_forward(pack: PackedRegnet, cost: Optional[torch.Tensor], engine: Optional[str] = None,

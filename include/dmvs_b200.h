@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 9
+#define DMVS_ABI_VERSION 10
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -128,7 +128,10 @@ typedef struct {
    * NULL: the layer always runs on the fp32 path. */
   const void* w_tc;
   /* optional, Cin = 8 / Cout = 2 (`prob`) only: the depth tap folded into the UMMA N dimension,
-   * [1][9 taps (kh,kw)][kc = 2][n = 16][8 halfs] with n = 4*kd + co (hi, both kc) and n = 4*kd + 2 + co (lo, kc = 0). */
+   * [1][9 taps (kh,kw)][kc = 2][n = 16][8 halfs] with n = 4*kd + co (hi, both kc) and n = 4*kd + 2 + co (lo, kc = 0).
+   * Also, Cin = 16 / Cout = 8 transposed (`conv11`): the 27 taps folded by input shift,
+   * [chunk j = 2][shift (sz,sy,sx) = 8][kc = 2][n = 8 parity classes x 16][8 halfs]: class block c = (pz,py,px) holds the w_tc
+   * columns of tap k with k = 1 (p = 0, s = 0), 2 (p = 1, s = 0), 0 (p = 1, s = 1) per axis, zeros where p = 0 and s = 1. */
   const void* w_tc_kd;
 } dmvs_conv_layer;
 
@@ -141,6 +144,11 @@ typedef struct {
 #define DMVS_REGNET_LAYERS 11
 typedef struct {
   dmvs_conv_layer layer[DMVS_REGNET_LAYERS];
+  /* optional, read from branches[0] only (w_tc NULL = absent): conv0 of BOTH branches as one 2 -> 16 layer (channels 0..7 =
+   * cosR_small, 8..15 = cosR_huge; w_tc in the K-packed conv0 layout with Cout = 16, scale / shift [16]).  Both branches
+   * read the same cost volume and the tensor-core kernel's time is set by how often the 4 KB input tile is re-read, not
+   * by N, so one launch with N = 32 replaces two with N = 16.  Used on the tensor engine with cost_cells and B == 1. */
+  dmvs_conv_layer conv0_pair;
 } dmvs_regnet_branch;
 
 /* bytes of scratch dmvs_regnet_forward_f32 needs for these dimensions */
