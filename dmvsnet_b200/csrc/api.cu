@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...) {
 }
 
 extern int g_tc2_max_ctas;
+extern int g_head_px;
 
 }  // namespace dmvs
 
@@ -24,6 +25,10 @@ extern int g_tc2_max_ctas;
 extern "C" int dmvs_debug_set(const char* key, int value) {
   if (key && !strcmp(key, "tc2_max_ctas") && value >= 1) {
     dmvs::g_tc2_max_ctas = value;
+    return DMVS_OK;
+  }
+  if (key && !strcmp(key, "head_px") && (value == 32 || value == 64 || value == 128)) {
+    dmvs::g_head_px = value;
     return DMVS_OK;
   }
   dmvs::set_error("dmvs_debug_set: unknown key or bad value");

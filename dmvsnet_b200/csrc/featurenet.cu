@@ -232,6 +232,71 @@ static int launch_feat(const FeatConvParams& p, cudaStream_t st) {
   return check_launch("conv2d");
 }
 
+// 1x1 lateral with few input channels (inner2: 8 -> 32 at full resolution, + the upsampled coarser map): pure streaming,
+// 192 bytes per pixel.  Thread = 4 x-consecutive pixels: CIN float4 loads up front, then COUT outputs in groups of 8
+// (weights broadcast from shared memory), float4 stores.  No input tile: nothing is reused between threads.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) feat_pointwise_kernel(const __grid_constant__ FeatConvParams p) {
+  __shared__ float s_w[CIN * COUT + COUT];
+  for (int i = threadIdx.x; i < CIN * COUT; i += 256) s_w[i] = __ldg(p.w + i);  // [CIN][COUT]
+  for (int i = threadIdx.x; i < COUT; i += 256) s_w[CIN * COUT + i] = p.shift ? __ldg(p.shift + i) : 0.0f;
+  __syncthreads();
+  const int w4 = p.Wo >> 2;  // Wo % 4 == 0 (checked by the launcher)
+  const long long n4 = (long long)p.Ho * w4;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= n4) return;
+  const int b = blockIdx.y;
+  const int oy = (int)(t / w4), ox = (int)(t - (long long)oy * w4) * 4;
+  const long long hw = (long long)p.Ho * p.Wo;
+  const float* xp = p.x + (long long)b * CIN * hw + (long long)oy * p.Wo + ox;
+  float4 xin[CIN];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) xin[c] = __ldg(reinterpret_cast<const float4*>(xp + c * hw));
+  const int hw2 = (p.Ho >> 1) * (p.Wo >> 1);
+  const float* up = p.up_add ? p.up_add + (long long)b * COUT * hw2 + (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1) : nullptr;
+  float* yp = p.y_nchw + (long long)b * COUT * hw + (long long)oy * p.Wo + ox;
+#pragma unroll 1
+  for (int g = 0; g < COUT; g += 8) {
+    float2 u[8];
+    if (up) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = __ldg(reinterpret_cast<const float2*>(up + (long long)(g + j) * hw2));
+    }
+    float4 acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float4 wa = *reinterpret_cast<const float4*>(s_w + c * COUT + g), wb = *reinterpret_cast<const float4*>(s_w + c * COUT + g + 4);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j].x = fmaf(xin[c].x, wv[j], acc[j].x);
+        acc[j].y = fmaf(xin[c].y, wv[j], acc[j].y);
+        acc[j].z = fmaf(xin[c].z, wv[j], acc[j].z);
+        acc[j].w = fmaf(xin[c].w, wv[j], acc[j].w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sc = p.scale ? __ldg(p.scale + g + j) : 1.0f, sh = s_w[CIN * COUT + g + j];
+      float4 v = make_float4(fmaf(acc[j].x, sc, sh), fmaf(acc[j].y, sc, sh), fmaf(acc[j].z, sc, sh), fmaf(acc[j].w, sc, sh));
+      if (p.relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+      if (up) { v.x += u[j].x; v.y += u[j].x; v.z += u[j].y; v.w += u[j].y; }
+      *reinterpret_cast<float4*>(yp + (long long)(g + j) * hw) = v;
+    }
+  }
+}
+
+template <int CIN, int COUT>
+static int launch_pointwise(const FeatConvParams& p, cudaStream_t st) {
+  const long long n4 = (long long)p.Ho * (p.Wo >> 2);
+  dim3 grid((unsigned)((n4 + 255) / 256), p.B, 1);
+  DMVS_REQUIRE(grid.y <= 65535, DMVS_ERR_BAD_SHAPE, "conv2d: batch too large");
+  feat_pointwise_kernel<CIN, COUT><<<grid, 256, 0, st>>>(p);
+  return check_launch("conv2d_pointwise");
+}
+
 }  // namespace dmvs
 
 extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
@@ -263,8 +328,15 @@ extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scal
     case 313232: return launch_feat<3, 1, 32, 32>(p, st);   // conv2.1, conv2.2, out2
     case 313216: return launch_feat<3, 1, 32, 16>(p, st);   // out3
     case 113264: return launch_feat<1, 1, 32, 64>(p, st);   // out1
-    case 111632: return launch_feat<1, 1, 16, 32>(p, st);   // inner1
-    case 110832: return launch_feat<1, 1, 8, 32>(p, st);    // inner2
+    case 111632:                                            // inner1
+      if (y_nchw && !y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
+        return launch_pointwise<16, 32>(p, st);
+      return launch_feat<1, 1, 16, 32>(p, st);
+    case 110832:                                            // inner2
+      // streaming kernel when it applies (NCHW output only, 4-pixel groups aligned); the tiled kernel otherwise
+      if (y_nchw && !y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
+        return launch_pointwise<8, 32>(p, st);
+      return launch_feat<1, 1, 8, 32>(p, st);
     default:
       set_error("conv2d: (K=%d, stride=%d, Cin=%d, Cout=%d) is not a FeatureNet layer shape", K, stride, Cin, Cout);
       return DMVS_ERR_BAD_SHAPE;

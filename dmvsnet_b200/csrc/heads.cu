@@ -44,18 +44,20 @@ __device__ __forceinline__ void dual_depth_tail(const float (&d4)[4], int x, int
   conf[(long long)b * hw + pix] = confidence_of(d4, interval);
 }
 
-// Block = 32 pixels of one row x the 4 logit channels (threadIdx.y = channel): each thread owns one (pixel, channel)
+// Block = PXB pixels of one row x the 4 logit channels (threadIdx.y = channel): each thread owns one (pixel, channel)
 // softmax column.  With D known at compile time the D logits live in registers - read from memory exactly once with D
 // independent loads in flight, exponentiated once, probability volume written in the same pass.  The four regressed
 // depths of a pixel meet in shared memory for the dual-depth tail.
-template <int DT>  // DT > 0: compile-time D (registers); DT == 0: any D, three streaming passes (2nd / 3rd hit L2)
-__global__ void __launch_bounds__(128, 4) depth_head_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
+// PXB pixels per block: the block's loads of one (channel, plane) row are PXB*4 contiguous bytes - with 32 they are single
+// 128-byte lines scattered over 4*D planes 2-8 MB apart (DRAM row misses), 64-128 keep a DRAM row open for the block.
+template <int DT, int PXB>  // DT > 0: compile-time D (registers); DT == 0: any D, three streaming passes (2nd / 3rd hit L2)
+__global__ void __launch_bounds__(PXB * 4) depth_head_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
                                                          const float* __restrict__ interval_p, float* __restrict__ prob,
                                                          float* __restrict__ d4o, float* __restrict__ hyp_c,
                                                          float* __restrict__ conf, int Drt, int h, int w) {
-  __shared__ float d4s[4][32];
+  __shared__ float d4s[4][PXB];
   const int D = (DT > 0) ? DT : Drt;
-  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int x = blockIdx.x * PXB + threadIdx.x;
   const int y = blockIdx.y;
   const int c = threadIdx.y;
   const int b = blockIdx.z;
@@ -261,6 +263,8 @@ __global__ void __launch_bounds__(128) hypotheses_next_kernel(const float* __res
   }
 }
 
+int g_head_px = 32;  // pixels per block of the depth head (dmvs_debug_set("head_px", 32 | 64 | 128))
+
 static inline dim3 pixel_grid(int B, int h, int w) { return dim3(ceil_div(w, 32), ceil_div(h, 4), B); }
 
 }  // namespace dmvs
@@ -272,19 +276,26 @@ extern "C" int dmvs_depth_head_f32(const float* logits, const float* hyp, const 
   DMVS_REQUIRE(logits && hyp && interval && d4 && hyp_c && conf, DMVS_ERR_BAD_POINTER, "depth_head: null pointer");
   DMVS_REQUIRE(B >= 1 && B <= 65535 && D >= 1 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE, "depth_head: bad dims");
   DMVS_REQUIRE(h <= 65535, DMVS_ERR_BAD_SHAPE, "depth_head: h=%d too large", h);
-  const dim3 grid(ceil_div(w, 32), h, B), block(32, 4);
   cudaStream_t st = (cudaStream_t)stream;
+  const int pxb = g_head_px;
+#define DMVS_HEAD_LAUNCH(N, P)                                                                                              \
+  depth_head_kernel<N, P><<<dim3(ceil_div(w, P), h, B), dim3(P, 4), 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, D, h, w)
+#define DMVS_HEAD_CASE(N)                                 \
+  case N:                                                 \
+    if (pxb == 32) DMVS_HEAD_LAUNCH(N, 32);               \
+    else if (pxb == 128) DMVS_HEAD_LAUNCH(N, 128);        \
+    else DMVS_HEAD_LAUNCH(N, 64);                         \
+    break;
   switch (D) {
-#define DMVS_HEAD_CASE(N) \
-  case N: depth_head_kernel<N><<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, D, h, w); break;
     DMVS_HEAD_CASE(8)
     DMVS_HEAD_CASE(16)
     DMVS_HEAD_CASE(32)
     DMVS_HEAD_CASE(48)
     DMVS_HEAD_CASE(64)
-#undef DMVS_HEAD_CASE
-    default: depth_head_kernel<0><<<grid, block, 0, st>>>(logits, hyp, interval, prob, d4, hyp_c, conf, D, h, w);
+    default: DMVS_HEAD_LAUNCH(0, 64);
   }
+#undef DMVS_HEAD_CASE
+#undef DMVS_HEAD_LAUNCH
   return check_launch("depth_head");
 }
 

@@ -33,8 +33,9 @@ def timeit(fn, n=5):
 
 
 with torch.no_grad():
-    for ctas in (1, 2):
-        lib.dmvs_debug_set(b"tc2_max_ctas", ctas)
+    for px in (32, 64, 128):
+        lib.dmvs_debug_set(b"head_px", px)
+        ctas = px
         ops.PROFILE = None
         ms = timeit(lambda: net.cascade(feats, proj, dv, (H, W)))
         ops.PROFILE = []
@@ -43,7 +44,7 @@ with torch.no_grad():
         for tag, a, b, _ in ops.PROFILE:
             groups[tag.split(":")[0]] = groups.get(tag.split(":")[0], 0.0) + a.elapsed_time(b)
         ops.PROFILE = None
-        print("tc2_max_ctas=%d  hot path %.2f ms  %s" % (ctas, ms, {k: round(v, 2) for k, v in groups.items()}), flush=True)
+        print("head_px=%d  hot path %.2f ms  %s" % (ctas, ms, {k: round(v, 2) for k, v in groups.items()}), flush=True)
     for g in (1, 2, 3, 5):
         net.infer_view_groups = g
         print("infer_view_groups=%d  e2e %.2f ms" % (g, timeit(lambda: net.infer(imgs_host, proj, dv_host))), flush=True)
