@@ -26,7 +26,7 @@
 
 namespace dmvs {
 
-enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2 };
+enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2, FMT_NHWC2 = 4 };
 enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4, M2_C0T = 5, M2_TRF = 6 };
 __host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mode == M2_C0T; }
 // TRF: transposed conv with the 27 taps folded by input shift: the taps that read the same shifted A view (shift in {0,1}^3,
@@ -331,6 +331,14 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
           for (int c = 0; c < 8; ++c)
             if (c0 + c < p.Cout)
               yf[(long long)tc.b * p.y_bs + ((long long)(c0 + c) * p.Do + oz) * oplane + (long long)oy * p.Wo + ox] = v[c];
+        } else if (p.out_fmt == FMT_NHWC2) {
+          // two channel-last fp32 buffers back to back, [2][B][Do][Ho][Wo][Cout/2]: the lane's 8 channels are 32 contiguous bytes
+          const int half = p.Cout >> 1;
+          const int hsel = c0 >= half ? 1 : 0, cc = c0 - hsel * half;
+          float* yb = reinterpret_cast<float*>(p.y) + (long long)hsel * p.B * p.Do * p.Ho * p.Wo * half +
+                      ((((long long)tc.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * half + cc;
+          *reinterpret_cast<float4*>(yb) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(yb + 4) = make_float4(v[4], v[5], v[6], v[7]);
         } else {
           uint4 hi, lo;
           split_pack8(v, hi, lo);
@@ -655,16 +663,27 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc2: null pointer");
   DMVS_REQUIRE(aligned16(L.w_tc) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
                "conv_tc2: pointers must be 16-byte aligned");
-  DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P, DMVS_ERR_BAD_SHAPE, "conv_tc2: bad out_fmt %d", out_fmt);
+  DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P || out_fmt == FMT_NHWC2, DMVS_ERR_BAD_SHAPE,
+               "conv_tc2: bad out_fmt %d", out_fmt);
+  DMVS_REQUIRE(out_fmt != FMT_NHWC2 || (kd == 1 && !transposed && stride == 1 && Cin == 32 && (Cout == 16 || Cout == 32)), DMVS_ERR_BAD_SHAPE,
+               "conv_tc2: the split channel-last output exists for FeatureNet's 32-channel 3x3 heads only");
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   p.wtc = reinterpret_cast<const uint4*>(L.w_tc); p.scale = L.scale; p.shift = L.shift;
   p.skip = reinterpret_cast<const uint4*>(skip); p.y = y;
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.relu = relu; p.out_fmt = out_fmt;
   p.y_bs = y_bs_f32;
-  if (kd == 1) {  // the refine net's 2-D bottleneck: depth is a batch of planes
-    DMVS_REQUIRE(out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE, "conv_tc2: the 2-D layers write CH16");
+  if (kd == 1) {  // 2-D layers (the refine net's bottleneck, FeatureNet's 3x3 heads): depth is a batch of planes
     p.Do = Di;
+    if (!transposed && stride == 1 && Cin == 32 && (Cout == 16 || Cout == 32)) {  // FeatureNet out3 / out2: weights resident, 4 chunks
+      DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");
+      DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2, DMVS_ERR_BAD_SHAPE, "conv_tc2: FeatureNet heads write fp32 (NCHW or split channel-last)");
+      p.Ho = Hi; p.Wo = Wi;
+      if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
+      if (Cout == 16) return launch2<M2_S1, 32, 32, 32, 1, 4, 1>(p, x, st);
+      return launch2<M2_S1, 32, 32, 64, 1, 3, 1>(p, x, st);
+    }
+    DMVS_REQUIRE(out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE, "conv_tc2: the 2-D layers write CH16");
     if (transposed) {
       p.Ho = 2 * Hi; p.Wo = 2 * Wi;
       if (Cin == 64 && Cout == 32) return launch2<M2_TR, 64, 8, 64, 1, 4, 1>(p, x, st);  // conv7 (2-D)

@@ -14,7 +14,7 @@
 //     two feature sets (`stageK` / `stageK_c` = the channel halves, module.py:326-336) so the W1 gather kernel reads
 //     them in place.
 // Arithmetic is plain fp32 FMA in (ci, kh, kw) order: differences to cuDNN are summation order only.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dmvs {
 
@@ -27,6 +27,7 @@ struct FeatConvParams {
   float* y_nchw;        // [B,COUT,Ho,Wo] or null
   float* y_nhwc0;       // [B,Ho,Wo,COUT/2] channels [0,COUT/2) or null
   float* y_nhwc1;       // [B,Ho,Wo,COUT/2] channels [COUT/2,COUT) or null
+  uint4* y_cells;       // CH16 cells [B][2*COUT/8 planes][Ho][Wo] (fp16 hi/lo, input format of the tensor-core 3x3 heads) or null
   int B, Hi, Wi, Ho, Wo, relu;
 };
 
@@ -254,7 +255,8 @@ __global__ void __launch_bounds__(256) feat_pointwise_kernel(const __grid_consta
   for (int c = 0; c < CIN; ++c) xin[c] = __ldg(reinterpret_cast<const float4*>(xp + c * hw));
   const int hw2 = (p.Ho >> 1) * (p.Wo >> 1);
   const float* up = p.up_add ? p.up_add + (long long)b * COUT * hw2 + (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1) : nullptr;
-  float* yp = p.y_nchw + (long long)b * COUT * hw + (long long)oy * p.Wo + ox;
+  float* yp = p.y_nchw ? p.y_nchw + (long long)b * COUT * hw + (long long)oy * p.Wo + ox : nullptr;
+  uint4* cp = p.y_cells ? p.y_cells + (long long)b * (COUT / 4) * hw + (long long)oy * p.Wo + ox : nullptr;
 #pragma unroll 1
   for (int g = 0; g < COUT; g += 8) {
     float2 u[8];
@@ -283,7 +285,21 @@ __global__ void __launch_bounds__(256) feat_pointwise_kernel(const __grid_consta
       float4 v = make_float4(fmaf(acc[j].x, sc, sh), fmaf(acc[j].y, sc, sh), fmaf(acc[j].z, sc, sh), fmaf(acc[j].w, sc, sh));
       if (p.relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
       if (up) { v.x += u[j].x; v.y += u[j].x; v.z += u[j].y; v.w += u[j].y; }
-      *reinterpret_cast<float4*>(yp + (long long)(g + j) * hw) = v;
+      if (yp) *reinterpret_cast<float4*>(yp + (long long)(g + j) * hw) = v;
+      acc[j] = v;
+    }
+    if (cp) {  // the 8 channels of this group are one (hi, lo) cell pair per pixel; planes 2*(g/8) and 2*(g/8)+1
+      uint4* c0p = cp + (long long)(g / 4) * hw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v8[j] = (i == 0) ? acc[j].x : (i == 1) ? acc[j].y : (i == 2) ? acc[j].z : acc[j].w;
+        uint4 hi, lo;
+        split_pack8(v8, hi, lo);
+        c0p[i] = hi;
+        c0p[hw + i] = lo;
+      }
     }
   }
 }
@@ -300,10 +316,11 @@ static int launch_pointwise(const FeatConvParams& p, cudaStream_t st) {
 }  // namespace dmvs
 
 extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
-                               float* y_nchw, float* y_nhwc0, float* y_nhwc1, int B, int Cin, int Cout, int Hi, int Wi, int K,
-                               int stride, int relu, void* stream) {
+                               float* y_nchw, float* y_nhwc0, float* y_nhwc1, void* y_cells, int B, int Cin, int Cout, int Hi, int Wi,
+                               int K, int stride, int relu, void* stream) {
   using namespace dmvs;
-  DMVS_REQUIRE(x && w && (y_nchw || (y_nhwc0 && y_nhwc1)), DMVS_ERR_BAD_POINTER, "conv2d: null pointer");
+  DMVS_REQUIRE(x && w && (y_nchw || (y_nhwc0 && y_nhwc1) || y_cells), DMVS_ERR_BAD_POINTER, "conv2d: null pointer");
+  DMVS_REQUIRE(!y_cells || aligned16(y_cells), DMVS_ERR_BAD_POINTER, "conv2d: y_cells must be 16-byte aligned");
   DMVS_REQUIRE((y_nhwc0 == nullptr) == (y_nhwc1 == nullptr), DMVS_ERR_BAD_POINTER, "conv2d: both channel-last outputs or none");
   DMVS_REQUIRE((!y_nhwc0 || aligned16(y_nhwc0)) && (!y_nhwc1 || aligned16(y_nhwc1)) && (!y_nchw || aligned16(y_nchw)),
                DMVS_ERR_BAD_POINTER, "conv2d: outputs must be 16-byte aligned");
@@ -311,7 +328,7 @@ extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scal
   DMVS_REQUIRE((K == 1 || K == 3 || K == 5) && (stride == 1 || stride == 2), DMVS_ERR_BAD_SHAPE, "conv2d: K=%d stride=%d unsupported", K, stride);
   FeatConvParams p;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.up_add = up_add;
-  p.y_nchw = y_nchw; p.y_nhwc0 = y_nhwc0; p.y_nhwc1 = y_nhwc1;
+  p.y_nchw = y_nchw; p.y_nhwc0 = y_nhwc0; p.y_nhwc1 = y_nhwc1; p.y_cells = reinterpret_cast<uint4*>(y_cells);
   p.B = B; p.Hi = Hi; p.Wi = Wi; p.relu = relu;
   const int pad = K / 2;
   p.Ho = (Hi + 2 * pad - K) / stride + 1;
@@ -319,6 +336,7 @@ extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scal
   DMVS_REQUIRE(!up_add || ((p.Ho % 2) == 0 && (p.Wo % 2) == 0), DMVS_ERR_BAD_SHAPE, "conv2d: up_add needs even output size, got %dx%d", p.Ho, p.Wo);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int key = ((K * 10 + stride) * 100 + Cin) * 100 + Cout;
+  DMVS_REQUIRE(!y_cells || key == 110832 || key == 111632, DMVS_ERR_BAD_SHAPE, "conv2d: cell output is implemented for the 1x1 laterals (16->32, 8->32)");
   switch (key) {
     case 310308: return launch_feat<3, 1, 3, 8>(p, st);     // conv0.0
     case 310808: return launch_feat<3, 1, 8, 8>(p, st);     // conv0.1
@@ -329,13 +347,15 @@ extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scal
     case 313216: return launch_feat<3, 1, 32, 16>(p, st);   // out3
     case 113264: return launch_feat<1, 1, 32, 64>(p, st);   // out1
     case 111632:                                            // inner1
-      if (y_nchw && !y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
+      if (!y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
         return launch_pointwise<16, 32>(p, st);
+      DMVS_REQUIRE(!y_cells, DMVS_ERR_BAD_SHAPE, "conv2d: cell output needs Wo %% 4 == 0 and aligned inputs");
       return launch_feat<1, 1, 16, 32>(p, st);
     case 110832:                                            // inner2
       // streaming kernel when it applies (NCHW output only, 4-pixel groups aligned); the tiled kernel otherwise
-      if (y_nchw && !y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
+      if (!y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
         return launch_pointwise<8, 32>(p, st);
+      DMVS_REQUIRE(!y_cells, DMVS_ERR_BAD_SHAPE, "conv2d: cell output needs Wo %% 4 == 0 and aligned inputs");
       return launch_feat<1, 1, 8, 32>(p, st);
     default:
       set_error("conv2d: (K=%d, stride=%d, Cin=%d, Cout=%d) is not a FeatureNet layer shape", K, stride, Cin, Cout);

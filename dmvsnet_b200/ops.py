@@ -226,10 +226,12 @@ class PackedConv2d:
         self.stride, self.relu = stride, relu
 
 
-def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] = None, nchw: bool = True, split_nhwc: bool = False):
+def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] = None, nchw: bool = True, split_nhwc: bool = False,
+           cells: bool = False):
     """x [B,Cin,H,W] -> conv (+BN/bias, ReLU, + nearest-x2 ``up_add``).  Returns ``y`` ([B,Cout,Ho,Wo] NCHW) when ``nchw``;
     with ``split_nhwc`` additionally the two channel halves as channel-last buffers, each returned as a [B,Cout/2,Ho,Wo]
-    view (torch channels_last strides): ``(y_or_None, half0, half1)``."""
+    view (torch channels_last strides): ``(y_or_None, half0, half1)``; with ``cells`` (1x1 laterals only) additionally the
+    output as CH16 cells (int32 [B, Cout/4, 1, Ho, Wo, 4]) for ``conv2d_head_tensor``: ``(y_or_None, cells)``."""
     lib = N.load()
     x = _req(x, "x").contiguous()
     b, cin, hi, wi = x.shape
@@ -242,17 +244,37 @@ def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] 
     if split_nhwc:
         h0 = torch.empty(b, ho, wo, layer.cout // 2, device=x.device, dtype=torch.float32)
         h1 = torch.empty_like(h0)
+    yc = torch.empty(b, layer.cout // 4, 1, ho, wo, 4, device=x.device, dtype=torch.int32) if cells else None
     if up_add is not None:
         up_add = _req(up_add, "up_add").contiguous()
         if up_add.shape != (b, layer.cout, ho // 2, wo // 2):
             raise ValueError("conv2d: up_add has shape %s, expected %s" % (tuple(up_add.shape), (b, layer.cout, ho // 2, wo // 2)))
     with _timed("featnet:k%ds%d_%dto%d_%dx%d" % (layer.k, layer.stride, cin, layer.cout, ho, wo)):
         rc = lib.dmvs_conv2d_f32(x.data_ptr(), layer.w.data_ptr(), _ptr(layer.scale), _ptr(layer.shift), _ptr(up_add), _ptr(y),
-                                 _ptr(h0), _ptr(h1), b, cin, layer.cout, hi, wi, layer.k, layer.stride, int(layer.relu), _stream())
+                                 _ptr(h0), _ptr(h1), _ptr(yc), b, cin, layer.cout, hi, wi, layer.k, layer.stride, int(layer.relu), _stream())
     N.check(rc, "dmvs_conv2d_f32")
     if split_nhwc:
         return y, h0.permute(0, 3, 1, 2), h1.permute(0, 3, 1, 2)
+    if cells:
+        return y, yc
     return y
+
+
+def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer"):
+    """FeatureNet's bare 3x3 heads out2 / out3 (module.py:326-336, Cin = 32, no BN / ReLU / bias) on the tcgen05 engine:
+    CH16 cells [B, 8, 1, H, W, 4] -> the two feature sets as channel-last maps, returned as [B,Cout/2,H,W] views."""
+    lib = N.load()
+    b, planes, d, h, w, _ = cells.shape
+    if planes != 8 or d != 1 or layer.cin != 32 or layer.kd != 1 or layer.w_tc is None:
+        raise ValueError("conv2d_head_tensor: expects 32-channel cells and a packed 2-D 3x3 layer")
+    half = layer.cout // 2
+    y = torch.empty(2, b, h, w, half, device=cells.device, dtype=torch.float32)
+    cl = layer.c_struct()
+    with _timed("featnet:tc3x3_32to%d_%dx%d" % (layer.cout, h, w)):
+        rc = lib.dmvs_conv3d_ch16(cells.data_ptr(), 0, ctypes.byref(cl), None, y.data_ptr(), b, 32, layer.cout, 1, h, w, 1, 1, 0, 0,
+                                  N.FMT_NHWC2, _stream())
+    N.check(rc, "dmvs_conv3d_ch16")
+    return y[0].permute(0, 3, 1, 2), y[1].permute(0, 3, 1, 2)
 
 
 # ----------------------------------------------------------------------------- R1

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 10
+#define DMVS_ABI_VERSION 11
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -102,11 +102,13 @@ int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float* y, int B,
  *   y_nchw  nullable [B,Cout,Ho,Wo];  y_nhwc0 / y_nhwc1 nullable (both or none): channel-last [B,Ho,Wo,Cout/2] buffers that
  *           receive channels [0,Cout/2) and [Cout/2,Cout) - the `stageK` / `stageK_c` halves (module.py:326-336) in the
  *           layout dmvs_warp_corr_nhwc_f32 gathers from
+ *   y_cells nullable, the 1x1 laterals only: the output as DMVS_FMT_CH16 cells [B][2*Cout/8][1][Ho][Wo] for the tensor-core
+ *           3x3 heads (dmvs_conv3d_ch16 with kd = 1); at least one of the three output forms must be given
  *   (K, stride, Cin, Cout) must be one of FeatureNet's: (3,1,3,8) (3,1,8,8) (5,2,8,16) (3,1,16,16) (5,2,16,32)
  *   (3,1,32,32) (3,1,32,16) (1,1,32,64) (1,1,16,32) (1,1,8,32); Ho = (Hi + 2*(K/2) - K)/stride + 1. */
 int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
-                    float* y_nchw, float* y_nhwc0, float* y_nhwc1, int B, int Cin, int Cout, int Hi, int Wi, int K, int stride,
-                    int relu, void* stream);
+                    float* y_nchw, float* y_nhwc0, float* y_nhwc1, void* y_cells, int B, int Cin, int Cout, int Hi, int Wi, int K,
+                    int stride, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * R1  3-D regularisation U-Nets.
@@ -177,12 +179,15 @@ int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* s
 #define DMVS_FMT_CH16 1
 #define DMVS_FMT_CH16P 2
 #define DMVS_FMT_COST2 3 /* conv0 input written by dmvs_warp_corr_f32(cost_cells), see there */
+#define DMVS_FMT_NHWC2 4 /* output only, FeatureNet's 3x3 heads (kd = 1, Cin = 32, Cout = 16 / 32): two channel-last fp32 buffers
+                            back to back, [2][B][D][H][W][Cout/2] = the `stageK` / `stageK_c` feature sets */
 
 /* fp32 NCDHW <-> CH16 / CH16P (C % 8 == 0; CH16P: W even).  to_ch16 != 0: x fp32 -> y cells; else x cells -> y fp32. */
 int dmvs_convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, void* stream);
 
 /* One conv block of the tensor path on CH16 activations (TMA-fed persistent tcgen05 kernel; kd = 3: 3x3x3,
- * kd = 1: the 1x3x3 layers of the refine net's bottleneck, depth treated as a batch of planes).
+ * kd = 1: the 1x3x3 layers of the refine net's bottleneck and FeatureNet's 32-channel 3x3 heads out2 / out3
+ * (networks/module.py:326-336), depth treated as a batch of planes).
  *   x     CH16 (stride 1, transposed), CH16P (stride 2); when Cin == 2 (conv0): fp32 [B,2,D,H,W] (in_cells == 0) or
  *         DMVS_FMT_COST2 cells (in_cells != 0)
  *   skip  CH16P with the output's shape, transposed convs only (nullable)

@@ -156,6 +156,14 @@ def test_feature_net_native_vs_oracle(b, n, h, w):
         with torch.no_grad():
             got = net.extract_features(cuda(imgs))
         assert (_lib_launches() - launches == 13) == (engine == "native")
+        if engine == "native":  # ... and with the 3x3 heads on the fp32 kernels instead of the tensor cores
+            net.feature.tensor_heads = False
+            with torch.no_grad():
+                got32 = net.extract_features(cuda(imgs))
+            net.feature.tensor_heads = True
+            for v in range(n):
+                for key, ref in want[v].items():
+                    assert rel_linf(got32[v][key], ref) < 1e-5, ("fp32 heads", v, key)
         for v in range(n):
             for key, ref in want[v].items():
                 assert got[v][key].shape == ref.shape
