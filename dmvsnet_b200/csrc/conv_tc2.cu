@@ -675,11 +675,14 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   p.y_bs = y_bs_f32;
   if (kd == 1) {  // 2-D layers (the refine net's bottleneck, FeatureNet's 3x3 heads): depth is a batch of planes
     p.Do = Di;
-    if (!transposed && stride == 1 && Cin == 32 && (Cout == 16 || Cout == 32)) {  // FeatureNet out3 / out2: weights resident, 4 chunks
+    if (!transposed && stride == 1 && ((Cin == 32 && (Cout == 16 || Cout == 32)) || (Cin == 16 && Cout == 16))) {
+      // FeatureNet's 3x3 layers (out3 / out2 and conv2.1-2 / conv1.1-2): weights resident, all channel chunks in one pass
       DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");
-      DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2, DMVS_ERR_BAD_SHAPE, "conv_tc2: FeatureNet heads write fp32 (NCHW or split channel-last)");
+      DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2 || out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE,
+                   "conv_tc2: FeatureNet layers write fp32 (NCHW or split channel-last) or CH16");
       p.Ho = Hi; p.Wo = Wi;
       if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
+      if (Cin == 16) return launch2<M2_S1, 16, 16, 32, 1, 4, 1>(p, x, st);
       if (Cout == 16) return launch2<M2_S1, 32, 32, 32, 1, 4, 1>(p, x, st);
       return launch2<M2_S1, 32, 32, 64, 1, 3, 1>(p, x, st);
     }

@@ -199,6 +199,25 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
       }
     }
   }
+  if (p.y_cells) {  // CH16 cells for a tensor-core consumer: 8 channels = one (hi, lo) cell pair per pixel
+    const long long hw = (long long)p.Ho * p.Wo;
+#pragma unroll
+    for (int j8 = 0; j8 < CT / 8; ++j8) {
+      uint4* cp = p.y_cells + ((long long)b * (COUT / 4) + (cz * CT + 8 * j8) / 4) * hw + (long long)oy * p.Wo + ox;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < nvalid) {
+          float v8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v8[c] = acc[i][8 * j8 + c];
+          uint4 hi, lo;
+          split_pack8(v8, hi, lo);
+          cp[i] = hi;
+          cp[hw + i] = lo;
+        }
+      }
+    }
+  }
   if (p.y_nhwc0) {
     constexpr int HALF = COUT / 2;
 #pragma unroll
@@ -336,7 +355,6 @@ extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scal
   DMVS_REQUIRE(!up_add || ((p.Ho % 2) == 0 && (p.Wo % 2) == 0), DMVS_ERR_BAD_SHAPE, "conv2d: up_add needs even output size, got %dx%d", p.Ho, p.Wo);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int key = ((K * 10 + stride) * 100 + Cin) * 100 + Cout;
-  DMVS_REQUIRE(!y_cells || key == 110832 || key == 111632, DMVS_ERR_BAD_SHAPE, "conv2d: cell output is implemented for the 1x1 laterals (16->32, 8->32)");
   switch (key) {
     case 310308: return launch_feat<3, 1, 3, 8>(p, st);     // conv0.0
     case 310808: return launch_feat<3, 1, 8, 8>(p, st);     // conv0.1
@@ -349,13 +367,11 @@ extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scal
     case 111632:                                            // inner1
       if (!y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
         return launch_pointwise<16, 32>(p, st);
-      DMVS_REQUIRE(!y_cells, DMVS_ERR_BAD_SHAPE, "conv2d: cell output needs Wo %% 4 == 0 and aligned inputs");
       return launch_feat<1, 1, 16, 32>(p, st);
     case 110832:                                            // inner2
       // streaming kernel when it applies (NCHW output only, 4-pixel groups aligned); the tiled kernel otherwise
       if (!y_nhwc0 && (p.Wo & 3) == 0 && aligned16(x) && (!up_add || (((p.Wo >> 1) & 1) == 0 && (reinterpret_cast<uintptr_t>(up_add) & 7u) == 0)))
         return launch_pointwise<8, 32>(p, st);
-      DMVS_REQUIRE(!y_cells, DMVS_ERR_BAD_SHAPE, "conv2d: cell output needs Wo %% 4 == 0 and aligned inputs");
       return launch_feat<1, 1, 8, 32>(p, st);
     default:
       set_error("conv2d: (K=%d, stride=%d, Cin=%d, Cout=%d) is not a FeatureNet layer shape", K, stride, Cin, Cout);

@@ -150,6 +150,8 @@ class FeatureNet(nn.Module):
                   "conv2": [block(m) for m in self.conv2],
                   "out1": ops.PackedConv2d(self.out1.weight), "out2": ops.PackedConv2d(self.out2.weight),
                   "out3": ops.PackedConv2d(self.out3.weight),
+                  "conv1_tc": [self.conv1[1].packed(), self.conv1[2].packed()],
+                  "conv2_tc": [self.conv2[1].packed(), self.conv2[2].packed()],
                   "out2_tc": ops.PackedLayer(self.out2.weight, False, None), "out3_tc": ops.PackedLayer(self.out3.weight, False, None),
                   "inner1": ops.PackedConv2d(self.inner1.weight, bias=self.inner1.bias),
                   "inner2": ops.PackedConv2d(self.inner2.weight, bias=self.inner2.bias)}
@@ -164,12 +166,23 @@ class FeatureNet(nn.Module):
         for layer in pk["conv0"]:
             t = ops.conv2d(t, layer)
         c0 = t
-        for layer in pk["conv1"]:
-            t = ops.conv2d(t, layer)
-        c1 = t
-        for layer in pk["conv2"]:
-            t = ops.conv2d(t, layer)
-        c2 = t
+        if self.tensor_heads and t.shape[-1] % 8 == 0:
+            # the 3x3 layers behind each stride-2 5x5 (16->16, 32->32; BN + ReLU in the epilogue) on the tensor cores too:
+            # the 5x5 emits CH16 cells, the last 3x3 of a level returns fp32 NCHW for the fp32 consumers (laterals, next 5x5)
+            for name in ("conv1", "conv2"):
+                _, cells = ops.conv2d(t, pk[name][0], nchw=False, cells=True)
+                cells = ops.conv3d_ch16(cells, pk[name + "_tc"][0], relu=True, out_fmt="ch16")
+                t = ops.conv3d_ch16(cells, pk[name + "_tc"][1], relu=True, out_fmt="f32").squeeze(2)
+                if name == "conv1":
+                    c1 = t
+            c2 = t
+        else:
+            for layer in pk["conv1"]:
+                t = ops.conv2d(t, layer)
+            c1 = t
+            for layer in pk["conv2"]:
+                t = ops.conv2d(t, layer)
+            c2 = t
         out = {}
         _, out["stage1"], out["stage1_c"] = ops.conv2d(c2, pk["out1"], nchw=False, split_nhwc=True)
         if self.tensor_heads and c1.shape[-1] % 4 == 0:

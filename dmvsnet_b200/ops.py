@@ -230,7 +230,7 @@ def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] 
            cells: bool = False):
     """x [B,Cin,H,W] -> conv (+BN/bias, ReLU, + nearest-x2 ``up_add``).  Returns ``y`` ([B,Cout,Ho,Wo] NCHW) when ``nchw``;
     with ``split_nhwc`` additionally the two channel halves as channel-last buffers, each returned as a [B,Cout/2,Ho,Wo]
-    view (torch channels_last strides): ``(y_or_None, half0, half1)``; with ``cells`` (1x1 laterals only) additionally the
+    view (torch channels_last strides): ``(y_or_None, half0, half1)``; with ``cells`` additionally the
     output as CH16 cells (int32 [B, Cout/4, 1, Ho, Wo, 4]) for ``conv2d_head_tensor``: ``(y_or_None, cells)``."""
     lib = N.load()
     x = _req(x, "x").contiguous()

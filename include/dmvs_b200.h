@@ -102,8 +102,8 @@ int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float* y, int B,
  *   y_nchw  nullable [B,Cout,Ho,Wo];  y_nhwc0 / y_nhwc1 nullable (both or none): channel-last [B,Ho,Wo,Cout/2] buffers that
  *           receive channels [0,Cout/2) and [Cout/2,Cout) - the `stageK` / `stageK_c` halves (module.py:326-336) in the
  *           layout dmvs_warp_corr_nhwc_f32 gathers from
- *   y_cells nullable, the 1x1 laterals only: the output as DMVS_FMT_CH16 cells [B][2*Cout/8][1][Ho][Wo] for the tensor-core
- *           3x3 heads (dmvs_conv3d_ch16 with kd = 1); at least one of the three output forms must be given
+ *   y_cells nullable: the output as DMVS_FMT_CH16 cells [B][2*Cout/8][1][Ho][Wo] for the tensor-core
+ *           3x3 layers (dmvs_conv3d_ch16 with kd = 1); at least one of the three output forms must be given
  *   (K, stride, Cin, Cout) must be one of FeatureNet's: (3,1,3,8) (3,1,8,8) (5,2,8,16) (3,1,16,16) (5,2,16,32)
  *   (3,1,32,32) (3,1,32,16) (1,1,32,64) (1,1,16,32) (1,1,8,32); Ho = (Hi + 2*(K/2) - K)/stride + 1. */
 int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
