@@ -176,3 +176,63 @@ def test_synthetic_rig_is_in_frustum():
         g = O.sampling_grid(rot, tr, hyp)
         fr.append(float(((g.abs() <= 1).all(-1)).float().mean()))
     assert min(fr) > 0.8, fr
+
+
+def test_shift_folded_transposed_conv_packing_reproduces_conv_transpose3d():
+    """conv11's tensor-core weights with the 27 taps folded by input shift (ops._pack_tensor_core_tr_fold): emulate the 8 MMAs
+    per channel chunk (A = the input shifted by (sz,sy,sx), N = 8 parity-class blocks of [hi | lo] columns) in torch and
+    compare with F.conv_transpose3d - this pins the class/shift/tap bookkeeping without a GPU."""
+    import torch.nn.functional as F
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    cin, cout = 16, 8
+    w = 0.2 * torch.randn(cin, cout, 3, 3, 3, generator=g)
+    x = torch.randn(1, cin, 3, 4, 5, generator=g)
+    want = F.conv_transpose3d(x, w, stride=2, padding=1, output_padding=1)
+    layer = ops.PackedLayer(w, True, None)
+    img = layer.w_tc_kd.float()
+    assert img.shape == (2, 8, 2, 128, 8)
+    d, h, wd = x.shape[2:]
+    xpad = F.pad(x, (0, 1, 0, 1, 0, 1))
+    got = torch.zeros_like(want)
+    for c in range(8):
+        pz, py, px = (c >> 2) & 1, (c >> 1) & 1, c & 1
+        acc = torch.zeros(cout, d, h, wd)
+        for s in range(8):
+            sz, sy, sx = (s >> 2) & 1, (s >> 1) & 1, s & 1
+            for j in range(2):
+                blk = img[j, s, :, c * 16:(c + 1) * 16]                 # [kc][16 columns][8 k]
+                assert torch.equal(blk[1, :8], blk[0, :8]) and float(blk[1, 8:].abs().max()) == 0.0  # A_lo only meets W_hi
+                weff = blk[0, :8] + blk[0, 8:]                           # hi + lo, [co][k]
+                xs = xpad[0, 8 * j:8 * j + 8, sz:sz + d, sy:sy + h, sx:sx + wd]
+                acc += torch.einsum("ok,kdhw->odhw", weff, xs)
+        got[0, :, pz::2, py::2, px::2] = acc
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+
+
+def test_conv0_pair_packing():
+    """conv0 of both regularisation branches as one 2 -> 16 layer: K-packed weights with Cout = 16, BN vectors concatenated."""
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(8)
+
+    def branch():
+        layers = [ops.PackedLayer(torch.randn(8, 2, 3, 3, 3, generator=g), False,
+                                  (torch.rand(8, generator=g) + 0.5, torch.randn(8, generator=g), torch.randn(8, generator=g), torch.rand(8, generator=g) + 0.5))]
+        layers += [ops.PackedLayer(torch.randn(8, 8, 3, 3, 3, generator=g), False, None) for _ in range(10)]
+        return layers
+    a, b = branch(), branch()
+    pack = ops.PackedRegnet([a, b], refine=False)
+    assert pack.pair is not None and pack.pair[0].shape == (1, 9, 2, 32, 8)
+    assert torch.equal(pack.pair[0][:, :, :, :8], a[0].w_tc[:, :, :, :8]) and torch.equal(pack.pair[0][:, :, :, 8:16], b[0].w_tc[:, :, :, :8])
+    assert torch.equal(pack.pair[0][:, :, :, 16:24], a[0].w_tc[:, :, :, 8:16]) and torch.equal(pack.pair[0][:, :, :, 24:32], b[0].w_tc[:, :, :, 8:16])
+    assert torch.equal(pack.pair[1], torch.cat([a[0].scale, b[0].scale]))
+
+
+def test_channel_last_stride_detection():
+    from dmvsnet_b200 import ops
+    t = torch.zeros(2, 16, 6, 8).contiguous(memory_format=torch.channels_last)
+    assert ops._nhwc_strides(t) == (16, 6 * 8 * 16)
+    assert ops._nhwc_strides(t.split([8, 8], 1)[1]) == (16, 6 * 8 * 16)
+    assert ops._nhwc_strides(torch.zeros(2, 16, 6, 8)) is None
+    assert ops._batch_stride(torch.zeros(2, 32, 6, 8).split([16, 16], 1)[1]) == 32 * 48
+    assert ops._batch_stride(t) == -1
