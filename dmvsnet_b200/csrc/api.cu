@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
 
 extern int g_tc2_max_ctas;
 extern int g_head_px;
+extern int g_pb_td8;
 
 }  // namespace dmvs
 
@@ -25,6 +26,10 @@ extern int g_head_px;
 extern "C" int dmvs_debug_set(const char* key, int value) {
   if (key && !strcmp(key, "tc2_max_ctas") && value >= 1) {
     dmvs::g_tc2_max_ctas = value;
+    return DMVS_OK;
+  }
+  if (key && !strcmp(key, "pb_td8") && (value == 0 || value == 1)) {
+    dmvs::g_pb_td8 = value;
     return DMVS_OK;
   }
   if (key && !strcmp(key, "head_px") && (value == 32 || value == 64 || value == 128)) {

@@ -605,7 +605,8 @@ static int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int 
   return DMVS_OK;
 }
 
-int g_tc2_max_ctas = 1;  // debug knob (dmvs_debug_set("tc2_max_ctas", n))
+int g_tc2_max_ctas = 1;
+int g_pb_td8 = 1;       // debug knob (dmvs_debug_set("pb_td8", 0 | 1)): prob layer with 8-plane tiles  // debug knob (dmvs_debug_set("tc2_max_ctas", n))
 
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
 static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
@@ -675,13 +676,14 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   p.y_bs = y_bs_f32;
   if (kd == 1) {  // 2-D layers (the refine net's bottleneck, FeatureNet's 3x3 heads): depth is a batch of planes
     p.Do = Di;
-    if (!transposed && stride == 1 && ((Cin == 32 && (Cout == 16 || Cout == 32)) || (Cin == 16 && Cout == 16))) {
+    if (!transposed && stride == 1 && ((Cin == 32 && (Cout == 16 || Cout == 32)) || (Cin == 16 && Cout == 16) || (Cin == 8 && Cout == 8))) {
       // FeatureNet's 3x3 layers (out3 / out2 and conv2.1-2 / conv1.1-2): weights resident, all channel chunks in one pass
       DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");
       DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2 || out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE,
                    "conv_tc2: FeatureNet layers write fp32 (NCHW or split channel-last) or CH16");
       p.Ho = Hi; p.Wo = Wi;
       if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
+      if (Cin == 8) return launch2<M2_S1, 8, 8, 16, 1, 4, 1>(p, x, st);
       if (Cin == 16) return launch2<M2_S1, 16, 16, 32, 1, 4, 1>(p, x, st);
       if (Cout == 16) return launch2<M2_S1, 32, 32, 32, 1, 4, 1>(p, x, st);
       return launch2<M2_S1, 32, 32, 64, 1, 3, 1>(p, x, st);
@@ -737,6 +739,8 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
     DMVS_REQUIRE(out_fmt == FMT_F32 || Cout == 8, DMVS_ERR_BAD_SHAPE, "conv_tc2: Cout < 8 needs an fp32 output");
     if (Cout == 2 && L.w_tc_kd) {  // prob with kd folded into N
       p.wtc = reinterpret_cast<const uint4*>(L.w_tc_kd);
+      // MMAs per output plane = 9 * (TD + 2) / TD: 8-plane tiles (10 accumulators, 2 stages) where the volume has them
+      if (Di >= 8 && g_pb_td8) return launch2<M2_PB, 8, 8, 16, 8, 2>(p, x, st);
       return launch2<M2_PB, 8, 8, 16, 4, 4>(p, x, st);
     }
     return launch2<M2_S1, 8, 8, 16, 4, 4>(p, x, st);

@@ -110,6 +110,7 @@ class FeatureNet(nn.Module):
     # native engine: run out2 / out3 on the tensor cores (fp16 hi/lo split operands, fp32 accumulate: same 1e-6 error as the
     # fp32 FMA kernels, 2.6x faster); False keeps them on the fp32 direct convolution
     tensor_heads = True
+    tensor_conv0 = False  # conv0.1 (8 -> 8 at full resolution) on the tensor engine: measured slower (3.57 vs 3.47 ms), kept as an option
 
     def forward(self, x):
         if x.is_cuda and self.engine == "native" and not self.training and self.mode == "fpn" and self.num_stage == 3:
@@ -150,6 +151,7 @@ class FeatureNet(nn.Module):
                   "conv2": [block(m) for m in self.conv2],
                   "out1": ops.PackedConv2d(self.out1.weight), "out2": ops.PackedConv2d(self.out2.weight),
                   "out3": ops.PackedConv2d(self.out3.weight),
+                  "conv0_tc": self.conv0[1].packed(),
                   "conv1_tc": [self.conv1[1].packed(), self.conv1[2].packed()],
                   "conv2_tc": [self.conv2[1].packed(), self.conv2[2].packed()],
                   "out2_tc": ops.PackedLayer(self.out2.weight, False, None), "out3_tc": ops.PackedLayer(self.out3.weight, False, None),
@@ -163,8 +165,12 @@ class FeatureNet(nn.Module):
         channel-last (what the W1 kernels read in place)."""
         pk = self.packed()
         t = x
-        for layer in pk["conv0"]:
-            t = ops.conv2d(t, layer)
+        if self.tensor_heads and self.tensor_conv0:
+            _, cells = ops.conv2d(t, pk["conv0"][0], nchw=False, cells=True)
+            t = ops.conv3d_ch16(cells, pk["conv0_tc"], relu=True, out_fmt="f32").squeeze(2)
+        else:
+            for layer in pk["conv0"]:
+                t = ops.conv2d(t, layer)
         c0 = t
         if self.tensor_heads and t.shape[-1] % 8 == 0:
             # the 3x3 layers behind each stride-2 5x5 (16->16, 32->32; BN + ReLU in the epilogue) on the tensor cores too:
