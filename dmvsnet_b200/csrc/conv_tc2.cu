@@ -723,7 +723,7 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   if (stride == 2) {
     p.Do = (Di - 1) / 2 + 1; p.Ho = (Hi - 1) / 2 + 1; p.Wo = (Wi - 1) / 2 + 1;
     DMVS_REQUIRE(Wi % 2 == 0, DMVS_ERR_BAD_SHAPE, "conv_tc2: stride-2 input width must be even");
-    if (Cin == 8 && Cout == 16) return launch2<M2_S2, 8, 8, 32, 1, 2>(p, x, st);     // conv1
+    if (Cin == 8 && Cout == 16) return launch2<M2_S2, 8, 8, 32, 1, 3>(p, x, st);     // conv1
     if (Cin == 16 && Cout == 32) return launch2<M2_S2, 16, 8, 64, 1, 2>(p, x, st);   // conv3, 2 passes
     if (Cin == 32 && Cout == 64) return launch2<M2_S2, 32, 8, 128, 1, 1>(p, x, st);  // conv5, 4 passes
     return 1;
