@@ -86,7 +86,7 @@ struct C2 {
   static constexpr int PROD_WARPS = (MODE == M2_C0) ? 12 : 1;
   // epilogue warps: TMEM quadrant = warp % 4, so a multiple of 4; the full-resolution layers' epilogues are latency-bound
   // instruction streams (2 warps per scheduler issue 30-40 % of the cycles), so the cheap-in-registers modes get 16
-  static constexpr int EPI_WARPS = (MODE == M2_PB || MODE == M2_C0T) ? 16 : 8;
+  static constexpr int EPI_WARPS = (MODE == M2_PB || MODE == M2_C0T) ? 16 : (MODE == M2_TRF) ? 12 : 8;
   static constexpr int NPART = EPI_WARPS / 4;
   // one MMA-issuing warp per accumulator set: tile k is issued by warp k % MMA_WARPS into set k % 2, so the (serial,
   // single-thread) descriptor arithmetic of consecutive tiles overlaps
@@ -730,7 +730,10 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   }
   p.Do = Di; p.Ho = Hi; p.Wo = Wi;
   if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
-  if (Cin == 2 && Cout == 16 && in_cells) return launch2<M2_C0T, 2, 2, 32, 4, 4>(p, x, st);  // conv0 of both branches (conv0_pair)
+  if (Cin == 2 && Cout == 16 && in_cells) {                                          // conv0 of both branches (conv0_pair)
+    if (Di >= 8 && g_pb_td8) return launch2<M2_C0T, 2, 2, 32, 8, 4>(p, x, st);
+    return launch2<M2_C0T, 2, 2, 32, 4, 4>(p, x, st);
+  }
   if (Cin == 2 && Cout == 8) {                                                       // conv0
     if (in_cells) return launch2<M2_C0T, 2, 2, 16, 4, 4>(p, x, st);
     return launch2<M2_C0, 2, 2, 16, 4, 4>(p, x, st);
