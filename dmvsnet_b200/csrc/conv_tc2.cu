@@ -86,7 +86,7 @@ struct C2 {
   static constexpr int PROD_WARPS = (MODE == M2_C0) ? 12 : 1;
   // epilogue warps: TMEM quadrant = warp % 4, so a multiple of 4; the full-resolution layers' epilogues are latency-bound
   // instruction streams (2 warps per scheduler issue 30-40 % of the cycles), so the cheap-in-registers modes get 16
-  static constexpr int EPI_WARPS = (MODE == M2_PB || MODE == M2_C0T) ? 16 : (MODE == M2_TRF) ? 12 : 8;
+  static constexpr int EPI_WARPS = (MODE == M2_PB || MODE == M2_C0T || MODE == M2_TRF) ? 16 : (MODE == M2_TR || MODE == M2_S2) ? 12 : 8;
   static constexpr int NPART = EPI_WARPS / 4;
   // one MMA-issuing warp per accumulator set: tile k is issued by warp k % MMA_WARPS into set k % 2, so the (serial,
   // single-thread) descriptor arithmetic of consecutive tiles overlaps
