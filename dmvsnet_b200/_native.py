@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ul
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 FMT_NHWC2 = 4
 ENGINE_FP32, ENGINE_TENSOR = 0, 1
@@ -47,7 +47,8 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_warp_corr_flag_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dmvs_features_nhwc_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "dmvs_conv2d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "dmvs_features_s2d_cells_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_conv2d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_regnet_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "dmvs_regnet_forward_f32": (c_int, [POINTER(RegnetBranch), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

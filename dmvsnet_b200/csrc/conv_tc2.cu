@@ -676,6 +676,11 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   p.y_bs = y_bs_f32;
   if (kd == 1) {  // 2-D layers (the refine net's bottleneck, FeatureNet's 3x3 heads): depth is a batch of planes
     p.Do = Di;
+    if (!transposed && stride == 1 && Cin == 64 && Cout == 32) {  // FeatureNet conv2.0 (5x5 stride 2 on 16 ch = 3x3 on 64 unshuffled ch)
+      DMVS_REQUIRE(skip == nullptr && out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE, "conv_tc2: the 64 -> 32 2-D layer writes CH16, no skip");
+      p.Ho = Hi; p.Wo = Wi;
+      return launch2<M2_S1, 64, 32, 64, 1, 2, 1>(p, x, st);
+    }
     if (!transposed && stride == 1 && ((Cin == 32 && (Cout == 16 || Cout == 32)) || (Cin == 16 && Cout == 16) || (Cin == 8 && Cout == 8))) {
       // FeatureNet's 3x3 layers (out3 / out2 and conv2.1-2 / conv1.1-2): weights resident, all channel chunks in one pass
       DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");

@@ -29,6 +29,7 @@ struct FeatConvParams {
   float* y_nhwc1;       // [B,Ho,Wo,COUT/2] channels [COUT/2,COUT) or null
   uint4* y_cells;       // CH16 cells [B][2*COUT/8 planes][Ho][Wo] (fp16 hi/lo, input format of the tensor-core 3x3 heads) or null
   int B, Hi, Wi, Ho, Wo, relu;
+  int cells_s2d;        // y_cells holds the 2x2 pixel-unshuffled map: [B][2*(4*COUT)/8][Ho/2][Wo/2], channel (dy*2+dx)*COUT + c
 };
 
 template <int K, int S, int CIN, int COUT>
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
 #pragma unroll
     for (int j8 = 0; j8 < CT / 8; ++j8) {
       uint4* cp = p.y_cells + ((long long)b * (COUT / 4) + (cz * CT + 8 * j8) / 4) * hw + (long long)oy * p.Wo + ox;
+      const long long hw4 = (long long)(p.Ho >> 1) * (p.Wo >> 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (i < nvalid) {
@@ -212,8 +214,18 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
           for (int c = 0; c < 8; ++c) v8[c] = acc[i][8 * j8 + c];
           uint4 hi, lo;
           split_pack8(v8, hi, lo);
-          cp[i] = hi;
-          cp[hw + i] = lo;
+          if (p.cells_s2d) {
+            // space-to-depth: pixel (oy, ox+i) is sub-position (dy,dx) of block (oy/2, (ox+i)/2); its 8 channels are chunk
+            // (dy*2+dx)*COUT/8 + c/8 of the 4*COUT-channel unshuffled map
+            const int sub = (oy & 1) * 2 + ((ox + i) & 1);
+            const int chunk = sub * (COUT / 8) + (cz * CT + 8 * j8) / 8;
+            uint4* q = p.y_cells + ((long long)b * COUT + 2 * chunk) * hw4 + (long long)(oy >> 1) * (p.Wo >> 1) + ((ox + i) >> 1);
+            q[0] = hi;
+            q[hw4] = lo;
+          } else {
+            cp[i] = hi;
+            cp[hw + i] = lo;
+          }
         }
       }
     }
@@ -332,11 +344,45 @@ static int launch_pointwise(const FeatConvParams& p, cudaStream_t st) {
   return check_launch("conv2d_pointwise");
 }
 
+// fp32 NCHW -> CH16 cells of the 2x2 pixel-unshuffled map (input of a 5x5 stride-2 layer run as a 3x3 stride-1 layer on
+// 4*C channels): one thread per (b, 8-channel chunk, y, x)
+__global__ void __launch_bounds__(256) f32_to_s2d_cells_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, int H, int W,
+                                                               long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int xx = (int)(i % W);
+  long long r = i / W;
+  const int yy = (int)(r % H); r /= H;
+  const int j = (int)(r % (C / 8));
+  const int b = (int)(r / (C / 8));
+  const long long hw = (long long)H * W, hw4 = (long long)(H >> 1) * (W >> 1);
+  const float* src = x + ((long long)b * C + j * 8) * hw + (long long)yy * W + xx;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c * hw);
+  uint4 hi, lo;
+  split_pack8(v, hi, lo);
+  const int chunk = ((yy & 1) * 2 + (xx & 1)) * (C / 8) + j;
+  uint4* q = y + ((long long)b * C + 2 * chunk) * hw4 + (long long)(yy >> 1) * (W >> 1) + (xx >> 1);
+  q[0] = hi;
+  q[hw4] = lo;
+}
+
 }  // namespace dmvs
 
+extern "C" int dmvs_features_s2d_cells_f32(const float* x, void* y_cells, int B, int C, int H, int W, void* stream) {
+  using namespace dmvs;
+  DMVS_REQUIRE(x && y_cells && aligned16(y_cells), DMVS_ERR_BAD_POINTER, "features_s2d_cells: null or misaligned pointer");
+  DMVS_REQUIRE(B >= 1 && C >= 8 && C % 8 == 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, DMVS_ERR_BAD_SHAPE,
+               "features_s2d_cells: need C %% 8 == 0 and even H, W (B=%d C=%d H=%d W=%d)", B, C, H, W);
+  const long long n = (long long)B * (C / 8) * H * W;
+  f32_to_s2d_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<uint4*>(y_cells), C, H, W, n);
+  return check_launch("features_s2d_cells");
+}
+
 extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
-                               float* y_nchw, float* y_nhwc0, float* y_nhwc1, void* y_cells, int B, int Cin, int Cout, int Hi, int Wi,
-                               int K, int stride, int relu, void* stream) {
+                               float* y_nchw, float* y_nhwc0, float* y_nhwc1, void* y_cells, int cells_s2d, int B, int Cin, int Cout, int Hi,
+                               int Wi, int K, int stride, int relu, void* stream) {
   using namespace dmvs;
   DMVS_REQUIRE(x && w && (y_nchw || (y_nhwc0 && y_nhwc1) || y_cells), DMVS_ERR_BAD_POINTER, "conv2d: null pointer");
   DMVS_REQUIRE(!y_cells || aligned16(y_cells), DMVS_ERR_BAD_POINTER, "conv2d: y_cells must be 16-byte aligned");
@@ -348,10 +394,12 @@ extern "C" int dmvs_conv2d_f32(const float* x, const float* w, const float* scal
   FeatConvParams p;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.up_add = up_add;
   p.y_nchw = y_nchw; p.y_nhwc0 = y_nhwc0; p.y_nhwc1 = y_nhwc1; p.y_cells = reinterpret_cast<uint4*>(y_cells);
-  p.B = B; p.Hi = Hi; p.Wi = Wi; p.relu = relu;
+  p.B = B; p.Hi = Hi; p.Wi = Wi; p.relu = relu; p.cells_s2d = cells_s2d;
   const int pad = K / 2;
   p.Ho = (Hi + 2 * pad - K) / stride + 1;
   p.Wo = (Wi + 2 * pad - K) / stride + 1;
+  DMVS_REQUIRE(!cells_s2d || (y_cells && (p.Ho % 2) == 0 && (p.Wo % 2) == 0 && Cout % 8 == 0 && K != 1), DMVS_ERR_BAD_SHAPE,
+               "conv2d: the pixel-unshuffled cell output needs y_cells, even output size and a tiled (K > 1) layer");
   DMVS_REQUIRE(!up_add || ((p.Ho % 2) == 0 && (p.Wo % 2) == 0), DMVS_ERR_BAD_SHAPE, "conv2d: up_add needs even output size, got %dx%d", p.Ho, p.Wo);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int key = ((K * 10 + stride) * 100 + Cin) * 100 + Cout;

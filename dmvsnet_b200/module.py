@@ -110,6 +110,7 @@ class FeatureNet(nn.Module):
     # native engine: run out2 / out3 on the tensor cores (fp16 hi/lo split operands, fp32 accumulate: same 1e-6 error as the
     # fp32 FMA kernels, 2.6x faster); False keeps them on the fp32 direct convolution
     tensor_heads = True
+    tensor_s2 = True  # the two 5x5 stride-2 layers on the tensor engine through a 2x2 pixel-unshuffle (space-to-depth)
     tensor_conv0 = False  # conv0.1 (8 -> 8 at full resolution) on the tensor engine: measured slower (3.57 vs 3.47 ms), kept as an option
 
     def forward(self, x):
@@ -147,11 +148,16 @@ class FeatureNet(nn.Module):
             def block(m):
                 bn = (m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var)
                 return ops.PackedConv2d(m.conv.weight, bn=bn, eps=m.bn.eps, stride=m.stride, relu=m.relu)
+
+            def s2d_layer(m):  # 5x5 stride-2 block as a 3x3 stride-1 tensor-core layer on the pixel-unshuffled input
+                bn = (m.bn.weight, m.bn.bias, m.bn.running_mean, m.bn.running_var)
+                return ops.PackedLayer(ops.s2d_weight(m.conv.weight.detach()), False, bn, m.bn.eps)
             pk = {"conv0": [block(m) for m in self.conv0], "conv1": [block(m) for m in self.conv1],
                   "conv2": [block(m) for m in self.conv2],
                   "out1": ops.PackedConv2d(self.out1.weight), "out2": ops.PackedConv2d(self.out2.weight),
                   "out3": ops.PackedConv2d(self.out3.weight),
                   "conv0_tc": self.conv0[1].packed(),
+                  "conv1_s2d": s2d_layer(self.conv1[0]), "conv2_s2d": s2d_layer(self.conv2[0]),
                   "conv1_tc": [self.conv1[1].packed(), self.conv1[2].packed()],
                   "conv2_tc": [self.conv2[1].packed(), self.conv2[2].packed()],
                   "out2_tc": ops.PackedLayer(self.out2.weight, False, None), "out3_tc": ops.PackedLayer(self.out3.weight, False, None),
@@ -165,18 +171,28 @@ class FeatureNet(nn.Module):
         channel-last (what the W1 kernels read in place)."""
         pk = self.packed()
         t = x
+        s2d = self.tensor_heads and self.tensor_s2 and x.shape[-1] % 8 == 0 and x.shape[-2] % 4 == 0
         if self.tensor_heads and self.tensor_conv0:
             _, cells = ops.conv2d(t, pk["conv0"][0], nchw=False, cells=True)
             t = ops.conv3d_ch16(cells, pk["conv0_tc"], relu=True, out_fmt="f32").squeeze(2)
+            cells0 = ops.s2d_cells(t) if s2d else None
         else:
-            for layer in pk["conv0"]:
-                t = ops.conv2d(t, layer)
+            t = ops.conv2d(t, pk["conv0"][0])
+            if s2d:  # conv0.1 hands its output out twice: fp32 NCHW (lateral inner2) and unshuffled cells (conv1.0 on the tensor cores)
+                t, cells0 = ops.conv2d(t, pk["conv0"][1], cells=True, s2d=True)
+            else:
+                t, cells0 = ops.conv2d(t, pk["conv0"][1]), None
         c0 = t
         if self.tensor_heads and t.shape[-1] % 8 == 0:
-            # the 3x3 layers behind each stride-2 5x5 (16->16, 32->32; BN + ReLU in the epilogue) on the tensor cores too:
-            # the 5x5 emits CH16 cells, the last 3x3 of a level returns fp32 NCHW for the fp32 consumers (laterals, next 5x5)
+            # the 3x3 layers behind each stride-2 5x5 (16->16, 32->32; BN + ReLU in the epilogue) run on the tensor cores, and
+            # so do the 5x5 stride-2 layers themselves as 3x3 stride-1 layers on the 2x2 pixel-unshuffled input (4x channels);
+            # the last 3x3 of a level returns fp32 NCHW for the fp32 consumers (laterals)
             for name in ("conv1", "conv2"):
-                _, cells = ops.conv2d(t, pk[name][0], nchw=False, cells=True)
+                if s2d:
+                    cells = cells0 if name == "conv1" else ops.s2d_cells(t)
+                    cells = ops.conv3d_ch16(cells, pk[name + "_s2d"], relu=True, out_fmt="ch16")
+                else:
+                    _, cells = ops.conv2d(t, pk[name][0], nchw=False, cells=True)
                 cells = ops.conv3d_ch16(cells, pk[name + "_tc"][0], relu=True, out_fmt="ch16")
                 t = ops.conv3d_ch16(cells, pk[name + "_tc"][1], relu=True, out_fmt="f32").squeeze(2)
                 if name == "conv1":

@@ -227,11 +227,12 @@ class PackedConv2d:
 
 
 def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] = None, nchw: bool = True, split_nhwc: bool = False,
-           cells: bool = False):
+           cells: bool = False, s2d: bool = False):
     """x [B,Cin,H,W] -> conv (+BN/bias, ReLU, + nearest-x2 ``up_add``).  Returns ``y`` ([B,Cout,Ho,Wo] NCHW) when ``nchw``;
     with ``split_nhwc`` additionally the two channel halves as channel-last buffers, each returned as a [B,Cout/2,Ho,Wo]
     view (torch channels_last strides): ``(y_or_None, half0, half1)``; with ``cells`` additionally the
-    output as CH16 cells (int32 [B, Cout/4, 1, Ho, Wo, 4]) for ``conv2d_head_tensor``: ``(y_or_None, cells)``."""
+    output as CH16 cells (int32 [B, Cout/4, 1, Ho, Wo, 4]; with ``s2d`` the cells of the 2x2 pixel-unshuffled map,
+    int32 [B, Cout, 1, Ho/2, Wo/2, 4]) for the tensor-core layers: ``(y_or_None, cells)``."""
     lib = N.load()
     x = _req(x, "x").contiguous()
     b, cin, hi, wi = x.shape
@@ -244,20 +245,47 @@ def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] 
     if split_nhwc:
         h0 = torch.empty(b, ho, wo, layer.cout // 2, device=x.device, dtype=torch.float32)
         h1 = torch.empty_like(h0)
-    yc = torch.empty(b, layer.cout // 4, 1, ho, wo, 4, device=x.device, dtype=torch.int32) if cells else None
+    yc = None
+    if cells:
+        yc = (torch.empty(b, layer.cout, 1, ho // 2, wo // 2, 4, device=x.device, dtype=torch.int32) if s2d else
+              torch.empty(b, layer.cout // 4, 1, ho, wo, 4, device=x.device, dtype=torch.int32))
     if up_add is not None:
         up_add = _req(up_add, "up_add").contiguous()
         if up_add.shape != (b, layer.cout, ho // 2, wo // 2):
             raise ValueError("conv2d: up_add has shape %s, expected %s" % (tuple(up_add.shape), (b, layer.cout, ho // 2, wo // 2)))
     with _timed("featnet:k%ds%d_%dto%d_%dx%d" % (layer.k, layer.stride, cin, layer.cout, ho, wo)):
         rc = lib.dmvs_conv2d_f32(x.data_ptr(), layer.w.data_ptr(), _ptr(layer.scale), _ptr(layer.shift), _ptr(up_add), _ptr(y),
-                                 _ptr(h0), _ptr(h1), _ptr(yc), b, cin, layer.cout, hi, wi, layer.k, layer.stride, int(layer.relu), _stream())
+                                 _ptr(h0), _ptr(h1), _ptr(yc), int(bool(cells and s2d)), b, cin, layer.cout, hi, wi, layer.k, layer.stride,
+                                 int(layer.relu), _stream())
     N.check(rc, "dmvs_conv2d_f32")
     if split_nhwc:
         return y, h0.permute(0, 3, 1, 2), h1.permute(0, 3, 1, 2)
     if cells:
         return y, yc
     return y
+
+
+def s2d_cells(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [B,C,H,W] -> CH16 cells of the 2x2 pixel-unshuffled map, int32 [B, C, 1, H/2, W/2, 4] (dmvs_features_s2d_cells_f32)."""
+    lib = N.load()
+    x = _req(x, "x").contiguous()
+    b, c, h, w = x.shape
+    y = torch.empty(b, c, 1, h // 2, w // 2, 4, device=x.device, dtype=torch.int32)
+    with _timed("featnet:s2d_%d_%dx%d" % (c, h, w)):
+        rc = lib.dmvs_features_s2d_cells_f32(x.data_ptr(), y.data_ptr(), b, c, h, w, _stream())
+    N.check(rc, "dmvs_features_s2d_cells_f32")
+    return y
+
+
+def s2d_weight(w5: torch.Tensor) -> torch.Tensor:
+    """5x5 stride-2 (padding 2) conv weight [Cout,C,5,5] -> the equivalent 3x3 stride-1 (padding 1) weight [Cout,4C,3,3] on the
+    2x2 pixel-unshuffled input (channel (dy*2+dx)*C + c): output (y,x) reads input rows 2y-2..2y+2 = blocks y-1..y+1, so the
+    kernel is zero-padded to 6x6 (index 5 is never read) and regrouped."""
+    cout, c = w5.shape[0], w5.shape[1]
+    w6 = torch.zeros(cout, c, 6, 6, dtype=w5.dtype, device=w5.device)
+    w6[:, :, :5, :5] = w5
+    w6 = w6.reshape(cout, c, 3, 2, 3, 2)               # [co][c][bh][dy][bw][dx]
+    return w6.permute(0, 3, 5, 1, 2, 4).reshape(cout, 4 * c, 3, 3).contiguous()
 
 
 def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer"):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 11
+#define DMVS_ABI_VERSION 12
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -102,13 +102,19 @@ int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float* y, int B,
  *   y_nchw  nullable [B,Cout,Ho,Wo];  y_nhwc0 / y_nhwc1 nullable (both or none): channel-last [B,Ho,Wo,Cout/2] buffers that
  *           receive channels [0,Cout/2) and [Cout/2,Cout) - the `stageK` / `stageK_c` halves (module.py:326-336) in the
  *           layout dmvs_warp_corr_nhwc_f32 gathers from
- *   y_cells nullable: the output as DMVS_FMT_CH16 cells [B][2*Cout/8][1][Ho][Wo] for the tensor-core
+ *   y_cells nullable: the output as DMVS_FMT_CH16 cells [B][2*Cout/8][1][Ho][Wo] (cells_s2d != 0: of the 2x2 pixel-unshuffled
+ *           map, see dmvs_features_s2d_cells_f32) for the tensor-core
  *           3x3 layers (dmvs_conv3d_ch16 with kd = 1); at least one of the three output forms must be given
  *   (K, stride, Cin, Cout) must be one of FeatureNet's: (3,1,3,8) (3,1,8,8) (5,2,8,16) (3,1,16,16) (5,2,16,32)
  *   (3,1,32,32) (3,1,32,16) (1,1,32,64) (1,1,16,32) (1,1,8,32); Ho = (Hi + 2*(K/2) - K)/stride + 1. */
 int dmvs_conv2d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* up_add,
-                    float* y_nchw, float* y_nhwc0, float* y_nhwc1, void* y_cells, int B, int Cin, int Cout, int Hi, int Wi, int K,
-                    int stride, int relu, void* stream);
+                    float* y_nchw, float* y_nhwc0, float* y_nhwc1, void* y_cells, int cells_s2d, int B, int Cin, int Cout, int Hi, int Wi,
+                    int K, int stride, int relu, void* stream);
+
+/* fp32 [B,C,H,W] -> DMVS_FMT_CH16 cells of the 2x2 pixel-unshuffled map [B][2*(4C)/8][1][H/2][W/2] (channel (dy*2+dx)*C + c at
+ * block (y/2, x/2)): FeatureNet's 5x5 stride-2 layers (module.py:304,308) run as 3x3 stride-1 layers on 4C channels on the tensor
+ * engine (kernel zero-padded to 6x6 and regrouped by the caller).  dmvs_conv2d_f32(cells_s2d = 1) emits the same layout directly. */
+int dmvs_features_s2d_cells_f32(const float* x, void* y_cells, int B, int C, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * R1  3-D regularisation U-Nets.

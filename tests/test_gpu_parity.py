@@ -155,7 +155,8 @@ def test_feature_net_native_vs_oracle(b, n, h, w):
         launches = _lib_launches()
         with torch.no_grad():
             got = net.extract_features(cuda(imgs))
-        assert (_lib_launches() - launches == 13) == (engine == "native")
+        # 13 layers + the pixel-unshuffle of c1 for the second 5x5 stride-2 layer; the cuDNN engine launches nothing of ours
+        assert _lib_launches() - launches == (14 if engine == "native" else 0)
         if engine == "native":  # ... and with the 3x3 heads on the fp32 kernels instead of the tensor cores
             net.feature.tensor_heads = False
             with torch.no_grad():

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for name in declared:
         assert hasattr(native_lib, name), "libdmvs_b200.so does not export %s" % name
     assert sorted(_native.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 11
+    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 12
     assert native_lib.dmvs_launch_count() == 0
 
 
@@ -236,3 +236,19 @@ def test_channel_last_stride_detection():
     assert ops._nhwc_strides(torch.zeros(2, 16, 6, 8)) is None
     assert ops._batch_stride(torch.zeros(2, 32, 6, 8).split([16, 16], 1)[1]) == 32 * 48
     assert ops._batch_stride(t) == -1
+
+
+def test_space_to_depth_weight_transform():
+    """FeatureNet's 5x5 stride-2 layers run as 3x3 stride-1 layers on the 2x2 pixel-unshuffled input: ops.s2d_weight must make the
+    two convolutions identical (channel order (dy*2+dx)*C + c, as dmvs_features_s2d_cells_f32 writes it)."""
+    import torch.nn.functional as F
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 12, 16, generator=g, dtype=torch.float64)
+    w = torch.randn(16, 8, 5, 5, generator=g, dtype=torch.float64)
+    want = F.conv2d(x, w, stride=2, padding=2)
+    xs = F.pixel_unshuffle(x, 2)  # torch orders the channels c*4 + dy*2 + dx
+    b, _, h, wd = xs.shape
+    xs = xs.reshape(b, 8, 4, h, wd).permute(0, 2, 1, 3, 4).reshape(b, 32, h, wd)
+    got = F.conv2d(xs, ops.s2d_weight(w), stride=1, padding=1)
+    assert float((got - want).abs().max()) < 1e-10

@@ -1,0 +1,29 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): native FeatureNet + 3-stage cascade from images,
+all three W1 kernels, B = 2."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dmvsnet_b200 import MVSNet, ops, synthetic as syn
+
+b, n, h, w, nd, ratios = 2, 3, 64, 96, [16, 8, 8], [4, 2, 1]
+net = MVSNet(nd, ratios, inverse_depth=True)
+net.load_state_dict(syn.randomise_regnet_state(net.state_dict(), seed=5))
+net = net.cuda().eval()
+imgs = syn.make_images(h, w, n, b, seed=6)
+proj = syn.make_proj_matrices(h, w, n, b, num_stages=3)
+dv = syn.make_depth_values(b, 192, inverse=True)
+with torch.no_grad():
+    out = net(imgs.cuda(), proj, dv.cuda())
+    torch.cuda.synchronize()
+    host = net.infer(imgs[:1], {k: v[:1] for k, v in proj.items()}, dv[:1])
+    g = torch.Generator().manual_seed(1)
+    feats = [torch.randn(1, 16, 40, 72, generator=g).cuda() for _ in range(4)]
+    rt = ops.relative_projections(syn.make_proj_matrices(160, 288, 4, 1, num_stages=1)["stage1"]).cuda()
+    hyp = (425 + 500 * torch.rand(1, 8, 40, 72, generator=g)).cuda()
+    ref = None
+    for layout in ("nchw", "nhwc", "staged"):
+        c = ops.warp_corr(feats, rt, hyp, layout=layout)
+        ref = c if ref is None else ref
+        assert float((c - ref).abs().max()) < 1e-4
+    torch.cuda.synchronize()
+print("ok", float(out["depth"].mean()), float(host["depth"].mean()))
