@@ -299,17 +299,22 @@ def run_gpu_arm(args, cfg_name):
     e2e_single_ms = t0.elapsed_time(t1)
     for host in net.infer_many([(imgs_host, proj, dv_host)] * 2):
         pass
-    barrier()
-    wall0 = time.perf_counter()
-    t0.record()
-    n_out = 0
-    for host in net.infer_many([(imgs_host, proj, dv_host)] * e2e_steps):
-        n_out += 1
-    t1.record()
-    barrier()
-    e2e_ms = t0.elapsed_time(t1)  # t1 is recorded after the generator has waited for the last D2H
-    e2e_wall_ms = (time.perf_counter() - wall0) * 1e3
-    assert n_out == e2e_steps
+    # two passes of e2e_steps items each, the faster one is reported (both are listed): a single host-side hiccup (pinned
+    # allocator growth, a page-fault burst on a fresh box) otherwise lands on 10 steps
+    e2e_passes = []
+    for _ in range(2):
+        barrier()
+        wall0 = time.perf_counter()
+        t0.record()
+        n_out = 0
+        for host in net.infer_many([(imgs_host, proj, dv_host)] * e2e_steps):
+            n_out += 1
+        t1.record()
+        barrier()
+        assert n_out == e2e_steps
+        # t1 is recorded after the generator has waited for the last D2H
+        e2e_passes.append((t0.elapsed_time(t1), (time.perf_counter() - wall0) * 1e3))
+    e2e_ms, e2e_wall_ms = min(e2e_passes)
     h2d = imgs_host.numel() * 4 + dv_host.numel() * 4 + sum(v.numel() * 4 for v in proj.values())
     d2h = sum(v.numel() * 4 for v in host.values())
 
@@ -373,7 +378,7 @@ def run_gpu_arm(args, cfg_name):
             "clocks": clocks,
             "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "api": "MVSNet.infer_many (streaming: copies of neighbouring steps overlap compute)",
-                    "wall_ms_per_step": e2e_wall_ms / e2e_steps, "single_request_ms": e2e_single_ms / e2e_steps, "single_request_views_per_s": world * e2e_steps / (e2e_single_ms * 1e-3)},
+                    "wall_ms_per_step": e2e_wall_ms / e2e_steps, "passes_ms_per_step": [p[0] / e2e_steps for p in e2e_passes], "single_request_ms": e2e_single_ms / e2e_steps, "single_request_views_per_s": world * e2e_steps / (e2e_single_ms * 1e-3)},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "warp_corr_kernel / warp_corr_nhwc_kernel (W1, 6 launches/step pooled; source repack reported as w1_layout in the breakdown)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
