@@ -38,6 +38,7 @@ struct W1cParams {
   const unsigned char* flags;  // nullable, [B][tiles_y][tiles_x][D]: compute and write only the flagged (tile, plane) pairs
   long long ref_bs, src_bs;
   int src_ps, ref_ps;
+  int src_cs;  // floats between the two x-corners of a footprint: src_ps for a plain channel-last map, C for the pair layout
   int B, D, h, w, n_src, d_begin, d_end, n_chunks;
   float half_w, half_h;
 };
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kW1Warps * 32) warp_corr_nhwc_kernel(const __g
 #pragma unroll 1
     for (int s = 0; s < p.n_src; ++s) {
       const float* m = s_rt + s * 12;
-      const float* sp = p.src[s] + (long long)b * p.src_bs + dx * p.src_ps + k * 4;  // dense maps: lig * 4
+      const float* sp = p.src[s] + (long long)b * p.src_bs + dx * p.src_cs + k * 4;  // dense maps and pairs: lig * 4
       // rot @ (x, y, 1), shared by all planes of this source
       const float rx = __fadd_rn(__fmaf_rn(m[1], fy, __fmul_rn(m[0], fx)), m[2]);
       const float ry = __fadd_rn(__fmaf_rn(m[4], fy, __fmul_rn(m[3], fx)), m[5]);
@@ -320,13 +321,14 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 
 // pass 2 of dmvs_warp_corr_staged_f32 (arguments already validated there)
 int launch_w1_pass2(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src, long long src_bstride,
-                    int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
+                    int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
                     const unsigned char* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, cudaStream_t st) {
   W1cParams p;
   p.ref = ref;
   for (int i = 0; i < DMVS_MAX_SRC; ++i) p.src[i] = (i < n_src) ? src[i] : nullptr;
   p.rt = rt; p.hyp = hyp; p.cost = cost; p.cells = reinterpret_cast<uint2*>(cost_cells); p.flags = flags;
   p.ref_bs = ref_bstride; p.src_bs = src_bstride; p.src_ps = src_pixstride; p.ref_ps = ref_pixstride;
+  p.src_cs = src_cornerstride ? src_cornerstride : src_pixstride;
   p.B = B; p.D = D; p.h = h; p.w = w; p.n_src = n_src; p.d_begin = d_begin; p.d_end = d_end; p.n_chunks = 1;
   p.half_w = (float)((double)(w - 1) / 2.0);
   p.half_h = (float)((double)(h - 1) / 2.0);
@@ -357,7 +359,7 @@ extern "C" int dmvs_features_nhwc_f32(const float* x, long long x_bstride, float
 }
 
 extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
-                                       long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost,
+                                       long long src_bstride, int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost,
                                        void* cost_cells, int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream) {
   using namespace dmvs;
   DMVS_REQUIRE(ref && src && rt && hyp && (cost || cost_cells), DMVS_ERR_BAD_POINTER, "warp_corr_nhwc: null pointer");
@@ -368,6 +370,8 @@ extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, 
                d_begin, d_end, D);
   DMVS_REQUIRE(src_pixstride >= C && src_pixstride % 4 == 0 && src_bstride % 4 == 0, DMVS_ERR_BAD_SHAPE,
                "warp_corr_nhwc: pixel stride %d / batch stride %lld must be multiples of 4 floats and >= C", src_pixstride, src_bstride);
+  DMVS_REQUIRE(src_cornerstride == 0 || (src_cornerstride >= C && src_cornerstride % 4 == 0), DMVS_ERR_BAD_SHAPE,
+               "warp_corr_nhwc: corner stride %d must be 0 or a multiple of 4 floats >= C", src_cornerstride);
   DMVS_REQUIRE(ref_pixstride == 0 || (ref_pixstride >= C && ref_pixstride % 4 == 0 && ref_bstride % 4 == 0 && aligned16(ref)),
                DMVS_ERR_BAD_SHAPE, "warp_corr_nhwc: channel-last reference needs pixel stride %d >= C, strides multiples of 4 floats, 16-byte alignment",
                ref_pixstride);
@@ -388,6 +392,7 @@ extern "C" int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, 
   p.ref_bs = ref_bstride;
   p.src_bs = src_bstride;
   p.src_ps = src_pixstride;
+  p.src_cs = src_cornerstride ? src_cornerstride : src_pixstride;
   p.ref_ps = ref_pixstride;
   p.B = B; p.D = D; p.h = h; p.w = w; p.n_src = n_src; p.d_begin = d_begin; p.d_end = d_end; p.n_chunks = 1;
   p.half_w = (float)((double)(w - 1) / 2.0);

@@ -269,7 +269,7 @@ static EncodeTiledFnW1 encode_fn_w1() {
 }
 
 int launch_w1_pass2(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src, long long src_bstride,
-                    int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
+                    int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
                     const unsigned char* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, cudaStream_t st);
 
 template <int C, int DP>
@@ -325,7 +325,7 @@ extern "C" size_t dmvs_warp_corr_flag_bytes(int B, int D, int h, int w) {
 }
 
 extern "C" int dmvs_warp_corr_staged_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
-                                         long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp,
+                                         long long src_bstride, int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp,
                                          float* cost, void* cost_cells, void* flags, int B, int C, int D, int h, int w, int d_begin,
                                          int d_end, void* stream) {
   using namespace dmvs;
@@ -361,6 +361,6 @@ extern "C" int dmvs_warp_corr_staged_f32(const float* ref, long long ref_bstride
     default: set_error("warp_corr_staged: C=%d unsupported (8, 16, 32)", C); return DMVS_ERR_BAD_SHAPE;
   }
   if (rc != DMVS_OK) return rc;
-  return launch_w1_pass2(ref, ref_bstride, ref_pixstride, src, src_bstride, src_pixstride, n_src, rt, hyp, cost, cost_cells,
+  return launch_w1_pass2(ref, ref_bstride, ref_pixstride, src, src_bstride, src_pixstride, src_cornerstride, n_src, rt, hyp, cost, cost_cells,
                          static_cast<const unsigned char*>(flags), B, C, D, h, w, d_begin, d_end, st);
 }

@@ -110,6 +110,10 @@ class FeatureNet(nn.Module):
     # native engine: run out2 / out3 on the tensor cores (fp16 hi/lo split operands, fp32 accumulate: same 1e-6 error as the
     # fp32 FMA kernels, 2.6x faster); False keeps them on the fp32 direct convolution
     tensor_heads = True
+    # stage-2 / stage-3 feature maps in the pair layout (entry x = pixel x | copy of pixel x+1): a bilinear footprint row is then
+    # one aligned run that never straddles a 128-byte line (ops.mark_pairs).  Measured on DTU: W1 3.42 -> 3.58 ms, FeatureNet
+    # 2.99 -> 3.12 ms - the doubled maps cost more L1/L2 misses than the straddles they remove - so it is off.
+    pair_layout = False
     tensor_s2 = True  # the two 5x5 stride-2 layers on the tensor engine through a 2x2 pixel-unshuffle (space-to-depth)
     tensor_conv0 = False  # conv0.1 (8 -> 8 at full resolution) on the tensor engine: measured slower (3.57 vs 3.47 ms), kept as an option
 
@@ -211,9 +215,9 @@ class FeatureNet(nn.Module):
             # the two 32-channel 3x3 heads (57 % of FeatureNet's flops) on the tcgen05 engine: the laterals emit their sums as
             # fp16 hi/lo cells (top2 only as cells: nobody else reads it), the heads write the channel-last feature sets
             top, cells = ops.conv2d(c1, pk["inner1"], up_add=c2, cells=True)
-            out["stage2"], out["stage2_c"] = ops.conv2d_head_tensor(cells, pk["out2_tc"])
+            out["stage2"], out["stage2_c"] = ops.conv2d_head_tensor(cells, pk["out2_tc"], pairs=self.pair_layout)
             _, cells = ops.conv2d(c0, pk["inner2"], up_add=top, nchw=False, cells=True)
-            out["stage3"], out["stage3_c"] = ops.conv2d_head_tensor(cells, pk["out3_tc"])
+            out["stage3"], out["stage3_c"] = ops.conv2d_head_tensor(cells, pk["out3_tc"], pairs=self.pair_layout)
             return out
         top = ops.conv2d(c1, pk["inner1"], up_add=c2)
         _, out["stage2"], out["stage2_c"] = ops.conv2d(top, pk["out2"], nchw=False, split_nhwc=True)

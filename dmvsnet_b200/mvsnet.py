@@ -165,7 +165,11 @@ class MVSNet(nn.Module):
         reference's per-view list of dicts; every entry is a strided view into the batched output (no copies)."""
         b, n = imgs.shape[0], imgs.shape[1]
         out = self.feature(imgs.reshape(b * n, *imgs.shape[2:]))
-        return [{k: t.view(b, n, *t.shape[1:])[:, v] for k, t in out.items()} for v in range(n)]
+
+        def view_of(t, v):
+            s = t.view(b, n, *t.shape[1:])[:, v]
+            return ops.mark_pairs(s) if ops.is_pairs(t) else s
+        return [{k: view_of(t, v) for k, t in out.items()} for v in range(n)]
 
     # ------------------------------------------------------------------ host-buffer entry (SURVEY §8f N3)
     # views per H2D / FeatureNet group in infer(): the copy of group k+1 (side stream) runs under FeatureNet of group k

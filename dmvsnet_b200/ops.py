@@ -165,11 +165,15 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         if min(strides) < 0 or len(set(strides)) != 1:
             srcs = [f.contiguous() for f in srcs]
             strides = [c * h * w] * n_src
-        src_ps, src_bs = 0, strides[0]
+        src_ps, src_bs, src_cs = 0, strides[0], 0
     else:
         st = [_nhwc_strides(f) for f in srcs]
-        if any(x is None for x in st) or len(set(st)) != 1:
-            srcs = [f if x == (c, h * w * c) else features_nhwc(f) for f, x in zip(srcs, st)]
+        pr = [is_pairs(f) for f in srcs]
+        src_cs = 0
+        if all(pr) and all(x is not None for x in st) and len(set(st)) == 1:
+            src_cs = c  # pair layout: the x+1 corner is the second slot of the same entry
+        elif any(x is None for x in st) or len(set(st)) != 1 or any(pr):
+            srcs = [f if (x == (c, h * w * c) and not q) else features_nhwc(f) for f, x, q in zip(srcs, st, pr)]
             st = [(c, h * w * c)] * n_src
         src_ps, src_bs = st[0]
     hyp = _req(hyp, "hyp").contiguous()
@@ -192,10 +196,10 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
             rc = lib.dmvs_warp_corr_f32(ref.data_ptr(), ref_bs, src_ptrs, src_bs, n_src, rt.data_ptr(), hyp.data_ptr(),
                                         _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
         elif layout == "nhwc":
-            rc = lib.dmvs_warp_corr_nhwc_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(), hyp.data_ptr(),
+            rc = lib.dmvs_warp_corr_nhwc_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, src_cs, n_src, rt.data_ptr(), hyp.data_ptr(),
                                              _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
         else:
-            rc = lib.dmvs_warp_corr_staged_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(),
+            rc = lib.dmvs_warp_corr_staged_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, src_cs, n_src, rt.data_ptr(),
                                                hyp.data_ptr(), _ptr(out), _ptr(cells), flags.data_ptr(), b, c, d, h, w, lo, hi, _stream())
     N.check(rc, "dmvs_warp_corr_f32[%s]" % layout)
     if layout == "staged":
@@ -288,20 +292,36 @@ def s2d_weight(w5: torch.Tensor) -> torch.Tensor:
     return w6.permute(0, 3, 5, 1, 2, 4).reshape(cout, 4 * c, 3, 3).contiguous()
 
 
-def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer"):
+def mark_pairs(t: torch.Tensor) -> torch.Tensor:
+    """Tag a [B,C,h,w] view of a PAIR-layout buffer ([B,h,w,2,C]: entry x = pixel x followed by a copy of pixel x+1).  As a
+    strided tensor it is an ordinary channel-last map with pixel stride 2C; the tag tells ops.warp_corr that the x+1 corner of a
+    footprint sits C floats behind the x corner, so a footprint row is one aligned run (include/dmvs_b200.h, src_cornerstride)."""
+    t._dmvs_pairs = True
+    return t
+
+
+def is_pairs(t: torch.Tensor) -> bool:
+    return bool(getattr(t, "_dmvs_pairs", False)) and t.dim() == 4 and t.stride(1) == 1 and t.stride(3) == 2 * t.shape[1]
+
+
+def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer", pairs: bool = False):
     """FeatureNet's bare 3x3 heads out2 / out3 (module.py:326-336, Cin = 32, no BN / ReLU / bias) on the tcgen05 engine:
-    CH16 cells [B, 8, 1, H, W, 4] -> the two feature sets as channel-last maps, returned as [B,Cout/2,H,W] views."""
+    CH16 cells [B, 8, 1, H, W, 4] -> the two feature sets as channel-last maps, returned as [B,Cout/2,H,W] views (``pairs``: in
+    the pair layout, tagged with ``mark_pairs``; the last column's second slot is never read and stays unwritten)."""
     lib = N.load()
     b, planes, d, h, w, _ = cells.shape
     if planes != 8 or d != 1 or layer.cin != 32 or layer.kd != 1 or layer.w_tc is None:
         raise ValueError("conv2d_head_tensor: expects 32-channel cells and a packed 2-D 3x3 layer")
     half = layer.cout // 2
-    y = torch.empty(2, b, h, w, half, device=cells.device, dtype=torch.float32)
+    y = (torch.empty(2, b, h, w, 2, half, device=cells.device, dtype=torch.float32) if pairs else
+         torch.empty(2, b, h, w, half, device=cells.device, dtype=torch.float32))
     cl = layer.c_struct()
     with _timed("featnet:tc3x3_32to%d_%dx%d" % (layer.cout, h, w)):
         rc = lib.dmvs_conv3d_ch16(cells.data_ptr(), 0, ctypes.byref(cl), None, y.data_ptr(), b, 32, layer.cout, 1, h, w, 1, 1, 0, 0,
-                                  N.FMT_NHWC2, _stream())
+                                  N.FMT_NHWC2P if pairs else N.FMT_NHWC2, _stream())
     N.check(rc, "dmvs_conv3d_ch16")
+    if pairs:
+        return mark_pairs(y[0][:, :, :, 0].permute(0, 3, 1, 2)), mark_pairs(y[1][:, :, :, 0].permute(0, 3, 1, 2))
     return y[0].permute(0, 3, 1, 2), y[1].permute(0, 3, 1, 2)
 
 

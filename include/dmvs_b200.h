@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 12
+#define DMVS_ABI_VERSION 13
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -70,10 +70,12 @@ int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* con
  * [B,h,w,C] with `src_pixstride` floats between pixels (>= C, multiple of 4; FeatureNet's [B,2C,h,w] output in
  * channels_last memory format has stride 2C and its channel slices are consumed in place) and `src_bstride` between
  * batches; pointers 16-byte aligned.  The reference view is NCHW when `ref_pixstride` == 0, else channel-last too.  A bilinear footprint row is then one contiguous
- * run of 2*C floats that C/2 lanes fetch with one 16-byte load each, which is what makes the gather cheap when the
+ * run of 2*C floats that C/2 lanes fetch with one 16-byte load each (`src_cornerstride` = floats between the two x-corners of a
+ * footprint: 0 / src_pixstride for a plain channel-last map; C for the PAIR layout [..][w][2][C] whose entry x stores pixel x
+ * followed by a copy of pixel x+1 (pixel stride 2C), so that a footprint row is an aligned run that never straddles a 128-byte line), which is what makes the gather cheap when the
  * per-pixel hypotheses are rough (see csrc/warp_corr_nhwc.cu).  All other arguments as above. */
 int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
-                            long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
+                            long long src_bstride, int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
                             int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
 
 /* W1, TMA-staged.  Same result and arguments as dmvs_warp_corr_nhwc_f32 plus a scratch byte array `flags` of
@@ -83,7 +85,7 @@ int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, int ref_pix
  * per-pixel hypotheses, depth discontinuities) are flagged instead; (2) the channel-last gather kernel computes exactly the
  * flagged (tile, plane) pairs.  Which pairs take which pass depends only on the inputs, not on [d_begin, d_end). */
 int dmvs_warp_corr_staged_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
-                              long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost,
+                              long long src_bstride, int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost,
                               void* cost_cells, void* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
 size_t dmvs_warp_corr_flag_bytes(int B, int D, int h, int w);
 
@@ -185,6 +187,7 @@ int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* s
 #define DMVS_FMT_CH16 1
 #define DMVS_FMT_CH16P 2
 #define DMVS_FMT_COST2 3 /* conv0 input written by dmvs_warp_corr_f32(cost_cells), see there */
+#define DMVS_FMT_NHWC2P 5 /* like DMVS_FMT_NHWC2 in the pair layout [2][B][D][H][W][2][Cout/2]: entry x = (pixel x | pixel x+1) */
 #define DMVS_FMT_NHWC2 4 /* output only, FeatureNet's 3x3 heads (kd = 1, Cin = 32, Cout = 16 / 32): two channel-last fp32 buffers
                             back to back, [2][B][D][H][W][Cout/2] = the `stageK` / `stageK_c` feature sets */
 

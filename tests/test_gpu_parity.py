@@ -132,6 +132,36 @@ def test_warp_corr_channels_last_sources_in_place():
         assert torch.equal(repacked, views[1]) and ops._nhwc_strides(repacked) == (c, h * w * c)
 
 
+@pytest.mark.parametrize("c,d", [(8, 8), (16, 4), (32, 6)])
+def test_warp_corr_pair_layout_sources(c, d):
+    """Pair layout (entry x = pixel x | copy of pixel x+1, ops.mark_pairs): same bits as the plain channel-last gather; the
+    second slot of the last column is never read (poisoned with NaN here)."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(13)
+    b, h, w, n = 2, 18, 44, 3
+    feats = [cuda(torch.randn(b, c, h, w, generator=g)) for _ in range(n)]
+    proj = syn.make_proj_matrices(h * 4, w * 4, n, b, num_stages=1)["stage1"]
+    rt = cuda(ops.relative_projections(proj))
+    hyp = cuda(425 + 500 * torch.rand(b, d, h, w, generator=g))
+
+    def pairs_of(f):
+        buf = torch.full((b, h, w, 2, c), float("nan"), device=f.device)
+        cl = f.permute(0, 2, 3, 1)
+        buf[:, :, :, 0] = cl
+        buf[:, :, :-1, 1] = cl[:, :, 1:]
+        return ops.mark_pairs(buf[:, :, :, 0].permute(0, 3, 1, 2))
+    paired = [feats[0]] + [pairs_of(f) for f in feats[1:]]
+    assert ops.is_pairs(paired[1]) and torch.equal(paired[1], feats[1])
+    for layout in ("nhwc", "staged"):
+        want = ops.warp_corr(feats, rt, hyp, layout=layout)
+        launches = _lib_launches()
+        got = ops.warp_corr(paired, rt, hyp, layout=layout)
+        assert _lib_launches() - launches == (1 if layout == "nhwc" else 2)  # consumed in place, no repack
+        assert torch.equal(got, want)
+    # the reference-layout kernel needs a repack of such views and must still agree
+    assert rel_linf(ops.warp_corr(paired, rt, hyp, layout="nchw"), want) < 2e-6
+
+
 def _lib_launches():
     from dmvsnet_b200 import _native
     return _native.launch_count()
