@@ -380,7 +380,7 @@ def run_gpu_arm(args, cfg_name):
                     "ms_per_step": e2e_ms / e2e_steps, "api": "MVSNet.infer_many (streaming: copies of neighbouring steps overlap compute)",
                     "wall_ms_per_step": e2e_wall_ms / e2e_steps, "passes_ms_per_step": [p[0] / e2e_steps for p in e2e_passes], "single_request_ms": e2e_single_ms / e2e_steps, "single_request_views_per_s": world * e2e_steps / (e2e_single_ms * 1e-3)},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "warp_corr_kernel / warp_corr_nhwc_kernel (W1, 6 launches/step pooled; source repack reported as w1_layout in the breakdown)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "W1 = warp_corr_staged_kernel (stage-1 planes) + warp_corr_nhwc_kernel (regressed hypotheses), 6 passes / 7 launches per step pooled", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": w1_bytes_total, "ms_per_step": w1_ms},
             "roofline_per_launch": roof_rows,
