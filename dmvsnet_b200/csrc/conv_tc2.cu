@@ -34,6 +34,9 @@ __host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mod
 // that shift).  Every MMA re-reads its 4 KB A tile from shared memory at 64 B/clk whatever its N, so 8 MMAs instead of 27.
 __host__ __device__ constexpr bool is_tr(int mode) { return mode == M2_TR || mode == M2_TRF; }
 constexpr int T_H = 16, T_W = 8;
+#ifndef SUBISSUE
+#define SUBISSUE 2
+#endif
 
 struct Tc2Params {
   const float* x_f32;  // C0 only
@@ -94,7 +97,14 @@ struct C2 {
   // a full/empty mbarrier is then always consumed by one warp in order - parity waits cannot alias a phase two uses away.
   static constexpr int MMA_WARPS = (ACC_SETS == 2 && STAGES % 2 == 0) ? 2 : 1;
   static constexpr int HS = STAGES / MMA_WARPS;
-  static constexpr int THREADS = (PROD_WARPS + MMA_WARPS + EPI_WARPS) * 32;
+  // SUB issuing threads share one tile: thread `sub` issues the accumulator rows (planes) t with t % SUB == sub.  The MMAs of
+  // different planes write different accumulators, so no order is needed between the threads; both commit to the stage's
+  // empty barrier and to the accumulator-full barrier (arrival count SUB).  A single thread issues about one tcgen05.mma
+  // per ~100 cycles; with two tile-alternating issuers the layers sit at 64 cycles per MMA, splitting prob / conv0 tiles over
+  // two more threads brings them to 60 (4-way: no further gain - the smem -> tensor-core A read is the floor).
+  static constexpr int SUB = (KD == 3 && TD >= 2 && (MODE == M2_PB || MODE == M2_C0T)) ? SUBISSUE : 1;  // S1 (conv2) measured slower with it
+  static constexpr int ISSUE_WARPS = MMA_WARPS * SUB;
+  static constexpr int THREADS = (PROD_WARPS + ISSUE_WARPS + EPI_WARPS) * 32;
   static_assert(COLS <= 512, "accumulators exceed TMEM");
   static_assert(SMEM <= 227 * 1024, "pipeline does not fit shared memory");
   static_assert(CIN % CIN_P == 0 || is_c0(MODE), "channel passes");
@@ -139,7 +149,7 @@ __device__ __forceinline__ long long cell_index(int fmt, int b, int np, int pl, 
 // compile time: every descriptor is "base descriptor + constant" (the 14-bit address field never carries: smem < 256 KB),
 // i.e. one 64-bit add per operand and the tcgen05.mma itself.
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD>
-__device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_base, bool fresh) {
+__device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_base, bool fresh, int sub) {
   using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
   constexpr uint32_t idesc = make_idesc(Cfg::NMMA);
   const uint64_t adesc0 = make_desc(a0, Cfg::A_LBO, Cfg::A_SBO);
@@ -147,6 +157,7 @@ __device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_ba
   const uint32_t fresh_acc = fresh ? 0u : 1u;
 #pragma unroll
   for (int t = 0; t < ((MODE == M2_PB) ? TD + 2 : TD); ++t) {
+    if (Cfg::SUB > 1 && (t % Cfg::SUB) != sub) continue;
 #pragma unroll
     for (int tap = 0; tap < Cfg::TAPS; ++tap) {
       int acc, off;
@@ -390,10 +401,10 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, (MODE == M2_C0) ? Cfg::PROD_WARPS * 32 : 1);
-      mbar_init(empty + s, 1);
+      mbar_init(empty + s, Cfg::SUB);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(accfull + a, 1);
+      mbar_init(accfull + a, Cfg::SUB);
       mbar_init(accempty + a, Cfg::EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -492,9 +503,9 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
         }
       }
     }
-  } else if (warp < MMA_WARP + Cfg::MMA_WARPS) {
+  } else if (warp < MMA_WARP + Cfg::ISSUE_WARPS) {
     // ---------------------------------------------------------------- MMA issuers (one thread each)
-    const int me = warp - MMA_WARP;
+    const int me = (warp - MMA_WARP) % Cfg::MMA_WARPS, sub = (warp - MMA_WARP) / Cfg::MMA_WARPS;
     int tile_k = 0;
     for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
       if (lane == 0 && (tile_k % Cfg::MMA_WARPS) == me) {
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
           tc_fence_after();
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           issue2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>(smem_u32(st), Cfg::RESIDENT ? smem_u32(sB) : smem_u32(st + Cfg::A_BYTES),
-                                                   tmem_base + a * Cfg::COLS, pass == 0);
+                                                   tmem_base + a * Cfg::COLS, pass == 0, sub);
           umma_commit(empty + s);
         }
         umma_commit(accfull + a);
@@ -516,7 +527,7 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
     }
   } else {
     // ---------------------------------------------------------------- epilogue (8 warps)
-    const int ew = warp - MMA_WARP - Cfg::MMA_WARPS;
+    const int ew = warp - MMA_WARP - Cfg::ISSUE_WARPS;
     const int q = warp & 3, part = ew >> 2;
     int tile_k = 0;
     for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
