@@ -42,7 +42,8 @@ int dmvs_abi_version(void);
 const char* dmvs_last_error(void);
 /* number of kernels this library has launched from the calling process (all threads) */
 unsigned long long dmvs_launch_count(void);
-/* tuning knobs for experiments ("tc2_max_ctas": persistent CTAs per SM of the tensor-core convolutions, default 1; 2 measured no gain) */
+/* tuning knobs for experiments: "tc2_max_ctas" (persistent CTAs per SM of the tensor-core convolutions, default 1; 2 measured no
+ * gain), "head_px" (pixels per block of the depth head: 32 | 64 | 128, default 32), "pb_td8" (prob / conv0 on 8-plane tiles, default 1) */
 int dmvs_debug_set(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------
