@@ -297,7 +297,7 @@ def run_gpu_arm(args, cfg_name):
     t1.record()
     barrier()
     e2e_single_ms = t0.elapsed_time(t1)
-    for host in net.infer_many([(imgs_host, proj, dv_host)] * 2):
+    for host in net.infer_many([(imgs_host, proj, dv_host)] * 4):  # warm-up: fills the pipeline, so every pinned result buffer exists
         pass
     # two passes of e2e_steps items each, the faster one is reported (both are listed): a single host-side hiccup (pinned
     # allocator growth, a page-fault burst on a fresh box) otherwise lands on 10 steps
