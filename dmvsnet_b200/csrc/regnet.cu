@@ -69,9 +69,9 @@ extern "C" size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, i
   return (size_t)make_plan(refine, B, D, h, w).total * sizeof(float);
 }
 
-extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
-                                       float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
-                                       void* stream) {
+static int regnet_forward_impl(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
+                               float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
+                               int branch_mask, void* stream) {
   DMVS_REQUIRE(engine == DMVS_ENGINE_FP32 || engine == DMVS_ENGINE_TENSOR, DMVS_ERR_BAD_SHAPE, "regnet: unknown engine %d", engine);
   DMVS_REQUIRE(branches && (cost || cost_cells) && logits && workspace, DMVS_ERR_BAD_POINTER, "regnet: null pointer");
   DMVS_REQUIRE(B >= 1 && h >= 8 && w >= 8 && h % 8 == 0 && w % 8 == 0, DMVS_ERR_BAD_SHAPE,
@@ -102,7 +102,7 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
     enum { F32 = DMVS_FMT_F32, CH = DMVS_FMT_CH16, CHP = DMVS_FMT_CH16P };
     // conv0 of both branches in one launch: a 2 -> 16 layer whose CH16P output holds branch 0 in planes 0,1 and branch 1
     // in planes 2,3 (contiguous per branch when B == 1)
-    const bool pair = cost_cells && B == 1 && branches[0].conv0_pair.w_tc != nullptr;
+    const bool pair = cost_cells && B == 1 && branch_mask == 3 && branches[0].conv0_pair.w_tc != nullptr;
     if (pair) {
       const int rc0 = conv_layer_tc2(cost_cells, 1, branches[0].conv0_pair, nullptr, c0, 0, B, 2, 16, L0->D, L0->H, L0->W, 3, 1, 0, 1, CHP, st);
       if (rc0 > 0) { set_error("regnet: conv0_pair has no tensor specialisation"); return DMVS_ERR_BAD_SHAPE; }
@@ -110,6 +110,7 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
     }
     float* const c0_base = c0;
     for (int br = 0; br < 2; ++br) {
+      if (!((branch_mask >> br) & 1)) continue;
       const dmvs_conv_layer* L = branches[br].layer;
       int rc;
       c0 = pair ? c0_base + (long long)br * 8 * V0 : c0_base;
@@ -146,6 +147,7 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
     return DMVS_OK;
   }
   for (int br = 0; br < 2; ++br) {
+    if (!((branch_mask >> br) & 1)) continue;
     const dmvs_conv_layer* L = branches[br].layer;
     int rc;
 #define RUN(...)                 \
@@ -166,6 +168,19 @@ extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int r
 #undef RUN
   }
   return DMVS_OK;
+}
+
+extern "C" int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
+                                       float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
+                                       void* stream) {
+  return regnet_forward_impl(branches, refine, cost, cost_cells, logits, workspace, workspace_bytes, B, D, h, w, engine, 3, stream);
+}
+
+extern "C" int dmvs_regnet_forward_branches_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
+                                                float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w,
+                                                int engine, int branch_mask, void* stream) {
+  DMVS_REQUIRE(branch_mask >= 1 && branch_mask <= 3, DMVS_ERR_BAD_SHAPE, "regnet: branch_mask %d not in 1..3", branch_mask);
+  return regnet_forward_impl(branches, refine, cost, cost_cells, logits, workspace, workspace_bytes, B, D, h, w, engine, branch_mask, stream);
 }
 
 extern "C" int dmvs_convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, void* stream) {

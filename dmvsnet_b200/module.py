@@ -312,9 +312,14 @@ class _DualRegNet(nn.Module):
             self._pack_key = key
         return self._pack
 
-    def forward(self, x, cost_cells=None):
-        """x: cost volume [B,2,D,h,w] (may be None when ``cost_cells`` - W1's cell-format output - feeds the tensor engine)."""
+    def forward(self, x, cost_cells=None, branch_group=None):
+        """x: cost volume [B,2,D,h,w] (may be None when ``cost_cells`` - W1's cell-format output - feeds the tensor engine).
+        ``branch_group``: a 2-rank process group - rank r runs branch r only and the logit halves are exchanged with one
+        all-gather (the two U-Nets are independent, module.py:343-349); every rank must hold the same input."""
         _require_inference(self)
+        if branch_group is not None:
+            from . import parallel
+            return parallel.regnet_branch_sharded(self.packed(), x, cost_cells, branch_group)
         return ops.regnet_forward(self.packed(), x, cost_cells=cost_cells)
 
 

@@ -95,13 +95,15 @@ class MVSNet(nn.Module):
     # ------------------------------------------------------------------ the hot path
     def cascade(self, features: Sequence[Dict[str, torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
                 depth_values: torch.Tensor, image_hw: Sequence[int], keep_seams: bool = False,
-                rts: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, object]:
+                rts: Optional[Sequence[torch.Tensor]] = None, branch_group=None) -> Dict[str, object]:
         """The stage loop (reference mvsnet.py:208-258) on precomputed per-view feature dicts.
 
         ``keep_seams`` additionally returns the cost volumes and logits (``_cost``, ``_logits``, ``_cost_c``,
         ``_logits_c``) per stage, for the parity tests.  ``rts`` overrides the per-stage homographies
         ([B,N-1,12] each, see ops.relative_projections): fp32 ``inverse(P_ref)`` is ill-conditioned (entries ~1e5),
-        two hosts' LAPACKs differ by ~1e-4 relative in H, so cross-machine fixtures carry the reference's own H."""
+        two hosts' LAPACKs differ by ~1e-4 relative in H, so cross-machine fixtures carry the reference's own H.
+        ``branch_group``: a 2-rank ``torch.distributed`` group holding the same inputs - single-view latency mode: every
+        regularisation net runs one branch per rank (parallel.regnet_branch_sharded), everything else is replicated."""
         _require_inference(self)
         dev = features[0]["stage1"].device
         # K1: all homographies up front, on the host, exactly as the reference computes them; one small upload.
@@ -131,7 +133,7 @@ class MVSNet(nn.Module):
                                                                   coherent=(s == 0))
             else:
                 cost, cells = ops.warp_corr([f[name] for f in features], rts[s], hyp, coherent=(s == 0)), None
-            logits = self.cost_regularization[s](cost, cost_cells=cells)
+            logits = self.cost_regularization[s](cost, cost_cells=cells, branch_group=branch_group)
             stage_out = self.DepthNet(logits, hyp, num_depth=self.ndepths[s], interval=interval, stage=s)
             seams = {"_cost": cost, "_logits": logits} if keep_seams else {}
             del cost, logits, cells
@@ -141,7 +143,7 @@ class MVSNet(nn.Module):
                                                                       want_f32=keep_seams)
             else:
                 cost_c, cells_c = self.cost_aggregation([f[name + "_c"] for f in features], None, hyp_c, s, rt=rts[s]), None
-            logits_c = self.cost_regularization_refine[s](cost_c, cost_cells=cells_c)
+            logits_c = self.cost_regularization_refine[s](cost_c, cost_cells=cells_c, branch_group=branch_group)
             refine_out = self.DepthNet.refine(logits_c, hyp_c, num_depth=4, interval=interval)
             if keep_seams:
                 seams.update({"_cost_c": cost_c, "_logits_c": logits_c})

@@ -562,8 +562,10 @@ class PackedRegnet:
 
 
 def regnet_forward(pack: PackedRegnet, cost: Optional[torch.Tensor], engine: Optional[str] = None,
-                   cost_cells: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """cost [B,2,D,h,w] (and / or its cell form from ``warp_corr(want_cells=True)``) -> logits [B,4,D,h,w]."""
+                   cost_cells: Optional[torch.Tensor] = None, branch_mask: int = 3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cost [B,2,D,h,w] (and / or its cell form from ``warp_corr(want_cells=True)``) -> logits [B,4,D,h,w].
+    ``branch_mask`` (bit 0 = cosR_small -> channels 0,1; bit 1 = cosR_huge -> channels 2,3) runs a subset of the two independent
+    branches and writes only their channels of ``out`` (multi-GPU branch sharding, parallel.regnet_branch_sharded)."""
     lib = N.load()
     if cost is not None:
         cost = _req(cost, "cost").contiguous()
@@ -576,13 +578,16 @@ def regnet_forward(pack: PackedRegnet, cost: Optional[torch.Tensor], engine: Opt
             raise ValueError("regnet_forward needs the fp32 cost volume unless the tensor engine gets cost_cells")
         b, d, h, w = cost_cells.shape[0], cost_cells.shape[1], cost_cells.shape[2], cost_cells.shape[3] - 1
         dev = cost_cells.device
-    logits = torch.empty(b, 4, d, h, w, device=dev, dtype=torch.float32)
+    logits = out if out is not None else torch.empty(b, 4, d, h, w, device=dev, dtype=torch.float32)
+    if logits.shape != (b, 4, d, h, w) or not logits.is_contiguous():
+        raise ValueError("regnet_forward: `out` must be a contiguous [B,4,D,h,w] tensor")
     nbytes = lib.dmvs_regnet_workspace_bytes(int(pack.refine), b, d, h, w)
     ws = torch.empty((nbytes + 3) // 4, device=dev, dtype=torch.float32)
     with _timed("regnet%s:D%d_%dx%d" % ("_refine" if pack.refine else "", d, h, w), 4 * b * 6 * d * h * w):
-        rc = lib.dmvs_regnet_forward_f32(pack.c_branches, int(pack.refine), _ptr(cost), _ptr(cost_cells), logits.data_ptr(), ws.data_ptr(),
-                                         ws.numel() * 4, b, d, h, w, _ENGINES[engine or DEFAULT_ENGINE], _stream())
-    N.check(rc, "dmvs_regnet_forward_f32")
+        rc = lib.dmvs_regnet_forward_branches_f32(pack.c_branches, int(pack.refine), _ptr(cost), _ptr(cost_cells), logits.data_ptr(),
+                                                  ws.data_ptr(), ws.numel() * 4, b, d, h, w, _ENGINES[engine or DEFAULT_ENGINE],
+                                                  int(branch_mask), _stream())
+    N.check(rc, "dmvs_regnet_forward_branches_f32")
     return logits
 
 

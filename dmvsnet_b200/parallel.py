@@ -8,7 +8,10 @@ What shards and what does not (DESIGN.md "Multi-GPU"):
   warp+corr can be split over ranks by plane range and re-assembled with a single all-gather
   (``gather_planes`` / ``warp_corr_depth_sharded``).  Exact: every plane is computed by exactly one rank with the
   same kernel, so sharded == unsharded bit for bit.
-* **R1 regularisation nets** - do NOT shard by depth (receptive field +-24 planes >= D) - replicated.
+* **R1 regularisation nets** - do NOT shard by depth (receptive field +-24 planes >= D).  Their two branches
+  (cosR_small / cosR_huge, reference module.py:343-349) are independent networks on the same input, so two ranks take one
+  each and exchange their two logit channels with one all-gather (``regnet_branch_sharded``): exact, and the single-view
+  latency mode of ``MVSNet.cascade(..., branch_group=...)``.
 
 The gather logic is device agnostic (it is exercised with gloo on CPU in tests/test_parallel_gloo.py); only
 ``warp_corr_depth_sharded`` touches the CUDA op.
@@ -74,3 +77,40 @@ def warp_corr_depth_sharded(features: Sequence[torch.Tensor], rt: torch.Tensor, 
         return full[:, :, lo:hi]
 
     return gather_planes(compute, d, group, plane_dim=2)
+
+
+def exchange_channel_halves(logits: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """``logits`` [B,4,D,h,w]: rank r (of 2) has written channels 2r, 2r+1; after the call every rank holds all four.
+    B == 1: the halves are contiguous, one in-place all-gather without staging copies; otherwise via contiguous copies."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world != 2:
+        raise ValueError("branch sharding needs a 2-rank group, got %d ranks" % world)
+    b = logits.shape[0]
+    if b == 1 and logits.is_contiguous() and logits.is_cuda:
+        flat = logits.view(2, -1)
+        dist.all_gather_into_tensor(flat, flat[rank], group=group)  # NCCL in-place form: input = output + rank * count
+        return logits
+    mine = logits[:, 2 * rank:2 * rank + 2].contiguous()
+    parts = [torch.empty_like(mine) for _ in range(2)]
+    dist.all_gather(parts, mine, group=group)
+    for r in range(2):
+        logits[:, 2 * r:2 * r + 2] = parts[r]
+    return logits
+
+
+def regnet_branch_sharded(pack, cost: Optional[torch.Tensor], cost_cells: Optional[torch.Tensor],
+                          group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """CostRegNet / CostRegNet_refine over 2 ranks: rank r runs branch r (dmvs_regnet_forward_branches_f32), one all-gather of
+    the logit halves.  Bit-identical to the unsharded call except for conv0, which the single-GPU path runs as one paired
+    launch: same arithmetic per output channel, same bits."""
+    from . import ops
+    rank = dist.get_rank(group)
+    src = cost if cost is not None else cost_cells
+    if cost is not None:
+        b, _, d, h, w = cost.shape
+    else:
+        b, d, h, w = cost_cells.shape[0], cost_cells.shape[1], cost_cells.shape[2], cost_cells.shape[3] - 1
+    logits = torch.empty(b, 4, d, h, w, device=src.device, dtype=torch.float32)
+    ops.regnet_forward(pack, cost, cost_cells=cost_cells, branch_mask=1 << rank, out=logits)
+    return exchange_channel_halves(logits, group)
+

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 13
+#define DMVS_ABI_VERSION 14
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -173,6 +173,13 @@ size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, int w);
 int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
                             float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
                             void* stream);
+
+/* The same with a branch selection: bit 0 = cosR_small (logit channels 0,1), bit 1 = cosR_huge (channels 2,3); only the selected
+ * branches run and only their logit channels are written.  The two branches are independent (module.py:343-349), so two GPUs
+ * can take one each and exchange their channel halves with one all-gather (dmvsnet_b200/parallel.py). */
+int dmvs_regnet_forward_branches_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
+                                     float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
+                                     int branch_mask, void* stream);
 
 /* single layers (exposed for unit tests and for callers that want their own schedule).
  *   x [B,Cin,Di,Hi,Wi] -> y [B,Cout,Do,Ho,Wo];  kd in {1,3} (1 = the 2-D convs of the refine net)

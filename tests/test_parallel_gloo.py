@@ -63,3 +63,26 @@ def test_depth_sharded_cost_volume_equals_unsharded(tmp_path, world, planes):
     mp.spawn(_worker, args=(world, port, planes, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def _branch_worker(rank, world, port, batch, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11)
+        full = torch.randn(batch, 4, 3, 5, 7, generator=g)       # what an unsharded regnet would return (same on every rank)
+        mine = torch.full_like(full, float("nan"))                # rank r only computes its branch: channels 2r, 2r+1
+        mine[:, 2 * rank:2 * rank + 2] = full[:, 2 * rank:2 * rank + 2]
+        got = parallel.exchange_channel_halves(mine)
+        open(os.path.join(result_dir, "rank%d" % rank), "w").write("ok" if torch.equal(got, full) else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_branch_sharded_logits_exchange(tmp_path, batch):
+    """Regularisation-net branch sharding over 2 ranks: each rank fills its two logit channels, one all-gather completes both."""
+    port = _free_port()
+    mp.spawn(_branch_worker, args=(2, port, batch, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
