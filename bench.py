@@ -353,6 +353,14 @@ def run_gpu_arm(args, cfg_name):
         roof_rows.append({"launch": k, "ms": v[0] / v[1], "alg_MB": v[2] / 1e6, "GBps": gbs, "frac": gbs / peak,
                           "in_bounds": inb.get(k)})
     achieved = w1_bytes_total / (w1_ms * 1e-3) / 1e9 if w1_ms > 0 else 0.0
+    # What actually bounds a fused bilinear gather: every sample pulls 4 corners x C floats through the SM's
+    # L1 / shared-memory data path (128 B per clock per SM), whatever HBM does.  Tags are "w1:C<c>_D<d>_<h>x<w>".
+    gather_bytes = 0.0
+    for k in w1:
+        c_, d_, hw_ = k[3:].split("_")
+        h_, w_ = hw_.split("x")
+        gather_bytes += float(h_) * float(w_) * int(d_[1:]) * (views - 1) * 4 * int(c_[1:]) * 4
+    sm_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9  # GB/s
     traffic = None
     tp = os.path.join(ROOT, "profiles", "w1_traffic.json")
     if os.path.exists(tp) and cfg_name == "dtu":
@@ -382,7 +390,11 @@ def run_gpu_arm(args, cfg_name):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "W1 = warp_corr_staged_kernel (stage-1 planes) + warp_corr_nhwc_kernel (regressed hypotheses), 6 passes / 7 launches per step pooled", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": w1_bytes_total, "ms_per_step": w1_ms},
+                         "algorithmic_bytes_per_step": w1_bytes_total, "ms_per_step": w1_ms,
+                         "on_chip": {"what": "bytes the gather moves through the SMs' L1/shared-memory data path (samples x 4 corners x C x 4 B) "
+                                             "against 148 SMs x 128 B/clk at the sampled SM clock: the floor of any fp32 gather formulation",
+                                     "bytes_per_step": gather_bytes, "peak_GBps": sm_peak, "floor_ms": gather_bytes / sm_peak / 1e6,
+                                     "frac": (gather_bytes / sm_peak / 1e6) / w1_ms if w1_ms > 0 else None}},
             "roofline_per_launch": roof_rows,
             "breakdown_ms_per_step": dict(groups, w1=w1_ms),
             "full_forward_device_ms": full_ms,
