@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ul
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 FMT_NHWC2 = 4
 FMT_NHWC2P = 5
@@ -61,6 +61,8 @@ SIGNATURES = {
     "dmvs_convert_layout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_conv3d_ch16": (c_int, [c_void_p, c_int, POINTER(ConvLayer), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_geo_consistency_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
     "dmvs_depth_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_refine_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,

@@ -1,0 +1,118 @@
+// N4: the geometric-consistency check of the depth-map fusion, the consumer of the path's output.
+//
+// Replaces reference filter/pcd.py:152-242 (reproject_with_depth_pytorch + check_geometric_consistency[_pytorch]) and the
+// accumulation of filter_depth (pcd.py:283-304): for every reference pixel and source view
+//   unproject with the reference depth -> source camera -> source pixel -> bilinear sample of the SOURCE depth map
+//   (F.grid_sample, zeros padding, align_corners=True) -> unproject with the sampled depth -> back to the reference camera ->
+//   reprojected depth and pixel -> mask = |p_reproj - p| < 1*alpha  and  |d_reproj - d| / d < 0.01*alpha,
+// fused over all S source views in one pass: the reference depth map is read once, nothing but the requested outputs is
+// written (the reference materialises ~12 [H*W]-sized temporaries per source view and copies them to the host).
+// One thread = one reference pixel; the six small matrices per source (precomputed on the host with the reference's own
+// torch calls) sit in shared memory.  fp32 throughout, dot products as FMA chains.
+#include "common.cuh"
+
+namespace dmvs {
+
+constexpr int kGeoMats = 60;  // inv(K_ref) 9 | (E_src inv(E_ref))[:3,:4] 12 | K_src 9 | inv(K_src) 9 | (E_ref inv(E_src))[:3,:4] 12 | K_ref 9
+constexpr int kGeoMaxSrc = 32;
+
+__device__ __forceinline__ void mat3(const float* m, float a, float b, float c, float& x, float& y, float& z) {
+  x = fmaf(m[2], c, fmaf(m[1], b, m[0] * a));
+  y = fmaf(m[5], c, fmaf(m[4], b, m[3] * a));
+  z = fmaf(m[8], c, fmaf(m[7], b, m[6] * a));
+}
+__device__ __forceinline__ void mat34(const float* m, float a, float b, float c, float& x, float& y, float& z) {
+  x = fmaf(m[2], c, fmaf(m[1], b, m[0] * a)) + m[3];
+  y = fmaf(m[6], c, fmaf(m[5], b, m[4] * a)) + m[7];
+  z = fmaf(m[10], c, fmaf(m[9], b, m[8] * a)) + m[11];
+}
+
+__global__ void __launch_bounds__(256) geo_consistency_kernel(const float* __restrict__ depth_ref, const float* __restrict__ depth_src,
+                                                              const float* __restrict__ mats, int S, int H, int W, float dist_th,
+                                                              float rel_th, unsigned char* __restrict__ mask,
+                                                              float* __restrict__ depth_reproj, float* __restrict__ xy_src,
+                                                              int* __restrict__ mask_sum, float* __restrict__ depth_avg) {
+  __shared__ float sm[kGeoMaxSrc * kGeoMats];
+  for (int i = threadIdx.x; i < S * kGeoMats; i += 256) sm[i] = __ldg(mats + i);
+  __syncthreads();
+  const long long hw = (long long)H * W;
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= hw) return;
+  const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
+  const float fx = (float)x, fy = (float)y;
+  const float d0 = __ldg(depth_ref + pix);
+  const float dref = (d0 == 0.0f) ? 1e-4f : d0;             // pcd.py:212: depth_ref[depth_ref == 0] = 1e-4 (before the ratio)
+  const float half_w = (float)((double)(W - 1) / 2.0), half_h = (float)((double)(H - 1) / 2.0);
+  int count = 0;
+  float dsum = 0.0f;
+  for (int s = 0; s < S; ++s) {
+    const float* m = sm + s * kGeoMats;
+    // step 1: reference pixel -> source view (pcd.py:164-172); the homogeneous pixel is scaled by the depth first
+    float X, Y, Z;
+    mat3(m, fx * d0, fy * d0, d0, X, Y, Z);
+    float Xs, Ys, Zs;
+    mat34(m + 9, X, Y, Z, Xs, Ys, Zs);
+    float kx, ky, kz;
+    mat3(m + 21, Xs, Ys, Zs, kx, ky, kz);
+    const float u = kx / kz, v = ky / kz;
+    // step 2: sample the source depth map (pcd.py:176-179; grid_sample bilinear / zeros / align_corners=True)
+    const float un = u / half_w - 1.0f, vn = v / half_h - 1.0f;
+    const float ix = (un + 1.0f) * half_w, iy = (vn + 1.0f) * half_h;
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx1 = ix - x0f, wy1 = iy - y0f, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    float sd = 0.0f;
+    const bool finite = fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f;
+    if (finite) {
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const float* ds = depth_src + (long long)s * hw;
+      const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W, ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+      const float v00 = (xa && ya) ? __ldg(ds + (long long)y0 * W + x0) : 0.0f;
+      const float v01 = (xb && ya) ? __ldg(ds + (long long)y0 * W + x0 + 1) : 0.0f;
+      const float v10 = (xa && yb) ? __ldg(ds + (long long)(y0 + 1) * W + x0) : 0.0f;
+      const float v11 = (xb && yb) ? __ldg(ds + (long long)(y0 + 1) * W + x0 + 1) : 0.0f;
+      sd = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+    } else {
+      sd = __int_as_float(0x7fc00000);  // the reference propagates NaN positions into the sample; the mask below rejects them
+    }
+    // back-projection with the sampled depth (pcd.py:186-198)
+    mat3(m + 30, u * sd, v * sd, sd, X, Y, Z);
+    float Xr, Yr, Zr;
+    mat34(m + 39, X, Y, Z, Xr, Yr, Zr);
+    float rx, ry, rz;
+    mat3(m + 51, Xr, Yr, Zr, rx, ry, rz);
+    if (rz == 0.0f) rz += 0.00001f;
+    const float xr = rx / rz, yr = ry / rz;
+    // consistency (pcd.py:209-221)
+    const float ddx = xr - fx, ddy = yr - fy;
+    const float dist = sqrtf(ddx * ddx + ddy * ddy);
+    const float rel = fabsf(Zr - dref) / dref;
+    const bool ok = (dist < dist_th) && (rel < rel_th);
+    const float dr = ok ? Zr : 0.0f;
+    if (mask) mask[(long long)s * hw + pix] = ok ? 1 : 0;
+    if (depth_reproj) depth_reproj[(long long)s * hw + pix] = dr;
+    if (xy_src) {
+      xy_src[((long long)s * 2) * hw + pix] = un;
+      xy_src[((long long)s * 2 + 1) * hw + pix] = vn;
+    }
+    count += ok ? 1 : 0;
+    dsum += dr;  // python sum(): ((0 + d_1) + d_2) + ...
+  }
+  if (mask_sum) mask_sum[pix] = count;
+  if (depth_avg) depth_avg[pix] = (dsum + dref) / (float)(count + 1);  // pcd.py:298 (the reference depth was patched in place)
+}
+
+}  // namespace dmvs
+
+extern "C" int dmvs_geo_consistency_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W,
+                                        float dist_thresh, float rel_thresh, unsigned char* mask, float* depth_reproj, float* xy_src,
+                                        int* mask_sum, float* depth_avg, void* stream) {
+  using namespace dmvs;
+  DMVS_REQUIRE(depth_ref && depth_src && mats, DMVS_ERR_BAD_POINTER, "geo_consistency: null pointer");
+  DMVS_REQUIRE(mask || depth_reproj || xy_src || mask_sum || depth_avg, DMVS_ERR_BAD_POINTER, "geo_consistency: no output requested");
+  DMVS_REQUIRE(S >= 1 && S <= kGeoMaxSrc && H >= 2 && W >= 2, DMVS_ERR_BAD_SHAPE, "geo_consistency: bad dims S=%d H=%d W=%d (S <= %d)", S, H, W,
+               kGeoMaxSrc);
+  const long long hw = (long long)H * W;
+  geo_consistency_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      depth_ref, depth_src, mats, S, H, W, dist_thresh, rel_thresh, mask, depth_reproj, xy_src, mask_sum, depth_avg);
+  return check_launch("geo_consistency");
+}

@@ -147,6 +147,20 @@ def _scene_plane():
     return n, float(n[2] * 640.0)
 
 
+def scene_depth_view(height: int, width: int, proj_full: torch.Tensor, view: int) -> torch.Tensor:
+    """Depth map [height, width] of the rendered plane as camera ``view`` of the rig sees it (z in that camera's frame)."""
+    n, c = _scene_plane()
+    k = proj_full[0, view, 1, :3, :3].double()
+    e = proj_full[0, view, 0].double()
+    rot, t = e[:3, :3], e[:3, 3]
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float64), torch.arange(width, dtype=torch.float64), indexing="ij")
+    dirs = rot.T @ torch.linalg.solve(k, torch.stack([xs, ys, torch.ones_like(xs)], 0).reshape(3, -1))
+    centre = -(rot.T @ t)
+    lam = (c - float(n @ centre)) / (n[:, None] * dirs).sum(0)
+    pts = centre[:, None] + lam * dirs
+    return (rot @ pts + t[:, None])[2].reshape(height, width).float()
+
+
 def make_scene_images(height: int, width: int, num_views: int, proj_full: torch.Tensor, seed: int = 0,
                       noise: float = 0.01) -> torch.Tensor:
     """[1, N, 3, H, W] renderings of ONE textured plane seen by the rig's cameras (``proj_full`` = the full-resolution

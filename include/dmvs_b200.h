@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 14
+#define DMVS_ABI_VERSION 15
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -240,6 +240,21 @@ int dmvs_hypotheses_first_f32(const float* depth_values, int Nd, float* hyp, flo
                               int w, int inverse, void* stream);
 int dmvs_hypotheses_next_f32(const float* last_depth, const float* interval_pixel, float* hyp, float* interval_out,
                              int B, int D, int h0, int w0, int h, int w, int inverse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * N4  geometric-consistency check of the depth-map fusion (the consumer of the path's output).
+ * Replaces reproject_with_depth_pytorch + check_geometric_consistency[_pytorch] (filter/pcd.py:152-242) and the accumulation
+ * of filter_depth (pcd.py:283-304), fused over the S source views of one reference view.
+ *   depth_ref [H,W], depth_src [S,H,W] (all views at the same resolution, as the reference requires)
+ *   mats [S,60]: per source, row-major  inv(K_ref) 3x3 | (E_src @ inv(E_ref))[:3,:4] | K_src 3x3 | inv(K_src) 3x3 |
+ *                (E_ref @ inv(E_src))[:3,:4] | K_ref 3x3  - computed by the caller with the reference's own calls
+ *   dist_thresh, rel_thresh: 1*alpha and 0.01*alpha (pcd.py:219)
+ *   outputs, each nullable: mask [S,H,W] (0/1), depth_reproj [S,H,W] (0 where the mask is 0), xy_src [S,2,H,W] (the NORMALISED
+ *   source coordinates the reference returns), mask_sum [H,W] int32, depth_avg [H,W] = (sum_s depth_reproj + depth_ref) /
+ *   (mask_sum + 1) with reference zeros replaced by 1e-4 like pcd.py:212.  S <= 32. */
+int dmvs_geo_consistency_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W, float dist_thresh,
+                             float rel_thresh, unsigned char* mask, float* depth_reproj, float* xy_src, int* mask_sum, float* depth_avg,
+                             void* stream);
 
 #ifdef __cplusplus
 }
