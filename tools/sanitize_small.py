@@ -26,4 +26,11 @@ with torch.no_grad():
         ref = c if ref is None else ref
         assert float((c - ref).abs().max()) < 1e-4
     torch.cuda.synchronize()
-print("ok", float(out["depth"].mean()), float(host["depth"].mean()))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from make_golden_fusion import fusion_case
+    from dmvsnet_b200 import fusion
+    depths, ks, es = fusion_case(40, 56, 4, seed=3)
+    fz = fusion.geometric_filter(depths[0].cuda(), ks[0], es[0], [depths[v].cuda() for v in (1, 2, 3)], [ks[v] for v in (1, 2, 3)],
+                                 [es[v] for v in (1, 2, 3)], thres_view=2, per_source=True)
+    torch.cuda.synchronize()
+print("ok", float(out["depth"].mean()), float(host["depth"].mean()), int(fz["geo_mask_sum"].sum()))
