@@ -252,3 +252,22 @@ def test_space_to_depth_weight_transform():
     xs = xs.reshape(b, 8, 4, h, wd).permute(0, 2, 1, 3, 4).reshape(b, 32, h, wd)
     got = F.conv2d(xs, ops.s2d_weight(w), stride=1, padding=1)
     assert float((got - want).abs().max()) < 1e-10
+
+
+def test_fusion_source_matrices_layout():
+    """fusion.source_matrices: the [60] block the consistency kernel reads = the six matrices of filter/pcd.py:164-191."""
+    from dmvsnet_b200 import fusion, synthetic as syn
+    proj = syn.make_proj_matrices(64, 96, 3, 1, num_stages=3)["stage3"]
+    k0, e0, k1, e1 = proj[0, 0, 1, :3, :3], proj[0, 0, 0], proj[0, 2, 1, :3, :3], proj[0, 2, 0]
+    m = fusion.source_matrices(k0, e0, k1.numpy(), e1.numpy())     # numpy and torch inputs both accepted
+    assert m.shape == (60,) and m.dtype == torch.float32
+    t1 = e1 @ torch.linalg.inv(e0)
+    t2 = e0 @ torch.linalg.inv(e1)
+    assert torch.equal(m[:9].view(3, 3), torch.linalg.inv(k0)) and torch.equal(m[9:21].view(3, 4), t1[:3])
+    assert torch.equal(m[21:30].view(3, 3), k1) and torch.equal(m[30:39].view(3, 3), torch.linalg.inv(k1))
+    assert torch.equal(m[39:51].view(3, 4), t2[:3]) and torch.equal(m[51:60].view(3, 3), k0)
+    # a point of the reference view at depth d maps into the source view and back onto itself
+    x = torch.tensor([40.0, 25.0, 1.0]) * 650.0
+    p_src = t1[:3, :3] @ (torch.linalg.inv(k0) @ x) + t1[:3, 3]
+    back = t2[:3, :3] @ p_src + t2[:3, 3]
+    assert float(((k0 @ back) / (k0 @ back)[2] - torch.tensor([40.0, 25.0, 1.0])).abs().max()) < 1e-2
