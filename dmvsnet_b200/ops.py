@@ -208,6 +208,68 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     return (out, cells) if want_cells else out
 
 
+def warp_corr_backward(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor, grad_cost: torch.Tensor) -> List[torch.Tensor]:
+    """Gradients of ``warp_corr``'s cost volume w.r.t. every feature map (reference view first): N x [B,C,h,w] tensors in
+    channels_last memory (dmvs_warp_corr_backward_f32).  What autograd would record for networks/mvsnet.py:137-146 and
+    module.py:247-249; the sampling grid carries no gradient in the reference (module.py:222), so neither do ``hyp`` / ``rt``."""
+    lib = N.load()
+    ref = _req(features[0], "features[0]")
+    b, c, h, w = ref.shape
+    n_src = len(features) - 1
+    if n_src < 1 or n_src > N.MAX_SRC:
+        raise ValueError("need 1..%d source views, got %d" % (N.MAX_SRC, n_src))
+    maps = []
+    for i, f in enumerate(features):
+        f = _req(f, "features[%d]" % i).detach()
+        if f.shape != ref.shape:
+            raise ValueError("features[%d] has shape %s, expected %s" % (i, tuple(f.shape), tuple(ref.shape)))
+        maps.append(f if (_nhwc_strides(f) is not None and not is_pairs(f)) else features_nhwc(f))
+    st = [_nhwc_strides(f) for f in maps[1:]]
+    if len(set(st)) != 1:  # the sources share one stride pair in the ABI
+        maps[1:] = [f if x == (c, h * w * c) else features_nhwc(f) for f, x in zip(maps[1:], st)]
+        st = [(c, h * w * c)] * n_src
+    ref_ps, ref_bs = _nhwc_strides(maps[0])
+    src_ps, src_bs = st[0]
+    hyp = _req(hyp, "hyp").contiguous()
+    rt = _req(rt, "rt").contiguous()
+    d = hyp.shape[1]
+    grad_cost = _req(grad_cost, "grad_cost").contiguous()
+    if hyp.shape != (b, d, h, w) or rt.shape != (b, n_src, 12) or grad_cost.shape != (b, 2, d, h, w):
+        raise ValueError("hyp %s / rt %s / grad_cost %s do not match features %s"
+                         % (tuple(hyp.shape), tuple(rt.shape), tuple(grad_cost.shape), tuple(ref.shape)))
+    grads = [torch.empty(b, h, w, c, device=ref.device, dtype=torch.float32) for _ in range(n_src + 1)]
+    src_ptrs = (ctypes.c_void_p * n_src)(*[f.data_ptr() for f in maps[1:]])
+    gsrc_ptrs = (ctypes.c_void_p * n_src)(*[g.data_ptr() for g in grads[1:]])
+    # algorithmic bytes: features and their gradients once each, hypotheses and the cost gradient once
+    nbytes = 4 * b * h * w * (2 * (n_src + 1) * c + 3 * d)
+    with _timed("w1_bwd:C%d_D%d_%dx%d" % (c, d, h, w), nbytes):
+        rc = lib.dmvs_warp_corr_backward_f32(maps[0].data_ptr(), ref_bs, ref_ps, src_ptrs, src_bs, src_ps, n_src, rt.data_ptr(),
+                                             hyp.data_ptr(), grad_cost.data_ptr(), grads[0].data_ptr(), gsrc_ptrs, b, c, d, h, w, _stream())
+    N.check(rc, "dmvs_warp_corr_backward_f32")
+    return [g.permute(0, 3, 1, 2) for g in grads]
+
+
+class _WarpCorrFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rt, hyp, layout, coherent, *features):
+        ctx.save_for_backward(rt, hyp, *features)
+        return warp_corr([f.detach() for f in features], rt, hyp, layout=layout, coherent=coherent)
+
+    @staticmethod
+    def backward(ctx, grad_cost):
+        rt, hyp, *features = ctx.saved_tensors
+        grads = warp_corr_backward(features, rt, hyp, grad_cost)
+        need = ctx.needs_input_grad[4:]
+        return (None, None, None, None) + tuple(g if n else None for g, n in zip(grads, need))
+
+
+def warp_corr_autograd(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor, layout: Optional[str] = None,
+                       coherent: bool = False) -> torch.Tensor:
+    """Differentiable W1: ``warp_corr`` forward, ``warp_corr_backward`` recorded for autograd (gradients to the feature maps
+    only, like the reference: module.py:222 builds the grid under no_grad, mvsnet.py:221 detaches the depth between stages)."""
+    return _WarpCorrFunction.apply(rt, hyp.detach(), layout, coherent, *features)
+
+
 # ----------------------------------------------------------------------------- N1 (FeatureNet)
 def _fold_bn(bn, eps: float):
     gamma, beta, mean, var = [t.detach().to(torch.float32) for t in bn]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 15
+#define DMVS_ABI_VERSION 16
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -89,6 +89,20 @@ int dmvs_warp_corr_staged_f32(const float* ref, long long ref_bstride, int ref_p
                               long long src_bstride, int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost,
                               void* cost_cells, void* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
 size_t dmvs_warp_corr_flag_bytes(int B, int D, int h, int w);
+
+/* W1 backward (the W1 part): gradients of dmvs_warp_corr_*'s cost volume w.r.t. the feature maps -
+ * what autograd records for reference networks/mvsnet.py:137-146 (product, group mean, sum over views) and
+ * networks/module.py:247-249 (F.grid_sample).  The sampling grid is built under torch.no_grad() in the reference
+ * (module.py:222): no gradient w.r.t. hyp / rt.
+ *   ref, src[i]   the forward's feature maps, channel-last ([B,h,w,C], `*_pixstride` floats between pixels, >= C, multiple of 4)
+ *   grad_cost     [B,2,D,h,w]
+ *   grad_ref, grad_src[i]   dense channel-last [B,h,w,C], OVERWRITTEN (zeroed, then accumulated with 16-byte vector
+ *                 reductions; summation order across samples is not fixed -> equal to fp32 rounding, not bit for bit)
+ * Samples whose position is not finite contribute nothing.  C in {8,16,32}. */
+int dmvs_warp_corr_backward_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
+                                long long src_bstride, int src_pixstride, int n_src, const float* rt, const float* hyp,
+                                const float* grad_cost, float* grad_ref, float* const* grad_src, int B, int C, int D, int h, int w,
+                                void* stream);
 
 /* NCHW -> channel-last repack of one feature map for the call above: x [B,C,h,w] (batch stride x_bstride) -> y [B,h,w,C]
  * dense.  Replaces nothing in the reference (it is `tensor.permute(0,2,3,1).contiguous()`); callers whose FeatureNet

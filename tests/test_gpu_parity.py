@@ -162,6 +162,70 @@ def test_warp_corr_pair_layout_sources(c, d):
     assert rel_linf(ops.warp_corr(paired, rt, hyp, layout="nchw"), want) < 2e-6
 
 
+# ------------------------------------------------------------------------------------------ W1 backward (N2)
+@pytest.mark.parametrize("c,d,n,b,h,w", [(32, 6, 3, 1, 37, 50), (16, 9, 4, 2, 24, 40), (8, 8, 3, 1, 64, 97), (8, 3, 7, 1, 40, 33),
+                                          (16, 1, 2, 1, 9, 130)])
+def test_warp_corr_backward_vs_oracle_autograd(c, d, n, b, h, w):
+    """dmvs_warp_corr_backward_f32 against autograd through the oracle (F.grid_sample backward on the CPU): gradients
+    w.r.t. the reference and every source feature map.  Tolerance 1e-5 of the largest gradient entry: the sums over
+    samples are taken in a different (and, for the scatter, unordered) sequence."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(c * 100 + d)
+    feats = [torch.randn(b, c, h, w, generator=g, requires_grad=True) for _ in range(n)]
+    proj = syn.make_proj_matrices(max(h, 8) * 4, max(w, 8) * 4, n, b, num_stages=1)["stage1"]
+    hyp = 425 + 500 * torch.rand(b, d, h, w, generator=g)
+    gout = torch.randn(b, 2, d, h, w, generator=g)
+    O.warp_corr(feats, proj, hyp).backward(gout)
+    want = [f.grad for f in feats]
+    dev = [cuda(f.detach()).requires_grad_(True) for f in feats]
+    rt = cuda(ops.relative_projections(proj))
+    cost = ops.warp_corr_autograd(dev, rt, cuda(hyp))
+    assert torch.equal(cost.detach(), ops.warp_corr([f.detach() for f in dev], rt, cuda(hyp)))
+    cost.backward(cuda(gout))
+    for i in range(n):
+        assert dev[i].grad.shape == want[i].shape
+        assert rel_linf(dev[i].grad, want[i]) < 1e-5, (i, rel_linf(dev[i].grad, want[i]))
+
+
+def test_warp_corr_backward_layouts_padding_and_partial_grads():
+    """Channel-last / channel-sliced inputs give the same gradients as dense NCHW ones; samples in the zero padding carry
+    no gradient; only the inputs that require a gradient receive one; the adjoint identity <g, W1(f)> = <dW1^T g, f> / 1
+    holds for the bilinear form (W1 is linear in the sources for a fixed reference map)."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(77)
+    b, c, h, w, d, n = 2, 8, 21, 52, 5, 3
+    both = [cuda(torch.randn(b, 2 * c, h, w, generator=g)) for _ in range(n)]
+    proj = syn.make_proj_matrices(h * 4, w * 4, n, b, num_stages=1)["stage1"]
+    rt = cuda(ops.relative_projections(proj))
+    hyp = cuda(425 + 500 * torch.rand(b, d, h, w, generator=g))
+    gout = cuda(torch.randn(b, 2, d, h, w, generator=g))
+    both_cl = [t.contiguous(memory_format=torch.channels_last) for t in both]
+    views = [t.split([c, c], 1)[1] for t in both]
+    views_cl = [t.split([c, c], 1)[1] for t in both_cl]
+    dense = ops.warp_corr_backward([v.contiguous() for v in views], rt, hyp, gout)
+    for other in (ops.warp_corr_backward(views, rt, hyp, gout), ops.warp_corr_backward(views_cl, rt, hyp, gout)):
+        for a, o in zip(dense, other):
+            assert rel_linf(o, a) < 1e-5
+    # linear in the sources: <gout, cost> == sum_s <grad_src_s, src_s>, and == <grad_ref, ref>
+    cost = ops.warp_corr(views, rt, hyp)
+    lhs = float((cost.double() * gout.double()).sum())
+    via_src = sum(float((gs.double() * v.double()).sum()) for gs, v in zip(dense[1:], views[1:]))
+    via_ref = float((dense[0].double() * views[0].double()).sum())
+    scale = float((cost.double() * gout.double()).abs().sum())
+    assert abs(lhs - via_src) < 1e-5 * scale and abs(lhs - via_ref) < 1e-5 * scale
+    # a translation that throws every sample far outside the source images (zero padding) -> exact zero gradients
+    far = rt.clone()
+    far[:, :, 9] = 1e7
+    assert float(ops.warp_corr(views, far, hyp).abs().max()) == 0.0
+    zero = ops.warp_corr_backward(views, far, hyp, gout)
+    assert all(float(z.abs().max()) == 0.0 for z in zero)
+    # partial requires_grad
+    leaf = [v.contiguous().requires_grad_(i != 1) for i, v in enumerate(views)]
+    ops.warp_corr_autograd(leaf, rt, hyp).backward(gout)
+    assert leaf[1].grad is None and leaf[0].grad is not None and leaf[2].grad is not None
+    assert rel_linf(leaf[2].grad, dense[2]) < 1e-5
+
+
 def _lib_launches():
     from dmvsnet_b200 import _native
     return _native.launch_count()

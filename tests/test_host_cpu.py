@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for name in declared:
         assert hasattr(native_lib, name), "libdmvs_b200.so does not export %s" % name
     assert sorted(_native.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 15
+    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 16
     assert native_lib.dmvs_launch_count() == 0
 
 
@@ -42,6 +42,8 @@ def test_bad_arguments_return_errors_not_crashes(native_lib):
     rc = native_lib.dmvs_warp_corr_staged_f32(None, 0, 0, None, 0, 8, 0, 1, None, None, None, None, None, 1, 8, 4, 8, 8, 0, 4, None)
     assert rc == -2 and b"null" in native_lib.dmvs_last_error()
     assert native_lib.dmvs_warp_corr_flag_bytes(2, 48, 296, 400) == 2 * 37 * 13 * 48
+    rc = native_lib.dmvs_warp_corr_backward_f32(None, 0, 8, None, 0, 8, 1, None, None, None, None, None, 1, 8, 4, 8, 8, None)
+    assert rc == -2 and b"null" in native_lib.dmvs_last_error()
     rc = native_lib.dmvs_features_nhwc_f32(None, 0, None, 1, 8, 8, 8, None)
     assert rc == -2 and b"null" in native_lib.dmvs_last_error()
     assert native_lib.dmvs_regnet_workspace_bytes(0, 1, 8, 16, 16) > 0

@@ -10,6 +10,9 @@ after 3 warm-ups; the feature maps of one launch set (>= 150 MB) exceed nothing 
 256 MB scratch write flushes L2 between launches when --flush is given.
 
     python tools/bench_w1.py [--config dtu] [--layouts nhwc,nchw] [--kinds smooth,noise] [--flush]
+
+The pseudo-layout "bwd" times the backward kernel (dmvs_warp_corr_backward_f32, gradients to all feature maps) on the
+same launches; "--config train" is the reference's 640x512 training crop.
 """
 import argparse
 import json
@@ -23,7 +26,7 @@ import torch  # noqa: E402
 from dmvsnet_b200 import ops, synthetic as syn  # noqa: E402
 
 CONFIGS = {"dtu": (1184, 1600, 5, [48, 32, 8]), "bmvs": (576, 768, 7, [48, 32, 8]), "tnt": (1056, 1920, 11, [48, 32, 8]),
-           "small": (256, 320, 5, [48, 32, 8])}
+           "small": (256, 320, 5, [48, 32, 8]), "train": (512, 640, 5, [48, 32, 8])}  # train: the reference's DTU training crop
 
 
 def depth_map(kind, h, w, g, dev):
@@ -79,21 +82,27 @@ def main():
             hyp_c = torch.stack([last + step * (k - 1.5) for k in range(4)], 1).contiguous()
             for name, hy in (("main", hyp), ("refine", hyp_c)):
                 d = hy.shape[1]
-                alg = 4 * h * w * (views * c + 3 * d)
                 for layout in args.layouts.split(","):
+                    alg = 4 * h * w * (views * c + 3 * d)
                     fs = feats if layout == "nchw" else feats_cl
+                    run = lambda: ops.warp_corr(fs, rt, hy, layout=layout)  # noqa: E731
+                    if layout == "bwd":
+                        fs_all = [ops.features_nhwc(feats[0])] + feats_cl[1:]
+                        gout = torch.randn(1, 2, d, h, w, generator=g).to(dev)
+                        alg = 4 * h * w * (2 * views * c + 3 * d)
+                        run = lambda: ops.warp_corr_backward(fs_all, rt, hy, gout)  # noqa: E731
                     if args.once:
-                        ops.warp_corr(fs, rt, hy, layout=layout)
+                        run()
                         continue
                     for _ in range(3):
-                        out = ops.warp_corr(fs, rt, hy, layout=layout)
+                        out = run()
                     ms = 0.0
                     for _ in range(args.iters):
                         if scratch is not None:
                             scratch.zero_()
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                        out = ops.warp_corr(fs, rt, hy, layout=layout)
+                        out = run()
                         e1.record()
                         torch.cuda.synchronize()
                         ms += e0.elapsed_time(e1)
@@ -123,7 +132,7 @@ def main():
         for layout in args.layouts.split(","):
             sel = [r for r in rows if r[2] == kind and r[3] == layout]
             ms = sum(r[8] for r in sel)
-            alg = sum(4 * r[6] * r[7] * (views * r[4] + 3 * r[5]) for r in sel)
+            alg = sum(r[9] * r[8] * 1e6 for r in sel)
             print("TOTAL %-6s %-4s  %7.3f ms per step  %7.1f GB/s pooled  %.3f of HBM peak" % (kind, layout, ms, alg / ms / 1e6, alg / ms / 1e6 / peak))
 
 
