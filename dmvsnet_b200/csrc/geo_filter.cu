@@ -101,6 +101,113 @@ __global__ void __launch_bounds__(256) geo_consistency_kernel(const float* __res
   if (depth_avg) depth_avg[pix] = (dsum + dref) / (float)(count + 1);  // pcd.py:298 (the reference depth was patched in place)
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Dynamic-threshold variant: reference filter/dypcd_tanks.py:61-98 (reproject_with_depth, the numpy + cv2.remap form),
+// :164-184 (check_geometric_consistency: nine threshold levels i = 2..10, dist < i*dist_base and rel < i*rel_diff_base) and the
+// accumulation of filter_depth (:237-270).  What differs from the kernel above, because the reference's numpy code differs:
+//   * the projective chain runs in float64 (numpy promotes int64 pixel grids x float32 depths to float64); the matrices stay the
+//     float32 values numpy computed, promoted exactly
+//   * the source depth is sampled like cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0): coordinates rounded to 1/32 pixel
+//     (cvRound(x * 32), ties to even), the four weights products of the 1-D float taps, float accumulation
+//   * the pixel distance is float64 (float32 coordinates minus an int64 grid), the relative depth difference float32, zeros of the
+//     reference depth are NOT patched (0/0 and x/0 fail every comparison)
+//   * a (pixel, source) pair gets the smallest level it passes; masks[i-2] = level <= i; the reprojected depth is kept where level
+//     10 passes; the fused mask is  OR_{i=2..S} (#sources passing level i) >= i  and the average is taken in float64.
+__device__ __forceinline__ void dmat3(const float* m, double a, double b, double c, double& x, double& y, double& z) {
+  x = fma((double)m[2], c, fma((double)m[1], b, (double)m[0] * a));
+  y = fma((double)m[5], c, fma((double)m[4], b, (double)m[3] * a));
+  z = fma((double)m[8], c, fma((double)m[7], b, (double)m[6] * a));
+}
+__device__ __forceinline__ void dmat34(const float* m, double a, double b, double c, double& x, double& y, double& z) {
+  x = fma((double)m[2], c, fma((double)m[1], b, (double)m[0] * a)) + (double)m[3];
+  y = fma((double)m[6], c, fma((double)m[5], b, (double)m[4] * a)) + (double)m[7];
+  z = fma((double)m[10], c, fma((double)m[9], b, (double)m[8] * a)) + (double)m[11];
+}
+
+// cv2.remap, INTER_LINEAR, BORDER_CONSTANT(0) on a float32 image: fixed-point coordinates with 5 fractional bits
+__device__ __forceinline__ float remap_linear_q5(const float* __restrict__ img, int H, int W, float xs, float ys) {
+  if (!(fabsf(xs) < 3.0e7f) || !(fabsf(ys) < 3.0e7f)) return 0.0f;  // NaN / far outside (cvRound saturates): all four taps are border
+  const int sx = __float2int_rn(xs * 32.0f), sy = __float2int_rn(ys * 32.0f);
+  const int x0 = sx >> 5, y0 = sy >> 5;
+  const float ax = (float)(sx & 31) * (1.0f / 32.0f), ay = (float)(sy & 31) * (1.0f / 32.0f);
+  const float tx0 = 1.0f - ax, ty0 = 1.0f - ay;
+  const bool xa = x0 >= 0 && x0 < W, xb = x0 + 1 >= 0 && x0 + 1 < W, ya = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+  const float v00 = (xa && ya) ? __ldg(img + (long long)y0 * W + x0) : 0.0f;
+  const float v01 = (xb && ya) ? __ldg(img + (long long)y0 * W + x0 + 1) : 0.0f;
+  const float v10 = (xa && yb) ? __ldg(img + (long long)(y0 + 1) * W + x0) : 0.0f;
+  const float v11 = (xb && yb) ? __ldg(img + (long long)(y0 + 1) * W + x0 + 1) : 0.0f;
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, ty0 * tx0), __fmul_rn(v01, ty0 * ax)), __fmul_rn(v10, ay * tx0)), __fmul_rn(v11, ay * ax));
+}
+
+__global__ void __launch_bounds__(256) geo_consistency_dynamic_kernel(const float* __restrict__ depth_ref, const float* __restrict__ depth_src,
+                                                                      const float* __restrict__ mats, int S, int H, int W, double dist_base,
+                                                                      double rel_base, unsigned char* __restrict__ level,
+                                                                      float* __restrict__ depth_reproj, float* __restrict__ xy_src,
+                                                                      int* __restrict__ mask_sum, unsigned char* __restrict__ geo_mask,
+                                                                      float* __restrict__ depth_avg) {
+  __shared__ float sm[kGeoMaxSrc * kGeoMats];
+  for (int i = threadIdx.x; i < S * kGeoMats; i += 256) sm[i] = __ldg(mats + i);
+  __syncthreads();
+  const long long hw = (long long)H * W;
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= hw) return;
+  const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
+  const float d0 = __ldg(depth_ref + pix);
+  const double dx = (double)x, dy = (double)y, dd = (double)d0;
+  int cnt[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) cnt[i] = 0;
+  float dsum = 0.0f;
+  for (int s = 0; s < S; ++s) {
+    const float* m = sm + s * kGeoMats;
+    double X, Y, Z, Xs, Ys, Zs, kx, ky, kz;
+    dmat3(m, dx * dd, dy * dd, dd, X, Y, Z);            // :66-67
+    dmat34(m + 9, X, Y, Z, Xs, Ys, Zs);                  // :69-70
+    dmat3(m + 21, Xs, Ys, Zs, kx, ky, kz);               // :72
+    const double u = kx / kz, v = ky / kz;               // :73
+    const float xs = (float)u, ys = (float)v;            // :77-78
+    const float sd = remap_linear_q5(depth_src + (long long)s * hw, H, W, xs, ys);  // :79
+    const double sdd = (double)sd;
+    dmat3(m + 30, u * sdd, v * sdd, sdd, X, Y, Z);       // :84-85
+    double Xr, Yr, Zr, rx, ry, rz;
+    dmat34(m + 39, X, Y, Z, Xr, Yr, Zr);                 // :87-88
+    dmat3(m + 51, Xr, Yr, Zr, rx, ry, rz);               // :91
+    if (rz == 0.0) rz += 0.00001;
+    const float drep = (float)Zr, xr = (float)(rx / rz), yr = (float)(ry / rz);  // :90, :94-95
+    // :170-175
+    const double ex = (double)xr - dx, ey = (double)yr - dy;
+    const double dist = sqrt(ex * ex + ey * ey);
+    const float rel = __fdiv_rn(fabsf(__fsub_rn(drep, d0)), d0);
+    int lv = 0;
+#pragma unroll
+    for (int i = 10; i >= 2; --i) {
+      const bool ok = (dist < (double)i * dist_base) && (rel < (float)((double)i * rel_base));
+      if (ok) lv = i;
+      cnt[i - 2] += ok ? 1 : 0;
+    }
+    // thresholds grow with i, so the levels that pass form a suffix i >= lv and cnt[i-2] counts exactly masks[i-2]
+    const bool ok10 = lv != 0;
+    const float dr = ok10 ? drep : 0.0f;
+    if (level) level[(long long)s * hw + pix] = (unsigned char)lv;
+    if (depth_reproj) depth_reproj[(long long)s * hw + pix] = dr;
+    if (xy_src) {
+      xy_src[((long long)s * 2) * hw + pix] = xs;
+      xy_src[((long long)s * 2 + 1) * hw + pix] = ys;
+    }
+    dsum = __fadd_rn(dsum, dr);
+  }
+  const int sum10 = cnt[8];
+  if (mask_sum) mask_sum[pix] = sum10;
+  if (geo_mask) {
+    bool g = sum10 >= S + 1;  // :262 (dy_range = S + 1: never true, kept for fidelity)
+#pragma unroll
+    for (int i = 2; i <= 10; ++i)
+      if (i <= S) g = g || (cnt[i - 2] >= i);
+    geo_mask[pix] = g ? 1 : 0;
+  }
+  if (depth_avg) depth_avg[pix] = (float)((double)__fadd_rn(dsum, d0) / (double)(sum10 + 1));  // :256, float32 / int32 -> float64 in numpy
+}
+
 }  // namespace dmvs
 
 extern "C" int dmvs_geo_consistency_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W,
@@ -115,4 +222,21 @@ extern "C" int dmvs_geo_consistency_f32(const float* depth_ref, const float* dep
   geo_consistency_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       depth_ref, depth_src, mats, S, H, W, dist_thresh, rel_thresh, mask, depth_reproj, xy_src, mask_sum, depth_avg);
   return check_launch("geo_consistency");
+}
+
+extern "C" int dmvs_geo_consistency_dynamic_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W,
+                                                double dist_base, double rel_diff_base, unsigned char* level, float* depth_reproj,
+                                                float* xy_src, int* mask_sum, unsigned char* geo_mask, float* depth_avg, void* stream) {
+  using namespace dmvs;
+  DMVS_REQUIRE(depth_ref && depth_src && mats, DMVS_ERR_BAD_POINTER, "geo_consistency_dynamic: null pointer");
+  DMVS_REQUIRE(level || depth_reproj || xy_src || mask_sum || geo_mask || depth_avg, DMVS_ERR_BAD_POINTER,
+               "geo_consistency_dynamic: no output requested");
+  DMVS_REQUIRE(S >= 1 && S <= kGeoMaxSrc && H >= 2 && W >= 2, DMVS_ERR_BAD_SHAPE, "geo_consistency_dynamic: bad dims S=%d H=%d W=%d (S <= %d)",
+               S, H, W, kGeoMaxSrc);
+  // the reference indexes its nine masks with i - 2 for i in [2, S]: more than 10 source views raise IndexError there
+  DMVS_REQUIRE(!geo_mask || S <= 10, DMVS_ERR_BAD_SHAPE, "geo_consistency_dynamic: the fused mask is defined for at most 10 source views, got %d", S);
+  const long long hw = (long long)H * W;
+  geo_consistency_dynamic_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      depth_ref, depth_src, mats, S, H, W, dist_base, rel_diff_base, level, depth_reproj, xy_src, mask_sum, geo_mask, depth_avg);
+  return check_launch("geo_consistency_dynamic");
 }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 16
+#define DMVS_ABI_VERSION 17
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -269,6 +269,20 @@ int dmvs_hypotheses_next_f32(const float* last_depth, const float* interval_pixe
 int dmvs_geo_consistency_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W, float dist_thresh,
                              float rel_thresh, unsigned char* mask, float* depth_reproj, float* xy_src, int* mask_sum, float* depth_avg,
                              void* stream);
+
+/* N4, dynamic-threshold variant.  Replaces reproject_with_depth + check_geometric_consistency of filter/dypcd_tanks.py:61-98,
+ * 164-184 and the accumulation of its filter_depth (:237-270).  Same inputs; `mats` are the float32 matrices numpy computes
+ * (np.linalg.inv / np.matmul on float32).  The projective chain runs in float64 and the source depth is sampled like
+ * cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) - 1/32-pixel fixed-point coordinates - because that is what the reference's numpy
+ * code does.  Nine threshold levels i = 2..10: dist < i * dist_base (float64) and rel < i * rel_diff_base (float32).
+ *   outputs, each nullable: level [S,H,W] uint8 = the smallest level the pair passes, 0 = none (masks[i-2] = 0 < level <= i);
+ *   depth_reproj [S,H,W] (0 where level 10 fails); xy_src [S,2,H,W] = the float32 PIXEL coordinates in the source view;
+ *   mask_sum [H,W] int32 = number of sources passing level 10; geo_mask [H,W] 0/1 = OR_{i=2..S} (#sources passing level i) >= i
+ *   (S <= 10 when requested: the reference raises IndexError beyond); depth_avg [H,W] = float32((sum_s depth_reproj + depth_ref)
+ *   / float64(mask_sum + 1)); zeros of depth_ref are not patched in this variant. */
+int dmvs_geo_consistency_dynamic_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W,
+                                     double dist_base, double rel_diff_base, unsigned char* level, float* depth_reproj, float* xy_src,
+                                     int* mask_sum, unsigned char* geo_mask, float* depth_avg, void* stream);
 
 #ifdef __cplusplus
 }

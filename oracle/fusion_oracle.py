@@ -65,3 +65,68 @@ def geometric_filter(depth_ref: torch.Tensor, k_ref, e_ref, depth_srcs: Sequence
     depth_avg = (sum(all_depth) + depth_ref) / (geo_mask_sum + 1)                                              # :298
     return {"geo_mask_sum": geo_mask_sum, "depth_est_averaged": depth_avg, "geo_mask": geo_mask_sum >= thres_view,
             "masks": torch.stack(masks), "depth_reprojected": torch.stack(all_depth), "x2d_src": torch.stack(xs), "y2d_src": torch.stack(ys)}
+
+
+# ----------------------------------------------------------------------------- dynamic thresholds (filter/dypcd_tanks.py)
+def reproject_with_depth_numpy(depth_ref, k_ref, e_ref, depth_src, k_src, e_src):
+    """dypcd_tanks.py:61-98: numpy float32 inputs; int64 pixel grids promote the chain to float64; cv2.remap samples the source."""
+    import cv2
+    import numpy as np
+    height, width = depth_ref.shape
+    x_ref, y_ref = np.meshgrid(np.arange(0, width), np.arange(0, height))                                       # :63
+    x_ref, y_ref = x_ref.reshape([-1]), y_ref.reshape([-1])
+    xyz_ref = np.matmul(np.linalg.inv(k_ref), np.vstack((x_ref, y_ref, np.ones_like(x_ref))) * depth_ref.reshape([-1]))   # :66
+    xyz_src = np.matmul(np.matmul(e_src, np.linalg.inv(e_ref)), np.vstack((xyz_ref, np.ones_like(x_ref))))[:3]            # :69
+    k_xyz_src = np.matmul(k_src, xyz_src)
+    xy_src = k_xyz_src[:2] / k_xyz_src[2:3]                                                                     # :73
+    x_src = xy_src[0].reshape([height, width]).astype(np.float32)
+    y_src = xy_src[1].reshape([height, width]).astype(np.float32)
+    sampled = cv2.remap(depth_src, x_src, y_src, interpolation=cv2.INTER_LINEAR)                                # :79
+    xyz_src = np.matmul(np.linalg.inv(k_src), np.vstack((xy_src, np.ones_like(x_ref))) * sampled.reshape([-1]))           # :84
+    xyz_rep = np.matmul(np.matmul(e_ref, np.linalg.inv(e_src)), np.vstack((xyz_src, np.ones_like(x_ref))))[:3]            # :87
+    depth_rep = xyz_rep[2].reshape([height, width]).astype(np.float32)
+    k_xyz_rep = np.matmul(k_ref, xyz_rep)
+    k_xyz_rep[2:3][k_xyz_rep[2:3] == 0] += 0.00001
+    xy_rep = k_xyz_rep[:2] / k_xyz_rep[2:3]
+    return (depth_rep, xy_rep[0].reshape([height, width]).astype(np.float32), xy_rep[1].reshape([height, width]).astype(np.float32),
+            x_src, y_src)
+
+
+def check_geometric_consistency_dynamic(dist_base, rel_diff_base, depth_ref, k_ref, e_ref, depth_src, k_src, e_src):
+    """dypcd_tanks.py:164-184: nine levels i = 2..10; returns (masks, mask, depth_reprojected, x2d_src, y2d_src)."""
+    import numpy as np
+    height, width = depth_ref.shape
+    x_ref, y_ref = np.meshgrid(np.arange(0, width), np.arange(0, height))
+    depth_rep, x_rep, y_rep, x_src, y_src = reproject_with_depth_numpy(depth_ref, k_ref, e_ref, depth_src, k_src, e_src)
+    dist = np.sqrt((x_rep - x_ref) ** 2 + (y_rep - y_ref) ** 2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(depth_rep - depth_ref) / depth_ref
+        masks = [np.logical_and(dist < i * dist_base, rel < i * rel_diff_base) for i in range(2, 11)]
+    mask = masks[-1]
+    depth_rep[~mask] = 0
+    return masks, mask, depth_rep, x_src, y_src
+
+
+def geometric_filter_dynamic(dist_base, rel_diff_base, depth_ref, k_ref, e_ref, depth_srcs, k_srcs, e_srcs):
+    """The per-reference-view loop of dypcd's filter_depth, dypcd_tanks.py:237-270."""
+    import numpy as np
+    geo_mask_sum = 0
+    dy_range = len(depth_srcs) + 1
+    geo_mask_sums = [0] * (dy_range - 2)
+    all_depth, levels = [], []
+    for d, k, e in zip(depth_srcs, k_srcs, e_srcs):
+        masks, mask, depth_rep, x_src, y_src = check_geometric_consistency_dynamic(dist_base, rel_diff_base, depth_ref, k_ref, e_ref, d, k, e)
+        geo_mask_sum = geo_mask_sum + mask.astype(np.int32)
+        for i in range(2, dy_range):
+            geo_mask_sums[i - 2] = geo_mask_sums[i - 2] + masks[i - 2].astype(np.int32)
+        all_depth.append(depth_rep)
+        lv = np.zeros(mask.shape, np.uint8)
+        for i in range(10, 1, -1):
+            lv[masks[i - 2]] = i
+        levels.append(lv)
+    depth_avg = (sum(all_depth) + depth_ref) / (geo_mask_sum + 1)                                              # :248
+    geo_mask = geo_mask_sum >= dy_range
+    for i in range(2, dy_range):
+        geo_mask = np.logical_or(geo_mask, geo_mask_sums[i - 2] >= i)
+    return {"geo_mask_sum": geo_mask_sum, "depth_est_averaged": depth_avg.astype(np.float32), "geo_mask": geo_mask,
+            "levels": np.stack(levels), "depth_reprojected": np.stack(all_depth)}

@@ -89,3 +89,97 @@ def test_geo_consistency_kernel_vs_live_reference_fixture():
     assert float(same.float().mean()) >= 0.995
     rel = ((got["depth_est_averaged"].cpu().double() - torch.from_numpy(g["depth_est_averaged"])).abs() / torch.from_numpy(g["depth_est_averaged"]).abs())[same]
     assert float(rel.max()) < 1e-5
+
+
+# ----------------------------------------------------------------------------- dynamic thresholds (filter/dypcd_tanks.py)
+def _golden_dynamic():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fusion_dynamic.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _np_case(h=48, w=64, views=4, seed=0):
+    depths, ks, es = fusion_case(h, w, views, seed=seed)
+    return depths.numpy(), ks.numpy(), es.numpy()
+
+
+def test_dynamic_oracle_matches_live_reference_outputs():
+    """Same numpy / cv2 calls in the same order as dypcd_tanks.py: the restatement reproduces the live reference's outputs exactly."""
+    g = _golden_dynamic()
+    depths, ks, es = _np_case()
+    srcs = [1, 2, 3]
+    out = FO.geometric_filter_dynamic(float(g["dist_base"]), float(g["rel_diff_base"]), depths[0].copy(), ks[0], es[0],
+                                      [depths[v].copy() for v in srcs], [ks[v] for v in srcs], [es[v] for v in srcs])
+    for i, v in enumerate(srcs):
+        for k in range(9):
+            lv = out["levels"][i]
+            assert np.array_equal(np.logical_and(lv != 0, lv <= k + 2), g["masks_%d" % v][k])
+        assert np.array_equal(out["depth_reprojected"][i], g["depth_reprojected_%d" % v])
+    assert np.array_equal(out["geo_mask_sum"], g["geo_mask_sum"]) and np.array_equal(out["geo_mask"], g["geo_mask"])
+    assert np.array_equal(out["depth_est_averaged"], g["depth_est_averaged"])
+
+
+def _check_dynamic(got, want_levels, want_drep, want_sum, want_mask, want_avg):
+    """Threshold decisions on (float64 / float32) chains evaluated in a different operation order: allow a 0.2 % disagreement on
+    the levels, compare values where the decisions agree."""
+    lv = got["levels"].cpu().numpy()
+    agree = lv == want_levels
+    assert agree.mean() >= 0.998, agree.mean()
+    drep = got["depth_reprojected"].cpu().numpy()
+    both = np.logical_and(agree, want_levels != 0)
+    assert 0.2 < both.mean() < 0.99
+    assert np.abs(drep[both] - want_drep[both]).max() <= 1e-6 * np.abs(want_drep[both]).max()
+    assert np.abs(drep[lv == 0]).max() == 0.0
+    same = got["geo_mask_sum"].cpu().numpy() == want_sum
+    assert same.mean() >= 0.995
+    pix_ok = agree.all(0)                                    # pixels whose every per-source decision agrees
+    assert np.array_equal(got["geo_mask"].cpu().numpy()[pix_ok], want_mask[pix_ok])
+    avg = got["depth_est_averaged"].cpu().numpy()
+    assert np.abs(avg[pix_ok] - want_avg[pix_ok]).max() <= 1e-6 * np.abs(want_avg[pix_ok]).max()
+
+
+@pytest.mark.gpu
+def test_dynamic_kernel_vs_live_reference_fixture():
+    from dmvsnet_b200 import fusion
+    g = _golden_dynamic()
+    depths, ks, es = _np_case()
+    srcs = [1, 2, 3]
+    got = fusion.geometric_filter_dynamic(depths[0], ks[0], es[0], [depths[v] for v in srcs], [ks[v] for v in srcs], [es[v] for v in srcs],
+                                          float(g["dist_base"]), float(g["rel_diff_base"]), per_source=True)
+    want_levels = np.zeros((3,) + depths[0].shape, np.uint8)
+    for i, v in enumerate(srcs):
+        for k in range(8, -1, -1):
+            want_levels[i][g["masks_%d" % v][k]] = k + 2
+    _check_dynamic(got, want_levels, np.stack([g["depth_reprojected_%d" % v] for v in srcs]), g["geo_mask_sum"], g["geo_mask"], g["depth_est_averaged"])
+    for i, v in enumerate(srcs):                              # the float32 pixel coordinates handed to cv2.remap
+        assert np.abs(got["x2d_src"][i].cpu().numpy() - g["x2d_src_%d" % v]).max() <= 1e-4
+        assert np.abs(got["y2d_src"][i].cpu().numpy() - g["y2d_src_%d" % v]).max() <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,views,dist_base,rel_base", [(48, 64, 4, 0.25, 1 / 1300), (96, 160, 6, 0.5, 1 / 800), (40, 56, 11, 0.25, 1 / 1300)])
+def test_dynamic_kernel_vs_oracle(h, w, views, dist_base, rel_base):
+    import types
+    from dmvsnet_b200 import fusion
+    depths, ks, es = _np_case(h, w, views, seed=2)
+    srcs = list(range(1, views))
+    want = FO.geometric_filter_dynamic(dist_base, rel_base, depths[0].copy(), ks[0], es[0], [depths[v].copy() for v in srcs],
+                                       [ks[v] for v in srcs], [es[v] for v in srcs])
+    got = fusion.geometric_filter_dynamic(torch.from_numpy(depths[0]).cuda(), ks[0], es[0], [depths[v] for v in srcs], [ks[v] for v in srcs],
+                                          [es[v] for v in srcs], dist_base, rel_base, per_source=True)
+    _check_dynamic(got, want["levels"], want["depth_reprojected"], want["geo_mask_sum"], want["geo_mask"], want["depth_est_averaged"])
+    # the reference-signature entry point (one source view, numpy results)
+    args = types.SimpleNamespace(dist_base=dist_base, rel_diff_base=rel_base)
+    masks, mask, drep, x2d, y2d = fusion.check_geometric_consistency_dynamic(args, depths[0], ks[0], es[0], depths[1], ks[1], es[1])
+    assert len(masks) == 9 and masks[0].dtype == np.bool_ and mask is masks[-1] and drep.shape == (h, w) and x2d.shape == (h, w)
+    lv = got["levels"][0].cpu().numpy()
+    assert all(np.array_equal(masks[k], np.logical_and(lv != 0, lv <= k + 2)) for k in range(9))
+    assert all((masks[k] <= masks[k + 1]).all() for k in range(8))          # the levels are nested
+
+
+@pytest.mark.gpu
+def test_dynamic_fused_mask_rejects_more_than_ten_sources():
+    from dmvsnet_b200 import fusion
+    depths, ks, es = _np_case(16, 24, 12, seed=0)
+    srcs = list(range(1, 12))
+    with pytest.raises(Exception, match="at most 10 source views"):
+        fusion.geometric_filter_dynamic(depths[0], ks[0], es[0], [depths[v] for v in srcs], [ks[v] for v in srcs], [es[v] for v in srcs], 0.25, 1 / 1300)

@@ -1,6 +1,6 @@
 """Golden vectors for the geometric-consistency check from the LIVE reference (build container only).
 
-    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden_fusion.py        # -> tests/golden/fusion.npz
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden_fusion.py        # -> tests/golden/fusion.npz, fusion_dynamic.npz
 
 Imports /root/reference/filter/pcd.py unmodified.  Three of its imports are unrelated to the check and absent here (plyfile,
 tomlkit, yacs via filter.tank_test_config): they are stubbed.  The check itself runs torch ops after ``.cuda()``; there is no GPU in
@@ -64,6 +64,34 @@ def main():
     out["depth_est_averaged"] = (sum(all_d) + ref_depth) / (geo_mask_sum + 1)   # pcd.py:298
     path = os.path.join(ROOT, "tests", "golden", "fusion.npz")
     np.savez_compressed(path, **out)
+
+    # dynamic-threshold variant: filter/dypcd_tanks.py check_geometric_consistency (numpy + cv2.remap) and the accumulation of
+    # its filter_depth (:237-270), on the same depth maps
+    import filter.dypcd_tanks as dy
+    args = types.SimpleNamespace(dist_base=1 / 4, rel_diff_base=1 / 1300)
+    ref_depth = depths[0].numpy().copy()
+    dyn = {"dist_base": args.dist_base, "rel_diff_base": args.rel_diff_base}
+    src_views = list(range(1, views))
+    geo_mask_sum = 0
+    dy_range = len(src_views) + 1
+    geo_mask_sums = [0] * (dy_range - 2)
+    all_d = []
+    for v in src_views:
+        masks, geo_mask, d_rep, x2d, y2d = dy.check_geometric_consistency(args, ref_depth, ks[0].numpy(), es[0].numpy(), depths[v].numpy().copy(),
+                                                                          ks[v].numpy(), es[v].numpy())
+        dyn["masks_%d" % v], dyn["depth_reprojected_%d" % v], dyn["x2d_src_%d" % v], dyn["y2d_src_%d" % v] = np.stack(masks), d_rep, x2d, y2d
+        geo_mask_sum = geo_mask_sum + geo_mask.astype(np.int32)                  # dypcd_tanks.py:240
+        for i in range(2, dy_range):
+            geo_mask_sums[i - 2] = geo_mask_sums[i - 2] + masks[i - 2].astype(np.int32)
+        all_d.append(d_rep)
+    dyn["geo_mask_sum"] = geo_mask_sum
+    dyn["depth_est_averaged"] = ((sum(all_d) + ref_depth) / (geo_mask_sum + 1)).astype(np.float32)   # :248, cast at :250
+    geo_mask = geo_mask_sum >= dy_range                                          # :253
+    for i in range(2, dy_range):
+        geo_mask = np.logical_or(geo_mask, geo_mask_sums[i - 2] >= i)
+    dyn["geo_mask"] = geo_mask
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fusion_dynamic.npz"), **dyn)
+    print("dynamic: levels pass fractions", [float(dyn["masks_1"][k].mean()) for k in range(9)], "geo_mask", float(geo_mask.mean()))
     print("wrote", path, {k: (v.shape, str(v.dtype)) for k, v in out.items() if k.startswith(("mask_1", "geo", "depth_est"))},
           "consistent fraction per source:", [float(out["mask_%d" % v].mean()) for v in range(1, views)])
 
