@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 FMT_NHWC2 = 4
 FMT_NHWC2P = 5
@@ -67,6 +67,7 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p]),
     "dmvs_geo_consistency_dynamic_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p,
                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dmvs_backproject_world_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dmvs_depth_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_refine_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,

@@ -208,6 +208,27 @@ __global__ void __launch_bounds__(256) geo_consistency_dynamic_kernel(const floa
   if (depth_avg) depth_avg[pix] = (float)((double)__fadd_rn(dsum, d0) / (double)(sum10 + 1));  // :256, float32 / int32 -> float64 in numpy
 }
 
+// Back-projection of a depth map to world points: reference filter/pcd.py:340-343 (the same lines in dypcd_tanks.py:310-313).
+// numpy runs it in float64 (int64 pixel grid x depth), the float32 matrices promoted; the vertices are cast to float32 for the PLY.
+// Every pixel is projected, [H,W,3]; the caller selects the valid ones.
+__global__ void __launch_bounds__(256) backproject_kernel(const float* __restrict__ depth, const float* __restrict__ mats, int H, int W,
+                                                          float* __restrict__ xyz) {
+  __shared__ float sm[21];  // inv(K) 9 | inv(E)[:3,:4] 12
+  if (threadIdx.x < 21) sm[threadIdx.x] = __ldg(mats + threadIdx.x);
+  __syncthreads();
+  const long long hw = (long long)H * W;
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= hw) return;
+  const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
+  const double d = (double)__ldg(depth + pix);
+  double X, Y, Z, wx, wy, wz;
+  dmat3(sm, (double)x * d, (double)y * d, d, X, Y, Z);
+  dmat34(sm + 9, X, Y, Z, wx, wy, wz);
+  xyz[pix * 3 + 0] = (float)wx;
+  xyz[pix * 3 + 1] = (float)wy;
+  xyz[pix * 3 + 2] = (float)wz;
+}
+
 }  // namespace dmvs
 
 extern "C" int dmvs_geo_consistency_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W,
@@ -239,4 +260,13 @@ extern "C" int dmvs_geo_consistency_dynamic_f32(const float* depth_ref, const fl
   geo_consistency_dynamic_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       depth_ref, depth_src, mats, S, H, W, dist_base, rel_diff_base, level, depth_reproj, xy_src, mask_sum, geo_mask, depth_avg);
   return check_launch("geo_consistency_dynamic");
+}
+
+extern "C" int dmvs_backproject_world_f32(const float* depth, const float* mats, int H, int W, float* xyz, void* stream) {
+  using namespace dmvs;
+  DMVS_REQUIRE(depth && mats && xyz, DMVS_ERR_BAD_POINTER, "backproject_world: null pointer");
+  DMVS_REQUIRE(H >= 1 && W >= 1, DMVS_ERR_BAD_SHAPE, "backproject_world: bad dims H=%d W=%d", H, W);
+  const long long hw = (long long)H * W;
+  backproject_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(depth, mats, H, W, xyz);
+  return check_launch("backproject_world");
 }

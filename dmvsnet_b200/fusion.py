@@ -157,3 +157,89 @@ def geometric_filter_dynamic(depth_ref, intrinsics_ref, extrinsics_ref, depth_sr
     if per_source:
         out.update({"levels": level, "depth_reprojected": drep, "x2d_src": xy[:, 0], "y2d_src": xy[:, 1]})
     return out
+
+
+# ----------------------------------------------------------------------------- point cloud (filter_depth)
+@torch.no_grad()
+def backproject_world(depth, intrinsics, extrinsics) -> torch.Tensor:
+    """depth [H,W] -> world points [H,W,3] float32 for every pixel (pcd.py:340-343; float64 chain inside the kernel)."""
+    lib = N.load()
+    dev = depth.device if isinstance(depth, torch.Tensor) and depth.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    d = _t(depth, dev).contiguous()
+    k, e = _np32(intrinsics), _np32(extrinsics)
+    mats = torch.from_numpy(np.concatenate([np.linalg.inv(k[:3, :3]).reshape(-1), np.linalg.inv(e)[:3, :4].reshape(-1)]).astype(np.float32)).to(dev)
+    h, w = d.shape
+    xyz = torch.empty(h, w, 3, device=dev, dtype=torch.float32)
+    N.check(lib.dmvs_backproject_world_f32(d.data_ptr(), mats.data_ptr(), h, w, xyz.data_ptr(), ops._stream()), "dmvs_backproject_world_f32")
+    return xyz
+
+
+def _read_img(filename: str) -> np.ndarray:
+    from PIL import Image
+    return np.array(Image.open(filename), dtype=np.float32) / 255.0          # pcd.py:44-48
+
+
+def _save_mask(filename: str, mask: np.ndarray) -> None:
+    from PIL import Image
+    Image.fromarray(mask.astype(np.uint8) * 255).save(filename)                # pcd.py:36-40
+
+
+def filter_depth(args, pair_folder: str, scan_folder: str, out_folder: str, plyfilename: str, dynamic: bool = False, verbose: bool = False):
+    """The reference's ``filter_depth`` (filter/pcd.py:244-361; with ``dynamic`` the dypcd form, filter/dypcd_tanks.py:186-326) on the
+    GPU: same folder layout in (``pair.txt``, ``cams/*_cam.txt``, ``images/*.jpg``, ``depth_est/*.pfm``, ``confidence/*[_stageK].pfm``)
+    and out (``mask/*_{photo,geo,final}.png``, the PLY; ``dynamic`` also writes ``depth_est/*_averaged.pfm``), same ``args`` fields
+    (``ndepths``, ``conf``, ``thres_view`` | ``dist_base``, ``rel_diff_base``).  Per reference view: ONE launch for the geometric check
+    over all its source views, one for the back-projection; masks, selection and colours are torch ops on the device.
+    Returns (points [N,3] float32, colors [N,3] uint8) as numpy arrays, in the order they are written."""
+    import os
+
+    from . import formats
+
+    num_stage = len(args.ndepths)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pts, cols = [], []
+    cam = lambda v: formats.read_camera_parameters(os.path.join(scan_folder, "cams/{:0>8}_cam.txt".format(v)))  # noqa: E731
+    pfm = lambda sub, name: np.ascontiguousarray(formats.read_pfm(os.path.join(out_folder, sub, name))[0])  # noqa: E731
+    for ref_view, src_views in formats.read_pair_file(os.path.join(pair_folder, "pair.txt")):
+        k_ref, e_ref = cam(ref_view)
+        ref_img = _read_img(os.path.join(scan_folder, "images/{:0>8}.jpg".format(ref_view)))
+        ref_depth = pfm("depth_est", "{:0>8}.pfm".format(ref_view))
+        conf = pfm("confidence", "{:0>8}.pfm".format(ref_view))
+        if os.path.exists(os.path.join(out_folder, "confidence/{:0>8}_stage2.pfm".format(ref_view))):
+            conf2 = pfm("confidence", "{:0>8}_stage2.pfm".format(ref_view))
+            conf1 = pfm("confidence", "{:0>8}_stage1.pfm".format(ref_view))
+        else:
+            conf2 = conf1 = conf
+        c, c2, c1 = [torch.from_numpy(a).to(dev) for a in (conf, conf2, conf1)]
+        photo_mask = (c > args.conf[2]) & (c2 > args.conf[1]) & (c1 > args.conf[0])                 # pcd.py:273
+        cams = [cam(v) for v in src_views]
+        depths = [pfm("depth_est", "{:0>8}.pfm".format(v)) for v in src_views]
+        if dynamic:
+            out = geometric_filter_dynamic(ref_depth, k_ref, e_ref, depths, [k for k, _ in cams], [e for _, e in cams], args.dist_base, args.rel_diff_base)
+            formats.save_pfm(os.path.join(out_folder, "depth_est/{:0>8}_averaged.pfm".format(ref_view)), out["depth_est_averaged"].cpu().numpy())
+        else:
+            out = geometric_filter(ref_depth, k_ref, e_ref, depths, [k for k, _ in cams], [e for _, e in cams], args.thres_view)
+        geo_mask = out["geo_mask"]
+        final_mask = photo_mask & geo_mask
+        os.makedirs(os.path.join(out_folder, "mask"), exist_ok=True)
+        for tag, m in (("photo", photo_mask), ("geo", geo_mask), ("final", final_mask)):
+            _save_mask(os.path.join(out_folder, "mask/{:0>8}_{}.png".format(ref_view, tag)), m.cpu().numpy())
+        if verbose:
+            print("processing {}, ref-view{:0>2}, photo/geo/final-mask:{}/{}/{}".format(scan_folder, ref_view, float(photo_mask.float().mean()),
+                                                                                        float(geo_mask.float().mean()), float(final_mask.float().mean())))
+        if num_stage == 1:
+            img = ref_img[1::4, 1::4, :]
+        elif num_stage == 2:
+            img = ref_img[1::2, 1::2, :]
+        else:
+            img = ref_img
+        xyz = backproject_world(out["depth_est_averaged"], k_ref, e_ref)
+        pts.append(xyz[final_mask].cpu().numpy())
+        color = torch.from_numpy(np.ascontiguousarray(img)).to(dev)[final_mask]
+        cols.append((color * 255).to(torch.uint8).cpu().numpy())                                    # pcd.py:345: truncation, not rounding
+    points, colors = np.concatenate(pts, 0), np.concatenate(cols, 0)
+    os.makedirs(os.path.dirname(os.path.abspath(plyfilename)), exist_ok=True)
+    formats.write_ply(plyfilename, points, colors)
+    if verbose:
+        print("saving the final model to", plyfilename)
+    return points, colors

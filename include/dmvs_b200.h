@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 17
+#define DMVS_ABI_VERSION 18
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -283,6 +283,11 @@ int dmvs_geo_consistency_f32(const float* depth_ref, const float* depth_src, con
 int dmvs_geo_consistency_dynamic_f32(const float* depth_ref, const float* depth_src, const float* mats, int S, int H, int W,
                                      double dist_base, double rel_diff_base, unsigned char* level, float* depth_reproj, float* xy_src,
                                      int* mask_sum, unsigned char* geo_mask, float* depth_avg, void* stream);
+
+/* N4, point cloud: depth map -> world points for every pixel.  Replaces filter/pcd.py:340-343: xyz = inv(E)[:3,:4] @ [inv(K) @
+ * ((x, y, 1) * depth); 1], evaluated in float64 like numpy does there, stored as float32 (the PLY's vertex type).
+ *   depth [H,W]; mats [21] = inv(K) 3x3 | inv(E)[:3,:4] (float32, computed by the caller with np.linalg.inv); xyz [H,W,3]. */
+int dmvs_backproject_world_f32(const float* depth, const float* mats, int H, int W, float* xyz, void* stream);
 
 #ifdef __cplusplus
 }

@@ -183,3 +183,54 @@ def test_dynamic_fused_mask_rejects_more_than_ten_sources():
     srcs = list(range(1, 12))
     with pytest.raises(Exception, match="at most 10 source views"):
         fusion.geometric_filter_dynamic(depths[0], ks[0], es[0], [depths[v] for v in srcs], [ks[v] for v in srcs], [es[v] for v in srcs], 0.25, 1 / 1300)
+
+
+# ----------------------------------------------------------------------------- filter_depth on a scan folder
+def _dense(points, colors, masks):
+    """Scatter the concatenated per-view point lists back onto their pixels: [V,H,W,3] maps (row-major selection order)."""
+    v, h, w = masks.shape
+    xyz = np.zeros((v, h, w, 3), np.float32)
+    rgb = np.zeros((v, h, w, 3), np.uint8)
+    at = 0
+    for i in range(v):
+        n = int(masks[i].sum())
+        xyz[i][masks[i]] = points[at:at + n]
+        rgb[i][masks[i]] = colors[at:at + n]
+        at += n
+    assert at == len(points)
+    return xyz, rgb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["static", "dynamic"])
+def test_filter_depth_scan_folder_vs_live_reference(tag, tmp_path):
+    """The whole fusion step on the committed scan folder against what the live reference's filter_depth produced from it
+    (tools/make_golden_scene.py): masks, vertices, colours, PLY file."""
+    import shutil
+    import types
+    from PIL import Image
+    from dmvsnet_b200 import formats, fusion
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_scene import ARGS
+    want = np.load(os.path.join(ROOT, "tests", "golden", "fusion_scene_expected.npz"))
+    work = str(tmp_path / "scan")
+    shutil.copytree(os.path.join(ROOT, "tests", "golden", "fusion_scene"), work)
+    ply = str(tmp_path / "pcd" / "out.ply")
+    points, colors = fusion.filter_depth(types.SimpleNamespace(**ARGS), work, work, work, ply, dynamic=(tag == "dynamic"))
+    got_masks = {k: np.stack([np.array(Image.open(os.path.join(work, "mask/{:0>8}_{}.png".format(v, k)))) > 0 for v in range(4)])
+                 for k in ("photo", "geo", "final")}
+    want_masks = {k: np.stack([want["%s_mask_%s_%d" % (tag, k, v)] for v in range(4)]) for k in ("photo", "geo", "final")}
+    assert np.array_equal(got_masks["photo"], want_masks["photo"])
+    for k in ("geo", "final"):
+        assert (got_masks[k] == want_masks[k]).mean() >= 0.995, (k, (got_masks[k] == want_masks[k]).mean())
+    got_xyz, got_rgb = _dense(points, colors, got_masks["final"])
+    want_xyz, want_rgb = _dense(want[tag + "_xyz"], want[tag + "_rgb"], want_masks["final"])
+    both = got_masks["final"] & want_masks["final"]
+    assert both.sum() > 300
+    scale = np.abs(want_xyz[both]).max()
+    assert np.abs(got_xyz[both] - want_xyz[both]).max() <= 2e-6 * scale
+    assert np.array_equal(got_rgb[both], want_rgb[both])
+    p2, c2 = formats.read_ply(ply)                            # what was written is what was returned
+    assert np.array_equal(p2, points) and np.array_equal(c2, colors)
+    if tag == "dynamic":
+        assert os.path.exists(os.path.join(work, "depth_est/00000000_averaged.pfm"))

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for name in declared:
         assert hasattr(native_lib, name), "libdmvs_b200.so does not export %s" % name
     assert sorted(_native.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 17
+    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 18
     assert native_lib.dmvs_launch_count() >= 0  # a process-wide counter: other tests of the same session may have launched already
 
 
@@ -43,6 +43,10 @@ def test_bad_arguments_return_errors_not_crashes(native_lib):
     assert rc == -2 and b"null" in native_lib.dmvs_last_error()
     assert native_lib.dmvs_warp_corr_flag_bytes(2, 48, 296, 400) == 2 * 37 * 13 * 48
     rc = native_lib.dmvs_warp_corr_backward_f32(None, 0, 8, None, 0, 8, 1, None, None, None, None, None, 1, 8, 4, 8, 8, None)
+    assert rc == -2 and b"null" in native_lib.dmvs_last_error()
+    rc = native_lib.dmvs_geo_consistency_dynamic_f32(None, None, None, 3, 8, 8, 0.25, 1 / 1300, None, None, None, None, None, None, None)
+    assert rc == -2 and b"null" in native_lib.dmvs_last_error()
+    rc = native_lib.dmvs_backproject_world_f32(None, None, 8, 8, None, None)
     assert rc == -2 and b"null" in native_lib.dmvs_last_error()
     rc = native_lib.dmvs_features_nhwc_f32(None, 0, None, 1, 8, 8, 8, None)
     assert rc == -2 and b"null" in native_lib.dmvs_last_error()
