@@ -62,6 +62,9 @@ class CostAgg(nn.Module):
         ``rt`` lets the cascade pass homographies it has already computed for this stage."""
         if rt is None:
             rt = ops.relative_projections(proj_matrices).to(features[0].device, non_blocking=True)
+        if torch.is_grad_enabled() and any(f.requires_grad for f in features):
+            # differentiable like the reference's (gradients to the feature maps; the grid is built under no_grad, module.py:222)
+            return ops.warp_corr_autograd(features, rt, depth_values)
         return ops.warp_corr(features, rt, depth_values)
 
     def forward_fused(self, features, depth_values, rt, want_f32=False, layout=None, coherent=False):

@@ -226,6 +226,51 @@ def test_warp_corr_backward_layouts_padding_and_partial_grads():
     assert rel_linf(leaf[2].grad, dense[2]) < 1e-5
 
 
+def test_cost_agg_module_is_differentiable_like_the_reference():
+    """``CostAgg.forward`` (mvsnet.py:111) with feature maps that require a gradient records the native backward; d loss / d features
+    equals autograd through the oracle.  Without requires_grad (or under no_grad) it stays the plain forward."""
+    from dmvsnet_b200 import CostAgg, synthetic as syn
+    g = torch.Generator().manual_seed(3)
+    b, c, h, w, d, n = 1, 16, 18, 30, 6, 3
+    feats = [torch.randn(b, c, h, w, generator=g) for _ in range(n)]
+    proj = syn.make_proj_matrices(h * 4, w * 4, n, b, num_stages=1)["stage1"]
+    hyp = 425 + 500 * torch.rand(b, d, h, w, generator=g)
+    leaf = [f.clone().requires_grad_(True) for f in feats]
+    (O.warp_corr(leaf, proj, hyp) ** 2).sum().backward()
+    dev = [cuda(f).requires_grad_(True) for f in feats]
+    agg = CostAgg("variance")
+    cost = agg(dev, proj, cuda(hyp), 0)
+    assert cost.requires_grad
+    (cost ** 2).sum().backward()
+    for a, o in zip(dev, leaf):
+        assert rel_linf(a.grad, o.grad) < 2e-5
+    with torch.no_grad():
+        assert not agg(dev, proj, cuda(hyp), 0).requires_grad
+    assert not agg([f.detach() for f in dev], proj, cuda(hyp), 0).requires_grad
+
+
+@pytest.mark.parametrize("c,d,h,w", [(8, 8, 1184, 1600), (32, 4, 296, 400)])
+def test_warp_corr_backward_full_size_adjoint_identity(c, d, h, w):
+    """DTU full-size W1 passes (N = 5): W1 is bilinear in (reference map, source maps), so <g, W1(ref, src)> = <dW1/dref^T g, ref>
+    = sum_s <dW1/dsrc_s^T g, src_s> - a size-independent check of the backward kernel against the forward one."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(c + d)
+    n = 5
+    feats = [cuda(torch.randn(1, c, h, w, generator=g)) for _ in range(n)]
+    scale = 1600 // w
+    proj = syn.make_proj_matrices(1184, 1600, n, 1, num_stages=3)["stage%d" % {4: 1, 2: 2, 1: 3}[scale]]
+    rt = cuda(ops.relative_projections(proj))
+    hyp = cuda(425 + 500 * torch.rand(1, d, h, w, generator=g))
+    gout = cuda(torch.randn(1, 2, d, h, w, generator=g))
+    cost = ops.warp_corr(feats, rt, hyp)
+    grads = ops.warp_corr_backward(feats, rt, hyp, gout)
+    lhs = float((cost.double() * gout.double()).sum())
+    norm = float((cost.double() * gout.double()).abs().sum())
+    via_ref = float((grads[0].double() * feats[0].double()).sum())
+    via_src = sum(float((gs.double() * f.double()).sum()) for gs, f in zip(grads[1:], feats[1:]))
+    assert abs(lhs - via_ref) < 1e-6 * norm and abs(lhs - via_src) < 1e-6 * norm, (lhs, via_ref, via_src, norm)
+
+
 def _lib_launches():
     from dmvsnet_b200 import _native
     return _native.launch_count()
