@@ -237,34 +237,71 @@ __device__ __forceinline__ float eval_range(const RangeSample& r, int k, int inv
   return inverse ? __fdiv_rn(1.0f, v) : v;
 }
 
+// Each output pixel blends the plane values of four pixels of the coarser map, and (for the x2 upsample of the cascade) every
+// coarse pixel feeds ~16 output pixels: the plane values - one IEEE division each in inverse-depth mode - are evaluated once
+// per coarse pixel of the block's footprint into shared memory, KP planes at a time, and the 128 output pixels blend from
+// there.  Same operations on the same operands as evaluating them per output pixel: bit-identical results.
+constexpr int kHypRows = 6, kHypCols = 34, kHypKP = 4;  // footprint of a 32x4 output block for scale <= 1: <= 5 x 33 coarse pixels
+
 __global__ void __launch_bounds__(128) hypotheses_next_kernel(const float* __restrict__ last_depth,
                                                               const float* __restrict__ interval_pixel,
                                                               float* __restrict__ hyp, float* __restrict__ interval_out,
                                                               int D, int h0, int w0, int h, int w, int inverse) {
+  __shared__ float s_val[kHypKP][kHypRows][kHypCols];
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 4 + threadIdx.y;
   const int b = blockIdx.z;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
   const float ip = __ldg(interval_pixel);
   if (interval_out && b == 0 && x == 0 && y == 0) *interval_out = __fdiv_rn(__fmul_rn((float)D, ip), (float)(D - 1));
-  if (x >= w || y >= h) return;
+  const float scy = (float)h0 / (float)h, scx = (float)w0 / (float)w;
   // F.interpolate(bilinear, align_corners=False): src = scale*(dst+0.5)-0.5 clamped at 0
-  const float sy = fmaxf(__fsub_rn(__fmul_rn((float)h0 / (float)h, (float)y + 0.5f), 0.5f), 0.f);
-  const float sx = fmaxf(__fsub_rn(__fmul_rn((float)w0 / (float)w, (float)x + 0.5f), 0.5f), 0.f);
+  const float sy = fmaxf(__fsub_rn(__fmul_rn(scy, (float)y + 0.5f), 0.5f), 0.f);
+  const float sx = fmaxf(__fsub_rn(__fmul_rn(scx, (float)x + 0.5f), 0.5f), 0.f);
   const int y0 = (int)sy, x0 = (int)sx;
   const int y1 = y0 + ((y0 < h0 - 1) ? 1 : 0), x1 = x0 + ((x0 < w0 - 1) ? 1 : 0);
   const float ly1 = sy - (float)y0, ly0 = 1.0f - ly1;
   const float lx1 = sx - (float)x0, lx0 = 1.0f - lx1;
+  // origin of the block's coarse footprint = (y0, x0) of its first output pixel (both are monotonic in y / x)
+  const int oy = (int)fmaxf(__fsub_rn(__fmul_rn(scy, (float)(blockIdx.y * 4) + 0.5f), 0.5f), 0.f);
+  const int ox = (int)fmaxf(__fsub_rn(__fmul_rn(scx, (float)(blockIdx.x * 32) + 0.5f), 0.5f), 0.f);
+  const bool valid = x < w && y < h;
   const float* lp = last_depth + (long long)b * h0 * w0;
-  const RangeSample r00 = make_range(__ldg(lp + y0 * w0 + x0), ((y0 + x0) & 1) == 0, D, ip, inverse);
-  const RangeSample r01 = make_range(__ldg(lp + y0 * w0 + x1), ((y0 + x1) & 1) == 0, D, ip, inverse);
-  const RangeSample r10 = make_range(__ldg(lp + y1 * w0 + x0), ((y1 + x0) & 1) == 0, D, ip, inverse);
-  const RangeSample r11 = make_range(__ldg(lp + y1 * w0 + x1), ((y1 + x1) & 1) == 0, D, ip, inverse);
+  // this thread's (up to two) coarse pixels of the footprint
+  RangeSample rs[2];
+  int sr[2], sc[2];
+  bool have[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = tid + j * 128;
+    sr[j] = idx / kHypCols;
+    sc[j] = idx - sr[j] * kHypCols;
+    const int gy = oy + sr[j], gx = ox + sc[j];
+    have[j] = idx < kHypRows * kHypCols && gy < h0 && gx < w0;
+    if (have[j]) rs[j] = make_range(__ldg(lp + gy * w0 + gx), ((gy + gx) & 1) == 0, D, ip, inverse);
+  }
+  const int r0 = y0 - oy, r1 = y1 - oy, c0 = x0 - ox, c1 = x1 - ox;
   const long long hw = (long long)h * w;
   float* op = hyp + (long long)b * D * hw + (long long)y * w + x;
-  for (int k = 0; k < D; ++k) {
-    const float top = __fadd_rn(__fmul_rn(lx0, eval_range(r00, k, inverse)), __fmul_rn(lx1, eval_range(r01, k, inverse)));
-    const float bot = __fadd_rn(__fmul_rn(lx0, eval_range(r10, k, inverse)), __fmul_rn(lx1, eval_range(r11, k, inverse)));
-    op[k * hw] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+  for (int k0 = 0; k0 < D; k0 += kHypKP) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (have[j]) {
+#pragma unroll
+        for (int kk = 0; kk < kHypKP; ++kk)
+          if (k0 + kk < D) s_val[kk][sr[j]][sc[j]] = eval_range(rs[j], k0 + kk, inverse);
+      }
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+      for (int kk = 0; kk < kHypKP; ++kk)
+        if (k0 + kk < D) {
+          const float top = __fadd_rn(__fmul_rn(lx0, s_val[kk][r0][c0]), __fmul_rn(lx1, s_val[kk][r0][c1]));
+          const float bot = __fadd_rn(__fmul_rn(lx0, s_val[kk][r1][c0]), __fmul_rn(lx1, s_val[kk][r1][c1]));
+          op[(long long)(k0 + kk) * hw] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+        }
+    }
+    __syncthreads();
   }
 }
 
@@ -328,6 +365,7 @@ extern "C" int dmvs_hypotheses_next_f32(const float* last_depth, const float* in
   DMVS_REQUIRE(last_depth && interval_pixel && hyp, DMVS_ERR_BAD_POINTER, "hypotheses_next: null pointer");
   DMVS_REQUIRE(B >= 1 && B <= 65535 && D >= 2 && h0 >= 1 && w0 >= 1 && h >= 1 && w >= 1, DMVS_ERR_BAD_SHAPE,
                "hypotheses_next: bad dims");
+  DMVS_REQUIRE(h0 <= h && w0 <= w, DMVS_ERR_BAD_SHAPE, "hypotheses_next: the hypotheses are upsampled, never reduced (%dx%d -> %dx%d)", h0, w0, h, w);
   hypotheses_next_kernel<<<pixel_grid(B, h, w), dim3(32, 4), 0, (cudaStream_t)stream>>>(last_depth, interval_pixel, hyp,
                                                                                       interval_out, D, h0, w0, h, w, inverse);
   return check_launch("hypotheses_next");
