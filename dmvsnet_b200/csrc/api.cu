@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
 extern int g_tc2_max_ctas;
 extern int g_head_px;
 extern int g_pb_td8;
+extern int g_tc2_pdl;
 
 }  // namespace dmvs
 
@@ -30,6 +31,10 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
   }
   if (key && !strcmp(key, "pb_td8") && (value == 0 || value == 1)) {
     dmvs::g_pb_td8 = value;
+    return DMVS_OK;
+  }
+  if (key && !strcmp(key, "tc2_pdl") && (value == 0 || value == 1)) {
+    dmvs::g_tc2_pdl = value;
     return DMVS_OK;
   }
   if (key && !strcmp(key, "head_px") && (value == 32 || value == 64 || value == 128)) {

@@ -418,6 +418,9 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // activations (and the skip tensor) are the predecessor's output: nothing of them is touched before this point
+  pdl_launch();
+  pdl_wait();
 
   if (warp < Cfg::PROD_WARPS) {
     // ---------------------------------------------------------------- producer
@@ -631,6 +634,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int 
 }
 
 int g_tc2_max_ctas = 1;
+int g_tc2_pdl = 1;      // programmatic dependent launch of the tensor convs (dmvs_debug_set("tc2_pdl", 0 | 1))
 int g_pb_td8 = 1;       // debug knob (dmvs_debug_set("pb_td8", 0 | 1)): prob layer with 8-plane tiles  // debug knob (dmvs_debug_set("tc2_max_ctas", n))
 
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
@@ -675,7 +679,22 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
   }
   const int want = kNumSMs * (ctas_per_sm < g_tc2_max_ctas ? ctas_per_sm : g_tc2_max_ctas);
   const int grid = p.n_tiles < want ? p.n_tiles : want;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, tmap);
+  if (g_tc2_pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p, tmap);
+  } else {
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, tmap);
+  }
   static char what[96];
   snprintf(what, sizeof(what), "conv_tc2<mode %d, Cin %d/%d, N %d, TD %d, stages %d, kd %d> tiles %d", MODE, CIN, CIN_P, NB, TD, STAGES, KD, p.n_tiles);
   return check_launch(what);

@@ -125,4 +125,11 @@ __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed and its writes are
+// visible, pdl_launch() lets the successor's CTAs be scheduled as soon as resources free up.  Everything before pdl_wait()
+// (barrier init, TMEM allocation, weights -> shared memory) overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace dmvs

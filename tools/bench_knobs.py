@@ -33,8 +33,8 @@ def timeit(fn, n=5):
 
 
 with torch.no_grad():
-    for px in (0, 1):
-        lib.dmvs_debug_set(b"pb_td8", px)
+    for px in (0, 1, 0, 1):
+        lib.dmvs_debug_set(b"tc2_pdl", px)
         ctas = px
         ops.PROFILE = None
         ms = timeit(lambda: net.cascade(feats, proj, dv, (H, W)))
@@ -44,7 +44,7 @@ with torch.no_grad():
         for tag, a, b, _ in ops.PROFILE:
             groups[tag.split(":")[0]] = groups.get(tag.split(":")[0], 0.0) + a.elapsed_time(b)
         ops.PROFILE = None
-        print("pb_td8=%d  hot path %.2f ms  %s" % (ctas, ms, {k: round(v, 2) for k, v in groups.items()}), flush=True)
-    for g in (1, 2, 3, 5):
+        print("tc2_pdl=%d  hot path %.2f ms  %s" % (ctas, ms, {k: round(v, 2) for k, v in groups.items()}), flush=True)
+    for g in (3,):
         net.infer_view_groups = g
         print("infer_view_groups=%d  e2e %.2f ms" % (g, timeit(lambda: net.infer(imgs_host, proj, dv_host))), flush=True)
