@@ -32,19 +32,24 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
+def run(label):
+    ops.PROFILE = None
+    ms = timeit(lambda: net.cascade(feats, proj, dv, (H, W)))
+    ops.PROFILE = []
+    net.cascade(feats, proj, dv, (H, W)); torch.cuda.synchronize()
+    groups = {}
+    for tag, a, b, _ in ops.PROFILE:
+        groups[tag.split(":")[0]] = groups.get(tag.split(":")[0], 0.0) + a.elapsed_time(b)
+    ops.PROFILE = None
+    print("%-18s hot path %.2f ms  %s" % (label, ms, {k: round(v, 2) for k, v in groups.items()}), flush=True)
+
+
 with torch.no_grad():
-    for px in (0, 1, 0, 1):
-        lib.dmvs_debug_set(b"tc2_pdl", px)
-        ctas = px
-        ops.PROFILE = None
-        ms = timeit(lambda: net.cascade(feats, proj, dv, (H, W)))
-        ops.PROFILE = []
-        net.cascade(feats, proj, dv, (H, W)); torch.cuda.synchronize()
-        groups = {}
-        for tag, a, b, _ in ops.PROFILE:
-            groups[tag.split(":")[0]] = groups.get(tag.split(":")[0], 0.0) + a.elapsed_time(b)
-        ops.PROFILE = None
-        print("tc2_pdl=%d  hot path %.2f ms  %s" % (ctas, ms, {k: round(v, 2) for k, v in groups.items()}), flush=True)
+    for key, values, default in ((b"tc2_pdl", (0, 1), 1), (b"tc2_max_ctas", (2, 1), 1), (b"head_px", (64, 128, 32), 32)):
+        for v in values:
+            lib.dmvs_debug_set(key, v)
+            run("%s=%d" % (key.decode(), v))
+        lib.dmvs_debug_set(key, default)
     for g in (3,):
         net.infer_view_groups = g
         print("infer_view_groups=%d  e2e %.2f ms" % (g, timeit(lambda: net.infer(imgs_host, proj, dv_host))), flush=True)
