@@ -461,6 +461,27 @@ def test_regnet_vs_oracle(refine, d, h, w, b, engine):
     assert rel_linf(small, want[:, :2]) < 1e-4
 
 
+@pytest.mark.parametrize("refine,d,h,w", [(False, 16, 40, 56), (True, 4, 48, 40)])
+def test_regnet_programmatic_dependent_launch_is_bit_identical(refine, d, h, w, native_lib):
+    """The tensor convs are launched as programmatic dependents (their prologue overlaps the predecessor's tail): the logits
+    must carry the same bits as with plain stream-ordered launches, run after run."""
+    from dmvsnet_b200 import MVSNet, synthetic as syn
+    net = MVSNet([8, 8, 8], [4, 2, 1])
+    net.load_state_dict(syn.randomise_regnet_state(net.state_dict(), seed=4))
+    net = net.to(DEV).eval()
+    mod = (net.cost_regularization_refine if refine else net.cost_regularization)[2]
+    x = cuda(torch.randn(1, 2, d, h, w, generator=torch.Generator().manual_seed(h)))
+    try:
+        with torch.no_grad():
+            assert native_lib.dmvs_debug_set(b"tc2_pdl", 0) == 0
+            plain = mod(x).clone()
+            assert native_lib.dmvs_debug_set(b"tc2_pdl", 1) == 0
+            for _ in range(5):
+                assert torch.equal(mod(x), plain)
+    finally:
+        native_lib.dmvs_debug_set(b"tc2_pdl", 1)
+
+
 # ------------------------------------------------------------------------------------------ E1 / E2 / S1
 @pytest.mark.parametrize("d,h,w,b", [(48, 9, 37, 1), (8, 16, 33, 2), (5, 7, 5, 1)])
 def test_depth_head_vs_oracle(d, h, w, b):
