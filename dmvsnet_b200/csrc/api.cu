@@ -20,6 +20,7 @@ extern int g_tc2_max_ctas;
 extern int g_head_px;
 extern int g_pb_td8;
 extern int g_tc2_pdl;
+extern int g_regnet_streams;
 
 }  // namespace dmvs
 
@@ -35,6 +36,10 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
   }
   if (key && !strcmp(key, "tc2_pdl") && (value == 0 || value == 1)) {
     dmvs::g_tc2_pdl = value;
+    return DMVS_OK;
+  }
+  if (key && !strcmp(key, "regnet_streams") && (value == 0 || value == 1)) {
+    dmvs::g_regnet_streams = value;
     return DMVS_OK;
   }
   if (key && !strcmp(key, "head_px") && (value == 32 || value == 64 || value == 128)) {

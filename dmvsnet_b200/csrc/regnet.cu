@@ -27,7 +27,27 @@ static int run_layer(int engine, const float* x, long long x_bs, const dmvs_conv
   return conv_layer(x, x_bs, L, skip, skip_bs, y, y_bs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, st);
 }
 
+int g_regnet_streams = 1;  // dmvs_debug_set("regnet_streams", 0 | 1): second branch on a side stream (tensor path, both branches)
+
 namespace {
+
+// One non-blocking side stream per device, created on first use and kept for the life of the process.
+cudaStream_t side_stream() {
+  static cudaStream_t streams[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+  return streams[dev];
+}
+
+// `to` waits for everything enqueued on `from` so far (the event is released as soon as the wait has been enqueued)
+bool stream_wait(cudaStream_t to, cudaStream_t from) {
+  cudaEvent_t e;
+  if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+  const bool ok = cudaEventRecord(e, from) == cudaSuccess && cudaStreamWaitEvent(to, e, 0) == cudaSuccess;
+  cudaEventDestroy(e);
+  return ok;
+}
 
 struct Level {
   int D, H, W;
@@ -38,6 +58,7 @@ struct Plan {
   Level lv[4];
   // element offsets into the workspace
   long long c0, u11, c1, c2, c3, c4, c5, c6, x4f, u7f, total;
+  long long second;  // element offset of the second branch's private copy of u11 .. c6 (two-stream schedule), 0 = none
 };
 
 Plan make_plan(int refine, int B, int D, int h, int w) {
@@ -55,6 +76,9 @@ Plan make_plan(int refine, int B, int D, int h, int w) {
   p.c3 = take(32, 2); p.c4 = take(32, 2);
   p.c5 = take(64, 3); p.c6 = take(64, 3);
   p.x4f = p.u7f = o;
+  // the two branches are independent once conv0 has run: a second set of u11 .. c6 lets them run on two streams
+  p.second = o - p.u11;
+  o += p.second;
   p.total = o;
   return p;
 }
@@ -109,11 +133,23 @@ static int regnet_forward_impl(const dmvs_regnet_branch* branches, int refine, c
       if (rc0 != DMVS_OK) return rc0;
     }
     float* const c0_base = c0;
+    // Two-stream schedule: after conv0 the branches share nothing, so branch 1 runs on a side stream with its own copy of
+    // u11 .. c6.  The coarse levels' kernels (20-130 CTAs) then fill the SMs the other branch leaves idle; the full-resolution
+    // layers, whose persistent CTAs do not fit an SM twice, queue behind each other as before.
+    cudaStream_t const main_st = st;
+    cudaStream_t side = (g_regnet_streams && pair && branch_mask == 3) ? side_stream() : nullptr;
+    if (side && !stream_wait(side, main_st)) side = nullptr;
     for (int br = 0; br < 2; ++br) {
       if (!((branch_mask >> br) & 1)) continue;
       const dmvs_conv_layer* L = branches[br].layer;
       int rc;
       c0 = pair ? c0_base + (long long)br * 8 * V0 : c0_base;
+      if (br == 1 && side) {
+        st = side;
+        u11 = ws + p.u11 + p.second; c1 = ws + p.c1 + p.second; c2 = ws + p.c2 + p.second; c3 = ws + p.c3 + p.second;
+        c4 = ws + p.c4 + p.second; c5 = ws + p.c5 + p.second; c6 = ws + p.c6 + p.second;
+        u9 = c1; u7 = c3;
+      }
 #define TC2(...)                                                                                         \
   rc = conv_layer_tc2(__VA_ARGS__);                                                                      \
   if (rc > 0) { set_error("regnet: layer has no tensor specialisation"); return DMVS_ERR_BAD_SHAPE; }   \
@@ -143,6 +179,10 @@ static int regnet_forward_impl(const dmvs_regnet_branch* branches, int refine, c
       TC2(u11, 0, L[10], nullptr, logits + (long long)br * 2 * V0, 4 * V0, B, 8, 2, L0->D, L0->H, L0->W, 3, 1, 0, 0, F32, st);
 #undef TC2
 #undef F32L
+    }
+    if (side && !stream_wait(main_st, side)) {
+      set_error("regnet: joining the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return DMVS_ERR_CUDA;
     }
     return DMVS_OK;
   }

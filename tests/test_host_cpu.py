@@ -57,12 +57,13 @@ def test_bad_arguments_return_errors_not_crashes(native_lib):
 def test_workspace_formula(native_lib):
     # main net, B=1, D=8, 16x16: levels (8,16,16) (4,8,8) (2,4,4) (1,2,2)
     v = [8 * 16 * 16, 4 * 8 * 8, 2 * 4 * 4, 1 * 2 * 2]
-    # level 0 holds conv0 of BOTH branches (16 channels, conv0_pair) + conv11's output (8)
-    want = 4 * (3 * 8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3])
+    # level 0 holds conv0 of BOTH branches (16 channels, conv0_pair); everything else (conv11's output, two buffers per coarser
+    # level) exists once per branch so that the branches can run on two streams
+    want = 4 * (2 * 8 * v[0] + 2 * (8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3]))
     assert native_lib.dmvs_regnet_workspace_bytes(0, 1, 8, 16, 16) == want
     # refine net: D 4 -> 2 -> 1, then a 2-D level
     v = [4 * 16 * 16, 2 * 8 * 8, 1 * 4 * 4, 1 * 2 * 2]
-    want = 4 * (3 * 8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3])
+    want = 4 * (2 * 8 * v[0] + 2 * (8 * v[0] + 2 * 16 * v[1] + 2 * 32 * v[2] + 2 * 64 * v[3]))
     assert native_lib.dmvs_regnet_workspace_bytes(1, 1, 4, 16, 16) == want
 
 

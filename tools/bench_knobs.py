@@ -45,7 +45,7 @@ def run(label):
 
 
 with torch.no_grad():
-    for key, values, default in ((b"tc2_pdl", (0, 1), 1), (b"tc2_max_ctas", (2, 1), 1), (b"head_px", (64, 128, 32), 32)):
+    for key, values, default in ((b"regnet_streams", (0, 1, 0, 1), 1), (b"tc2_pdl", (0, 1), 1)):
         for v in values:
             lib.dmvs_debug_set(key, v)
             run("%s=%d" % (key.decode(), v))
