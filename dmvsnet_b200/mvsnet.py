@@ -86,6 +86,8 @@ class MVSNet(nn.Module):
         self.cr_base_chs = cr_base_chs
         self.num_stage = len(ndepths)
         self.inverse_depth = inverse_depth
+        # infer_many: run FeatureNet of item k+1 on its own stream beside the cascade of item k
+        self.overlap_features = True
 
         self.feature = FeatureNet(base_channels=8, stride=4, num_stage=self.num_stage, mode=self.fea_mode)
         self.cost_aggregation = CostAgg(agg_mode, self.feature.out_channels)
@@ -247,20 +249,51 @@ class MVSNet(nn.Module):
                 ev.record(side)
             return dimgs, proj, dv, ev
 
+        feat_stream = None
+        if self.overlap_features:
+            feat_stream = getattr(self, "_feat_stream", None)
+            if feat_stream is None or feat_stream.device != dev:
+                feat_stream = self._feat_stream = torch.cuda.Stream(dev)
+
+        def features_of(up):
+            """FeatureNet of an uploaded item on the feature stream: it runs beside the previous item's cascade, whose
+            coarse-level kernels and fp32-idle tensor layers leave room on the SMs."""
+            dimgs, proj, dv, ev = up
+            with torch.cuda.stream(feat_stream):
+                feat_stream.wait_event(ev)
+                dimgs.record_stream(feat_stream)
+                feats = self.extract_features(dimgs)
+                fev = torch.cuda.Event()
+                fev.record(feat_stream)
+            for view in feats:
+                for t in view.values():
+                    t.record_stream(main)
+            return feats, tuple(dimgs.shape[-2:]), fev
+
         pending = None  # (host dict, event) of the previous item
         it = iter(inputs)
         nxt = next(it, None)
         cur = upload(nxt) if nxt is not None else None
+        cur_feats = features_of(cur) if (cur is not None and feat_stream is not None) else None
         while cur is not None:
             nxt = next(it, None)
             dimgs, proj, dv, ev = cur
-            main.wait_event(ev)
-            dimgs.record_stream(main)
-            out = self.forward(dimgs, proj, dv)
+            if feat_stream is None:
+                main.wait_event(ev)
+                dimgs.record_stream(main)
+                cur = upload(nxt) if nxt is not None else None
+                out = self.forward(dimgs, proj, dv)
+            else:
+                feats, hw, fev = cur_feats
+                # enqueue the next item's upload and FeatureNet first, then this item's cascade: they overlap on the device
+                cur = upload(nxt) if nxt is not None else None
+                cur_feats = features_of(cur) if cur is not None else None
+                main.wait_event(fev)
+                out = self.cascade(feats, proj, dv, hw)
+                del feats
             done = torch.cuda.Event()
             done.record(main)
-            # queue the next upload and this item's download behind each other on the side stream
-            cur = upload(nxt) if nxt is not None else None
+            # this item's download goes behind the next upload on the copy stream
             host = {}
             with torch.cuda.stream(side):
                 side.wait_event(done)
