@@ -88,6 +88,10 @@ class MVSNet(nn.Module):
         self.inverse_depth = inverse_depth
         # infer_many: run FeatureNet of item k+1 on its own stream beside the cascade of item k
         self.overlap_features = True
+        # infer_many: how many consecutive items may have their cascades in flight at once (one stream each).  Measured on
+        # B200 at DTU size: 2 or 3 concurrent cascades are 1.5 % SLOWER than 1 (15.55 vs 15.32 ms per item, tools/bench_overlap.py)
+        # - the step is GPU-bound and the co-running kernels evict each other's L2 lines - so the default stays 1.
+        self.concurrent_items = 1
 
         self.feature = FeatureNet(base_channels=8, stride=4, num_stage=self.num_stage, mode=self.fea_mode)
         self.cost_aggregation = CostAgg(agg_mode, self.feature.out_channels)
@@ -270,6 +274,13 @@ class MVSNet(nn.Module):
                     t.record_stream(main)
             return feats, tuple(dimgs.shape[-2:]), fev
 
+        cascade_streams = [main]
+        if feat_stream is not None and self.concurrent_items > 1:
+            extra = getattr(self, "_cascade_streams", None)
+            if extra is None or len(extra) != self.concurrent_items - 1 or extra[0].device != dev:
+                extra = self._cascade_streams = [torch.cuda.Stream(dev) for _ in range(self.concurrent_items - 1)]
+            cascade_streams = [main] + list(extra)
+        index = 0
         pending = None  # (host dict, event) of the previous item
         it = iter(inputs)
         nxt = next(it, None)
@@ -288,11 +299,19 @@ class MVSNet(nn.Module):
                 # enqueue the next item's upload and FeatureNet first, then this item's cascade: they overlap on the device
                 cur = upload(nxt) if nxt is not None else None
                 cur_feats = features_of(cur) if cur is not None else None
-                main.wait_event(fev)
-                out = self.cascade(feats, proj, dv, hw)
+                # consecutive items are independent requests: their cascades alternate between `concurrent_items` streams, so
+                # the L1-bound gathers of one item run beside the tensor-core layers of the other
+                cstream = cascade_streams[index % len(cascade_streams)]
+                cstream.wait_event(fev)
+                with torch.cuda.stream(cstream):
+                    for view in feats:
+                        for t in view.values():
+                            t.record_stream(cstream)
+                    out = self.cascade(feats, proj, dv, hw)
                 del feats
+            index += 1
             done = torch.cuda.Event()
-            done.record(main)
+            done.record(cstream if feat_stream is not None else main)
             # this item's download goes behind the next upload on the copy stream
             host = {}
             with torch.cuda.stream(side):
@@ -308,6 +327,8 @@ class MVSNet(nn.Module):
                 pending[1].synchronize()
                 yield pending[0]
             pending = (host, hev)
+        for cs in cascade_streams[1:]:
+            main.wait_stream(cs)
         if pending is not None:
             pending[1].synchronize()
             yield pending[0]

@@ -15,14 +15,14 @@ proj = syn.make_proj_matrices(H, W, views, 1, num_stages=3)
 dv = syn.make_depth_values(1, 192, inverse=True)
 ref = None
 for rep in range(2):
-    for overlap in (False, True):
-        net.overlap_features = overlap
+    for overlap, conc in ((False, 1), (True, 1), (True, 2), (True, 3)):
+        net.overlap_features, net.concurrent_items = overlap, conc
         for n, timed in ((4, False), (12, True)):
             torch.cuda.synchronize(); t0 = time.perf_counter()
             outs = list(net.infer_many([(imgs, proj, dv)] * n))
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
             if timed:
-                print("overlap_features=%s  %.2f ms per item over %d items" % (overlap, 1e3 * dt / n, n), flush=True)
+                print("overlap_features=%s concurrent_items=%d  %.2f ms per item over %d items" % (overlap, conc, 1e3 * dt / n, n), flush=True)
         if ref is None:
             ref = outs[-1]["depth"].clone()
         assert all(torch.equal(o["depth"], ref) for o in outs)
