@@ -176,14 +176,18 @@ typedef struct {
   dmvs_conv_layer conv0_pair;
 } dmvs_regnet_branch;
 
-/* bytes of scratch dmvs_regnet_forward_f32 needs for these dimensions */
+/* bytes of scratch dmvs_regnet_forward_f32 needs for these dimensions: conv0 of both branches (16 channels at full
+ * resolution) plus, per branch, conv11's input (8 channels) and two buffers per coarser level (16 / 32 / 64 channels) */
 size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, int w);
 
 /*   branches   host array of 2 (cosR_small, cosR_huge) descriptors holding device pointers
  *   refine     0: CostRegNet_part (D % 8 == 0), 1: CostRegNet_part_refine (D == 4, 2-D bottleneck)
  *   cost       [B,2,D,h,w]   logits [B,4,D,h,w] (channels 0,1 = small branch, 2,3 = huge branch)
  *   h % 8 == 0 and w % 8 == 0 */
-/*   cost_cells  nullable; with engine = DMVS_ENGINE_TENSOR the first layer then reads it by TMA and `cost` may be NULL */
+/*   cost_cells  nullable; with engine = DMVS_ENGINE_TENSOR the first layer then reads it by TMA and `cost` may be NULL
+ *   Scheduling: everything is ordered after the work already enqueued on `stream`, and everything enqueued on `stream`
+ *   after the call is ordered after it.  Internally (tensor engine, cost_cells, B == 1) the second branch runs on a
+ *   per-device side stream, forked and joined by events: no host synchronisation, capturable in a CUDA graph. */
 int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
                             float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
                             void* stream);
