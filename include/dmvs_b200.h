@@ -187,7 +187,7 @@ size_t dmvs_regnet_workspace_bytes(int refine, int B, int D, int h, int w);
 /*   cost_cells  nullable; with engine = DMVS_ENGINE_TENSOR the first layer then reads it by TMA and `cost` may be NULL
  *   Scheduling: everything is ordered after the work already enqueued on `stream`, and everything enqueued on `stream`
  *   after the call is ordered after it.  Internally (tensor engine, cost_cells, B == 1) the second branch runs on a
- *   per-device side stream, forked and joined by events: no host synchronisation, capturable in a CUDA graph. */
+ *   per-device side stream, forked and joined by events: no host synchronisation. */
 int dmvs_regnet_forward_f32(const dmvs_regnet_branch* branches, int refine, const float* cost, const void* cost_cells,
                             float* logits, void* workspace, size_t workspace_bytes, int B, int D, int h, int w, int engine,
                             void* stream);
