@@ -278,3 +278,21 @@ def test_fusion_source_matrices_layout():
     p_src = t1[:3, :3] @ (torch.linalg.inv(k0) @ x) + t1[:3, 3]
     back = t2[:3, :3] @ p_src + t2[:3, 3]
     assert float(((k0 @ back) / (k0 @ back)[2] - torch.tensor([40.0, 25.0, 1.0])).abs().max()) < 1e-2
+
+
+def test_fusion_matrices_numpy_and_torch_forms_agree():
+    """The dynamic-threshold kernel takes the matrices numpy computes (dypcd_tanks.py:66-91), the fixed-threshold kernel the ones
+    torch computes (pcd.py:164-191): same 60-float block layout, values equal to fp32 rounding of two LAPACK paths."""
+    import numpy as np
+    import torch
+    from dmvsnet_b200 import fusion, synthetic as syn
+    proj = syn.make_proj_matrices(48, 64, 3, 1, num_stages=3)["stage3"]
+    ks, es = proj[0, :, 1, :3, :3].float(), proj[0, :, 0].float()
+    a = fusion.source_matrices(ks[0], es[0], ks[1], es[1])
+    b = fusion.source_matrices_numpy(ks[0].numpy(), es[0].numpy(), ks[1].numpy(), es[1].numpy())
+    assert a.shape == b.shape == (60,) and b.dtype == torch.float32
+    assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max())
+    inv_k = np.linalg.inv(ks[0].numpy())
+    assert np.array_equal(b[:9].numpy().reshape(3, 3), inv_k)                      # block 0: inv(K_ref), numpy's own bits
+    assert np.array_equal(b[21:30].numpy().reshape(3, 3), ks[1].numpy())           # block 2: K_src
+    assert np.array_equal(b[51:60].numpy().reshape(3, 3), ks[0].numpy())           # block 5: K_ref
