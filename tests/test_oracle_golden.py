@@ -90,6 +90,33 @@ def test_c_oracle_vs_torch_oracle_random(c_oracle, c, d, n):
     assert rel_linf(got, want) < 1e-6
 
 
+@pytest.mark.parametrize("c,d,n", [(8, 4, 3), (16, 3, 2)])
+def test_c_oracle_backward_vs_autograd_through_torch_oracle(c_oracle, c, d, n):
+    """The plain-C restatement of the W1 backward (serial scatter-add) against autograd through the torch oracle
+    (F.grid_sample backward): the CPU-side pin of what dmvs_warp_corr_backward_f32 is tested against on the GPU."""
+    import ctypes
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(7 * c + d)
+    b, h, w = 2, 14, 22
+    feats = [torch.randn(b, c, h, w, generator=g, requires_grad=True) for _ in range(n)]
+    proj = syn.make_proj_matrices(h * 4, w * 4, n, b, num_stages=1)["stage1"]
+    hyp = 425 + 500 * torch.rand(b, d, h, w, generator=g)
+    gout = torch.randn(b, 2, d, h, w, generator=g)
+    O.warp_corr(feats, proj, hyp).backward(gout)
+    rt = ops.relative_projections(proj).contiguous()
+    dense = [f.detach().contiguous() for f in feats]
+    grads = [torch.full_like(f, float("nan")) for f in dense]
+    fp = ctypes.c_void_p
+    srcs = (fp * (n - 1))(*[f.data_ptr() for f in dense[1:]])
+    gsrcs = (fp * (n - 1))(*[t.data_ptr() for t in grads[1:]])
+    fn = c_oracle.dmvs_oracle_warp_corr_backward_f32
+    fn.argtypes = [fp, ctypes.POINTER(fp), ctypes.c_int, fp, fp, fp, fp, ctypes.POINTER(fp)] + [ctypes.c_int] * 5
+    assert fn(dense[0].data_ptr(), srcs, n - 1, rt.data_ptr(), hyp.contiguous().data_ptr(), gout.contiguous().data_ptr(),
+              grads[0].data_ptr(), gsrcs, b, c, d, h, w) == 0
+    for got, leaf in zip(grads, feats):
+        assert rel_linf(got, leaf.grad) < 2e-6, rel_linf(got, leaf.grad)
+
+
 def test_relative_projections_match_oracle():
     from dmvsnet_b200 import ops, synthetic as syn
     proj = syn.make_proj_matrices(128, 160, 5, 2)["stage2"]
