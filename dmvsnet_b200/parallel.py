@@ -8,10 +8,17 @@ What shards and what does not (DESIGN.md "Multi-GPU"):
   warp+corr can be split over ranks by plane range and re-assembled with a single all-gather
   (``gather_planes`` / ``warp_corr_depth_sharded``).  Exact: every plane is computed by exactly one rank with the
   same kernel, so sharded == unsharded bit for bit.
-* **R1 regularisation nets** - do NOT shard by depth (receptive field +-24 planes >= D).  Their two branches
+* **R1 regularisation nets** - do NOT shard by depth (the receptive field spans every plane).  Their two branches
   (cosR_small / cosR_huge, reference module.py:343-349) are independent networks on the same input, so two ranks take one
   each and exchange their two logit channels with one all-gather (``regnet_branch_sharded``): exact, and the single-view
   latency mode of ``MVSNet.cascade(..., branch_group=...)``.
+
+  For more than two ranks they shard by ROWS with a halo: ``row_bands`` plans bands whose edges are multiples of 8 (three
+  stride-2 levels) with a 32-row halo - the U-Nets' receptive field is +-30 rows (1+1+2+2+4+4+8 down, 4+2+1 up, 1 for prob);
+  measured on the oracle, a 24-row halo leaves a 2.5e-3 error, 32 rows reproduce the unsharded logits bit for bit - and
+  ``gather_rows`` re-assembles the owned rows with one all-gather.  Host logic only so far (gloo-tested with the oracle's
+  regularisation net as the per-band operator); the device side needs a row offset in W1 / S1 / E2, where the absolute row
+  enters the homography and the checkerboard.
 
 The gather logic is device agnostic (it is exercised with gloo on CPU in tests/test_parallel_gloo.py); only
 ``warp_corr_depth_sharded`` touches the CUDA op.
@@ -114,3 +121,51 @@ def regnet_branch_sharded(pack, cost: Optional[torch.Tensor], cost_cells: Option
     ops.regnet_forward(pack, cost, cost_cells=cost_cells, branch_mask=1 << rank, out=logits)
     return exchange_channel_halves(logits, group)
 
+
+
+# ----------------------------------------------------------------------------- row bands (R1 over more than two ranks)
+REGNET_HALO_ROWS = 32  # receptive field of CostRegNet / CostRegNet_refine along H and W is +-30, bands are cut at multiples of 8
+
+
+def row_bands(num_rows: int, world: int, halo: int = REGNET_HALO_ROWS, multiple: int = 8) -> List[Tuple[int, int, int, int]]:
+    """Per rank ``(own_lo, own_hi, band_lo, band_hi)``: the rows a rank owns (contiguous, edges at multiples of ``multiple``,
+    balanced to within one block) and the rows it has to compute on, i.e. its own rows plus ``halo`` rows either side clipped
+    to the image.  Ranks beyond the number of blocks own nothing (empty range, empty band)."""
+    if num_rows % multiple:
+        raise ValueError("num_rows=%d must be a multiple of %d" % (num_rows, multiple))
+    out = []
+    for lo, hi in plane_shards(num_rows // multiple, world):
+        own_lo, own_hi = lo * multiple, hi * multiple
+        if own_hi == own_lo:
+            out.append((own_lo, own_hi, own_lo, own_hi))
+        else:
+            out.append((own_lo, own_hi, max(own_lo - halo, 0), min(own_hi + halo, num_rows)))
+    return out
+
+
+def gather_rows(compute: Callable[[int, int, int, int], Optional[torch.Tensor]], num_rows: int,
+                group: Optional[dist.ProcessGroup] = None, row_dim: int = -2, halo: int = REGNET_HALO_ROWS,
+                multiple: int = 8, like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Each rank calls ``compute(own_lo, own_hi, band_lo, band_hi)`` and returns the result for its OWN rows (the halo rows it
+    computed on are its business); one all-gather re-assembles all ``num_rows`` along ``row_dim`` on every rank.  A rank that
+    owns nothing returns None from ``compute`` and passes ``like`` (any tensor with the result's dtype / device and its shape
+    except along ``row_dim``)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bands = row_bands(num_rows, world, halo, multiple)
+    own_lo, own_hi, band_lo, band_hi = bands[rank]
+    mine = compute(own_lo, own_hi, band_lo, band_hi) if own_hi > own_lo else None
+    proto = mine if mine is not None else like
+    if proto is None:
+        raise ValueError("rank %d owns no rows and got no `like` tensor to shape its part of the collective" % rank)
+    dim = row_dim % proto.dim()
+    if mine is not None and mine.shape[dim] != own_hi - own_lo:
+        raise ValueError("compute returned %d rows for the range [%d, %d)" % (mine.shape[dim], own_lo, own_hi))
+    widest = max(b[1] - b[0] for b in bands)
+    rest = tuple(proto.shape[:dim]) + tuple(proto.shape[dim + 1:])
+    send = proto.new_zeros((widest,) + rest)
+    if mine is not None:
+        send[: own_hi - own_lo] = mine.movedim(dim, 0)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    parts = [recv[r][: bands[r][1] - bands[r][0]] for r in range(world)]
+    return torch.cat(parts, 0).movedim(0, dim).contiguous()

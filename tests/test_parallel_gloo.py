@@ -86,3 +86,60 @@ def test_branch_sharded_logits_exchange(tmp_path, batch):
     mp.spawn(_branch_worker, args=(2, port, batch, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+# ----------------------------------------------------------------------------- row bands with a halo (R1 over > 2 ranks)
+def test_row_bands_plan():
+    for rows, world in ((296, 8), (592, 4), (1184, 8), (64, 3), (16, 4), (8, 1)):
+        bands = parallel.row_bands(rows, world)
+        assert len(bands) == world and bands[0][0] == 0 and max(b[1] for b in bands) == rows
+        owned = [b for b in bands if b[1] > b[0]]
+        assert all(a[1] == b[0] for a, b in zip(owned, owned[1:]))                       # the owned ranges tile the image
+        for own_lo, own_hi, band_lo, band_hi in owned:
+            assert own_lo % 8 == 0 and own_hi % 8 == 0
+            assert band_lo == max(own_lo - 32, 0) and band_hi == min(own_hi + 32, rows)
+        sizes = [b[1] - b[0] for b in bands]
+        assert max(sizes) - min(sizes) <= 8
+    assert parallel.row_bands(16, 4)[2:] == [(16, 16, 16, 16)] * 2                       # more ranks than 8-row blocks
+    with pytest.raises(ValueError):
+        parallel.row_bands(20, 2)
+
+
+def _row_worker(rank, world, port, refine, halo, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from dmvsnet_b200 import MVSNet, synthetic as syn
+        from oracle import dmvs_oracle as O
+        torch.set_num_threads(2)
+        state = syn.randomise_regnet_state(MVSNet([8, 8, 8], [4, 2, 1]).state_dict(), seed=2)
+        params = O._sub(state, "cost_regularization%s.1." % ("_refine" if refine else ""))
+        d, h, w = (4 if refine else 8), 120, 16
+        cost = torch.randn(1, 2, d, h, w, generator=torch.Generator().manual_seed(5))  # replicated, like the features W1 reads
+        with torch.no_grad():
+            full = O.regnet(cost, params, refine=refine)
+
+            def compute(own_lo, own_hi, band_lo, band_hi):  # CPU stand-in for W1 + R1 on the band
+                logits = O.regnet(cost[:, :, :, band_lo:band_hi].contiguous(), params, refine=refine)
+                return logits[:, :, :, own_lo - band_lo:own_hi - band_lo]
+
+            got = parallel.gather_rows(compute, h, row_dim=3, halo=halo, like=full[:, :, :, :0])
+        err = float((got - full).abs().max() / full.abs().max())
+        open(os.path.join(result_dir, "rank%d" % rank), "w").write("%.3e" % err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("refine", [False, True])
+def test_row_sharded_regnet_with_32_row_halo_equals_unsharded(tmp_path, refine):
+    """Three ranks, bands cut at multiples of 8 rows: with the 32-row halo the re-assembled logits are the unsharded ones
+    bit for bit; with SURVEY's 24 rows they are not (the receptive field is +-30 rows)."""
+    for halo, exact in ((32, True), (24, False)):
+        out = tmp_path / ("halo%d" % halo)
+        out.mkdir()
+        mp.spawn(_row_worker, args=(3, _free_port(), refine, halo, str(out)), nprocs=3, join=True)
+        errs = [float(open(os.path.join(str(out), "rank%d" % r)).read()) for r in range(3)]
+        assert len(set(errs)) == 1                                                        # every rank holds the same volume
+        assert (errs[0] == 0.0) if exact else (errs[0] > 1e-4), (halo, errs)
