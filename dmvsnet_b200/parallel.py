@@ -15,9 +15,9 @@ What shards and what does not (DESIGN.md "Multi-GPU"):
 
   For more than two ranks they shard by ROWS with a halo: ``row_bands`` plans bands whose edges are multiples of 8 (three
   stride-2 levels) with a 32-row halo - the U-Nets' receptive field is +-30 rows (1+1+2+2+4+4+8 down, 4+2+1 up, 1 for prob);
-  measured on the oracle, a 24-row halo leaves a 2.5e-3 error, 32 rows reproduce the unsharded logits bit for bit - and
-  ``gather_rows`` re-assembles the owned rows with one all-gather.  Host logic only so far (gloo-tested with the oracle's
-  regularisation net as the per-band operator); the device side needs a row offset in W1 / S1 / E2, where the absolute row
+  measured on the CPU restatement of the nets, a 24-row halo leaves a 2.5e-3 error, 32 rows reproduce the unsharded logits
+  bit for bit - and ``gather_rows`` re-assembles the owned rows with one all-gather.  Host logic only so far (gloo-tested in
+  tests/test_parallel_gloo.py with a CPU regularisation net as the per-band operator); the device side needs a row offset in W1 / S1 / E2, where the absolute row
   enters the homography and the checkerboard.
 
 The gather logic is device agnostic (it is exercised with gloo on CPU in tests/test_parallel_gloo.py); only
