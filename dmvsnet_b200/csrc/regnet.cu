@@ -57,7 +57,7 @@ struct Level {
 struct Plan {
   Level lv[4];
   // element offsets into the workspace
-  long long c0, u11, c1, c2, c3, c4, c5, c6, x4f, u7f, total;
+  long long c0, u11, c1, c2, c3, c4, c5, c6, total;
   long long second;  // element offset of the second branch's private copy of u11 .. c6 (two-stream schedule), 0 = none
 };
 
@@ -75,7 +75,6 @@ Plan make_plan(int refine, int B, int D, int h, int w) {
   p.c1 = take(16, 1); p.c2 = take(16, 1);
   p.c3 = take(32, 2); p.c4 = take(32, 2);
   p.c5 = take(64, 3); p.c6 = take(64, 3);
-  p.x4f = p.u7f = o;
   // the two branches are independent once conv0 has run: a second set of u11 .. c6 lets them run on two streams
   p.second = o - p.u11;
   o += p.second;
@@ -154,9 +153,6 @@ static int regnet_forward_impl(const dmvs_regnet_branch* branches, int refine, c
   rc = conv_layer_tc2(__VA_ARGS__);                                                                      \
   if (rc > 0) { set_error("regnet: layer has no tensor specialisation"); return DMVS_ERR_BAD_SHAPE; }   \
   if (rc != DMVS_OK) return rc;
-#define F32L(...)                \
-  rc = conv_layer(__VA_ARGS__);  \
-  if (rc != DMVS_OK) return rc;
       //  x,   layer, skip,    y,  y_bs, B, Cin, Cout, Di,    Hi,    Wi,   stride, transposed, relu, out_fmt
       if (!pair) {
         TC2(cost_cells ? cost_cells : (const void*)cost, cost_cells ? 1 : 0, L[0], nullptr, c0, 0, B, 2, 8, L0->D, L0->H, L0->W, 3, 1, 0, 1, CHP, st);
@@ -178,7 +174,6 @@ static int regnet_forward_impl(const dmvs_regnet_branch* branches, int refine, c
       TC2(u9, 0, L[9], c0, u11, 0, B, 16, 8, L1->D, L1->H, L1->W, 3, 2, 1, 1, CH, st);
       TC2(u11, 0, L[10], nullptr, logits + (long long)br * 2 * V0, 4 * V0, B, 8, 2, L0->D, L0->H, L0->W, 3, 1, 0, 0, F32, st);
 #undef TC2
-#undef F32L
     }
     if (side && !stream_wait(main_st, side)) {
       set_error("regnet: joining the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
