@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 FMT_NHWC2 = 4
 FMT_NHWC2P = 5
@@ -47,6 +47,9 @@ SIGNATURES = {
     "dmvs_warp_corr_staged_f32": (c_int, [c_void_p, c_longlong, c_int, POINTER(c_void_p), c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_warp_corr_flag_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "dmvs_warp_corr_h16_f32": (c_int, [c_void_p, c_longlong, c_int, POINTER(c_void_p), c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dmvs_features_nhwc_f16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_warp_corr_backward_f32": (c_int, [c_void_p, c_longlong, c_int, POINTER(c_void_p), c_longlong, c_int, c_int, c_void_p, c_void_p,
                                             c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_features_nhwc_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

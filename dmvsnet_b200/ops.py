@@ -126,6 +126,44 @@ def features_nhwc(t: torch.Tensor) -> torch.Tensor:
     return y.permute(0, 3, 1, 2)
 
 
+class HalfFeatures:
+    """A feature map rounded to fp16, dense channel-last in memory ([B,h,w,C] halfs): what dmvs_warp_corr_h16_f32 gathers
+    from.  ``shape`` is the logical [B,C,h,w] of the fp32 map it stands for."""
+
+    def __init__(self, data: torch.Tensor):
+        assert data.dtype == torch.float16 and data.dim() == 4 and data.is_contiguous()
+        self.data = data
+        b, h, w, c = data.shape
+        self.shape = torch.Size((b, c, h, w))
+        self.device = data.device
+
+    def float(self) -> torch.Tensor:
+        """Back to an fp32 [B,C,h,w] view-shaped tensor (values already rounded to fp16)."""
+        return self.data.float().permute(0, 3, 1, 2)
+
+
+def features_nhwc_f16(t) -> "HalfFeatures":
+    """fp32 [B,C,h,w] (NCHW with any batch stride, or channel-last in memory) -> HalfFeatures (dmvs_features_nhwc_f16)."""
+    if isinstance(t, HalfFeatures):
+        return t
+    lib = N.load()
+    _req(t, "features")
+    b, c, h, w = t.shape
+    cl = _nhwc_strides(t)
+    if cl is not None and not is_pairs(t):
+        ps, bs = cl
+    else:
+        ps, bs = 0, _batch_stride(t)
+        if bs < 0:
+            t = t.contiguous()
+            bs = c * h * w
+    y = torch.empty(b, h, w, c, device=t.device, dtype=torch.float16)
+    with _timed("w1_layout16:C%d_%dx%d" % (c, h, w), 6 * b * c * h * w):
+        rc = lib.dmvs_features_nhwc_f16(t.data_ptr(), bs, ps, y.data_ptr(), b, c, h, w, _stream())
+    N.check(rc, "dmvs_features_nhwc_f16")
+    return HalfFeatures(y)
+
+
 def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor,
               d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
               want_f32: bool = True, want_cells: bool = False, layout: Optional[str] = None, coherent: bool = False):
@@ -142,8 +180,12 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     layout = layout or W1_LAYOUT
     if layout == "auto":
         layout = "staged" if coherent else "nhwc"
-    if layout not in ("nhwc", "nchw", "staged"):
-        raise ValueError("layout must be 'nhwc', 'nchw' or 'staged'")
+    if layout not in ("nhwc", "nchw", "staged", "h16"):
+        raise ValueError("layout must be 'nhwc', 'nchw', 'staged' or 'h16'")
+    if layout == "h16":
+        return _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells)
+    if any(isinstance(f, HalfFeatures) for f in features):
+        raise TypeError("fp16 source maps (HalfFeatures) need layout='h16'")
     ref = _req(features[0], "features[0]")
     b, c, h, w = ref.shape
     n_src = len(features) - 1
@@ -205,6 +247,45 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     if layout == "staged":
         global LAST_W1_FLAGS
         LAST_W1_FLAGS = flags
+    return (out, cells) if want_cells else out
+
+
+def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells):
+    """``warp_corr(layout="h16")``: fp32 reference view, fp16 channel-last sources (fp32 sources are rounded on the fly)."""
+    lib = N.load()
+    ref = features[0].float() if isinstance(features[0], HalfFeatures) else _req(features[0], "features[0]")
+    b, c, h, w = ref.shape
+    n_src = len(features) - 1
+    if n_src < 1 or n_src > N.MAX_SRC:
+        raise ValueError("need 1..%d source views, got %d" % (N.MAX_SRC, n_src))
+    srcs = [features_nhwc_f16(f) for f in features[1:]]
+    for i, f in enumerate(srcs):
+        if f.shape != ref.shape:
+            raise ValueError("features[%d] has shape %s, expected %s" % (i + 1, tuple(f.shape), tuple(ref.shape)))
+    ref_bs, ref_ps = _batch_stride(ref), 0
+    if ref_bs < 0 and _nhwc_strides(ref) is not None and not is_pairs(ref):
+        ref_ps, ref_bs = _nhwc_strides(ref)
+    elif ref_bs < 0:
+        ref = ref.contiguous()
+        ref_bs = c * h * w
+    hyp = _req(hyp, "hyp").contiguous()
+    rt = _req(rt, "rt").contiguous()
+    d = hyp.shape[1]
+    if hyp.shape != (b, d, h, w) or rt.shape != (b, n_src, 12):
+        raise ValueError("hyp %s / rt %s do not match features %s" % (tuple(hyp.shape), tuple(rt.shape), tuple(ref.shape)))
+    if out is None and want_f32:
+        out = torch.empty(b, 2, d, h, w, device=ref.device, dtype=torch.float32)
+    cells = torch.empty(b, d, h, w + 1, 4, device=ref.device, dtype=torch.int32) if want_cells else None
+    lo, hi = (0, d) if d_range is None else d_range
+    src_ptrs = (ctypes.c_void_p * n_src)(*[f.data.data_ptr() for f in srcs])
+    if CAPTURE is not None:
+        CAPTURE.append(("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), rt, hyp))
+    # algorithmic bytes: SURVEY 8d's figure (fp32 maps once each + hypotheses + cost volume), whatever the storage format
+    nbytes = 4 * b * h * w * ((n_src + 1) * c + 3 * (hi - lo))
+    with _timed("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), nbytes):
+        rc = lib.dmvs_warp_corr_h16_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, h * w * c, c, n_src, rt.data_ptr(), hyp.data_ptr(),
+                                        _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
+    N.check(rc, "dmvs_warp_corr_h16_f32")
     return (out, cells) if want_cells else out
 
 

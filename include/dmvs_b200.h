@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 18
+#define DMVS_ABI_VERSION 19
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -89,6 +89,25 @@ int dmvs_warp_corr_staged_f32(const float* ref, long long ref_bstride, int ref_p
                               long long src_bstride, int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost,
                               void* cost_cells, void* flags, int B, int C, int D, int h, int w, int d_begin, int d_end, void* stream);
 size_t dmvs_warp_corr_flag_bytes(int B, int D, int h, int w);
+
+/* W1, fp16-staged ("h16").  Same cost volume as dmvs_warp_corr_nhwc_f32 up to the rounding of the SOURCE feature maps to
+ * fp16 (relative 2^-11 per element; the reference view, weights, products and sums stay fp32) and sample positions computed
+ * with a refined reciprocal instead of IEEE divisions (<= 2e-4 px): cost within 1e-3 of max|cost|, regressed depth within the
+ * 1e-3 contract (tests/test_gpu_h16.py).  Replaces the same reference lines (networks/mvsnet.py:111-153,
+ * networks/module.py:212-251).
+ *   src[i]   fp16 channel-last source maps [B,h,w,C], `src_pixstride` halfs between pixels (>= C, multiple of 8), 16-byte
+ *            aligned (dmvs_features_nhwc_f16 makes them)
+ * Per 16x16 pixel tile x plane chunk the footprint box of every source is derived from the tile's 8 corner projections,
+ * fetched by TMA (zero fill = zeros padding) into a ring of shared-memory slots and gathered with conflict-free 16-byte loads;
+ * a source whose box does not fit (rough hypotheses, wide baseline) is gathered from global memory by the same threads with
+ * the same arithmetic - one launch, no scratch, result independent of the path taken and of [d_begin, d_end). */
+int dmvs_warp_corr_h16_f32(const float* ref, long long ref_bstride, int ref_pixstride, const void* const* src, long long src_bstride,
+                           int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells, int B, int C,
+                           int D, int h, int w, int d_begin, int d_end, void* stream);
+
+/* fp32 feature map -> fp16 dense channel-last [B,h,w,C] (the source-map format of dmvs_warp_corr_h16_f32).  x is NCHW (dense
+ * (c,h,w), `x_bstride` floats between batches) when `x_pixstride` == 0, else channel-last with that pixel stride. */
+int dmvs_features_nhwc_f16(const float* x, long long x_bstride, int x_pixstride, void* y, int B, int C, int h, int w, void* stream);
 
 /* W1 backward (the W1 part): gradients of dmvs_warp_corr_*'s cost volume w.r.t. the feature maps -
  * what autograd records for reference networks/mvsnet.py:137-146 (product, group mean, sum over views) and

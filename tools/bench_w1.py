@@ -41,7 +41,7 @@ def depth_map(kind, h, w, g, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="dtu")
-    ap.add_argument("--layouts", default="staged,nhwc,nchw")
+    ap.add_argument("--layouts", default="h16,staged,nhwc,nchw")
     ap.add_argument("--kinds", default="smooth,noise")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--flush", action="store_true")
@@ -69,6 +69,7 @@ def main():
         rt = ops.relative_projections(proj["stage%d" % (s + 1)]).to(dev)
         feats = [torch.randn(1, c, h, w, generator=g).to(dev) for _ in range(views)]
         feats_cl = [feats[0]] + [ops.features_nhwc(f) for f in feats[1:]]
+        feats_h16 = [feats_cl[0]] + [ops.features_nhwc_f16(f) for f in feats_cl[1:]]
         for kind in args.kinds.split(","):
             if s == 0:
                 hyp, iv = ops.hypotheses_first(dv, nd[0], [h, w], True)
@@ -84,7 +85,7 @@ def main():
                 d = hy.shape[1]
                 for layout in args.layouts.split(","):
                     alg = 4 * h * w * (views * c + 3 * d)
-                    fs = feats if layout == "nchw" else feats_cl
+                    fs = feats if layout == "nchw" else (feats_h16 if layout == "h16" else feats_cl)
                     run = lambda: ops.warp_corr(fs, rt, hy, layout=layout)  # noqa: E731
                     if layout == "bwd":
                         fs_all = [ops.features_nhwc(feats[0])] + feats_cl[1:]
