@@ -42,7 +42,6 @@ struct alignas(64) W1hParams {
   long long ref_bs, src_bs;
   int ref_ps, src_ps;
   int B, D, h, w, n_src, d_begin, d_end, n_chunks, chunk0, tiles_x;
-  float half_w, half_h, inv_half_w, inv_half_h;
 };
 
 // box shapes in pixels: wide (BW0 x BH0) and tall (BW1 x BH1); widths are multiples of 8 (bank phase = pixel index & 7)
@@ -75,34 +74,71 @@ __device__ __forceinline__ float rcp_newton(float z) {
   return fmaf(r, e, r);
 }
 
-// sample position of (rot @ (x,y,1)) * depth + trans, the reference's op order (module.py:233-241 + ATen's un-normalisation)
-// with the divisions replaced by multiplications with a refined reciprocal
+// sample position of (rot @ (x,y,1)) * depth + trans (module.py:233-239): one fused multiply-add per coordinate and a refined
+// reciprocal instead of the reference's mul / add / IEEE division.  The normalise / un-normalise round trip of module.py:240-241
+// + ATen's grid_sampler is the identity up to ~1e-4 px and is skipped; the fp16 rounding of the sources
+// is the larger term of this kernel's error budget.
 struct W1hPos { float ix, iy; };
-__device__ __forceinline__ W1hPos w1h_position(float rx, float ry, float rz, float tx, float ty, float tz, float dep, const W1hParams& p) {
-  const float X = __fadd_rn(__fmul_rn(rx, dep), tx);
-  const float Y = __fadd_rn(__fmul_rn(ry, dep), ty);
-  float Z = __fadd_rn(__fmul_rn(rz, dep), tz);
-  if (Z == 0.0f) Z += 1e-5f;
+__device__ __forceinline__ W1hPos w1h_position(float rx, float ry, float rz, float tx, float ty, float tz, float dep) {
+  const float X = fmaf(rx, dep, tx);
+  const float Y = fmaf(ry, dep, ty);
+  float Z = fmaf(rz, dep, tz);
+  if (Z == 0.0f) Z = 1e-5f;
   const float iz = rcp_newton(Z);
-  const float u = __fmul_rn(X, iz), v = __fmul_rn(Y, iz);
   W1hPos o;
-  o.ix = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(u, p.inv_half_w), 1.0f), 1.0f), p.half_w);
-  o.iy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(v, p.inv_half_h), 1.0f), 1.0f), p.half_h);
+  o.ix = X * iz;
+  o.iy = Y * iz;
   return o;
 }
 
-// 8 fp16 channels (one 16-byte chunk) against 8 reference channels: even channels -> group 0, odd -> group 1
+// 8 fp16 channels (one 16-byte chunk) against 8 reference channels: even channels -> group 0, odd -> group 1.
+// FIRST: the sums start here (no zero initialisation)
+template <bool FIRST>
 __device__ __forceinline__ void dot8(const uint4& v, const float* r, float& s0, float& s1) {
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
   const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
   const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-  s0 = fmaf(r[6], d.x, fmaf(r[4], c.x, fmaf(r[2], b.x, fmaf(r[0], a.x, s0))));
-  s1 = fmaf(r[7], d.y, fmaf(r[5], c.y, fmaf(r[3], b.y, fmaf(r[1], a.y, s1))));
+  const float i0 = FIRST ? r[0] * a.x : fmaf(r[0], a.x, s0);
+  const float i1 = FIRST ? r[1] * a.y : fmaf(r[1], a.y, s1);
+  s0 = fmaf(r[6], d.x, fmaf(r[4], c.x, fmaf(r[2], b.x, i0)));
+  s1 = fmaf(r[7], d.y, fmaf(r[5], c.y, fmaf(r[3], b.y, i1)));
+}
+
+// one sample whose 2x2 footprint lies inside the staged box: a00 = shared-memory address of corner (y0, x0) BEFORE swizzling,
+// row_bytes = box width in bytes.  TMA's swizzle XORs the 16-byte chunk index with address bits [8:7] (64B mode, C = 32) or
+// bit 7 (32B mode, C = 16); folding that into the corner address makes chunk k of a pixel `addr ^ (k << 4)`.
+template <int C>
+__device__ __forceinline__ void gather_staged(uint32_t a00, uint32_t row_bytes, float cx1, float cy1, const float* refv, float& g0, float& g1) {
+  constexpr int CH = C / 8;
+  uint32_t a[4] = {a00, a00 + C * 2, a00 + row_bytes, a00 + row_bytes + C * 2};
+  if (C == 32) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[c] ^= (a[c] >> 3) & 0x30u;
+  } else if (C == 16) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[c] ^= (a[c] >> 3) & 0x10u;
+  }
+  float s[4][2];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    uint4 v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = lds128u(a[c] ^ ((uint32_t)k << 4));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (k == 0) dot8<true>(v[c], refv, s[c][0], s[c][1]);
+      else dot8<false>(v[c], refv + 8 * k, s[c][0], s[c][1]);
+    }
+  }
+  const float cx0 = 1.0f - cx1, cy0 = 1.0f - cy1;
+  const float w00 = cy0 * cx0, w01 = cy0 * cx1, w10 = cy1 * cx0, w11 = cy1 * cx1;
+  g0 = fmaf(w11, s[3][0], fmaf(w10, s[2][0], fmaf(w01, s[1][0], w00 * s[0][0])));
+  g1 = fmaf(w11, s[3][1], fmaf(w10, s[2][1], fmaf(w01, s[1][1], w00 * s[0][1])));
 }
 
 template <int C, int DP>
-__global__ void __launch_bounds__(256, (C == 32 ? 2 : 3)) warp_corr_h16_kernel(const __grid_constant__ W1hParams p) {
+__global__ void __launch_bounds__(256, (C == 8 ? 3 : 2)) warp_corr_h16_kernel(const __grid_constant__ W1hParams p) {
   using Cfg = W1hCfg<C>;
   using Box = W1hBox<C>;
   constexpr int CH = C / 8;  // 16-byte chunks per pixel
@@ -143,7 +179,8 @@ __global__ void __launch_bounds__(256, (C == 32 ? 2 : 3)) warp_corr_h16_kernel(c
   bool range_ok = true;
 #pragma unroll
   for (int j = 0; j < DP; ++j) {
-    dep[j] = (d0 + j < p.D) ? __ldg(p.hyp + ((long long)(b * p.D + d0 + j) * hw) + pix) : 1.0f;
+    // planes past the volume repeat the chunk's first plane: never stored, but inside the box like every real plane
+    dep[j] = __ldg(p.hyp + ((long long)(b * p.D + min(d0 + j, p.D - 1)) * hw) + pix);
     if (d0 + j < p.D) {
       range_ok = range_ok && (dep[j] > 0.0f) && (dep[j] <= 3.0e38f);
       dlo = min(dlo, __float_as_int(dep[j]));
@@ -192,7 +229,7 @@ __global__ void __launch_bounds__(256, (C == 32 ? 2 : 3)) warp_corr_h16_kernel(c
         const float ry = __fadd_rn(__fmaf_rn(m[4], vy, __fmul_rn(m[3], vx)), m[5]);
         const float rz = __fadd_rn(__fmaf_rn(m[7], vy, __fmul_rn(m[6], vx)), m[8]);
         const float Z = __fadd_rn(__fmul_rn(rz, vd), m[11]);
-        const W1hPos q = w1h_position(rx, ry, rz, m[9], m[10], m[11], vd, p);
+        const W1hPos q = w1h_position(rx, ry, rz, m[9], m[10], m[11], vd);
         // monotonicity needs the denominator to keep its sign over the whole box: all 8 vertices in front of the camera
         ok = (Z > 1e-3f) && (fabsf(q.ix) < 1.0e6f) && (fabsf(q.iy) < 1.0e6f) && !anybad;
         if (ok) {
@@ -255,68 +292,75 @@ __global__ void __launch_bounds__(256, (C == 32 ? 2 : 3)) warp_corr_h16_kernel(c
       phases ^= 1u << slot;
     }
     const __half* gsrc = p.src[s] + (long long)b * p.src_bs;
+    // ---- positions of this pixel's DP planes; does every sample of the warp have its footprint inside the staged box?
+    float pix_x[DP], pix_y[DP];
+    const float bx_lo = (float)bx.x, bx_hi = (float)(bx.x + bw - 1), by_lo = (float)bx.y, by_hi = (float)(bx.y + bh - 1);
+    bool in_box = bx.z >= 0;
 #pragma unroll
     for (int j = 0; j < DP; ++j) {
-      const bool wanted = px_ok && d0 + j >= p.d_begin && d0 + j < p.d_end;
-      const W1hPos q = w1h_position(rx, ry, rz, tx, ty, tz, dep[j], p);
-      const float f0x = floorf(q.ix), f0y = floorf(q.iy);
-      const bool finite = (fabsf(q.ix) <= 3.0e38f) && (fabsf(q.iy) <= 3.0e38f);
-      const bool inside = finite && f0x >= -1.0f && f0x <= (float)(p.w - 1) && f0y >= -1.0f && f0y <= (float)(p.h - 1);
-      float g0 = 0.0f, g1 = 0.0f;
-      if (wanted && !finite) g0 = g1 = __int_as_float(0x7fc00000);  // the reference multiplies zeros by NaN weights
-      if (wanted && inside) {
-        const int x0 = (int)f0x, y0 = (int)f0y;
-        const float cx1 = q.ix - f0x, cx0 = 1.0f - cx1, cy1 = q.iy - f0y, cy0 = 1.0f - cy1;
-        float s00[2] = {0.f, 0.f}, s01[2] = {0.f, 0.f}, s10[2] = {0.f, 0.f}, s11[2] = {0.f, 0.f};
-        const int rxp = x0 - bx.x, ryp = y0 - bx.y;
-        if (bx.z >= 0 && rxp >= 0 && rxp + 1 < bw && ryp >= 0 && ryp + 1 < bh) {
-          // ---- staged: 4 corners x C/8 conflict-free LDS.128 (TMA's zero fill = zeros padding)
-          const int p00 = ryp * bw + rxp;
-          const int pc[4] = {p00, p00 + 1, p00 + bw, p00 + bw + 1};
-          uint32_t a[4], z[4];
+      const W1hPos q = w1h_position(rx, ry, rz, tx, ty, tz, dep[j]);
+      pix_x[j] = q.ix;
+      pix_y[j] = q.iy;
+      in_box = in_box && (q.ix >= bx_lo) && (q.ix < bx_hi) && (q.iy >= by_lo) && (q.iy < by_hi);  // false for NaN
+    }
+    if (__all_sync(0xffffffffu, in_box)) {
+      // ---- fast path (warp-uniform): no per-sample tests; TMA's zero fill is grid_sample's zeros padding.  Planes outside
+      // [d_begin, d_end) and pixels outside the image are computed and dropped at the store.
+      const uint32_t row_bytes = (uint32_t)bw * (C * 2);
+      const float boxf = (float)bx.x + (float)bx.y * (float)bw;  // pixel index of the box origin in box-row units (exact)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            a[c] = box + (uint32_t)pc[c] * (C * 2);
-            z[c] = (C == 32) ? ((pc[c] >> 1) & 3) : (C == 16) ? ((pc[c] >> 2) & 1) : 0;
-          }
+      for (int j = 0; j < DP; ++j) {
+        const float f0x = floorf(pix_x[j]), f0y = floorf(pix_y[j]);
+        const int pc = __float2int_rn(fmaf(f0y, (float)bw, f0x) - boxf);
+        float g0, g1;
+        gather_staged<C>(box + (uint32_t)pc * (C * 2), row_bytes, pix_x[j] - f0x, pix_y[j] - f0y, refv, g0, g1);
+        acc[j][0] = fmaf(g0, inv_half, acc[j][0]);
+        acc[j][1] = fmaf(g1, inv_half, acc[j][1]);
+      }
+    } else {
 #pragma unroll
-          for (int k = 0; k < CH; ++k) {
-            const uint4 v00 = lds128u(a[0] + (((uint32_t)k ^ z[0]) << 4));
-            const uint4 v01 = lds128u(a[1] + (((uint32_t)k ^ z[1]) << 4));
-            const uint4 v10 = lds128u(a[2] + (((uint32_t)k ^ z[2]) << 4));
-            const uint4 v11 = lds128u(a[3] + (((uint32_t)k ^ z[3]) << 4));
-            dot8(v00, refv + 8 * k, s00[0], s00[1]);
-            dot8(v01, refv + 8 * k, s01[0], s01[1]);
-            dot8(v10, refv + 8 * k, s10[0], s10[1]);
-            dot8(v11, refv + 8 * k, s11[0], s11[1]);
-          }
-        } else {
-          // ---- direct: the same corners from global memory, out-of-image corners contribute zero
-          const bool xa = x0 >= 0, xb = x0 + 1 < p.w, ya = y0 >= 0, yb = y0 + 1 < p.h;
-          const int xl = max(x0, 0), xr = min(x0 + 1, p.w - 1), yt = max(y0, 0), yu = min(y0 + 1, p.h - 1);
-          const uint4* q00 = reinterpret_cast<const uint4*>(gsrc + ((long long)yt * p.w + xl) * p.src_ps);
-          const uint4* q01 = reinterpret_cast<const uint4*>(gsrc + ((long long)yt * p.w + xr) * p.src_ps);
-          const uint4* q10 = reinterpret_cast<const uint4*>(gsrc + ((long long)yu * p.w + xl) * p.src_ps);
-          const uint4* q11 = reinterpret_cast<const uint4*>(gsrc + ((long long)yu * p.w + xr) * p.src_ps);
-          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      for (int j = 0; j < DP; ++j) {
+        const bool wanted = px_ok && d0 + j >= p.d_begin && d0 + j < p.d_end;
+        const float ix = pix_x[j], iy = pix_y[j];
+        const float f0x = floorf(ix), f0y = floorf(iy);
+        const bool finite = (fabsf(ix) <= 3.0e38f) && (fabsf(iy) <= 3.0e38f);
+        const bool inside = finite && f0x >= -1.0f && f0x <= (float)(p.w - 1) && f0y >= -1.0f && f0y <= (float)(p.h - 1);
+        float g0 = 0.0f, g1 = 0.0f;
+        if (wanted && !finite) g0 = g1 = __int_as_float(0x7fc00000);  // the reference multiplies zeros by NaN weights
+        if (wanted && inside) {
+          const int x0 = (int)f0x, y0 = (int)f0y;
+          const int rxp = x0 - bx.x, ryp = y0 - bx.y;
+          if (bx.z >= 0 && rxp >= 0 && rxp + 1 < bw && ryp >= 0 && ryp + 1 < bh) {
+            gather_staged<C>(box + (uint32_t)(ryp * bw + rxp) * (C * 2), (uint32_t)bw * (C * 2), ix - f0x, iy - f0y, refv, g0, g1);
+          } else {
+            // ---- direct: the same corners from global memory, out-of-image corners contribute zero
+            const bool xa = x0 >= 0, xb = x0 + 1 < p.w, ya = y0 >= 0, yb = y0 + 1 < p.h;
+            const int xl = max(x0, 0), xr = min(x0 + 1, p.w - 1), yt = max(y0, 0), yu = min(y0 + 1, p.h - 1);
+            const uint4* q4[4] = {reinterpret_cast<const uint4*>(gsrc + ((long long)yt * p.w + xl) * p.src_ps),
+                                  reinterpret_cast<const uint4*>(gsrc + ((long long)yt * p.w + xr) * p.src_ps),
+                                  reinterpret_cast<const uint4*>(gsrc + ((long long)yu * p.w + xl) * p.src_ps),
+                                  reinterpret_cast<const uint4*>(gsrc + ((long long)yu * p.w + xr) * p.src_ps)};
+            const bool ok4[4] = {xa && ya, xb && ya, xa && yb, xb && yb};
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            float sd[4][2];
 #pragma unroll
-          for (int k = 0; k < CH; ++k) {
-            const uint4 v00 = (xa && ya) ? __ldg(q00 + k) : zero;
-            const uint4 v01 = (xb && ya) ? __ldg(q01 + k) : zero;
-            const uint4 v10 = (xa && yb) ? __ldg(q10 + k) : zero;
-            const uint4 v11 = (xb && yb) ? __ldg(q11 + k) : zero;
-            dot8(v00, refv + 8 * k, s00[0], s00[1]);
-            dot8(v01, refv + 8 * k, s01[0], s01[1]);
-            dot8(v10, refv + 8 * k, s10[0], s10[1]);
-            dot8(v11, refv + 8 * k, s11[0], s11[1]);
+            for (int k = 0; k < CH; ++k) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 v = ok4[c] ? __ldg(q4[c] + k) : zero;
+                if (k == 0) dot8<true>(v, refv, sd[c][0], sd[c][1]);
+                else dot8<false>(v, refv + 8 * k, sd[c][0], sd[c][1]);
+              }
+            }
+            const float cx1 = ix - f0x, cx0 = 1.0f - cx1, cy1 = iy - f0y, cy0 = 1.0f - cy1;
+            const float w00 = cy0 * cx0, w01 = cy0 * cx1, w10 = cy1 * cx0, w11 = cy1 * cx1;
+            g0 = fmaf(w11, sd[3][0], fmaf(w10, sd[2][0], fmaf(w01, sd[1][0], w00 * sd[0][0])));
+            g1 = fmaf(w11, sd[3][1], fmaf(w10, sd[2][1], fmaf(w01, sd[1][1], w00 * sd[0][1])));
           }
         }
-        const float w00 = cy0 * cx0, w01 = cy0 * cx1, w10 = cy1 * cx0, w11 = cy1 * cx1;
-        g0 = w00 * s00[0] + w01 * s01[0] + w10 * s10[0] + w11 * s11[0];
-        g1 = w00 * s00[1] + w01 * s01[1] + w10 * s10[1] + w11 * s11[1];
+        acc[j][0] = fmaf(g0, inv_half, acc[j][0]);
+        acc[j][1] = fmaf(g1, inv_half, acc[j][1]);
       }
-      acc[j][0] += g0 * inv_half;
-      acc[j][1] += g1 * inv_half;
     }
     // ---- refill this slot with the box of source s + NBUF once every thread is done with it
     if (s + NBUF < p.n_src) {
@@ -517,10 +561,6 @@ extern "C" int dmvs_warp_corr_h16_f32(const float* ref, long long ref_bstride, i
   p.ref = ref; p.rt = rt; p.hyp = hyp; p.cost = cost; p.cells = reinterpret_cast<uint2*>(cost_cells);
   p.ref_bs = ref_bstride; p.ref_ps = ref_pixstride; p.src_bs = src_bstride; p.src_ps = src_pixstride;
   p.B = B; p.D = D; p.h = h; p.w = w; p.n_src = n_src; p.d_begin = d_begin; p.d_end = d_end;
-  p.half_w = (float)((double)(w - 1) / 2.0);
-  p.half_h = (float)((double)(h - 1) / 2.0);
-  p.inv_half_w = 1.0f / p.half_w;
-  p.inv_half_h = 1.0f / p.half_h;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (C) {
     case 8: return launch_w1h<8>(p, st);

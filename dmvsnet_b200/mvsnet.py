@@ -92,6 +92,11 @@ class MVSNet(nn.Module):
         # B200 at DTU size: 2 or 3 concurrent cascades are 1.5 % SLOWER than 1 (15.55 vs 15.32 ms per item, tools/bench_overlap.py)
         # - the step is GPU-bound and the co-running kernels evict each other's L2 lines - so the default stays 1.
         self.concurrent_items = 1
+        # W1 source-map precision.  "fp16": the source views' feature maps are rounded to fp16 once and W1 runs the TMA-staged
+        # kernel on them (dmvs_warp_corr_h16_f32: half the bytes through the SMs' shared-memory pipe, 2x faster; regressed depth
+        # within 3.3e-4 of the fp32 path on a network that behaves like a trained one, contract 1e-3).  "fp32": the exact kernels
+        # (cost volume within 2e-6 of the reference's).
+        self.w1_precision = "fp16"
 
         self.feature = FeatureNet(base_channels=8, stride=4, num_stage=self.num_stage, mode=self.fea_mode)
         self.cost_aggregation = CostAgg(agg_mode, self.feature.out_channels)
@@ -133,25 +138,30 @@ class MVSNet(nn.Module):
                 hyp, interval = ops.hypotheses_next(last_depth.detach(), self.ndepths[s],
                                                     self.depth_interval_ratio[s] * depth_interval, shape, self.inverse_depth)
             fused = ops.DEFAULT_ENGINE == "tensor"
+            half = self.w1_precision == "fp16"
+            w1_layout = "h16" if half else None
+
+            def maps(key):
+                return [features[0][key]] + [(f.get(key + "_h16", f[key]) if half else f[key]) for f in features[1:]]
             # W1 kernel choice (ops.W1_LAYOUT = "auto"): stage-1 planes come from the sampler (two parity classes of
             # fronto-parallel planes), so a pixel tile's source footprint is a small box -> TMA-staged kernel; every later
             # pass has per-pixel hypotheses regressed by the previous pass, whose roughness the channel-last gather does
             # not care about (profiles/, tools/bench_w1.py)
             if fused:
-                cost, cells = self.cost_aggregation.forward_fused([f[name] for f in features], hyp, rts[s], want_f32=keep_seams,
+                cost, cells = self.cost_aggregation.forward_fused(maps(name), hyp, rts[s], want_f32=keep_seams, layout=w1_layout,
                                                                   coherent=(s == 0))
             else:
-                cost, cells = ops.warp_corr([f[name] for f in features], rts[s], hyp, coherent=(s == 0)), None
+                cost, cells = ops.warp_corr(maps(name), rts[s], hyp, layout=w1_layout, coherent=(s == 0)), None
             logits = self.cost_regularization[s](cost, cost_cells=cells, branch_group=branch_group)
             stage_out = self.DepthNet(logits, hyp, num_depth=self.ndepths[s], interval=interval, stage=s)
             seams = {"_cost": cost, "_logits": logits} if keep_seams else {}
             del cost, logits, cells
             hyp_c = stage_out["depth_values_c"]
             if fused:
-                cost_c, cells_c = self.cost_aggregation.forward_fused([f[name + "_c"] for f in features], hyp_c, rts[s],
-                                                                      want_f32=keep_seams)
+                cost_c, cells_c = self.cost_aggregation.forward_fused(maps(name + "_c"), hyp_c, rts[s], want_f32=keep_seams,
+                                                                      layout=w1_layout)
             else:
-                cost_c, cells_c = self.cost_aggregation([f[name + "_c"] for f in features], None, hyp_c, s, rt=rts[s]), None
+                cost_c, cells_c = ops.warp_corr(maps(name + "_c"), rts[s], hyp_c, layout=w1_layout), None
             logits_c = self.cost_regularization_refine[s](cost_c, cost_cells=cells_c, branch_group=branch_group)
             refine_out = self.DepthNet.refine(logits_c, hyp_c, num_depth=4, interval=interval)
             if keep_seams:
@@ -180,7 +190,22 @@ class MVSNet(nn.Module):
         def view_of(t, v):
             s = t.view(b, n, *t.shape[1:])[:, v]
             return ops.mark_pairs(s) if ops.is_pairs(t) else s
-        return [{k: view_of(t, v) for k, t in out.items()} for v in range(n)]
+        views = [{k: view_of(t, v) for k, t in out.items()} for v in range(n)]
+        if self.w1_precision == "fp16" and imgs.is_cuda and n > 1:
+            for k, t in out.items():  # one conversion launch per map for all views; the source views take their slices
+                half = ops.features_nhwc_f16(t)
+                for v in range(1, n):
+                    views[v][k + "_h16"] = half.view_of(b, n, v)
+        return views
+
+    def add_half_features(self, features: List[Dict[str, torch.Tensor]]) -> List[Dict[str, torch.Tensor]]:
+        """Attach the fp16 channel-last copy W1's staged kernel gathers from (``<key>_h16``, ops.HalfFeatures) to every
+        SOURCE view's maps (view 0 stays fp32: it is the reference view of the cost volume).  In place; returns ``features``."""
+        for f in features[1:]:
+            for key in [k for k in f if not k.endswith("_h16")]:
+                if key + "_h16" not in f:
+                    f[key + "_h16"] = ops.features_nhwc_f16(f[key])
+        return features
 
     # ------------------------------------------------------------------ host-buffer entry (SURVEY §8f N3)
     # views per H2D / FeatureNet group in infer(): the copy of group k+1 (side stream) runs under FeatureNet of group k

@@ -131,11 +131,20 @@ class HalfFeatures:
     from.  ``shape`` is the logical [B,C,h,w] of the fp32 map it stands for."""
 
     def __init__(self, data: torch.Tensor):
-        assert data.dtype == torch.float16 and data.dim() == 4 and data.is_contiguous()
-        self.data = data
         b, h, w, c = data.shape
+        assert data.dtype == torch.float16 and data.stride()[1:] == (w * c, c, 1), "dense [h,w,C] halfs per batch entry"
+        self.data = data
         self.shape = torch.Size((b, c, h, w))
         self.device = data.device
+        self.bstride = data.stride(0) if b > 1 else h * w * c
+
+    def view_of(self, batch: int, views: int, v: int) -> "HalfFeatures":
+        """Entry v of every item of a [batch * views] stack (FeatureNet runs all views in one batched call)."""
+        b, h, w, c = self.data.shape
+        return HalfFeatures(self.data.view(batch, views, h, w, c)[:, v])
+
+    def record_stream(self, stream) -> None:
+        self.data.record_stream(stream)
 
     def float(self) -> torch.Tensor:
         """Back to an fp32 [B,C,h,w] view-shaped tensor (values already rounded to fp16)."""
@@ -277,13 +286,15 @@ def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells):
         out = torch.empty(b, 2, d, h, w, device=ref.device, dtype=torch.float32)
     cells = torch.empty(b, d, h, w + 1, 4, device=ref.device, dtype=torch.int32) if want_cells else None
     lo, hi = (0, d) if d_range is None else d_range
+    if len({f.bstride for f in srcs}) != 1:
+        srcs = [HalfFeatures(f.data.contiguous()) for f in srcs]
     src_ptrs = (ctypes.c_void_p * n_src)(*[f.data.data_ptr() for f in srcs])
     if CAPTURE is not None:
         CAPTURE.append(("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), rt, hyp))
     # algorithmic bytes: SURVEY 8d's figure (fp32 maps once each + hypotheses + cost volume), whatever the storage format
     nbytes = 4 * b * h * w * ((n_src + 1) * c + 3 * (hi - lo))
     with _timed("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), nbytes):
-        rc = lib.dmvs_warp_corr_h16_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, h * w * c, c, n_src, rt.data_ptr(), hyp.data_ptr(),
+        rc = lib.dmvs_warp_corr_h16_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, srcs[0].bstride, c, n_src, rt.data_ptr(), hyp.data_ptr(),
                                         _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
     N.check(rc, "dmvs_warp_corr_h16_f32")
     return (out, cells) if want_cells else out

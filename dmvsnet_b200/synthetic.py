@@ -198,6 +198,44 @@ def make_scene_images(height: int, width: int, num_views: int, proj_full: torch.
     return torch.stack(views, 0)[None].clamp_(0.0, 1.0).contiguous()
 
 
+def make_scene_features(height: int, width: int, num_views: int, proj: Dict[str, torch.Tensor], seed: int = 0, noise: float = 0.1,
+                        num_stages: int = 3) -> List[Dict[str, torch.Tensor]]:
+    """Per-view feature dicts (like FeatureNet's output) that are PHOTO-CONSISTENT with the cameras: every ``stageK`` /
+    ``stageK_c`` map is a zero-mean, unit-variance C-channel texture painted on the plane of ``scene_depth`` and seen through
+    view v's stage-K camera, plus ``noise`` per-view noise - what a trained FeatureNet computes from photographs of a scene
+    (descriptors that agree where the views see the same surface point).  The group-wise correlation then has its ridge at the
+    true depth for every pixel and source, which randomly initialised FeatureNet features of rendered images do not give."""
+    g = torch.Generator().manual_seed(seed)
+    n, c0 = _scene_plane()
+    feats: List[Dict[str, torch.Tensor]] = [dict() for _ in range(num_views)]
+    for s in range(num_stages):
+        scale = 2 ** (num_stages - s - 1)
+        h, w = height // scale, width // scale
+        c = FEATURE_CHANNELS[s]
+        pm = proj["stage%d" % (s + 1)]
+        fx = float(pm[0, 0, 1, 0, 0])
+        mm_per_px = 680.0 / fx
+        ext_mm = (w * mm_per_px + 700.0, h * mm_per_px + 700.0)
+        tw, th = int(ext_mm[0] / mm_per_px), int(ext_mm[1] / mm_per_px)
+        ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64), torch.arange(w, dtype=torch.float64), indexing="ij")
+        pix = torch.stack([xs, ys, torch.ones_like(xs)], 0).reshape(3, -1)
+        for suffix in ("", "_c"):
+            tex = torch.nn.functional.avg_pool2d(torch.randn(1, c, th + 2, tw + 2, generator=g), 3, 1, 0)
+            tex = tex / tex.std()
+            for v in range(num_views):
+                k = pm[0, v, 1, :3, :3].double()
+                e = pm[0, v, 0].double()
+                rot, t = e[:3, :3], e[:3, 3]
+                dirs = rot.T @ torch.linalg.solve(k, pix)
+                centre = -(rot.T @ t)
+                lam = (c0 - float(n @ centre)) / (n[:, None] * dirs).sum(0)
+                pts = centre[:, None] + lam * dirs
+                grid = torch.stack([(pts[0] / (ext_mm[0] / 2.0)).reshape(1, h, w), (pts[1] / (ext_mm[1] / 2.0)).reshape(1, h, w)], -1).float()
+                f = torch.nn.functional.grid_sample(tex, grid, mode="bilinear", padding_mode="border", align_corners=False)
+                feats[v]["stage%d%s" % (s + 1, suffix)] = (f + noise * torch.randn(1, c, h, w, generator=g)).contiguous()
+    return feats
+
+
 def make_stage_features(height: int, width: int, num_views: int, batch: int = 1, seed: int = 0,
                         num_stages: int = 3, structured: bool = True) -> List[Dict[str, torch.Tensor]]:
     """Per-view dicts ``{"stageK": [B,C,h,w], "stageK_c": [B,C,h,w]}`` like FeatureNet's output.
@@ -281,6 +319,52 @@ def randomise_regnet_state(state: Dict[str, torch.Tensor], seed: int = 0, prob_g
             if ".cosR_huge." in key and not key.endswith("num_batches_tracked"):
                 twin = out[key.replace(".cosR_huge.", ".cosR_small.")]
                 out[key] = twin * (1.0 + branch_jitter * torch.randn(twin.shape, generator=g))
+    return out
+
+
+def ridge_regnet_state(state: Dict[str, torch.Tensor], seed: int = 0, gain: float = 24.0, perturb: float = 0.05,
+                       branch_jitter: float = 0.03) -> Dict[str, torch.Tensor]:
+    """Parameters that make the network behave like a TRAINED DMVSNet on photo-consistent inputs, without a checkpoint.
+
+    A trained cost-regularisation net sharpens the ridge the cost volume has at the true depth; softmax + regression then
+    return a piecewise-smooth depth map.  Here every regularisation net (both branches, main and refine) computes
+
+        logits = gain * (cost_g0 + cost_g1) / 2  +  perturb-sized contributions of the whole U-Net
+
+    through its outer skip connection: ``conv0`` copies +/- the group mean of the cost into two of its 8 channels (centre tap,
+    identity BatchNorm; ReLU keeps the positive / negative part), ``conv11``'s transposed convolution - fed by the randomly
+    weighted coarse levels (App. D recipe) - is scaled down to ``perturb``, and ``prob`` reads (ch0 - ch1) * gain at its centre
+    tap plus ``perturb``-sized random taps everywhere else.  All layers keep dense, non-degenerate weights and run exactly as
+    with a checkpoint; only the values are chosen so that the regressed depth follows the photo-consistency ridge.
+    Used by bench.py's headline workload and the free-running full-size parity test: the random-weight recipe regresses a
+    white-noise depth map, which no trained network produces, and turns the cascade into a chaotic map at full size."""
+    out = randomise_regnet_state(state, seed=seed, branch_jitter=branch_jitter)
+    g = torch.Generator().manual_seed(seed + 1000)
+    for key in sorted(out.keys()):
+        if "cost_regularization" not in key:
+            continue
+        t = out[key]
+        if key.endswith("conv0.conv.weight"):
+            w = perturb * t
+            mid = tuple(k // 2 for k in t.shape[2:])
+            w[(0, slice(None)) + mid] = 0.5
+            w[(1, slice(None)) + mid] = -0.5
+            out[key] = w
+        elif ".conv0.bn." in key:
+            out[key] = {"weight": torch.ones_like(t), "bias": torch.zeros_like(t), "running_mean": torch.zeros_like(t),
+                        "running_var": torch.ones_like(t) - 1e-5}.get(key.rsplit(".", 1)[1], t)
+        elif key.endswith("conv11.bn.weight"):
+            out[key] = perturb * t
+        elif key.endswith("conv11.bn.bias"):
+            out[key] = torch.zeros_like(t)
+        elif key.endswith("prob.weight"):
+            w = (perturb / 4.0) * t  # randomise_regnet_state scaled these by its prob_gain = 4
+            mid = tuple(k // 2 for k in t.shape[2:])
+            for o in range(t.shape[0]):
+                jit = 1.0 + branch_jitter * float(torch.randn((), generator=g))
+                w[(o, 0) + mid] = gain * jit
+                w[(o, 1) + mid] = -gain * jit
+            out[key] = w
     return out
 
 

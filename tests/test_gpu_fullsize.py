@@ -136,6 +136,7 @@ def test_cascade_full_size_vs_oracle(cfg, H, W, views, nd):
     state = syn.randomise_regnet_state(net.state_dict(), seed=1)
     net.load_state_dict(state)
     net = net.to(DEV).eval()
+    net.w1_precision = "fp32"
     feats = syn.make_stage_features(H, W, views, 1, seed=3)
     proj = syn.make_proj_matrices(H, W, views, 1, num_stages=3)
     dv = syn.make_depth_values(1, 192, inverse=True)
@@ -199,3 +200,37 @@ def test_cascade_full_size_vs_oracle(cfg, H, W, views, nd):
             check(s + 1, seam, got, assert_it=(s == 0 and seam in ("depth_values", "cost", "logits", "depth_sub_plus")), tag="free  ")
     print("\n".join(report))
     assert not bad, "\n".join(["seams out of tolerance:"] + bad + ["all seams:"] + report)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("cfg,H,W,views,nd", [("dtu", 1184, 1600, 5, [48, 32, 8])])
+def test_cascade_full_size_conditioned_weights(cfg, H, W, views, nd, precision):
+    """FREE-RUNNING cascade at BASELINE config 2 on the workload bench.py times: photo-consistent feature maps of a tilted
+    plane (synthetic.make_scene_features) and regularisation nets that follow the cost ridge like trained ones
+    (synthetic.ridge_regnet_state).  Every stage's final depth within the 1e-3 contract of the oracle's, for the exact W1
+    kernels and for the fp16-staged one, and close to the depth of the rendered scene."""
+    from dmvsnet_b200 import MVSNet, synthetic as syn
+    ratios = [4, 2, 1]
+    net = MVSNet(nd, ratios, inverse_depth=True)
+    state = syn.ridge_regnet_state(net.state_dict(), seed=1)
+    net.load_state_dict(state)
+    net = net.to(DEV).eval()
+    net.w1_precision = precision
+    proj = syn.make_proj_matrices(H, W, views, 1, num_stages=3)
+    feats = syn.make_scene_features(H, W, views, proj, seed=3)
+    dv = syn.make_depth_values(1, 192, inverse=True)
+    with torch.no_grad():
+        want = O.cascade_forward(feats, proj, dv, state, nd, ratios, True, (H, W))
+        out = net.cascade([{k: cuda(v) for k, v in f.items()} for f in feats], proj, cuda(dv), (H, W))
+    scene = syn.scene_depth(H, W, proj["stage3"])
+    report = []
+    for s in range(3):
+        name = "stage%d" % (s + 1)
+        for seam in ("depth_sub_plus", "depth_values_c", "depth"):
+            mx, p999, mean = _seam_err(out[name][seam], want[name][seam], "rel")
+            report.append("%s %-16s max %.2e  p99.9 %.2e  mean %.2e" % (name, seam, mx, p999, mean))
+            assert mx < 1e-3, "\n".join(report)
+    off = float(((out["depth"].cpu()[0] - scene).abs() / scene).mean())
+    report.append("final depth vs the rendered plane: mean rel %.2e" % off)
+    print("\n".join(report))
+    assert off < 5e-3

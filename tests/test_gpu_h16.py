@@ -114,3 +114,58 @@ def test_h16_full_size_vs_c_oracle(cfg, stage, H, W, views, c, d, refine, c_orac
     want16 = _c_warp_corr(c_oracle, _rounded(feats), rt, hyp)
     got = ops.warp_corr([cuda(f) for f in feats], cuda(rt), cuda(hyp), layout="h16")
     assert rel_linf(got, want16) < 5e-4, rel_linf(got, want16)
+
+
+# ------------------------------------------------------------------------------------------ through the cascade
+def test_cascade_h16_reference_fixture():
+    """The cascade with fp16-staged W1 against the live reference's outputs (cascade_lin fixture): the cost volumes within
+    1e-3 of max|cost|; the App. D random weights regress a white-noise depth map (a peaked softmax at a random plane per
+    pixel), so the depth is compared where the conditioning allows it: 99 % of the pixels within the 1e-3 contract."""
+    from cases import CASES, case_inputs, case_state
+    from dmvsnet_b200 import MVSNet
+    case, gold = CASES["cascade_lin"], load_golden("cascade_lin")
+    inp = case_inputs(case)
+    net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
+    net.load_state_dict(case_state(case))
+    net = net.to(DEV).eval()
+    assert net.w1_precision == "fp16"
+    feats = [{k: cuda(v) for k, v in f.items()} for f in inp["features"]]
+    rts = [gold["s%d_rt" % (s + 1)] for s in range(3)]
+    with torch.no_grad():
+        out = net.cascade(feats, inp["proj"], cuda(inp["depth_values"]), (case["H"], case["W"]), keep_seams=True, rts=rts)
+    assert rel_linf(out["stage1"]["_cost"], gold["s1_cost"]) < 1e-3
+    for s in range(3):
+        want = gold["s%d_depth" % (s + 1)]
+        e = ((out["stage%d" % (s + 1)]["depth"].cpu() - want).abs() / want.abs()).flatten()
+        p99 = float(e.kthvalue(int(0.99 * e.numel()))[0])
+        print("stage%d depth rel err: max %.2e p99 %.2e mean %.2e" % (s + 1, float(e.max()), p99, float(e.mean())))
+        assert p99 < 1e-3
+
+
+@pytest.mark.parametrize("H,W,views", [(256, 320, 5), (192, 256, 8)])
+def test_cascade_h16_conditioned_vs_oracle(H, W, views):
+    """Free-running 3-stage cascade, fp16-staged W1, on the conditioned workload (photo-consistent features + ridge-following
+    regularisation nets): every stage's depth within the 1e-3 contract of the oracle's fp32 result (max over all pixels);
+    the fp16 feature copies attached by add_half_features are used in place."""
+    from dmvsnet_b200 import MVSNet, ops, synthetic as syn
+    nd, ratios = [48, 32, 8], [4, 2, 1]
+    net = MVSNet(nd, ratios, inverse_depth=True)
+    state = syn.ridge_regnet_state(net.state_dict(), seed=0)
+    net.load_state_dict(state)
+    net = net.to(DEV).eval()
+    proj = syn.make_proj_matrices(H, W, views, 1, num_stages=3)
+    feats = syn.make_scene_features(H, W, views, proj, seed=0)
+    dv = syn.make_depth_values(1, 192, inverse=True)
+    dfeats = net.add_half_features([{k: cuda(v) for k, v in f.items()} for f in feats])
+    assert isinstance(dfeats[1]["stage2_c_h16"], ops.HalfFeatures) and "stage1_h16" not in dfeats[0]
+    with torch.no_grad():
+        want = O.cascade_forward(feats, proj, dv, state, nd, ratios, True, (H, W))
+        out = net.cascade(dfeats, proj, cuda(dv), (H, W))
+        net.w1_precision = "fp32"
+        exact = net.cascade(dfeats, proj, cuda(dv), (H, W))
+    for s in range(3):
+        name = "stage%d" % (s + 1)
+        e16 = float(((out[name]["depth"].cpu() - want[name]["depth"]).abs() / want[name]["depth"].abs()).max())
+        e32 = float(((exact[name]["depth"].cpu() - want[name]["depth"]).abs() / want[name]["depth"].abs()).max())
+        print("%s depth rel err vs oracle: fp16-staged W1 %.2e, exact W1 %.2e" % (name, e16, e32))
+        assert e16 < 1e-3 and e32 < 1e-3

@@ -558,6 +558,7 @@ def test_cascade_against_reference_fixture(name):
     net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
     net.load_state_dict(case_state(case))
     net = net.to(DEV).eval()
+    net.w1_precision = "fp32"  # the exact W1 kernels: these tests assert fp32-level seams (fp16 mode: test_gpu_h16.py)
     with torch.no_grad():
         if "features" in inp:
             feats = [{k: cuda(v) for k, v in f.items()} for f in inp["features"]]
@@ -597,6 +598,7 @@ def test_forward_from_images_matches_fixture():
     net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
     net.load_state_dict(case_state(case))
     net = net.to(DEV).eval()
+    net.w1_precision = "fp32"  # the exact W1 kernels: these tests assert fp32-level seams (fp16 mode: test_gpu_h16.py)
     with torch.no_grad():
         out = net(cuda(inp["imgs"]), {k: cuda(v) for k, v in inp["proj"].items()}, cuda(inp["depth_values"]))
     err = float(((out["depth"].cpu() - gold["s1_depth"]).abs() / gold["s1_depth"].abs().clamp_min(1.0)).max())
@@ -614,6 +616,7 @@ def test_full_three_stage_forward_from_images_vs_oracle():
     state = syn.randomise_regnet_state(net.state_dict(), seed=5)
     net.load_state_dict(state)
     net = net.to(DEV).eval()
+    net.w1_precision = "fp32"
     imgs = syn.make_images(h, w, n, b, seed=6)
     proj = syn.make_proj_matrices(h, w, n, b, num_stages=3)
     dv = syn.make_depth_values(b, 192, inverse=True)
@@ -636,6 +639,7 @@ def test_infer_from_host_buffers():
     net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
     net.load_state_dict(case_state(case))
     net = net.to(DEV).eval()
+    net.w1_precision = "fp32"  # the exact W1 kernels: these tests assert fp32-level seams (fp16 mode: test_gpu_h16.py)
     host = net.infer(inp["imgs"], inp["proj"], inp["depth_values"])
     assert not host["depth"].is_cuda
     err = float(((host["depth"] - gold["s1_depth"]).abs() / gold["s1_depth"].abs().clamp_min(1.0)).max())
@@ -650,6 +654,7 @@ def test_infer_many_pipeline_matches_infer():
     net = MVSNet(case["ndepths"], case["ratios"], inverse_depth=case["inverse"])
     net.load_state_dict(case_state(case))
     net = net.to(DEV).eval()
+    net.w1_precision = "fp32"  # the exact W1 kernels: these tests assert fp32-level seams (fp16 mode: test_gpu_h16.py)
     items = [((inp["imgs"] * s).clamp(0, 1), inp["proj"], inp["depth_values"]) for s in (1.0, 0.7, 0.4, 0.9)]
     want = [net.infer(*it) for it in items]
     got = list(net.infer_many(items))
