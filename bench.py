@@ -1,24 +1,34 @@
 #!/usr/bin/env python
-"""bench.py - views/sec of the DMVSNet cost-volume hot path on B200 (BASELINE.json metric).
+"""bench.py - views/sec of DMVSNet's cost-volume path on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config dtu|bmvs|tnt|synth|tiny]
 
-One step = one pass of the hot path (3-stage cascade: S1 -> W1 -> R1 -> E1 -> W1 -> R1 -> E2 per stage) over one
-synthetic DTU-shaped view set (1600x1184, N=5, D=[48,32,8]; BASELINE.json configs[1]).
+One step = one reference view of BASELINE.json configs[1] (DTU 1600x1184, N=5, D=[48,32,8]): MVSNet.forward = FeatureNet on
+the N images, then the 3-stage cascade (S1 -> W1 -> R1 -> E1 -> W1 -> R1 -> E2 per stage).
 
-  value      views/s, whole job, per-view features already resident in HBM (scope H of SURVEY 8d), CUDA-event timed
-  e2e        views/s through the public API MVSNet.infer_many(): per step pinned host images -> H2D -> FeatureNet
-             (dmvs_conv2d_f32) -> hot path -> D2H of depth + confidence (scope F + copies; the copies of neighbouring steps
-             overlap compute on a copy stream); e2e.single_request_ms = one blocking MVSNet.infer() per step
-  roofline   the fused warp+corr kernel (W1): algorithmic bytes 4*h*w*(N*C + 3*D) per launch over its CUDA-event time,
-             all six passes of a step pooled; per-pass numbers under "roofline_per_launch"
+  value      views/s of the full forward with the images already resident in HBM (scope F of SURVEY 8d, no copies), CUDA-event
+             timed, whole job over all ranks.  The reference arm (--impl reference) reports the same scope on the host CPU.
+  e2e        views/s through the public API MVSNet.infer_many(): per step pinned host images -> H2D -> FeatureNet -> cascade ->
+             D2H of depth + confidence (copies of neighbouring steps overlap compute on a copy stream; every step still pays its
+             own); e2e.single_request_ms = one blocking MVSNet.infer() per step
+  hot_path   the stage loop alone (scope H) on feature maps resident in HBM, on the CONDITIONED workload: photo-consistent
+             feature maps of a tilted plane (synthetic.make_scene_features) - what a trained FeatureNet hands the cascade -
+             so that the regressed depth maps, hence W1's gather pattern, are the piecewise-smooth ones of a trained network
+  roofline   the fused warp+corr kernel W1 inside the hot_path region: algorithmic bytes 4*h*w*(N*C + 3*D) per launch over
+             its CUDA-event time, six launches per step pooled, against the measured HBM peak; per launch under
+             "roofline_per_launch".  "roofline_full_forward": the same kernel inside the `value` region, where the feature maps
+             come from the randomly initialised FeatureNet (not discriminative -> rough regressed depth: the adversarial case)
   cpu_baseline / --impl reference
-             the oracle port of the reference's PyTorch-CPU path (oracle/dmvs_oracle.py; the reference itself is pure
-             Python and cannot travel to the GPU box) on the host cores, on a bounded sample (a 1600x160 band of the
-             same view set, all stages, incl. FeatureNet), scaled linearly in rows to a full view.
+             the oracle port of the reference's PyTorch-CPU path (oracle/dmvs_oracle.py; the reference itself is pure Python and
+             does not exist on the GPU box) on all host cores, on the SAME full view (no band, no scaling)
+  gpu_library_baseline
+             the same restatement with its tensors on the B200 (the reference's PyTorch-CUDA / cuDNN path), TF32 off and on
+  check      final depth of the benchmarked view against the oracle's (computed once, untimed)
 
-N > 1: launched by torchrun, one process per GPU, independent replicas (one view set each; the path has no
-data-path collective - DESIGN.md "Multi-GPU"), barrier + max-over-ranks timing, scaling "weak".
+Weights: FeatureNet random, regularisation nets synthetic.ridge_regnet_state (follow the cost ridge like trained
+ones; all layers dense).  N > 1: torchrun, one process per GPU, independent replicas (one view set each; the path has no
+data-path collective - DESIGN.md "Multi-GPU"), barrier + max-over-ranks timing, scaling "weak"; rank 0 additionally times the
+single-view sharded mode when --sharded is given.
 """
 import argparse
 import json
@@ -41,7 +51,6 @@ CONFIGS = {
 }
 RATIOS = {1: [4], 3: [4, 2, 1]}
 FEATURE_C = (32, 16, 8)
-CPU_BAND_ROWS = 160
 
 
 def peaks():
@@ -89,60 +98,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_band_step(state, ndepths, ratios, views, width, rows, seed=0):
-    import torch
-    from dmvsnet_b200 import synthetic as syn
-    from oracle import dmvs_oracle as O
-    imgs = syn.make_images(rows, width, views, 1, seed=seed, natural=True)
-    proj = syn.make_proj_matrices(rows, width, views, 1, num_stages=len(ndepths))
-    dv = syn.make_depth_values(1, 192, inverse=True)
-
-    def step():
-        with torch.no_grad():
-            out = O.mvsnet_forward(imgs, proj, dv, state, ndepths, ratios, inverse_depth=True)
-        return float(out["depth"].mean())
-    return step
-
-
-def cpu_state(ndepths, ratios):
+# ------------------------------------------------------------------------------------------ workload (both arms)
+def make_workload(cfg_name, seed, want_features=True):
+    """The inputs of one step: images of the rendered scene, cameras, depth range, the network state - identical for both arms -
+    and (GPU arm) the conditioned feature maps of the hot_path region."""
     from dmvsnet_b200 import MVSNet, synthetic as syn
-    net = MVSNet(ndepths, ratios, inverse_depth=True)
-    return syn.randomise_regnet_state(net.state_dict(), seed=0)
-
-
-def run_reference_arm(args, cfg_name):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
     H, W, views, ndepths = CONFIGS[cfg_name]
     ratios = RATIOS[len(ndepths)]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    rows = min(CPU_BAND_ROWS, H)
-    step = cpu_band_step(cpu_state(ndepths, ratios), ndepths, ratios, views, W, rows)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    scale = H / float(rows)
-    value = 1.0 / (dt * scale)
-    sample = "%dx%d band (%d of %d rows) of the same view set, all stages incl. FeatureNet, scaled x%.2f in rows" % (W, rows, rows, H, scale)
-    line = {
-        "impl": "reference", "metric": "views/sec", "value": value, "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(cfg_name), "scope": "MVSNet.forward incl. FeatureNet, PyTorch-CPU fp32", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample,
-                         "cpu": cpu_model(), "torch_threads": torch.get_num_threads()},
-        "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
-    return 0
+    proj = syn.make_proj_matrices(H, W, views, 1, num_stages=len(ndepths))
+    dv = syn.make_depth_values(1, 192, inverse=True)
+    imgs = syn.make_scene_images(H, W, views, proj["stage%d" % len(ndepths)], seed=seed)
+    net = MVSNet(ndepths, ratios, inverse_depth=True)
+    state = syn.ridge_regnet_state(net.state_dict(), seed=0)
+    feats = syn.make_scene_features(H, W, views, proj, seed=seed, num_stages=len(ndepths)) if want_features else None
+    return dict(H=H, W=W, views=views, ndepths=ndepths, ratios=ratios, proj=proj, dv=dv, imgs=imgs, net=net, state=state, feats=feats)
+
+
+def workload_name(cfg_name):
+    H, W, views, nd = CONFIGS[cfg_name]
+    return "%s %dx%d N=%d D=%s, B=1, 3-stage cascade, inverse_depth" % (cfg_name.upper(), W, H, views, nd)
 
 
 def cpu_model():
@@ -155,16 +129,66 @@ def cpu_model():
     return "unknown"
 
 
-def workload_name(cfg_name):
-    H, W, views, nd = CONFIGS[cfg_name]
-    return "%s %dx%d N=%d D=%s, B=1, 3-stage cascade, inverse_depth" % (cfg_name.upper(), W, H, views, nd)
+def oracle_forward(wl, device=None):
+    """MVSNet.forward of the oracle port on ``device`` (None: host CPU).  Returns a closure that runs one full view."""
+    import torch
+    from oracle import dmvs_oracle as O
+    if device is None:
+        imgs, proj, dv, state = wl["imgs"], wl["proj"], wl["dv"], wl["state"]
+    else:
+        imgs, dv = wl["imgs"].to(device), wl["dv"].to(device)
+        proj = {k: v.to(device) for k, v in wl["proj"].items()}
+        state = {k: v.to(device) for k, v in wl["state"].items()}
+
+    def step():
+        with torch.no_grad():
+            return O.mvsnet_forward(imgs, proj, dv, state, wl["ndepths"], wl["ratios"], inverse_depth=True)
+    return step
+
+
+def depth_errors(got, want):
+    """max / p99.9 / mean relative error and the fraction of pixels beyond the 1e-3 contract."""
+    e = ((got.detach().cpu().double() - want.detach().cpu().double()).abs() / want.detach().cpu().double().abs().clamp_min(1.0)).flatten()
+    k = max(1, int(0.999 * e.numel()))
+    return {"max": float(e.max()), "p99_9": float(e.kthvalue(k)[0]), "mean": float(e.mean()), "frac_beyond_1e-3": float((e > 1e-3).double().mean())}
+
+
+def run_reference_arm(args, cfg_name):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads, the same full view."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = make_workload(cfg_name, seed=0, want_features=False)
+    step = oracle_forward(wl)
+    # a full DTU view is ~25 s on 16 cores: the step count is capped so that the run ends within a few minutes
+    warm, timed = min(args.warmup, 1), max(1, min(args.steps, 2))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(timed):
+        out = step()
+    dt = (time.perf_counter() - t0) / timed
+    value = 1.0 / dt
+    sample = "the full %dx%d view (no band, no scaling), %d warm-up + %d timed passes (of --steps %d --warmup %d asked: one pass is ~%.0f s)" % (
+        wl["W"], wl["H"], warm, timed, args.steps, args.warmup, dt)
+    line = {
+        "impl": "reference", "metric": "views/sec", "value": value, "unit": "views/s", "n_gpus": args.gpus, "steps": timed,
+        "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg_name), "scope_value": "MVSNet.forward incl. FeatureNet (scope F), PyTorch-CPU fp32", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample,
+                         "cpu": cpu_model(), "torch_threads": torch.get_num_threads()},
+        "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "check": {"depth_mean": float(out["depth"].mean())},
+    }
+    print(json.dumps(line))
+    return 0
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def w1_bytes(h, w, n_views, c, d):
-    return 4 * h * w * (n_views * c + 3 * d)
-
-
 def in_bounds_fraction(rt, hyp, step=4):
     """Fraction of plane-sweep samples whose bilinear footprint centre lies inside the source image (subsampled)."""
     import torch
@@ -184,10 +208,38 @@ def in_bounds_fraction(rt, hyp, step=4):
     return float(torch.stack(fr).mean())
 
 
+def w1_roofline(prof, n_steps, views, peak, inb=None):
+    """Pool the W1 launches recorded by ops.PROFILE: (summary dict, per-launch rows, other groups' ms per step)."""
+    per_launch = {}
+    for (tag, ev0, ev1, nbytes) in prof:
+        d = per_launch.setdefault(tag, [0.0, 0, nbytes])
+        d[0] += ev0.elapsed_time(ev1); d[1] += 1
+    w1 = {k: v for k, v in per_launch.items() if k.startswith("w1:")}
+    w1_ms = sum(v[0] for v in w1.values()) / n_steps
+    w1_bytes_total = sum(v[2] * v[1] for v in w1.values()) / n_steps
+    rows = []
+    for k, v in sorted(w1.items()):
+        gbs = v[2] / (v[0] / v[1] * 1e-3) / 1e9
+        rows.append({"launch": k, "ms": v[0] / v[1], "alg_MB": v[2] / 1e6, "GBps": gbs, "frac": gbs / peak, "in_bounds": (inb or {}).get(k)})
+    achieved = w1_bytes_total / (w1_ms * 1e-3) / 1e9 if w1_ms > 0 else 0.0
+    # what the gather moves through the SMs' L1 / shared-memory data pipe: samples x 4 corners x C x 2 B (fp16 sources)
+    gather_bytes = 0.0
+    for k in w1:
+        c_, d_, hw_ = k[3:].split("_")
+        h_, w_ = hw_.split("x")
+        gather_bytes += float(h_) * float(w_) * int(d_[1:]) * (views - 1) * 4 * int(c_[1:]) * 2
+    groups = {}
+    for k, v in per_launch.items():
+        if not k.startswith("w1:"):
+            groups[k.split(":")[0]] = groups.get(k.split(":")[0], 0.0) + v[0] / n_steps
+    return {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_step": w1_bytes_total, "ms_per_step": w1_ms,
+            "gather_bytes_per_step": gather_bytes}, rows, dict(groups, w1=w1_ms)
+
+
 def run_gpu_arm(args, cfg_name):
     import torch
     import torch.distributed as dist
-    from dmvsnet_b200 import MVSNet, _native, ops, synthetic as syn
+    from dmvsnet_b200 import _native, ops
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,96 +264,95 @@ def run_gpu_arm(args, cfg_name):
             os.close(saved)
     _native.load()
 
-    H, W, views, ndepths = CONFIGS[cfg_name]
-    ratios = RATIOS[len(ndepths)]
-    net = MVSNet(ndepths, ratios, inverse_depth=True)
-    state = syn.randomise_regnet_state(net.state_dict(), seed=0)
-    net.load_state_dict(state)
+    # every rank works on its own view set (independent replicas)
+    wl = make_workload(cfg_name, seed=rank)
+    H, W, views, ndepths = wl["H"], wl["W"], wl["views"], wl["ndepths"]
+    net = wl["net"]
+    net.load_state_dict(wl["state"])
     net = net.to(dev).eval()
     net.DepthNet.return_prob_volume = True  # reference default: the probability volumes are part of the output
-
-    # every rank works on its own view set (independent replicas)
-    imgs_host = syn.make_images(H, W, views, 1, seed=rank, natural=True).pin_memory()
-    proj = syn.make_proj_matrices(H, W, views, 1, num_stages=len(ndepths))
-    dv_host = syn.make_depth_values(1, 192, inverse=True)
+    net.w1_precision = args.w1
+    imgs_host = wl["imgs"].pin_memory()
+    proj, dv_host = wl["proj"], wl["dv"]
     dv = dv_host.to(dev)
-    torch.backends.cudnn.benchmark = True  # reference model.py:25
-
+    imgs_dev = imgs_host.to(dev)
     with torch.no_grad():
-        imgs_dev = imgs_host.to(dev)
-        feats = net.extract_features(imgs_dev)
-        del imgs_dev
+        cond = [{k: v.to(dev) for k, v in f.items()} for f in wl["feats"]]
+        if net.w1_precision == "fp16":
+            net.add_half_features(cond)  # what FeatureNet's epilogue emits for the source views
     torch.cuda.synchronize()
+
+    def full_step():
+        with torch.no_grad():
+            return net(imgs_dev, proj, dv)
 
     def hot_step():
         with torch.no_grad():
-            return net.cascade(feats, proj, dv, (H, W))
+            return net.cascade(cond, proj, dv, (H, W))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also JIT-free: everything is precompiled), then the timed hot-path region
-    for _ in range(max(args.warmup, 3)):
-        out = hot_step()
-    del out
+    def timed(fn, steps, profile=False):
+        if profile:
+            ops.PROFILE = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = _native.launch_count()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        prof, ops.PROFILE = ops.PROFILE, None
+        return e0.elapsed_time(e1), out, prof, _native.launch_count() - l0
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        full_step()
+        hot_step()
     barrier()
     if args.profile_step:
-        # exactly one hot-path step between cudaProfilerStart/Stop, for `ncu --profile-from-start off`
+        # exactly one step between cudaProfilerStart/Stop, for `ncu --profile-from-start off`
         torch.cuda.cudart().cudaProfilerStart()
-        hot_step()
+        (full_step if args.profile_step == "full" else hot_step)()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return 0
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    ops.PROFILE = []
-    launches0 = _native.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = hot_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _native.launch_count() - launches0
-    prof, ops.PROFILE = ops.PROFILE, None
+    # ---- value: the full forward, images resident in HBM.  The per-op CUDA events of ops.PROFILE ride along (a few us each).
+    ms, out, prof_full, launches = timed(full_step, args.steps, profile=True)
+    depth_full = out["depth"].clone()
+    # ---- hot_path: the stage loop on the conditioned feature maps
+    hot_ms, out, prof_hot, hot_launches = timed(hot_step, args.steps, profile=True)
+    depth_hot = out["depth"].clone()
     clocks = sampler.stop()
-    depth_mean = float(out["depth"].mean())
-
-    # in-bounds fraction of the six W1 launches (one extra untimed step, recorded hypotheses)
-    inb = {}
-    ops.CAPTURE = []
-    hot_step()
-    for tag, rt_t, hyp_t in ops.CAPTURE:
-        inb[tag] = in_bounds_fraction(rt_t, hyp_t)
-    ops.CAPTURE = None
     del out
 
-    # ---- e2e: host images in, host depth/confidence out, every step.  Two numbers: `e2e` = the streaming loop a test run
-    # executes (Model.test visits one reference view after the other): MVSNet.infer_many, where item k+1's H2D and item
-    # k-1's D2H run on a copy stream under item k's compute - every step still performs its own copies inside the timed
-    # region; `e2e_single` = one blocking MVSNet.infer() call per step (latency of a lone request).
+    # in-bounds fraction of the six W1 launches (one extra untimed step each, recorded hypotheses)
+    inb_hot, inb_full = {}, {}
+    for fn, dst in ((hot_step, inb_hot), (full_step, inb_full)):
+        ops.CAPTURE = []
+        fn()
+        for tag, rt_t, hyp_t in ops.CAPTURE:
+            dst[tag] = in_bounds_fraction(rt_t, hyp_t)
+        ops.CAPTURE = None
+
+    # ---- e2e: host images in, host depth/confidence out, every step
     for _ in range(2):
         host = net.infer(imgs_host, proj, dv_host)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     e2e_steps = max(3, min(args.steps, 10))
-    barrier()
-    t0.record()
-    for _ in range(e2e_steps):
-        host = net.infer(imgs_host, proj, dv_host)
-    t1.record()
-    barrier()
-    e2e_single_ms = t0.elapsed_time(t1)
+    e2e_single_ms, _, _, _ = timed(lambda: net.infer(imgs_host, proj, dv_host), e2e_steps)
     for host in net.infer_many([(imgs_host, proj, dv_host)] * 4):  # warm-up: fills the pipeline, so every pinned result buffer exists
         pass
     # two passes of e2e_steps items each, the faster one is reported (both are listed): a single host-side hiccup (pinned
     # allocator growth, a page-fault burst on a fresh box) otherwise lands on 10 steps
     e2e_passes = []
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(2):
         barrier()
         wall0 = time.perf_counter()
@@ -312,106 +363,114 @@ def run_gpu_arm(args, cfg_name):
         t1.record()
         barrier()
         assert n_out == e2e_steps
-        # t1 is recorded after the generator has waited for the last D2H
         e2e_passes.append((t0.elapsed_time(t1), (time.perf_counter() - wall0) * 1e3))
     e2e_ms, e2e_wall_ms = min(e2e_passes)
-    h2d = imgs_host.numel() * 4 + dv_host.numel() * 4 + sum(v.numel() * 4 for v in proj.values())
+    h2d = imgs_host.numel() * imgs_host.element_size() + dv_host.numel() * 4 + sum(v.numel() * 4 for v in proj.values())
     d2h = sum(v.numel() * 4 for v in host.values())
 
-    # ---- device-resident full forward (scope F without the copies), for the breakdown
-    imgs_dev = imgs_host.to(dev)
-    with torch.no_grad():
-        net(imgs_dev, proj, dv)
-        barrier()
-        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(3):
-            net(imgs_dev, proj, dv)
-        f1.record()
-        barrier()
-    full_ms = f0.elapsed_time(f1) / 3
-
     # ---- reduce over ranks (max time)
-    t = torch.tensor([ms, e2e_ms, full_ms, e2e_single_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, hot_ms, e2e_ms, e2e_single_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, full_ms, e2e_single_ms = [float(x) for x in t]
+    ms, hot_ms, e2e_ms, e2e_single_ms = [float(x) for x in t]
 
-    # ---- W1 roofline from the per-launch events recorded inside the timed region
     peak, peak_src, _ = peaks()
-    per_launch = {}
-    for (tag, ev0, ev1, nbytes) in prof:
-        d = per_launch.setdefault(tag, [0.0, 0, nbytes])
-        d[0] += ev0.elapsed_time(ev1); d[1] += 1
     n_steps = float(args.steps)
-    w1 = {k: v for k, v in per_launch.items() if k.startswith("w1:")}
-    w1_ms = sum(v[0] for v in w1.values()) / n_steps
-    w1_bytes_total = sum(v[2] * v[1] for v in w1.values()) / n_steps
-    roof_rows = []
-    for i, (k, v) in enumerate(sorted(w1.items())):
-        gbs = v[2] / (v[0] / v[1] * 1e-3) / 1e9
-        roof_rows.append({"launch": k, "ms": v[0] / v[1], "alg_MB": v[2] / 1e6, "GBps": gbs, "frac": gbs / peak,
-                          "in_bounds": inb.get(k)})
-    achieved = w1_bytes_total / (w1_ms * 1e-3) / 1e9 if w1_ms > 0 else 0.0
-    # What actually bounds a fused bilinear gather: every sample pulls 4 corners x C floats through the SM's
-    # L1 / shared-memory data path (128 B per clock per SM), whatever HBM does.  Tags are "w1:C<c>_D<d>_<h>x<w>".
-    gather_bytes = 0.0
-    for k in w1:
-        c_, d_, hw_ = k[3:].split("_")
-        h_, w_ = hw_.split("x")
-        gather_bytes += float(h_) * float(w_) * int(d_[1:]) * (views - 1) * 4 * int(c_[1:]) * 4
-    sm_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9  # GB/s
+    roof_hot, rows_hot, groups_hot = w1_roofline(prof_hot, n_steps, views, peak, inb_hot)
+    roof_full, rows_full, groups_full = w1_roofline(prof_full, n_steps, views, peak, inb_full)
+    sm_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9  # GB/s through the SMs' shared-memory data pipe
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "w1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_w1_traffic.json")
     if os.path.exists(tp) and cfg_name == "dtu":
         traffic = json.load(open(tp)).get("dram_bytes_per_step")
-    groups = {}
-    for k, v in per_launch.items():
-        if not k.startswith("w1:"):
-            groups[k.split(":")[0]] = groups.get(k.split(":")[0], 0.0) + v[0] / n_steps
 
     if rank == 0:
+        kernel = {"fp16": "W1 = warp_corr_h16_kernel (fp16 source maps staged by TMA; reference view, weights, sums fp32), 6 launches per step pooled",
+                  "fp32": "W1 = warp_corr_staged_kernel (stage-1 planes) + warp_corr_nhwc_kernel (regressed hypotheses), 6 passes / 7 launches per step pooled"}[net.w1_precision]
         line = {
             "metric": "views/sec", "value": world * args.steps / (ms * 1e-3), "unit": "views/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(cfg_name),
-                       "arithmetic": "W1 / heads / sampler fp32; regularisation nets on tcgen05 kind::f16 with hi/lo-split fp16 operands "
-                                     "(hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) = fp32-class accuracy; FeatureNet fp32 direct convolutions (dmvs_conv2d_f32)",
-                       "scope_value": "hot path (stage loop mvsnet.py:208-258), features resident in HBM",
-                       "scope_e2e": "MVSNet.infer_many: per step pinned host imgs -> H2D -> FeatureNet (dmvs_conv2d_f32) -> hot path -> D2H depth+confidence",
-                       "l2": "inputs (1.06 GB of features + >1 GB of activations per step) exceed the 126 MB L2; no flush needed",
-                       "parallelism": "replicas x%d (one view set per GPU, no collective)" % world, "weights": "random (SURVEY App. D recipe)",
+                       "arithmetic": "fp32 throughout, except: W1's SOURCE feature maps are stored as fp16 (w1_precision=%s; products and sums fp32); "
+                                     "regularisation nets and FeatureNet's 3x3 layers on tcgen05 kind::f16 with hi/lo-split fp16 operands "
+                                     "(hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) = fp32-class accuracy" % net.w1_precision,
+                       "scope_value": "MVSNet.forward incl. FeatureNet (scope F), images resident in HBM",
+                       "scope_e2e": "MVSNet.infer_many: per step pinned host imgs -> H2D -> FeatureNet -> cascade -> D2H depth+confidence",
+                       "scope_hot_path": "stage loop mvsnet.py:208-258 (scope H) on photo-consistent feature maps resident in HBM",
+                       "l2": "inputs (113 MB of images, 1.06 GB of features, >1 GB of activations per step) exceed the 126 MB L2; no flush needed",
+                       "parallelism": "replicas x%d (one view set per GPU, no collective)" % world,
+                       "weights": "FeatureNet random (SURVEY App. D); regularisation nets follow the cost ridge like trained ones (synthetic.ridge_regnet_state)",
+                       "images": "renderings of a textured tilted plane seen by the rig's cameras (synthetic.make_scene_images)",
                        "prob_volume": "kept (reference default)"},
             "clocks": clocks,
             "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "api": "MVSNet.infer_many (streaming: copies of neighbouring steps overlap compute)",
-                    "wall_ms_per_step": e2e_wall_ms / e2e_steps, "passes_ms_per_step": [p[0] / e2e_steps for p in e2e_passes], "single_request_ms": e2e_single_ms / e2e_steps, "single_request_views_per_s": world * e2e_steps / (e2e_single_ms * 1e-3)},
+                    "wall_ms_per_step": e2e_wall_ms / e2e_steps, "passes_ms_per_step": [p[0] / e2e_steps for p in e2e_passes],
+                    "single_request_ms": e2e_single_ms / e2e_steps, "single_request_views_per_s": world * e2e_steps / (e2e_single_ms * 1e-3)},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "W1 = warp_corr_staged_kernel (stage-1 planes) + warp_corr_nhwc_kernel (regressed hypotheses), 6 passes / 7 launches per step pooled", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": w1_bytes_total, "ms_per_step": w1_ms,
-                         "on_chip": {"what": "bytes the gather moves through the SMs' L1/shared-memory data path (samples x 4 corners x C x 4 B) "
-                                             "against 148 SMs x 128 B/clk at the sampled SM clock: the floor of any fp32 gather formulation",
-                                     "bytes_per_step": gather_bytes, "peak_GBps": sm_peak, "floor_ms": gather_bytes / sm_peak / 1e6,
-                                     "frac": (gather_bytes / sm_peak / 1e6) / w1_ms if w1_ms > 0 else None}},
-            "roofline_per_launch": roof_rows,
-            "breakdown_ms_per_step": dict(groups, w1=w1_ms),
-            "full_forward_device_ms": full_ms,
-            "check": {"depth_mean": depth_mean},
+            "hot_path": {"value": world * args.steps / (hot_ms * 1e-3), "unit": "views/s", "ms_per_step": hot_ms / args.steps,
+                         "gpu_launches": int(hot_launches), "breakdown_ms_per_step": groups_hot},
+            "roofline": dict({"kernel": kernel, "bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": traffic, "peak_source": peak_src,
+                              "workload": "hot_path region (conditioned feature maps: the regressed depth is piecewise smooth, as a trained network's)",
+                              "on_chip": {"what": "bytes the gather moves through the SMs' shared-memory data pipe (samples x 4 corners x C x 2 B) against 148 SMs x "
+                                                  "128 B/clk at the sampled SM clock: the floor of this gather formulation; the kernel is instruction-issue bound above it",
+                                          "peak_GBps": sm_peak, "floor_ms": roof_hot["gather_bytes_per_step"] / sm_peak / 1e6,
+                                          "frac": (roof_hot["gather_bytes_per_step"] / sm_peak / 1e6) / roof_hot["ms_per_step"] if roof_hot["ms_per_step"] > 0 else None}},
+                             **{k: v for k, v in roof_hot.items() if k != "gather_bytes_per_step"}),
+            "roofline_per_launch": rows_hot,
+            "roofline_full_forward": dict({"workload": "value region: feature maps from the randomly initialised FeatureNet are not discriminative, the regressed "
+                                                       "depth is rough and most source footprints miss their staged box (direct global gathers)"},
+                                          **{k: v for k, v in roof_full.items() if k != "gather_bytes_per_step"}, per_launch=rows_full),
+            "breakdown_ms_per_step": groups_full,
+            "check": {"depth_mean": float(depth_full.mean()), "depth_mean_hot_path": float(depth_hot.mean())},
         }
         if world == 1 and not args.no_cpu:
-            import torch as _t
             cores = os.cpu_count() or 1
-            _t.set_num_threads(cores)
-            rows = min(CPU_BAND_ROWS, H)
-            step = cpu_band_step(state, ndepths, ratios, views, W, rows)
-            step()
-            t0c = time.perf_counter(); step(); dtc = time.perf_counter() - t0c
-            scale = H / float(rows)
-            line["cpu_baseline"] = {"value": 1.0 / (dtc * scale), "unit": "views/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
-                                    "sample": "%dx%d band (%d of %d rows), all stages incl. FeatureNet, 1 warm-up + 1 timed pass, scaled x%.2f"
-                                              % (W, rows, rows, H, scale), "seconds_for_sample": dtc}
+            torch.set_num_threads(cores)
+            from oracle import dmvs_oracle as O
+            # ---- cpu_baseline: the oracle port on the host cores, the same full view, one timed pass (the thread pool is warmed on
+            # a small problem first).  Its depth map doubles as the checker of the benchmarked view.
+            small = make_workload("tiny", seed=0, want_features=False)
+            oracle_forward(small)()
+            step = oracle_forward(wl)
+            t0c = time.perf_counter()
+            ref_out = step()
+            dtc = time.perf_counter() - t0c
+            line["cpu_baseline"] = {"value": 1.0 / dtc, "unit": "views/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+                                    "sample": "the full %dx%d view, all stages incl. FeatureNet (scope F), 1 timed pass after warming the thread pool on a "
+                                              "128x160 problem" % (W, H), "seconds_for_sample": dtc}
+            line["check"]["depth_rel_err_vs_oracle"] = dict(depth_errors(depth_full, ref_out["depth"]),
+                                                             what="final depth of the benchmarked full forward vs the oracle's on the same inputs")
+            for sname in ("stage1", "stage2"):
+                line["check"]["depth_rel_err_vs_oracle_" + sname] = depth_errors(full_step()[sname]["depth"], ref_out[sname]["depth"])
+            del ref_out
+            with torch.no_grad():
+                ref_hot = O.cascade_forward(wl["feats"], proj, dv_host, wl["state"], ndepths, wl["ratios"], True, (H, W))
+            line["check"]["depth_rel_err_vs_oracle_hot_path"] = dict(depth_errors(depth_hot, ref_hot["depth"]),
+                                                                      what="final depth of the hot_path region vs the oracle's cascade on the same feature maps")
+            del ref_hot
+            # ---- gpu_library_baseline: the same restatement on the B200 through ATen / cuDNN (reference model.py:25)
+            lib = {}
+            torch.backends.cudnn.benchmark = True
+            for name, tf32 in (("tf32_off", False), ("tf32_on", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                try:
+                    gstep = oracle_forward(wl, dev)
+                    for _ in range(2):
+                        gout = gstep()
+                    gms, gout, _, _ = timed(gstep, 3)
+                    lib[name] = {"value": 3 / (gms * 1e-3), "unit": "views/s", "ms_per_step": gms / 3,
+                                 "depth_rel_err_vs_product": depth_errors(gout["depth"], depth_full)}
+                    del gout
+                except Exception as e:  # e.g. out of memory on the largest configuration
+                    lib[name] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                torch.cuda.empty_cache()
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            lib["what"] = "oracle/dmvs_oracle.py (the reference's forward, restated) with its tensors on the B200: F.grid_sample, cuDNN conv3d / conv2d; images resident in HBM (scope F)"
+            line["gpu_library_baseline"] = lib
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -425,8 +484,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="dtu", choices=sorted(CONFIGS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--profile-step", action="store_true", help="run one hot-path step inside cudaProfilerStart/Stop and exit (for ncu)")
+    ap.add_argument("--w1", default="fp16", choices=["fp16", "fp32"], help="W1 source-map precision (MVSNet.w1_precision)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / check / gpu_library_baseline legs")
+    ap.add_argument("--profile-step", nargs="?", const="hot", default=None, choices=["hot", "full"],
+                    help="run one step (hot path or full forward) inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args, args.config)

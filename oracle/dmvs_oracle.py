@@ -3,8 +3,11 @@
 This file is a functional restatement, on PyTorch-CPU fp32, of the reference's
 algorithm for the path ``BASELINE.json:north_star`` names.  It is the checker
 for the CUDA path; nothing under ``dmvsnet_b200/`` may import it.  Only
-``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (``cpu_baseline`` leg
-and ``--impl reference``) use it.
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (``cpu_baseline`` leg,
+``--impl reference``, and the ``gpu_library_baseline`` leg, which times this
+same restatement with its tensors moved to the B200 - the reference's own
+PyTorch-CUDA / cuDNN path of SURVEY 8d - as a baseline beside the product,
+never inside it) use it.
 
 Parity pinning: the reference ships no tests, fixtures or golden vectors
  - "parity unpinned" by the reference's own tests.  The oracle is
@@ -57,8 +60,9 @@ def sampling_grid(rot: torch.Tensor, trans: torch.Tensor, hyp: torch.Tensor) -> 
     pixel, scale by depth, translate, patch exact zeros in Z, divide, normalise.
     """
     b, d, h, w = hyp.shape
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
-    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w)))  # [3,HW]
+    dev = hyp.device  # CPU in every parity test; bench.py's gpu_library_baseline leg runs the same code on the B200 through cuDNN
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev), torch.arange(w, dtype=torch.float32, device=dev), indexing="ij")
+    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w, device=dev)))  # [3,HW]
     rotated = torch.matmul(rot, pix.unsqueeze(0).expand(b, -1, -1))  # [B,3,HW]
     pts = rotated.unsqueeze(2) * hyp.reshape(b, 1, d, h * w) + trans.reshape(b, 3, 1, 1)
     z = pts[:, 2]
@@ -187,8 +191,8 @@ def depth_head(logits: torch.Tensor, hyp: torch.Tensor, interval: torch.Tensor) 
     g_lo2, g_hi2 = 2 * g_lo - g_hi, 2 * g_hi - g_lo
     s_lo2, s_hi2 = 2 * s_lo - s_hi, 2 * s_hi - s_lo
     stacks = [_stack6(s_lo, s_hi), _stack6(g_lo, g_hi), _stack6(s_lo2, s_hi2), _stack6(g_lo2, g_hi2)]
-    rows = (torch.arange(h) % 4).reshape(1, 1, h, 1)
-    cols = (torch.arange(w) % 2).reshape(1, 1, 1, w)
+    rows = (torch.arange(h, device=d4.device) % 4).reshape(1, 1, h, 1)
+    cols = (torch.arange(w, device=d4.device) % 2).reshape(1, 1, 1, w)
     nxt = torch.zeros_like(d4)
     for r in range(4):
         # rows 0,2 (small): even column -> low window; rows 1,3 (huge): even column -> high window
@@ -210,8 +214,8 @@ def refine_head(logits: torch.Tensor, hyp_c: torch.Tensor, interval: torch.Tenso
     b, _, h, w = d4.shape
     s_lo, s_hi = d4[:, 0:2].min(1)[0], d4[:, 0:2].max(1)[0]
     g_lo, g_hi = d4[:, 2:4].min(1)[0], d4[:, 2:4].max(1)[0]
-    ry = (torch.arange(h) % 2).reshape(1, h, 1)
-    cx = (torch.arange(w) % 2).reshape(1, 1, w)
+    ry = (torch.arange(h, device=d4.device) % 2).reshape(1, h, 1)
+    cx = (torch.arange(w, device=d4.device) % 2).reshape(1, 1, w)
     depth = torch.where(ry == 0, torch.where(cx == 0, s_lo, s_hi), torch.where(cx == 0, g_hi, g_lo))
     return {"depth": depth, "photometric_confidence_refine": _confidence(d4, interval), "depth_sub_plus_refine": d4}
 
@@ -232,25 +236,25 @@ def depth_hypotheses(last_depth: torch.Tensor, ndepth: int, interval_pixel, shap
         lo, hi = last_depth[:, 0], last_depth[:, -1]
         step = (hi - lo) / (ndepth - 1)
         si = step[0]  # batch 0 only, module.py:564,603
-        k = torch.arange(ndepth, dtype=last_depth.dtype).reshape(1, -1)
+        k = torch.arange(ndepth, dtype=last_depth.dtype, device=last_depth.device).reshape(1, -1)
         if not inverse:
             planes = lo.unsqueeze(1) + k * step.unsqueeze(1)
             planes_n, planes_p = planes - si, planes + si
         else:
             def inv_planes(a, b_):
-                return 1 / torch.stack([torch.linspace(float(1 / x), float(1 / y), ndepth) for x, y in zip(a, b_)])
+                return 1 / torch.stack([torch.linspace(float(1 / x), float(1 / y), ndepth, device=last_depth.device) for x, y in zip(a, b_)])
             # the interval is recomputed after the shift and comes out unchanged (module.py:606-621)
             planes_n = inv_planes(lo - si, hi - si)
             si2 = (((hi - si) - (lo - si)) / (ndepth - 1))[0]
             planes_p = inv_planes(lo + si2, hi + si2)
             si = ((((hi + si2) - (lo + si2)) / (ndepth - 1))[0])
-        ys = torch.arange(h).reshape(1, 1, h, 1)
-        xs = torch.arange(w).reshape(1, 1, 1, w)
+        ys = torch.arange(h, device=last_depth.device).reshape(1, 1, h, 1)
+        xs = torch.arange(w, device=last_depth.device).reshape(1, 1, 1, w)
         even = ((ys + xs) % 2) == 0
         samples = torch.where(even, planes_n.reshape(-1, ndepth, 1, 1), planes_p.reshape(-1, ndepth, 1, 1))
         return samples.float().contiguous(), si.float() if inverse else si
     b, h, w = last_depth.shape
-    k = torch.arange(ndepth, dtype=last_depth.dtype).reshape(1, -1, 1, 1)
+    k = torch.arange(ndepth, dtype=last_depth.dtype, device=last_depth.device).reshape(1, -1, 1, 1)
 
     def ranged(lo_off, hi_off):
         lo = last_depth - lo_off / 2 * interval_pixel
@@ -262,8 +266,8 @@ def depth_hypotheses(last_depth: torch.Tensor, ndepth: int, interval_pixel, shap
 
     samples_n = ranged(ndepth + 2, ndepth - 2)   # module.py:476-491 / 540-554
     samples_p = ranged(ndepth - 2, ndepth + 2)   # module.py:492-507 / 525-539
-    ys = torch.arange(h).reshape(1, 1, h, 1)
-    xs = torch.arange(w).reshape(1, 1, 1, w)
+    ys = torch.arange(h, device=last_depth.device).reshape(1, 1, h, 1)
+    xs = torch.arange(w, device=last_depth.device).reshape(1, 1, 1, w)
     even = ((ys + xs) % 2) == 0
     interval = (ndepth * interval_pixel) / (ndepth - 1)
     samples = torch.where(even, samples_n, samples_p)
