@@ -236,6 +236,62 @@ def w1_roofline(prof, n_steps, views, peak, inb=None):
             "gather_bytes_per_step": gather_bytes}, rows, dict(groups, w1=w1_ms)
 
 
+def sharded_leg(args, world, rank, dev, barrier):
+    """Single-view mode (BASELINE config 4): ONE view set on all `world` GPUs - FeatureNet by view + all-gather of the
+    fp16 source maps, the stage loop by row bands with a 32-row halo (dmvsnet_b200/parallel.py) - timed beside the same view on
+    one GPU (every rank runs the unsharded forward on the same inputs; max over ranks of both)."""
+    import torch
+    import torch.distributed as dist
+    from dmvsnet_b200 import parallel
+    cfg = args.sharded_config
+    wl = make_workload(cfg, seed=0, want_features=False)
+    net = wl["net"]
+    net.load_state_dict(wl["state"])
+    net = net.to(dev).eval()
+    net.DepthNet.return_prob_volume = False  # the sharded mode leaves the volumes on the ranks that own the rows
+    net.w1_precision = "fp16"
+    imgs = wl["imgs"].to(dev)
+    proj, dv = wl["proj"], wl["dv"].to(dev)
+
+    def single():
+        with torch.no_grad():
+            return net(imgs, proj, dv)
+
+    def sharded():
+        with torch.no_grad():
+            return parallel.infer_view_sharded(net, imgs, proj, dv)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps, out
+    for _ in range(3):
+        single(); sharded()
+    steps = max(3, min(args.steps, 10))
+    t1, ref = timed(single, steps)
+    tn, out = timed(sharded, steps)
+    same = all(torch.equal(out[k], ref[k]) for k in ("depth", "photometric_confidence")) and \
+        all(torch.equal(out["stage%d" % s]["depth"], ref["stage%d" % s]["depth"]) for s in (1, 2, 3))
+    worst = max(float((out["stage%d" % s]["depth"] - ref["stage%d" % s]["depth"]).abs().max() / ref["stage%d" % s]["depth"].abs().max()) for s in (1, 2, 3))
+    # the exchanged bytes of one view: fp16 source maps (all-gather) + the per-stage maps (all-reduce of zero-padded maps)
+    t = torch.tensor([t1, tn, 0.0 if same else 1.0, worst], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    H, W, views = wl["H"], wl["W"], wl["views"]
+    gather_bytes = sum(2 * 2 * c * (H >> (2 - s)) * (W >> (2 - s)) for s, c in enumerate(FEATURE_C)) * (views - 1)
+    reduce_bytes = sum(4 * 15 * (H >> (2 - s)) * (W >> (2 - s)) for s in range(3))
+    return {"workload": workload_name(cfg), "ranks": world, "ms_per_view_1gpu": float(t[0]), "ms_per_view": float(t[1]),
+            "speedup_vs_1gpu": float(t[0] / t[1]), "bit_identical": bool(t[2] == 0.0), "depth_max_rel_diff": float(t[3]),
+            "scope": "MVSNet.forward incl. FeatureNet, images resident on every GPU, depth + confidence re-assembled on every GPU",
+            "exchange": {"all_gather_fp16_source_maps_bytes": gather_bytes, "all_reduce_per_pixel_maps_bytes": reduce_bytes,
+                         "collectives_per_view": 6 + 2 * 3},
+            "partition": "FeatureNet by view (+ the reference view on every rank); stage loop by row bands, 32-row halo, edges at multiples of 8 rows"}
+
+
 def run_gpu_arm(args, cfg_name):
     import torch
     import torch.distributed as dist
@@ -374,6 +430,12 @@ def run_gpu_arm(args, cfg_name):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, hot_ms, e2e_ms, e2e_single_ms = [float(x) for x in t]
 
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        del cond
+        torch.cuda.empty_cache()
+        sharded = sharded_leg(args, world, rank, dev, barrier)
+
     peak, peak_src, _ = peaks()
     n_steps = float(args.steps)
     roof_hot, rows_hot, groups_hot = w1_roofline(prof_hot, n_steps, views, peak, inb_hot)
@@ -425,6 +487,8 @@ def run_gpu_arm(args, cfg_name):
             "breakdown_ms_per_step": groups_full,
             "check": {"depth_mean": float(depth_full.mean()), "depth_mean_hot_path": float(depth_hot.mean())},
         }
+        if sharded is not None:
+            line["sharded"] = sharded
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
@@ -485,6 +549,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="dtu", choices=sorted(CONFIGS))
     ap.add_argument("--w1", default="fp16", choices=["fp16", "fp32"], help="W1 source-map precision (MVSNet.w1_precision)")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the single-view sharded leg")
+    ap.add_argument("--sharded-config", default="tnt", choices=sorted(CONFIGS), help="N > 1: the view set of the single-view sharded leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / check / gpu_library_baseline legs")
     ap.add_argument("--profile-step", nargs="?", const="hot", default=None, choices=["hot", "full"],
                     help="run one step (hot path or full forward) inside cudaProfilerStart/Stop and exit (for ncu)")

@@ -48,7 +48,7 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_warp_corr_flag_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "dmvs_warp_corr_h16_f32": (c_int, [c_void_p, c_longlong, c_int, POINTER(c_void_p), c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                       c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                       c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_features_nhwc_f16": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_warp_corr_backward_f32": (c_int, [c_void_p, c_longlong, c_int, POINTER(c_void_p), c_longlong, c_int, c_int, c_void_p, c_void_p,
                                             c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p]),

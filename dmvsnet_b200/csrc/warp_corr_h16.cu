@@ -42,6 +42,8 @@ struct alignas(64) W1hParams {
   long long ref_bs, src_bs;
   int ref_ps, src_ps;
   int B, D, h, w, n_src, d_begin, d_end, n_chunks, chunk0, tiles_x;
+  int row0;  // absolute image row of row 0 of the reference band (ref / hyp / cost hold rows [row0, row0 + h) of the view)
+  int hs;    // rows of the (full) source maps
 };
 
 // box shapes in pixels: wide (BW0 x BH0) and tall (BW1 x BH1); widths are multiples of 8 (bank phase = pixel index & 7)
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(256, (C == 8 ? 3 : 2)) warp_corr_h16_kernel(co
     const float dmin = __int_as_float(lo), dmax = __int_as_float(hi);
     const int vtx = lane & 7;
     const float vx = (float)((vtx & 1) ? min(X0 + 15, p.w - 1) : X0);
-    const float vy = (float)((vtx & 2) ? min(Y0 + 15, p.h - 1) : Y0);
+    const float vy = (float)(((vtx & 2) ? min(Y0 + 15, p.h - 1) : Y0) + p.row0);
     const float vd = (vtx & 4) ? dmax : dmin;
     for (int sg = 0; sg < p.n_src; sg += 4) {
       const int s = sg + (lane >> 3);
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(256, (C == 8 ? 3 : 2)) warp_corr_h16_kernel(co
         int shape = -1;
         // footprints with at least one corner inside the image have x0 in [-1, w-1], y0 in [-1, h-1]; one pixel of slack
         mnx = max(mnx - 1, -1); mxx = min(mxx + 1, p.w - 1);
-        mny = max(mny - 1, -1); mxy = min(mxy + 1, p.h - 1);
+        mny = max(mny - 1, -1); mxy = min(mxy + 1, p.hs - 1);
         if (ok && mxx >= mnx && mxy >= mny) {
           const int needw = mxx - mnx + 2, needh = mxy - mny + 2;
           if (needw <= Box::BW0 && needh <= Box::BH0) shape = 0;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(256, (C == 8 ? 3 : 2)) warp_corr_h16_kernel(co
   float acc[DP][2];
 #pragma unroll
   for (int j = 0; j < DP; ++j) acc[j][0] = acc[j][1] = 0.0f;
-  const float fx = (float)xc, fy = (float)yc;
+  const float fx = (float)xc, fy = (float)(yc + p.row0);
   const float inv_half = 2.0f / (float)C;
   uint32_t phases = 0;  // bit i: parity to wait for on slot i
 
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(256, (C == 8 ? 3 : 2)) warp_corr_h16_kernel(co
         const float ix = pix_x[j], iy = pix_y[j];
         const float f0x = floorf(ix), f0y = floorf(iy);
         const bool finite = (fabsf(ix) <= 3.0e38f) && (fabsf(iy) <= 3.0e38f);
-        const bool inside = finite && f0x >= -1.0f && f0x <= (float)(p.w - 1) && f0y >= -1.0f && f0y <= (float)(p.h - 1);
+        const bool inside = finite && f0x >= -1.0f && f0x <= (float)(p.w - 1) && f0y >= -1.0f && f0y <= (float)(p.hs - 1);
         float g0 = 0.0f, g1 = 0.0f;
         if (wanted && !finite) g0 = g1 = __int_as_float(0x7fc00000);  // the reference multiplies zeros by NaN weights
         if (wanted && inside) {
@@ -334,8 +336,8 @@ __global__ void __launch_bounds__(256, (C == 8 ? 3 : 2)) warp_corr_h16_kernel(co
             gather_staged<C>(box + (uint32_t)(ryp * bw + rxp) * (C * 2), (uint32_t)bw * (C * 2), ix - f0x, iy - f0y, refv, g0, g1);
           } else {
             // ---- direct: the same corners from global memory, out-of-image corners contribute zero
-            const bool xa = x0 >= 0, xb = x0 + 1 < p.w, ya = y0 >= 0, yb = y0 + 1 < p.h;
-            const int xl = max(x0, 0), xr = min(x0 + 1, p.w - 1), yt = max(y0, 0), yu = min(y0 + 1, p.h - 1);
+            const bool xa = x0 >= 0, xb = x0 + 1 < p.w, ya = y0 >= 0, yb = y0 + 1 < p.hs;
+            const int xl = max(x0, 0), xr = min(x0 + 1, p.w - 1), yt = max(y0, 0), yu = min(y0 + 1, p.hs - 1);
             const uint4* q4[4] = {reinterpret_cast<const uint4*>(gsrc + ((long long)yt * p.w + xl) * p.src_ps),
                                   reinterpret_cast<const uint4*>(gsrc + ((long long)yt * p.w + xr) * p.src_ps),
                                   reinterpret_cast<const uint4*>(gsrc + ((long long)yu * p.w + xl) * p.src_ps),
@@ -488,7 +490,7 @@ static int launch_w1h(W1hParams& p, cudaStream_t st) {
   const CUtensorMapSwizzle swz = (C == 32) ? CU_TENSOR_MAP_SWIZZLE_64B : (C == 16) ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   for (int s = 0; s < p.n_src; ++s) {
     for (int shape = 0; shape < 2; ++shape) {
-      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.B};
+      const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)p.w, (cuuint64_t)p.hs, (cuuint64_t)p.B};
       const cuuint64_t strides[3] = {(cuuint64_t)p.src_ps * 2, (cuuint64_t)p.w * p.src_ps * 2, (cuuint64_t)p.src_bs * 2};
       const cuuint32_t bx[4] = {(cuuint32_t)C, (cuuint32_t)(shape ? Box::BW1 : Box::BW0), (cuuint32_t)(shape ? Box::BH1 : Box::BH0), 1};
       const cuuint32_t es[4] = {1, 1, 1, 1};
@@ -537,7 +539,7 @@ extern "C" int dmvs_features_nhwc_f16(const float* x, long long x_bstride, int x
 
 extern "C" int dmvs_warp_corr_h16_f32(const float* ref, long long ref_bstride, int ref_pixstride, const void* const* src, long long src_bstride,
                                       int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells, int B,
-                                      int C, int D, int h, int w, int d_begin, int d_end, void* stream) {
+                                      int C, int D, int h, int w, int d_begin, int d_end, int ref_row0, int src_rows, void* stream) {
   using namespace dmvs;
   DMVS_REQUIRE(ref && src && rt && hyp && (cost || cost_cells), DMVS_ERR_BAD_POINTER, "warp_corr_h16: null pointer");
   DMVS_REQUIRE(!cost_cells || aligned16(cost_cells), DMVS_ERR_BAD_POINTER, "warp_corr_h16: cost_cells must be 16-byte aligned");
@@ -550,7 +552,10 @@ extern "C" int dmvs_warp_corr_h16_f32(const float* ref, long long ref_bstride, i
                "warp_corr_h16: pixel stride %d / batch stride %lld must be multiples of 8 halfs and >= C", src_pixstride, src_bstride);
   DMVS_REQUIRE(ref_pixstride == 0 || (ref_pixstride >= C && ref_pixstride % 4 == 0 && ref_bstride % 4 == 0 && aligned16(ref)),
                DMVS_ERR_BAD_SHAPE, "warp_corr_h16: bad channel-last reference stride %d", ref_pixstride);
-  DMVS_REQUIRE((long long)src_pixstride * h * w < (1LL << 31) && (long long)C * h * w < (1LL << 31), DMVS_ERR_BAD_SHAPE,
+  if (src_rows == 0) src_rows = h;
+  DMVS_REQUIRE(ref_row0 >= 0 && src_rows >= 2 && ref_row0 + h <= src_rows, DMVS_ERR_BAD_SHAPE,
+               "warp_corr_h16: reference band rows [%d, %d) do not lie inside the %d source rows", ref_row0, ref_row0 + h, src_rows);
+  DMVS_REQUIRE((long long)src_pixstride * src_rows * w < (1LL << 31) && (long long)C * h * w < (1LL << 31), DMVS_ERR_BAD_SHAPE,
                "warp_corr_h16: feature map too large for 32-bit offsets");
   for (int i = 0; i < n_src; ++i)
     DMVS_REQUIRE(src[i] != nullptr && aligned16(src[i]), DMVS_ERR_BAD_POINTER, "warp_corr_h16: src[%d] is null or not 16-byte aligned", i);
@@ -561,6 +566,7 @@ extern "C" int dmvs_warp_corr_h16_f32(const float* ref, long long ref_bstride, i
   p.ref = ref; p.rt = rt; p.hyp = hyp; p.cost = cost; p.cells = reinterpret_cast<uint2*>(cost_cells);
   p.ref_bs = ref_bstride; p.ref_ps = ref_pixstride; p.src_bs = src_bstride; p.src_ps = src_pixstride;
   p.B = B; p.D = D; p.h = h; p.w = w; p.n_src = n_src; p.d_begin = d_begin; p.d_end = d_end;
+  p.row0 = ref_row0; p.hs = src_rows;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (C) {
     case 8: return launch_w1h<8>(p, st);

@@ -175,7 +175,8 @@ def features_nhwc_f16(t) -> "HalfFeatures":
 
 def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor,
               d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
-              want_f32: bool = True, want_cells: bool = False, layout: Optional[str] = None, coherent: bool = False):
+              want_f32: bool = True, want_cells: bool = False, layout: Optional[str] = None, coherent: bool = False,
+              row0: int = 0):
     """features: N x [B,C,h,w] (reference view first), rt [B,N-1,12] (device), hyp [B,D,h,w] -> cost [B,2,D,h,w].
 
     ``want_cells``: additionally (or, with ``want_f32=False``, only) emit the cost volume in the cell layout the tensor
@@ -192,7 +193,9 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     if layout not in ("nhwc", "nchw", "staged", "h16"):
         raise ValueError("layout must be 'nhwc', 'nchw', 'staged' or 'h16'")
     if layout == "h16":
-        return _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells)
+        return _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells, row0)
+    if row0:
+        raise ValueError("row bands (row0 != 0) need layout='h16'")
     if any(isinstance(f, HalfFeatures) for f in features):
         raise TypeError("fp16 source maps (HalfFeatures) need layout='h16'")
     ref = _req(features[0], "features[0]")
@@ -259,8 +262,9 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
     return (out, cells) if want_cells else out
 
 
-def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells):
-    """``warp_corr(layout="h16")``: fp32 reference view, fp16 channel-last sources (fp32 sources are rounded on the fly)."""
+def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells, row0=0):
+    """``warp_corr(layout="h16")``: fp32 reference view, fp16 channel-last sources (fp32 sources are rounded on the fly).
+    Row band: the reference map and ``hyp`` may hold only rows [row0, row0 + h) of the view; the sources stay whole."""
     lib = N.load()
     ref = features[0].float() if isinstance(features[0], HalfFeatures) else _req(features[0], "features[0]")
     b, c, h, w = ref.shape
@@ -268,9 +272,10 @@ def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells):
     if n_src < 1 or n_src > N.MAX_SRC:
         raise ValueError("need 1..%d source views, got %d" % (N.MAX_SRC, n_src))
     srcs = [features_nhwc_f16(f) for f in features[1:]]
+    src_rows = srcs[0].shape[2]
     for i, f in enumerate(srcs):
-        if f.shape != ref.shape:
-            raise ValueError("features[%d] has shape %s, expected %s" % (i + 1, tuple(f.shape), tuple(ref.shape)))
+        if f.shape != srcs[0].shape or (f.shape[0], f.shape[1], f.shape[3]) != (b, c, w) or row0 + h > src_rows:
+            raise ValueError("features[%d] has shape %s, reference band %s at row %d" % (i + 1, tuple(f.shape), tuple(ref.shape), row0))
     ref_bs, ref_ps = _batch_stride(ref), 0
     if ref_bs < 0 and _nhwc_strides(ref) is not None and not is_pairs(ref):
         ref_ps, ref_bs = _nhwc_strides(ref)
@@ -295,7 +300,7 @@ def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells):
     nbytes = 4 * b * h * w * ((n_src + 1) * c + 3 * (hi - lo))
     with _timed("w1:C%d_D%d_%dx%d" % (c, hi - lo, h, w), nbytes):
         rc = lib.dmvs_warp_corr_h16_f32(ref.data_ptr(), ref_bs, ref_ps, src_ptrs, srcs[0].bstride, c, n_src, rt.data_ptr(), hyp.data_ptr(),
-                                        _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, _stream())
+                                        _ptr(out), _ptr(cells), b, c, d, h, w, lo, hi, int(row0), src_rows, _stream())
     N.check(rc, "dmvs_warp_corr_h16_f32")
     return (out, cells) if want_cells else out
 

@@ -169,3 +169,166 @@ def gather_rows(compute: Callable[[int, int, int, int], Optional[torch.Tensor]],
     dist.all_gather(recv, send, group=group)
     parts = [recv[r][: bands[r][1] - bands[r][0]] for r in range(world)]
     return torch.cat(parts, 0).movedim(0, dim).contiguous()
+
+
+# ----------------------------------------------------------------------------- single-view mode: the whole forward over R ranks
+# One reference view on R GPUs (BASELINE config 4: T&T 1920x1056, N = 11 on 8 x B200).  What is exchanged, per view:
+#   * FeatureNet shards by VIEW (reference mvsnet.py:199-202 loops over views): every rank computes the reference view (the only
+#     map W1 reads in fp32, and only its own rows of it) and its share of the source views, then ONE all-gather per feature map of
+#     the fp16 source maps (the format W1's staged kernel gathers from) makes all sources resident everywhere - stage-1 maps
+#     first, the later stages' gathers overlap the earlier stages' compute on NCCL's stream;
+#   * the stage loop shards by ROW BANDS with a 32-row halo (``row_bands``): W1 is pointwise in the reference pixel, so a rank
+#     computes the cost volume of its band + halo itself from the resident features; the U-Nets see real data 32 rows beyond the
+#     rows the rank owns (their receptive field is +-30), so the owned rows carry the bits of the unsharded result;
+#   * per stage two small exchanges re-assemble per-pixel maps: ``depth_values_c`` [B,4,h,w] after the main pass (the refine
+#     pass needs it 32 rows beyond the owned rows) and ``depth`` / confidence [B,h,w] after the refine pass (the next stage's
+#     sampler upsamples it: +-1 row).  They are all-reduces of zero-padded maps: x + 0 == x exactly, any order.
+# Nothing else crosses NVLink: no cost volume, no logits, no probability volume (those stay row-sharded).
+
+
+class _CudaBackend:
+    """The per-band operators of ``cascade_row_sharded`` on the CUDA library (a CPU stand-in with the same methods drives the
+    gloo test)."""
+
+    def __init__(self, net):
+        self.net = net
+
+    def hypotheses_first(self, dv, ndepth, shape, inverse):
+        from . import ops
+        return ops.hypotheses_first(dv, ndepth, shape, inverse)
+
+    def hypotheses_next(self, last, ndepth, ip, shape, inverse):
+        from . import ops
+        return ops.hypotheses_next(last, ndepth, ip, shape, inverse)
+
+    def regularised_logits(self, key, ref_band, srcs, rt, hyp_band, row0, stage, refine):
+        """W1 on a row band (fp16-staged kernel, conv0 cells) + the stage's regularisation net -> logits [B,4,D,rows,w]."""
+        from . import ops
+        _, cells = ops.warp_corr([ref_band] + list(srcs), rt, hyp_band, want_f32=False, want_cells=True, layout="h16", row0=row0)
+        mod = (self.net.cost_regularization_refine if refine else self.net.cost_regularization)[stage]
+        return mod(None, cost_cells=cells)
+
+    def depth_head(self, logits, hyp, interval):
+        from . import ops
+        return ops.depth_head(logits, hyp, interval, want_prob=False)[1:]
+
+    def refine_head(self, logits, hyp_c, interval):
+        from . import ops
+        return ops.refine_head(logits, hyp_c, interval, 5.0)
+
+
+def _assemble_rows(part: torch.Tensor, own: Tuple[int, int], num_rows: int, group) -> torch.Tensor:
+    """``part``: this rank's OWNED rows along dim -2 ([..., own_hi - own_lo, w]) -> the full map on every rank."""
+    full = part.new_zeros(tuple(part.shape[:-2]) + (num_rows, part.shape[-1]))
+    if own[1] > own[0]:
+        full[..., own[0]:own[1], :] = part
+    dist.all_reduce(full, group=group)
+    return full
+
+
+def cascade_row_sharded(net, ref_feats, src_feats, proj_matrices, depth_values: torch.Tensor, image_hw: Sequence[int],
+                        group: Optional[dist.ProcessGroup] = None, backend=None, wait_for=None):
+    """The stage loop of ``MVSNet.cascade`` (reference mvsnet.py:208-258) for ONE view set over the ranks of ``group`` by row
+    bands.  ``ref_feats``: the reference view's feature dict (fp32); ``src_feats``: list of the source views' dicts (on CUDA:
+    ``ops.HalfFeatures`` under the plain keys); every rank holds all of them.  ``wait_for(key)`` (optional) is called before a
+    feature map is first used (outstanding all-gathers).  Returns per stage the re-assembled ``depth``,
+    ``photometric_confidence``, ``photometric_confidence_refine``, ``depth_values_c`` and the flattened last stage like the
+    reference; volumes (logits, probabilities) stay on the rank that owns the rows."""
+    from . import ops
+    be = backend or _CudaBackend(net)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    num_stage = net.num_stage
+    rts = [ops.relative_projections(proj_matrices["stage%d" % (s + 1)]) for s in range(num_stage)]
+    dev = depth_values.device
+    rts = [r.to(dev, torch.float32) for r in rts]
+    depth_interval = (depth_values[0, -1] - depth_values[0, 0]) / depth_values.size(1)
+    outputs, last_depth = {}, None
+    for s in range(num_stage):
+        name = "stage%d" % (s + 1)
+        scale = 2 ** (num_stage - s - 1)
+        h, w = int(image_hw[0]) // scale, int(image_hw[1]) // scale
+        own_lo, own_hi, band_lo, band_hi = row_bands(h, world)[rank]
+        owns = own_hi > own_lo
+        # the sampler is a per-pixel map with a +-1 row stencil (x2 bilinear upsample): every rank evaluates it for the whole
+        # image (0.1 ms at DTU size) and keeps its band
+        if s == 0:
+            hyp, interval = be.hypotheses_first(depth_values, net.ndepths[s], [h, w], net.inverse_depth)
+        else:
+            hyp, interval = be.hypotheses_next(last_depth, net.ndepths[s], net.depth_interval_ratio[s] * depth_interval, [h, w], net.inverse_depth)
+        if wait_for is not None:
+            wait_for(name)
+        d4 = hyp_c = conf = None
+        if owns:
+            hyp_b = hyp[:, :, band_lo:band_hi].contiguous()
+            logits = be.regularised_logits(name, ref_feats[name][:, :, band_lo:band_hi], [f[name] for f in src_feats], rts[s], hyp_b, band_lo, s, False)
+            d4, hyp_c, conf = be.depth_head(logits, hyp_b, interval)
+            del logits
+            keep = slice(own_lo - band_lo, own_hi - band_lo)
+            d4, hyp_c, conf = d4[:, :, keep], hyp_c[:, :, keep], conf[:, keep]
+        else:
+            b = hyp.shape[0]
+            d4 = hyp.new_zeros(b, 4, 0, w); hyp_c = hyp.new_zeros(b, 4, 0, w); conf = hyp.new_zeros(b, 0, w)
+        packed = _assemble_rows(torch.cat([hyp_c, d4, conf.unsqueeze(1)], 1), (own_lo, own_hi), h, group)   # [B,9,h,w]
+        hyp_c_full, d4_full, conf_full = packed[:, 0:4], packed[:, 4:8], packed[:, 8]
+        if wait_for is not None:
+            wait_for(name + "_c")
+        if owns:
+            hyp_cb = hyp_c_full[:, :, band_lo:band_hi].contiguous()
+            logits_c = be.regularised_logits(name + "_c", ref_feats[name + "_c"][:, :, band_lo:band_hi], [f[name + "_c"] for f in src_feats],
+                                             rts[s], hyp_cb, band_lo, s, True)
+            depth, conf_r, d4r = be.refine_head(logits_c, hyp_cb, interval)
+            del logits_c
+            depth, conf_r, d4r = depth[:, keep], conf_r[:, keep], d4r[:, :, keep]
+        else:
+            depth = hyp.new_zeros(b, 0, w); conf_r = hyp.new_zeros(b, 0, w); d4r = hyp.new_zeros(b, 4, 0, w)
+        packed = _assemble_rows(torch.cat([depth.unsqueeze(1), conf_r.unsqueeze(1), d4r], 1), (own_lo, own_hi), h, group)  # [B,6,h,w]
+        stage_out = {"depth": packed[:, 0], "photometric_confidence_refine": packed[:, 1], "depth_sub_plus_refine": packed[:, 2:6],
+                     "photometric_confidence": conf_full, "depth_sub_plus": d4_full, "depth_values_c": hyp_c_full,
+                     "depth_values": hyp, "interval": interval}
+        last_depth = stage_out["depth"]
+        outputs[name] = stage_out
+        outputs.update(stage_out)
+    return outputs
+
+
+def extract_features_view_sharded(net, imgs: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """FeatureNet for one view set ``imgs`` [1,N,3,H,W] (resident on every rank) over the ranks by VIEW: every rank computes
+    the reference view and its share of the source views (round robin), then one all-gather per feature map of the fp16
+    source maps.  Returns ``(ref_feats, src_feats, wait_for)``: the reference dict (fp32), the list of N-1 source dicts of
+    ``ops.HalfFeatures`` and a callable that blocks the current stream on the gather a key is still waiting for."""
+    from . import ops
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if imgs.shape[0] != 1:
+        raise ValueError("single-view mode takes one view set (B = 1)")
+    n = imgs.shape[1]
+    mine = list(range(1 + rank, n, world))
+    per = -(-(n - 1) // world)
+    out = net.feature(imgs[0, [0] + mine])                       # {key: [1 + len(mine), C, h, w]} channel-last
+    ref = {k: t[0:1] for k, t in out.items()}
+    gathered, works = {}, {}
+    for key in ("stage1", "stage1_c", "stage2", "stage2_c", "stage3", "stage3_c"):
+        t = out[key]
+        _, c, h, w = t.shape
+        send = torch.zeros(per, h, w, c, device=t.device, dtype=torch.float16)
+        if mine:
+            send[:len(mine)] = ops.features_nhwc_f16(t[1:]).data
+        recv = torch.empty(world * per, h, w, c, device=t.device, dtype=torch.float16)
+        works[key] = dist.all_gather_into_tensor(recv, send, group=group, async_op=True)
+        gathered[key] = recv
+    srcs = []
+    for v in range(1, n):
+        j = v - 1
+        slot = (j % world) * per + (j // world)
+        srcs.append({k: ops.HalfFeatures(g[slot:slot + 1]) for k, g in gathered.items()})
+
+    def wait_for(key):
+        wk = works.pop(key, None)
+        if wk is not None:
+            wk.wait()
+    return ref, srcs, wait_for
+
+
+def infer_view_sharded(net, imgs: torch.Tensor, proj_matrices, depth_values: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """``MVSNet.forward`` of ONE view set on all ranks of ``group`` (every rank passes the same inputs, resident on its GPU)."""
+    ref, srcs, wait_for = extract_features_view_sharded(net, imgs, group)
+    return cascade_row_sharded(net, ref, srcs, proj_matrices, depth_values, imgs.shape[-2:], group, wait_for=wait_for)

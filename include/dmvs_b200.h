@@ -100,10 +100,13 @@ size_t dmvs_warp_corr_flag_bytes(int B, int D, int h, int w);
  * Per 16x16 pixel tile x plane chunk the footprint box of every source is derived from the tile's 8 corner projections,
  * fetched by TMA (zero fill = zeros padding) into a ring of shared-memory slots and gathered with conflict-free 16-byte loads;
  * a source whose box does not fit (rough hypotheses, wide baseline) is gathered from global memory by the same threads with
- * the same arithmetic - one launch, no scratch, result independent of the path taken and of [d_begin, d_end). */
+ * the same arithmetic - one launch, no scratch, result independent of the path taken and of [d_begin, d_end).
+ * Row bands (single-view sharding): `ref`, `hyp`, `cost` / `cost_cells` may hold only rows [ref_row0, ref_row0 + h) of
+ * the view while the source maps stay whole (`src_rows` rows; 0 = h): the absolute row enters the homography
+ * (module.py:227-236), so a band's result carries the same bits as the same rows of the unsharded call. */
 int dmvs_warp_corr_h16_f32(const float* ref, long long ref_bstride, int ref_pixstride, const void* const* src, long long src_bstride,
                            int src_pixstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells, int B, int C,
-                           int D, int h, int w, int d_begin, int d_end, void* stream);
+                           int D, int h, int w, int d_begin, int d_end, int ref_row0, int src_rows, void* stream);
 
 /* fp32 feature map -> fp16 dense channel-last [B,h,w,C] (the source-map format of dmvs_warp_corr_h16_f32).  x is NCHW (dense
  * (c,h,w), `x_bstride` floats between batches) when `x_pixstride` == 0, else channel-last with that pixel stride. */
