@@ -287,7 +287,7 @@ def sharded_leg(args, world, rank, dev, barrier):
     return {"workload": workload_name(cfg), "ranks": world, "ms_per_view_1gpu": float(t[0]), "ms_per_view": float(t[1]),
             "speedup_vs_1gpu": float(t[0] / t[1]), "bit_identical": bool(t[2] == 0.0), "depth_max_rel_diff": float(t[3]),
             "scope": "MVSNet.forward incl. FeatureNet, images resident on every GPU, depth + confidence re-assembled on every GPU",
-            "exchange": {"all_gather_fp16_source_maps_bytes": gather_bytes, "all_reduce_per_pixel_maps_bytes": reduce_bytes,
+            "exchange": {"all_gather_fp16_source_maps_bytes": gather_bytes, "all_gather_per_pixel_maps_bytes": reduce_bytes,
                          "collectives_per_view": 6 + 2 * 3},
             "partition": "FeatureNet by view (+ the reference view on every rank); stage loop by row bands, 32-row halo, edges at multiples of 8 rows"}
 

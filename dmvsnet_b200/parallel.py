@@ -182,7 +182,7 @@ def gather_rows(compute: Callable[[int, int, int, int], Optional[torch.Tensor]],
 #     rows the rank owns (their receptive field is +-30), so the owned rows carry the bits of the unsharded result;
 #   * per stage two small exchanges re-assemble per-pixel maps: ``depth_values_c`` [B,4,h,w] after the main pass (the refine
 #     pass needs it 32 rows beyond the owned rows) and ``depth`` / confidence [B,h,w] after the refine pass (the next stage's
-#     sampler upsamples it: +-1 row).  They are all-reduces of zero-padded maps: x + 0 == x exactly, any order.
+#     sampler upsamples it: +-1 row).  They are all-gathers of the owned rows (equal slots of the widest band).
 # Nothing else crosses NVLink: no cost volume, no logits, no probability volume (those stay row-sharded).
 
 
@@ -218,16 +218,24 @@ class _CudaBackend:
 
 
 def _assemble_rows(part: torch.Tensor, own: Tuple[int, int], num_rows: int, group) -> torch.Tensor:
-    """``part``: this rank's OWNED rows along dim -2 ([..., own_hi - own_lo, w]) -> the full map on every rank."""
-    full = part.new_zeros(tuple(part.shape[:-2]) + (num_rows, part.shape[-1]))
+    """``part``: this rank's OWNED rows along dim -2 ([B,C,own_hi - own_lo,w]) -> the full map [B,C,num_rows,w] on every rank.
+    One all-gather of equal slots (the widest band, zero padded): every row crosses NVLink once."""
+    world = dist.get_world_size(group)
+    bands = row_bands(num_rows, world)
+    widest = max(b[1] - b[0] for b in bands)
+    send = part.new_zeros(tuple(part.shape[:-2]) + (widest, part.shape[-1]))
     if own[1] > own[0]:
-        full[..., own[0]:own[1], :] = part
-    dist.all_reduce(full, group=group)
-    return full
+        send[..., : own[1] - own[0], :] = part
+    recv = part.new_empty((world,) + tuple(send.shape))
+    if send.is_cuda:
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:  # gloo (the CPU tests) has no flat all-gather
+        dist.all_gather(list(recv.unbind(0)), send, group=group)
+    return torch.cat([recv[r][..., : bands[r][1] - bands[r][0], :] for r in range(world) if bands[r][1] > bands[r][0]], dim=-2)
 
 
 def cascade_row_sharded(net, ref_feats, src_feats, proj_matrices, depth_values: torch.Tensor, image_hw: Sequence[int],
-                        group: Optional[dist.ProcessGroup] = None, backend=None, wait_for=None):
+                        group: Optional[dist.ProcessGroup] = None, backend=None, wait_for=None, marks: Optional[list] = None):
     """The stage loop of ``MVSNet.cascade`` (reference mvsnet.py:208-258) for ONE view set over the ranks of ``group`` by row
     bands.  ``ref_feats``: the reference view's feature dict (fp32); ``src_feats``: list of the source views' dicts (on CUDA:
     ``ops.HalfFeatures`` under the plain keys); every rank holds all of them.  ``wait_for(key)`` (optional) is called before a
@@ -243,6 +251,13 @@ def cascade_row_sharded(net, ref_feats, src_feats, proj_matrices, depth_values: 
     rts = [r.to(dev, torch.float32) for r in rts]
     depth_interval = (depth_values[0, -1] - depth_values[0, 0]) / depth_values.size(1)
     outputs, last_depth = {}, None
+
+    def mark(label):
+        if marks is not None and depth_values.is_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((label, ev))
+    mark("start")
     for s in range(num_stage):
         name = "stage%d" % (s + 1)
         scale = 2 ** (num_stage - s - 1)
@@ -257,6 +272,7 @@ def cascade_row_sharded(net, ref_feats, src_feats, proj_matrices, depth_values: 
             hyp, interval = be.hypotheses_next(last_depth, net.ndepths[s], net.depth_interval_ratio[s] * depth_interval, [h, w], net.inverse_depth)
         if wait_for is not None:
             wait_for(name)
+        mark(name + " sampler+wait")
         d4 = hyp_c = conf = None
         if owns:
             hyp_b = hyp[:, :, band_lo:band_hi].contiguous()
@@ -268,10 +284,12 @@ def cascade_row_sharded(net, ref_feats, src_feats, proj_matrices, depth_values: 
         else:
             b = hyp.shape[0]
             d4 = hyp.new_zeros(b, 4, 0, w); hyp_c = hyp.new_zeros(b, 4, 0, w); conf = hyp.new_zeros(b, 0, w)
+        mark(name + " main pass")
         packed = _assemble_rows(torch.cat([hyp_c, d4, conf.unsqueeze(1)], 1), (own_lo, own_hi), h, group)   # [B,9,h,w]
         hyp_c_full, d4_full, conf_full = packed[:, 0:4], packed[:, 4:8], packed[:, 8]
         if wait_for is not None:
             wait_for(name + "_c")
+        mark(name + " exchange+wait")
         if owns:
             hyp_cb = hyp_c_full[:, :, band_lo:band_hi].contiguous()
             logits_c = be.regularised_logits(name + "_c", ref_feats[name + "_c"][:, :, band_lo:band_hi], [f[name + "_c"] for f in src_feats],
@@ -281,7 +299,9 @@ def cascade_row_sharded(net, ref_feats, src_feats, proj_matrices, depth_values: 
             depth, conf_r, d4r = depth[:, keep], conf_r[:, keep], d4r[:, :, keep]
         else:
             depth = hyp.new_zeros(b, 0, w); conf_r = hyp.new_zeros(b, 0, w); d4r = hyp.new_zeros(b, 4, 0, w)
+        mark(name + " refine pass")
         packed = _assemble_rows(torch.cat([depth.unsqueeze(1), conf_r.unsqueeze(1), d4r], 1), (own_lo, own_hi), h, group)  # [B,6,h,w]
+        mark(name + " exchange")
         stage_out = {"depth": packed[:, 0], "photometric_confidence_refine": packed[:, 1], "depth_sub_plus_refine": packed[:, 2:6],
                      "photometric_confidence": conf_full, "depth_sub_plus": d4_full, "depth_values_c": hyp_c_full,
                      "depth_values": hyp, "interval": interval}
@@ -331,4 +351,18 @@ def extract_features_view_sharded(net, imgs: torch.Tensor, group: Optional[dist.
 def infer_view_sharded(net, imgs: torch.Tensor, proj_matrices, depth_values: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
     """``MVSNet.forward`` of ONE view set on all ranks of ``group`` (every rank passes the same inputs, resident on its GPU)."""
     ref, srcs, wait_for = extract_features_view_sharded(net, imgs, group)
-    return cascade_row_sharded(net, ref, srcs, proj_matrices, depth_values, imgs.shape[-2:], group, wait_for=wait_for)
+    return cascade_row_sharded(net, ref, srcs, proj_matrices, depth_values, imgs.shape[-2:], exchange_group(group), wait_for=wait_for)
+
+
+_EXCHANGE_GROUPS = {}
+
+
+def exchange_group(group: Optional[dist.ProcessGroup] = None):
+    """A second communicator over the same ranks for the small per-stage exchanges: on the bulk group they would queue behind
+    the six feature all-gathers (one NCCL stream per communicator, in order) - 1.7 ms of waiting at T&T size on 8 GPUs.
+    Collective (every rank of ``group`` must call it the first time)."""
+    key = id(group) if group is not None else None
+    if key not in _EXCHANGE_GROUPS:
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+        _EXCHANGE_GROUPS[key] = dist.new_group(ranks=ranks)
+    return _EXCHANGE_GROUPS[key]

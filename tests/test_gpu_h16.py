@@ -169,3 +169,59 @@ def test_cascade_h16_conditioned_vs_oracle(H, W, views):
         e32 = float(((exact[name]["depth"].cpu() - want[name]["depth"]).abs() / want[name]["depth"].abs()).max())
         print("%s depth rel err vs oracle: fp16-staged W1 %.2e, exact W1 %.2e" % (name, e16, e32))
         assert e16 < 1e-3 and e32 < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ row bands / single-view sharding
+@pytest.mark.parametrize("c,d,h,w,n", [(8, 8, 96, 80, 4), (32, 5, 64, 48, 3)])
+def test_h16_row_band_equals_rows_of_the_full_call(c, d, h, w, n):
+    """dmvs_warp_corr_h16_f32 on rows [r0, r1) of the reference view (whole source maps, ref_row0 = r0) == the same rows of the
+    unsharded call, bit for bit: what the row-band cascade of the single-view sharded mode relies on."""
+    from dmvsnet_b200 import ops, synthetic as syn
+    g = torch.Generator().manual_seed(c + h)
+    feats = [cuda(torch.randn(1, c, h, w, generator=g)) for _ in range(n)]
+    proj = syn.make_proj_matrices(h * 4, w * 4, n, 1, num_stages=1)["stage1"]
+    rt = cuda(ops.relative_projections(proj))
+    hyp = ops.hypotheses_first(cuda(syn.make_depth_values(1, 192, inverse=True)), d, [h, w], True)[0]
+    hyp[:, :, :, w // 2:] = cuda(425 + 500 * torch.rand(1, d, h, w - w // 2, generator=g))  # half staged, half direct
+    half = [ops.features_nhwc(feats[0])] + [ops.features_nhwc_f16(f) for f in feats[1:]]
+    full = ops.warp_corr(half, rt, hyp, layout="h16")
+    for r0, r1 in ((0, 24), (24, 72), (40, h)):
+        band = ops.warp_corr([half[0][:, :, r0:r1]] + half[1:], rt, hyp[:, :, r0:r1].contiguous(), layout="h16", row0=r0)
+        assert torch.equal(band, full[:, :, :, r0:r1])
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dmvsnet_b200 import MVSNet, parallel, synthetic as syn
+        H, W, n, nd, ratios = 512, 320, 5, [16, 8, 8], [4, 2, 1]
+        net = MVSNet(nd, ratios, inverse_depth=True)
+        net.load_state_dict(syn.ridge_regnet_state(net.state_dict(), seed=3))
+        net = net.to("cuda:%d" % rank).eval()
+        proj = syn.make_proj_matrices(H, W, n, 1, num_stages=3)
+        imgs = syn.make_scene_images(H, W, n, proj["stage3"], seed=3).to("cuda:%d" % rank)
+        dv = syn.make_depth_values(1, 192, inverse=True).to("cuda:%d" % rank)
+        with torch.no_grad():
+            want = net(imgs, proj, dv)
+            got = parallel.infer_view_sharded(net, imgs, proj, dv)
+        ok = all(torch.equal(got["stage%d" % s][k], want["stage%d" % s][k]) for s in (1, 2, 3)
+                 for k in ("depth", "photometric_confidence", "photometric_confidence_refine", "depth_values_c", "depth_sub_plus"))
+        open(os.path.join(out_dir, "rank%d" % rank), "w").write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_single_view_sharded_mode_is_bit_identical_on_two_gpus(tmp_path):
+    """FeatureNet by view + fp16 source all-gather + row-band cascade over NCCL == the one-GPU forward, every re-assembled map of
+    every stage bit for bit (8 ranks at T&T size: tools/check_view_sharded_nccl.py, profiles/r2g_view_sharded_n8.txt)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(str(tmp_path / ("rank%d" % r))).read() == "ok"
