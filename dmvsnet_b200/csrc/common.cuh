@@ -41,4 +41,17 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+constexpr int kMaxDevices = 64;
+// Per-device one-time state of a kernel template instance (the > 48 KB shared-memory opt-in is a per-device function attribute, so
+// is the occupancy it allows).  Index with the CURRENT device; idempotent, racing threads write the same values.
+struct PerDevice {
+  bool configured[kMaxDevices] = {};
+  int value[kMaxDevices] = {};
+};
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
 }  // namespace dmvs

@@ -1,6 +1,6 @@
 // R1 tensor-core path, second generation: TMA-fed, persistent, warp-specialised implicit-GEMM convolutions (sm_100a).
 //
-// Same arithmetic as conv_tc.cu (fp16 hi/lo split operands, UMMA M = 128 voxels x N = 2*Cout, shifted-descriptor im2col,
+// Arithmetic: fp16 hi/lo split operands (x = hi + lo; hi*hi + hi*lo + lo*hi, only lo*lo is dropped), UMMA M = 128 voxels x N = 2*Cout, shifted-descriptor im2col,
 // fp32 accumulators in TMEM) - what changes is how operands get to shared memory:
 //
 //   * Activations between tensor layers live in HBM in the layout the tensor core consumes ("CH16"): 16-byte cells of 8 fp16,
@@ -26,7 +26,7 @@
 
 namespace dmvs {
 
-enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2, FMT_NHWC2 = 4, FMT_NHWC2P = 5 };
+enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2, FMT_NHWC2 = 4 };
 enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4, M2_C0T = 5, M2_TRF = 6 };
 __host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mode == M2_C0T; }
 // TRF: transposed conv with the 27 taps folded by input shift: the taps that read the same shifted A view (shift in {0,1}^3,
@@ -342,20 +342,6 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
           for (int c = 0; c < 8; ++c)
             if (c0 + c < p.Cout)
               yf[(long long)tc.b * p.y_bs + ((long long)(c0 + c) * p.Do + oz) * oplane + (long long)oy * p.Wo + ox] = v[c];
-        } else if (p.out_fmt == FMT_NHWC2P) {
-          // pair layout, [2][B][Do][Ho][Wo][2][Cout/2]: entry x = (pixel x | pixel x+1), so a bilinear footprint row is one
-          // aligned run of Cout floats that never straddles a 128-byte line.  Each pixel is written twice.
-          const int half = p.Cout >> 1;
-          const int hsel = c0 >= half ? 1 : 0, cc = c0 - hsel * half;
-          float* yb = reinterpret_cast<float*>(p.y) + (long long)hsel * p.B * p.Do * p.Ho * p.Wo * 2 * half +
-                      ((((long long)tc.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * 2 * half + cc;
-          const float4 v0 = make_float4(v[0], v[1], v[2], v[3]), v1 = make_float4(v[4], v[5], v[6], v[7]);
-          *reinterpret_cast<float4*>(yb) = v0;
-          *reinterpret_cast<float4*>(yb + 4) = v1;
-          if (ox > 0) {
-            *reinterpret_cast<float4*>(yb - half) = v0;
-            *reinterpret_cast<float4*>(yb - half + 4) = v1;
-          }
         } else if (p.out_fmt == FMT_NHWC2) {
           // two channel-last fp32 buffers back to back, [2][B][Do][Ho][Wo][Cout/2]: the lane's 8 channels are 32 contiguous bytes
           const int half = p.Cout >> 1;
@@ -658,25 +644,25 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
     if (rc != DMVS_OK) return rc;
   }
   auto kern = conv_tc2_kernel<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice state;  // per template instance
+  const int slot = current_device_slot();
+  DMVS_REQUIRE(slot >= 0, DMVS_ERR_CUDA, "conv_tc2: no current CUDA device");
+  if (!state.configured[slot]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) {
       set_error("conv_tc2: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
       return DMVS_ERR_CUDA;
     }
-    configured = true;
-  }
-  // persistent CTAs: as many per SM as shared memory, registers AND the 512 TMEM columns allow (the memory-bound
-  // full-resolution layers need the second CTA's loads in flight to cover HBM latency), never more than g_tc2_max_ctas
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM) != cudaSuccess || occ < 1) occ = 1;
     const int by_tmem = 512 / Cfg::TMEM_COLS;
-    ctas_per_sm = occ < by_tmem ? occ : by_tmem;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    state.value[slot] = occ < by_tmem ? occ : by_tmem;
+    if (state.value[slot] < 1) state.value[slot] = 1;
+    state.configured[slot] = true;
   }
+  // persistent CTAs: as many per SM as shared memory, registers AND the 512 TMEM columns allow (the memory-bound
+  // full-resolution layers need the second CTA's loads in flight to cover HBM latency), never more than g_tc2_max_ctas
+  const int ctas_per_sm = state.value[slot];
   const int want = kNumSMs * (ctas_per_sm < g_tc2_max_ctas ? ctas_per_sm : g_tc2_max_ctas);
   const int grid = p.n_tiles < want ? p.n_tiles : want;
   if (g_tc2_pdl) {
@@ -695,7 +681,7 @@ static int launch2(Tc2Params p, const void* x, cudaStream_t st) {
   } else {
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, tmap);
   }
-  static char what[96];
+  char what[128];
   snprintf(what, sizeof(what), "conv_tc2<mode %d, Cin %d/%d, N %d, TD %d, stages %d, kd %d> tiles %d", MODE, CIN, CIN_P, NB, TD, STAGES, KD, p.n_tiles);
   return check_launch(what);
 }
@@ -708,10 +694,10 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc2: null pointer");
   DMVS_REQUIRE(aligned16(L.w_tc) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
                "conv_tc2: pointers must be 16-byte aligned");
-  DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P || out_fmt == FMT_NHWC2 || out_fmt == FMT_NHWC2P,
+  DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P || out_fmt == FMT_NHWC2,
                DMVS_ERR_BAD_SHAPE,
                "conv_tc2: bad out_fmt %d", out_fmt);
-  DMVS_REQUIRE((out_fmt != FMT_NHWC2 && out_fmt != FMT_NHWC2P) || (kd == 1 && !transposed && stride == 1 && Cin == 32 && (Cout == 16 || Cout == 32)),
+  DMVS_REQUIRE((out_fmt != FMT_NHWC2) || (kd == 1 && !transposed && stride == 1 && Cin == 32 && (Cout == 16 || Cout == 32)),
                DMVS_ERR_BAD_SHAPE,
                "conv_tc2: the split channel-last output exists for FeatureNet's 32-channel 3x3 heads only");
   Tc2Params p;
@@ -730,7 +716,7 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
     if (!transposed && stride == 1 && ((Cin == 32 && (Cout == 16 || Cout == 32)) || (Cin == 16 && Cout == 16) || (Cin == 8 && Cout == 8))) {
       // FeatureNet's 3x3 layers (out3 / out2 and conv2.1-2 / conv1.1-2): weights resident, all channel chunks in one pass
       DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");
-      DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2 || out_fmt == FMT_NHWC2P || out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE,
+      DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2 || out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE,
                    "conv_tc2: FeatureNet layers write fp32 (NCHW or split channel-last) or CH16");
       p.Ho = Hi; p.Wo = Wi;
       if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;

@@ -249,14 +249,15 @@ __global__ void __launch_bounds__(256, 2) feat_conv_kernel(const __grid_constant
 template <int K, int S, int CIN, int COUT>
 static int launch_feat(const FeatConvParams& p, cudaStream_t st) {
   using Cfg = FeatCfg<K, S, CIN, COUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice state;  // per template instance; the opt-in is a per-device attribute
+  const int slot = current_device_slot();
+  if (slot < 0 || !state.configured[slot]) {
     cudaError_t e = cudaFuncSetAttribute(feat_conv_kernel<K, S, CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("conv2d: cannot reserve %zu bytes of shared memory: %s", Cfg::kSmem, cudaGetErrorString(e));
       return DMVS_ERR_CUDA;
     }
-    attr_set = true;
+    if (slot >= 0) state.configured[slot] = true;
   }
   dim3 grid(ceil_div(p.Wo, 32), ceil_div(p.Ho, 32), p.B * Cfg::NZ);
   DMVS_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DMVS_ERR_BAD_SHAPE, "conv2d: grid too large");

@@ -8,22 +8,16 @@ namespace dmvs {
 int conv_layer(const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs, float* y,
                long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
                cudaStream_t st);
-int conv_layer_tc(const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs, float* y,
-                  long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu,
-                  cudaStream_t st);
-
 int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const void* skip, void* y, long long y_bs_f32, int B, int Cin,
                    int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, cudaStream_t st);
 int convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, cudaStream_t st);
 
-// engine dispatch: tensor path where a specialisation exists (returns +1 otherwise), fp32 kernels as the exact path
+// single layers on fp32 NCDHW activations always run on the exact fp32 kernels; the tensor engine works on the cell layouts
+// (dmvs_conv3d_ch16 / the fused drivers below) and `engine` only selects it there
 static int run_layer(int engine, const float* x, long long x_bs, const dmvs_conv_layer& L, const float* skip, long long skip_bs,
                      float* y, long long y_bs, int B, int Cin, int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed,
                      int relu, cudaStream_t st) {
-  if (engine == DMVS_ENGINE_TENSOR) {
-    const int rc = conv_layer_tc(x, x_bs, L, skip, skip_bs, y, y_bs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, st);
-    if (rc <= 0) return rc;
-  }
+  (void)engine;
   return conv_layer(x, x_bs, L, skip, skip_bs, y, y_bs, B, Cin, Cout, Di, Hi, Wi, kd, stride, transposed, relu, st);
 }
 
@@ -31,13 +25,25 @@ int g_regnet_streams = 1;  // dmvs_debug_set("regnet_streams", 0 | 1): second br
 
 namespace {
 
-// One non-blocking side stream per device, created on first use and kept for the life of the process.
-cudaStream_t side_stream() {
-  static cudaStream_t streams[64] = {};
+// One non-blocking side stream per (device, caller stream), created on first use and kept for the life of the process: callers
+// that drive several cascades on different streams of one device do not meet in a shared side stream.
+cudaStream_t side_stream(cudaStream_t main) {
+  struct Entry { cudaStream_t main, side; bool used; };
+  static Entry table[64][4] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
-  return streams[dev];
+  Entry* row = table[dev];
+  for (int i = 0; i < 4; ++i)
+    if (row[i].used && row[i].main == main) return row[i].side;
+  for (int i = 0; i < 4; ++i) {
+    if (!row[i].used) {
+      if (cudaStreamCreateWithFlags(&row[i].side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      row[i].main = main;
+      row[i].used = true;
+      return row[i].side;
+    }
+  }
+  return row[0].side;  // more than four caller streams on one device: share the first (ordering stays correct, overlap may not)
 }
 
 // `to` waits for everything enqueued on `from` so far (the event is released as soon as the wait has been enqueued)
@@ -48,6 +54,15 @@ bool stream_wait(cudaStream_t to, cudaStream_t from) {
   cudaEventDestroy(e);
   return ok;
 }
+
+// joins the side stream back into the caller's stream on EVERY exit path once the fork has happened: the caller frees (and
+// torch recycles) the workspace as soon as the call returns, error or not
+struct SideJoin {
+  cudaStream_t main, side;
+  ~SideJoin() {
+    if (side) stream_wait(main, side);
+  }
+};
 
 struct Level {
   int D, H, W;
@@ -136,8 +151,9 @@ static int regnet_forward_impl(const dmvs_regnet_branch* branches, int refine, c
     // u11 .. c6.  The coarse levels' kernels (20-130 CTAs) then fill the SMs the other branch leaves idle; the full-resolution
     // layers, whose persistent CTAs do not fit an SM twice, queue behind each other as before.
     cudaStream_t const main_st = st;
-    cudaStream_t side = (g_regnet_streams && pair && branch_mask == 3) ? side_stream() : nullptr;
+    cudaStream_t side = (g_regnet_streams && pair && branch_mask == 3) ? side_stream(main_st) : nullptr;
     if (side && !stream_wait(side, main_st)) side = nullptr;
+    SideJoin join{main_st, side};
     for (int br = 0; br < 2; ++br) {
       if (!((branch_mask >> br) & 1)) continue;
       const dmvs_conv_layer* L = branches[br].layer;
@@ -175,6 +191,7 @@ static int regnet_forward_impl(const dmvs_regnet_branch* branches, int refine, c
       TC2(u11, 0, L[10], nullptr, logits + (long long)br * 2 * V0, 4 * V0, B, 8, 2, L0->D, L0->H, L0->W, 3, 1, 0, 0, F32, st);
 #undef TC2
     }
+    join.side = nullptr;  // normal exit: join here so that a failure is reported
     if (side && !stream_wait(main_st, side)) {
       set_error("regnet: joining the side stream failed: %s", cudaGetErrorString(cudaGetLastError()));
       return DMVS_ERR_CUDA;

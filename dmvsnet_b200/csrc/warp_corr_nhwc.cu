@@ -265,14 +265,15 @@ static int launch_w1c(const W1cParams& p0, cudaStream_t st) {
   using Cfg = W1cCfg<C, DP>;
   W1cParams p = p0;
   p.n_chunks = ceil_div(p.d_end - p.d_begin, DP);
-  static bool attr_set = false;  // idempotent, racing threads set the same value
-  if (!attr_set) {
+  static PerDevice state;  // per template instance; the opt-in is a per-device attribute
+  const int slot = current_device_slot();
+  if (slot < 0 || !state.configured[slot]) {
     cudaError_t e = cudaFuncSetAttribute(warp_corr_nhwc_kernel<C, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("warp_corr_nhwc: cannot reserve %zu bytes of shared memory: %s", Cfg::kSmem, cudaGetErrorString(e));
       return DMVS_ERR_CUDA;
     }
-    attr_set = true;
+    if (slot >= 0) state.configured[slot] = true;
   }
   dim3 block(kW1Warps * 32, 1, 1), grid(ceil_div(p.w, 32) * p.n_chunks, ceil_div(p.h, 8), p.B);
   DMVS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, DMVS_ERR_BAD_SHAPE, "warp_corr_nhwc: grid too large (h=%d, B=%d)", p.h, p.B);

@@ -275,14 +275,15 @@ int launch_w1_pass2(const float* ref, long long ref_bstride, int ref_pixstride, 
 template <int C, int DP>
 static int launch_w1s_dp(W1sParams& p, cudaStream_t st) {
   using Cfg = W1sCfg<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice state;  // per template instance; the opt-in is a per-device attribute
+  const int slot = current_device_slot();
+  if (slot < 0 || !state.configured[slot]) {
     cudaError_t e = cudaFuncSetAttribute(warp_corr_staged_kernel<C, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) {
       set_error("warp_corr_staged: cannot reserve %zu bytes of shared memory: %s", Cfg::kSmem, cudaGetErrorString(e));
       return DMVS_ERR_CUDA;
     }
-    attr_set = true;
+    if (slot >= 0) state.configured[slot] = true;
   }
   p.chunk0 = p.d_begin / DP;
   p.n_chunks = ceil_div(p.d_end, DP) - p.chunk0;

@@ -34,6 +34,7 @@ def source_matrices(k_ref, e_ref, k_src, e_src) -> torch.Tensor:
     return torch.cat([p.reshape(-1) for p in parts]).contiguous()
 
 
+@ops._on_device
 def _run(depth_ref, mats, depth_srcs, alpha, want_per_source, want_fused):
     lib = N.load()
     dev = depth_srcs.device
@@ -105,6 +106,7 @@ def source_matrices_numpy(k_ref, e_ref, k_src, e_src) -> torch.Tensor:
     return torch.from_numpy(np.concatenate([np.asarray(p, np.float32).reshape(-1) for p in parts]))
 
 
+@ops._on_device
 def _run_dynamic(depth_ref, mats, depth_srcs, dist_base, rel_diff_base, want_per_source, want_fused):
     lib = N.load()
     dev = depth_srcs.device
@@ -161,6 +163,7 @@ def geometric_filter_dynamic(depth_ref, intrinsics_ref, extrinsics_ref, depth_sr
 
 # ----------------------------------------------------------------------------- point cloud (filter_depth)
 @torch.no_grad()
+@ops._on_device
 def backproject_world(depth, intrinsics, extrinsics) -> torch.Tensor:
     """depth [H,W] -> world points [H,W,3] float32 for every pixel (pcd.py:340-343; float64 chain inside the kernel)."""
     lib = N.load()

@@ -3,8 +3,8 @@
 Same public names, constructor arguments, ``state_dict`` keys and tensor semantics as the
 reference, so that checkpoints and callers carry over unchanged; the arithmetic of the regularisation
 nets, the warp and the hypothesis sampler runs in libdmvs_b200.so (sm_100a CUDA) through
-``dmvsnet_b200.ops``.  ``FeatureNet`` sits above the hot path and stays a
-plain PyTorch/cuDNN module.
+``dmvsnet_b200.ops`` - and so does ``FeatureNet`` for CUDA tensors; its plain
+PyTorch definition remains for CPU tensors and as the ``engine = "cudnn"`` cross-check.
 
 Reference lines each piece answers to are cited per class / function.
 """
@@ -78,7 +78,8 @@ class Deconv3d(_ConvBlock):
 
 
 # --------------------------------------------------------------------------------------------
-# FeatureNet - reference networks/module.py:274-340.  Above the hot path; PyTorch/cuDNN as is.
+# FeatureNet - reference networks/module.py:274-340.  CUDA tensors run on this library's kernels (fp32 direct
+# convolutions + the tcgen05 engine, channel-last outputs for W1); CPU tensors and engine="cudnn" take the plain PyTorch graph.
 # --------------------------------------------------------------------------------------------
 class FeatureNet(nn.Module):
     def __init__(self, base_channels, num_stage=3, stride=4, mode="fpn", layernorm=False):
@@ -110,12 +111,7 @@ class FeatureNet(nn.Module):
     # native engine: run out2 / out3 on the tensor cores (fp16 hi/lo split operands, fp32 accumulate: same 1e-6 error as the
     # fp32 FMA kernels, 2.6x faster); False keeps them on the fp32 direct convolution
     tensor_heads = True
-    # stage-2 / stage-3 feature maps in the pair layout (entry x = pixel x | copy of pixel x+1): a bilinear footprint row is then
-    # one aligned run that never straddles a 128-byte line (ops.mark_pairs).  Measured on DTU: W1 3.42 -> 3.58 ms, FeatureNet
-    # 2.99 -> 3.12 ms - the doubled maps cost more L1/L2 misses than the straddles they remove - so it is off.
-    pair_layout = False
     tensor_s2 = True  # the two 5x5 stride-2 layers on the tensor engine through a 2x2 pixel-unshuffle (space-to-depth)
-    tensor_conv0 = False  # conv0.1 (8 -> 8 at full resolution) on the tensor engine: measured slower (3.57 vs 3.47 ms), kept as an option
 
     def forward(self, x):
         if x.is_cuda and self.engine == "native" and not self.training and self.mode == "fpn" and self.num_stage == 3:
@@ -146,6 +142,13 @@ class FeatureNet(nn.Module):
     def _state_key(self):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
+    def __getstate__(self):
+        # derived caches (repacked weights) are rebuilt on demand: copy.deepcopy / torch.save / pickle work like on the reference's module
+        state = self.__dict__.copy()
+        state.pop("_packed", None)
+        state.pop("_packed_key", None)
+        return state
+
     def packed(self):
         key = self._state_key()
         if getattr(self, "_packed_key", None) != key:
@@ -160,7 +163,6 @@ class FeatureNet(nn.Module):
                   "conv2": [block(m) for m in self.conv2],
                   "out1": ops.PackedConv2d(self.out1.weight), "out2": ops.PackedConv2d(self.out2.weight),
                   "out3": ops.PackedConv2d(self.out3.weight),
-                  "conv0_tc": self.conv0[1].packed(),
                   "conv1_s2d": s2d_layer(self.conv1[0]), "conv2_s2d": s2d_layer(self.conv2[0]),
                   "conv1_tc": [self.conv1[1].packed(), self.conv1[2].packed()],
                   "conv2_tc": [self.conv2[1].packed(), self.conv2[2].packed()],
@@ -176,16 +178,13 @@ class FeatureNet(nn.Module):
         pk = self.packed()
         t = x
         s2d = self.tensor_heads and self.tensor_s2 and x.shape[-1] % 8 == 0 and x.shape[-2] % 4 == 0
-        if self.tensor_heads and self.tensor_conv0:
-            _, cells = ops.conv2d(t, pk["conv0"][0], nchw=False, cells=True)
-            t = ops.conv3d_ch16(cells, pk["conv0_tc"], relu=True, out_fmt="f32").squeeze(2)
-            cells0 = ops.s2d_cells(t) if s2d else None
+        # the two full-resolution layers with few channels (3 -> 8, 8 -> 8) stay on the fp32 direct convolution (the tensor engine
+        # measured slower there: 3.57 vs 3.47 ms per DTU view set)
+        t = ops.conv2d(t, pk["conv0"][0])
+        if s2d:  # conv0.1 hands its output out twice: fp32 NCHW (lateral inner2) and unshuffled cells (conv1.0 on the tensor cores)
+            t, cells0 = ops.conv2d(t, pk["conv0"][1], cells=True, s2d=True)
         else:
-            t = ops.conv2d(t, pk["conv0"][0])
-            if s2d:  # conv0.1 hands its output out twice: fp32 NCHW (lateral inner2) and unshuffled cells (conv1.0 on the tensor cores)
-                t, cells0 = ops.conv2d(t, pk["conv0"][1], cells=True, s2d=True)
-            else:
-                t, cells0 = ops.conv2d(t, pk["conv0"][1]), None
+            t, cells0 = ops.conv2d(t, pk["conv0"][1]), None
         c0 = t
         if self.tensor_heads and t.shape[-1] % 8 == 0:
             # the 3x3 layers behind each stride-2 5x5 (16->16, 32->32; BN + ReLU in the epilogue) run on the tensor cores, and
@@ -215,9 +214,9 @@ class FeatureNet(nn.Module):
             # the two 32-channel 3x3 heads (57 % of FeatureNet's flops) on the tcgen05 engine: the laterals emit their sums as
             # fp16 hi/lo cells (top2 only as cells: nobody else reads it), the heads write the channel-last feature sets
             top, cells = ops.conv2d(c1, pk["inner1"], up_add=c2, cells=True)
-            out["stage2"], out["stage2_c"] = ops.conv2d_head_tensor(cells, pk["out2_tc"], pairs=self.pair_layout)
+            out["stage2"], out["stage2_c"] = ops.conv2d_head_tensor(cells, pk["out2_tc"])
             _, cells = ops.conv2d(c0, pk["inner2"], up_add=top, nchw=False, cells=True)
-            out["stage3"], out["stage3_c"] = ops.conv2d_head_tensor(cells, pk["out3_tc"], pairs=self.pair_layout)
+            out["stage3"], out["stage3_c"] = ops.conv2d_head_tensor(cells, pk["out3_tc"])
             return out
         top = ops.conv2d(c1, pk["inner1"], up_add=c2)
         _, out["stage2"], out["stage2_c"] = ops.conv2d(top, pk["out2"], nchw=False, split_nhwc=True)
@@ -301,6 +300,12 @@ class _DualRegNet(nn.Module):
 
     def _state_key(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def __getstate__(self):
+        # the cache holds ctypes structs with raw device pointers: not picklable, and stale in a copy anyway
+        state = self.__dict__.copy()
+        state["_pack"], state["_pack_key"] = None, None
+        return state
 
     def packed(self) -> ops.PackedRegnet:
         """Repacked weights, cached until a parameter/buffer is written, moved or reloaded."""

@@ -25,6 +25,14 @@ __all__ = ["MVSNet", "CostAgg", "DepthNet", "Align_Corners_Range"]
 Align_Corners_Range = False  # mvsnet.py:8; the fused sampler implements align_corners=False
 
 
+def _check_finite(flag: torch.Tensor) -> None:
+    if not bool(flag[0]):
+        raise FloatingPointError(
+            "dmvsnet_b200: the regressed depth map is not finite.  Either the inputs are (NaN / Inf depth range or images) or an "
+            "activation left the fp16 hi/lo range of the tensor engine (|x| > 65504, ops.FP16_SPLIT_MAX): run that network with "
+            "ops.DEFAULT_ENGINE = 'fp32'.")
+
+
 class DepthNet(nn.Module):
     """Dual-depth heads.  reference networks/mvsnet.py:11-100."""
 
@@ -88,10 +96,6 @@ class MVSNet(nn.Module):
         self.inverse_depth = inverse_depth
         # infer_many: run FeatureNet of item k+1 on its own stream beside the cascade of item k
         self.overlap_features = True
-        # infer_many: how many consecutive items may have their cascades in flight at once (one stream each).  Measured on
-        # B200 at DTU size: 2 or 3 concurrent cascades are 1.5 % SLOWER than 1 (15.55 vs 15.32 ms per item, tools/bench_overlap.py)
-        # - the step is GPU-bound and the co-running kernels evict each other's L2 lines - so the default stays 1.
-        self.concurrent_items = 1
         # W1 source-map precision.  "fp16": the source views' feature maps are rounded to fp16 once and W1 runs the TMA-staged
         # kernel on them (dmvs_warp_corr_h16_f32: half the bytes through the SMs' shared-memory pipe, 2x faster; regressed depth
         # within 3.3e-4 of the fp32 path on a network that behaves like a trained one, contract 1e-3).  "fp32": the exact kernels
@@ -106,10 +110,23 @@ class MVSNet(nn.Module):
             [CostRegNet_refine(in_channels=2, base_channels=self.cr_base_chs[i], stage=i) for i in range(self.num_stage)])
         self.DepthNet = DepthNet(depth_mode)
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in ("_copy_stream", "_feat_stream"):  # CUDA streams are per process / device: recreated on demand
+            state.pop(k, None)
+        return state
+
     # ------------------------------------------------------------------ the hot path
     def cascade(self, features: Sequence[Dict[str, torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
                 depth_values: torch.Tensor, image_hw: Sequence[int], keep_seams: bool = False,
                 rts: Optional[Sequence[torch.Tensor]] = None, branch_group=None) -> Dict[str, object]:
+        """``_cascade`` with the feature maps' device made current (the native launches go to the current device)."""
+        with torch.cuda.device(features[0]["stage1"].device):
+            return self._cascade(features, proj_matrices, depth_values, image_hw, keep_seams, rts, branch_group)
+
+    def _cascade(self, features: Sequence[Dict[str, torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
+                 depth_values: torch.Tensor, image_hw: Sequence[int], keep_seams: bool = False,
+                 rts: Optional[Sequence[torch.Tensor]] = None, branch_group=None) -> Dict[str, object]:
         """The stage loop (reference mvsnet.py:208-258) on precomputed per-view feature dicts.
 
         ``keep_seams`` additionally returns the cost volumes and logits (``_cost``, ``_logits``, ``_cost_c``,
@@ -188,8 +205,7 @@ class MVSNet(nn.Module):
         out = self.feature(imgs.reshape(b * n, *imgs.shape[2:]))
 
         def view_of(t, v):
-            s = t.view(b, n, *t.shape[1:])[:, v]
-            return ops.mark_pairs(s) if ops.is_pairs(t) else s
+            return t.view(b, n, *t.shape[1:])[:, v]
         views = [{k: view_of(t, v) for k, t in out.items()} for v in range(n)]
         if self.w1_precision == "fp16" and imgs.is_cuda and n > 1:
             for k, t in out.items():  # one conversion launch per map for all views; the source views take their slices
@@ -222,6 +238,10 @@ class MVSNet(nn.Module):
         still crossing PCIe."""
         _require_inference(self)
         dev = next(self.parameters()).device
+        with torch.cuda.device(dev):
+            return self._infer(imgs, proj_matrices, depth_values, keys, dev)
+
+    def _infer(self, imgs, proj_matrices, depth_values, keys, dev):
         if imgs.is_cuda:
             out = self.forward(imgs, proj_matrices, depth_values)
         else:
@@ -247,11 +267,14 @@ class MVSNet(nn.Module):
                 feats.extend(self.extract_features(part))
             out = self.cascade(feats, proj_matrices, depth_values, imgs.shape[-2:])
         host = {}
+        finite = torch.empty(1, dtype=torch.bool, pin_memory=True)
+        finite.copy_(torch.isfinite(out["depth"]).all().reshape(1), non_blocking=True)
         for k in keys:
             buf = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
             buf.copy_(out[k], non_blocking=True)
             host[k] = buf
         torch.cuda.current_stream().synchronize()
+        _check_finite(finite)
         return host
 
     @torch.no_grad()
@@ -264,6 +287,9 @@ class MVSNet(nn.Module):
         hidden.  Results are yielded one item late (after their D2H has completed)."""
         _require_inference(self)
         dev = next(self.parameters()).device
+        if dev.index != torch.cuda.current_device():
+            # a generator cannot hold a device context across its yields without leaking it to the consumer
+            raise RuntimeError("infer_many: make the model's device current first (torch.cuda.set_device(%d))" % dev.index)
         main = torch.cuda.current_stream(dev)
         side = getattr(self, "_copy_stream", None)
         if side is None or side.device != dev:
@@ -299,13 +325,6 @@ class MVSNet(nn.Module):
                     t.record_stream(main)
             return feats, tuple(dimgs.shape[-2:]), fev
 
-        cascade_streams = [main]
-        if feat_stream is not None and self.concurrent_items > 1:
-            extra = getattr(self, "_cascade_streams", None)
-            if extra is None or len(extra) != self.concurrent_items - 1 or extra[0].device != dev:
-                extra = self._cascade_streams = [torch.cuda.Stream(dev) for _ in range(self.concurrent_items - 1)]
-            cascade_streams = [main] + list(extra)
-        index = 0
         pending = None  # (host dict, event) of the previous item
         it = iter(inputs)
         nxt = next(it, None)
@@ -324,23 +343,17 @@ class MVSNet(nn.Module):
                 # enqueue the next item's upload and FeatureNet first, then this item's cascade: they overlap on the device
                 cur = upload(nxt) if nxt is not None else None
                 cur_feats = features_of(cur) if cur is not None else None
-                # consecutive items are independent requests: their cascades alternate between `concurrent_items` streams, so
-                # the L1-bound gathers of one item run beside the tensor-core layers of the other
-                cstream = cascade_streams[index % len(cascade_streams)]
-                cstream.wait_event(fev)
-                with torch.cuda.stream(cstream):
-                    for view in feats:
-                        for t in view.values():
-                            t.record_stream(cstream)
-                    out = self.cascade(feats, proj, dv, hw)
+                main.wait_event(fev)
+                out = self.cascade(feats, proj, dv, hw)
                 del feats
-            index += 1
             done = torch.cuda.Event()
-            done.record(cstream if feat_stream is not None else main)
+            done.record(main)
             # this item's download goes behind the next upload on the copy stream
             host = {}
             with torch.cuda.stream(side):
                 side.wait_event(done)
+                finite = torch.empty(1, dtype=torch.bool, pin_memory=True)
+                finite.copy_(torch.isfinite(out["depth"]).all().reshape(1), non_blocking=True)
                 for k in keys:
                     buf = torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True)
                     buf.copy_(out[k], non_blocking=True)
@@ -350,11 +363,11 @@ class MVSNet(nn.Module):
                 hev.record(side)
             if pending is not None:
                 pending[1].synchronize()
+                _check_finite(pending[2])
                 yield pending[0]
-            pending = (host, hev)
-        for cs in cascade_streams[1:]:
-            main.wait_stream(cs)
+            pending = (host, hev, finite)
         if pending is not None:
             pending[1].synchronize()
+            _check_finite(pending[2])
             yield pending[0]
 

@@ -54,6 +54,35 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _device_of(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.device if obj.is_cuda else None
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            d = _device_of(o)
+            if d is not None:
+                return d
+        return None
+    d = getattr(obj, "device", None)  # HalfFeatures
+    return d if isinstance(d, torch.device) and d.type == "cuda" else None
+
+
+def _on_device(fn):
+    """Run an op with the device of its first CUDA argument current: the native entry points launch on the CURRENT device and
+    on its current stream (``_stream()``), and the > 48 KB shared-memory opt-ins are per device - a model that lives on cuda:1
+    while cuda:0 is current would otherwise launch on the wrong device."""
+    import functools
+
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        dev = _device_of(args) or _device_of(tuple(kwargs.values()))
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return guarded
+
+
 # ----------------------------------------------------------------------------- projections (K1)
 def relative_projections(proj_matrices: torch.Tensor) -> torch.Tensor:
     """[B,N,2,4,4] -> rt [B,N-1,12] (row-major rot 3x3 then trans) on the CPU, fp32.
@@ -108,6 +137,7 @@ def _nhwc_strides(t: torch.Tensor):
     return (ps, bs) if bs % 4 == 0 else None
 
 
+@_on_device
 def features_nhwc(t: torch.Tensor) -> torch.Tensor:
     """[B,C,h,w] fp32 (dense (c,h,w), any batch stride) -> the same map physically channel-last, returned as a
     [B,C,h,w] view of a dense [B,h,w,C] buffer (torch channels_last strides), so it can be passed wherever the NCHW
@@ -151,6 +181,7 @@ class HalfFeatures:
         return self.data.float().permute(0, 3, 1, 2)
 
 
+@_on_device
 def features_nhwc_f16(t) -> "HalfFeatures":
     """fp32 [B,C,h,w] (NCHW with any batch stride, or channel-last in memory) -> HalfFeatures (dmvs_features_nhwc_f16)."""
     if isinstance(t, HalfFeatures):
@@ -159,7 +190,7 @@ def features_nhwc_f16(t) -> "HalfFeatures":
     _req(t, "features")
     b, c, h, w = t.shape
     cl = _nhwc_strides(t)
-    if cl is not None and not is_pairs(t):
+    if cl is not None:
         ps, bs = cl
     else:
         ps, bs = 0, _batch_stride(t)
@@ -173,6 +204,7 @@ def features_nhwc_f16(t) -> "HalfFeatures":
     return HalfFeatures(y)
 
 
+@_on_device
 def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor,
               d_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
               want_f32: bool = True, want_cells: bool = False, layout: Optional[str] = None, coherent: bool = False,
@@ -222,12 +254,9 @@ def warp_corr(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Ten
         src_ps, src_bs, src_cs = 0, strides[0], 0
     else:
         st = [_nhwc_strides(f) for f in srcs]
-        pr = [is_pairs(f) for f in srcs]
-        src_cs = 0
-        if all(pr) and all(x is not None for x in st) and len(set(st)) == 1:
-            src_cs = c  # pair layout: the x+1 corner is the second slot of the same entry
-        elif any(x is None for x in st) or len(set(st)) != 1 or any(pr):
-            srcs = [f if (x == (c, h * w * c) and not q) else features_nhwc(f) for f, x, q in zip(srcs, st, pr)]
+        src_cs = 0  # x-corners of a footprint one pixel stride apart
+        if any(x is None for x in st) or len(set(st)) != 1:
+            srcs = [f if x == (c, h * w * c) else features_nhwc(f) for f, x in zip(srcs, st)]
             st = [(c, h * w * c)] * n_src
         src_ps, src_bs = st[0]
     hyp = _req(hyp, "hyp").contiguous()
@@ -277,7 +306,7 @@ def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells, row0=0
         if f.shape != srcs[0].shape or (f.shape[0], f.shape[1], f.shape[3]) != (b, c, w) or row0 + h > src_rows:
             raise ValueError("features[%d] has shape %s, reference band %s at row %d" % (i + 1, tuple(f.shape), tuple(ref.shape), row0))
     ref_bs, ref_ps = _batch_stride(ref), 0
-    if ref_bs < 0 and _nhwc_strides(ref) is not None and not is_pairs(ref):
+    if ref_bs < 0 and _nhwc_strides(ref) is not None:
         ref_ps, ref_bs = _nhwc_strides(ref)
     elif ref_bs < 0:
         ref = ref.contiguous()
@@ -305,6 +334,7 @@ def _warp_corr_h16(features, rt, hyp, d_range, out, want_f32, want_cells, row0=0
     return (out, cells) if want_cells else out
 
 
+@_on_device
 def warp_corr_backward(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: torch.Tensor, grad_cost: torch.Tensor) -> List[torch.Tensor]:
     """Gradients of ``warp_corr``'s cost volume w.r.t. every feature map (reference view first): N x [B,C,h,w] tensors in
     channels_last memory (dmvs_warp_corr_backward_f32).  What autograd would record for networks/mvsnet.py:137-146 and
@@ -320,7 +350,7 @@ def warp_corr_backward(features: Sequence[torch.Tensor], rt: torch.Tensor, hyp: 
         f = _req(f, "features[%d]" % i).detach()
         if f.shape != ref.shape:
             raise ValueError("features[%d] has shape %s, expected %s" % (i, tuple(f.shape), tuple(ref.shape)))
-        maps.append(f if (_nhwc_strides(f) is not None and not is_pairs(f)) else features_nhwc(f))
+        maps.append(f if _nhwc_strides(f) is not None else features_nhwc(f))
     st = [_nhwc_strides(f) for f in maps[1:]]
     if len(set(st)) != 1:  # the sources share one stride pair in the ABI
         maps[1:] = [f if x == (c, h * w * c) else features_nhwc(f) for f, x in zip(maps[1:], st)]
@@ -389,6 +419,7 @@ class PackedConv2d:
         self.stride, self.relu = stride, relu
 
 
+@_on_device
 def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] = None, nchw: bool = True, split_nhwc: bool = False,
            cells: bool = False, s2d: bool = False):
     """x [B,Cin,H,W] -> conv (+BN/bias, ReLU, + nearest-x2 ``up_add``).  Returns ``y`` ([B,Cout,Ho,Wo] NCHW) when ``nchw``;
@@ -428,6 +459,7 @@ def conv2d(x: torch.Tensor, layer: PackedConv2d, up_add: Optional[torch.Tensor] 
     return y
 
 
+@_on_device
 def s2d_cells(x: torch.Tensor) -> torch.Tensor:
     """fp32 [B,C,H,W] -> CH16 cells of the 2x2 pixel-unshuffled map, int32 [B, C, 1, H/2, W/2, 4] (dmvs_features_s2d_cells_f32)."""
     lib = N.load()
@@ -451,40 +483,32 @@ def s2d_weight(w5: torch.Tensor) -> torch.Tensor:
     return w6.permute(0, 3, 5, 1, 2, 4).reshape(cout, 4 * c, 3, 3).contiguous()
 
 
-def mark_pairs(t: torch.Tensor) -> torch.Tensor:
-    """Tag a [B,C,h,w] view of a PAIR-layout buffer ([B,h,w,2,C]: entry x = pixel x followed by a copy of pixel x+1).  As a
-    strided tensor it is an ordinary channel-last map with pixel stride 2C; the tag tells ops.warp_corr that the x+1 corner of a
-    footprint sits C floats behind the x corner, so a footprint row is one aligned run (include/dmvs_b200.h, src_cornerstride)."""
-    t._dmvs_pairs = True
-    return t
-
-
-def is_pairs(t: torch.Tensor) -> bool:
-    return bool(getattr(t, "_dmvs_pairs", False)) and t.dim() == 4 and t.stride(1) == 1 and t.stride(3) == 2 * t.shape[1]
-
-
-def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer", pairs: bool = False):
+@_on_device
+def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer"):
     """FeatureNet's bare 3x3 heads out2 / out3 (module.py:326-336, Cin = 32, no BN / ReLU / bias) on the tcgen05 engine:
-    CH16 cells [B, 8, 1, H, W, 4] -> the two feature sets as channel-last maps, returned as [B,Cout/2,H,W] views (``pairs``: in
-    the pair layout, tagged with ``mark_pairs``; the last column's second slot is never read and stays unwritten)."""
+    CH16 cells [B, 8, 1, H, W, 4] -> the two feature sets as channel-last maps, returned as [B,Cout/2,H,W] views."""
     lib = N.load()
     b, planes, d, h, w, _ = cells.shape
     if planes != 8 or d != 1 or layer.cin != 32 or layer.kd != 1 or layer.w_tc is None:
         raise ValueError("conv2d_head_tensor: expects 32-channel cells and a packed 2-D 3x3 layer")
     half = layer.cout // 2
-    y = (torch.empty(2, b, h, w, 2, half, device=cells.device, dtype=torch.float32) if pairs else
-         torch.empty(2, b, h, w, half, device=cells.device, dtype=torch.float32))
+    y = torch.empty(2, b, h, w, half, device=cells.device, dtype=torch.float32)
     cl = layer.c_struct()
     with _timed("featnet:tc3x3_32to%d_%dx%d" % (layer.cout, h, w)):
         rc = lib.dmvs_conv3d_ch16(cells.data_ptr(), 0, ctypes.byref(cl), None, y.data_ptr(), b, 32, layer.cout, 1, h, w, 1, 1, 0, 0,
-                                  N.FMT_NHWC2P if pairs else N.FMT_NHWC2, _stream())
+                                  N.FMT_NHWC2, _stream())
     N.check(rc, "dmvs_conv3d_ch16")
-    if pairs:
-        return mark_pairs(y[0][:, :, :, 0].permute(0, 3, 1, 2)), mark_pairs(y[1][:, :, :, 0].permute(0, 3, 1, 2))
     return y[0].permute(0, 3, 1, 2), y[1].permute(0, 3, 1, 2)
 
 
 # ----------------------------------------------------------------------------- R1
+# Range of the tensor engine (ADVICE r1): activations between layers, cost-volume cells and weights are carried as fp16 hi + fp16 lo
+# (value = hi + lo).  |x| <= 65504 keeps hi finite; beyond it hi = inf, lo = -inf and the MMA produces NaN, which propagates to the
+# depth map - MVSNet.infer / infer_many check the finiteness of what they return and raise.  Feature maps, BN-folded activations and
+# costs of a trained DMVSNet are O(1) - O(100); a network whose activations leave the range must run with DEFAULT_ENGINE = "fp32".
+FP16_SPLIT_MAX = 65504.0
+
+
 class PackedLayer:
     """Device-side parameters of one conv block in the layout the kernels read."""
 
@@ -501,6 +525,9 @@ class PackedLayer:
         if cout_w != cout:
             w = torch.nn.functional.pad(w, (0, cout_w - cout))
         self.w = w.contiguous()
+        # the tensor engine splits every operand into fp16 hi + lo: a weight beyond the fp16 range has hi = inf (and NaN products)
+        if w.numel() and not bool((w.abs() <= FP16_SPLIT_MAX).all()):
+            raise ValueError("conv weight beyond +-%.0f cannot be split into fp16 hi/lo for the tensor engine (use ops.DEFAULT_ENGINE = 'fp32')" % FP16_SPLIT_MAX)
         if cin % 8 == 0:
             self.w_tc = _pack_tensor_core(w[:, :, :cout])
         elif cin == 2 and taps == 27 and not transposed:
@@ -619,6 +646,7 @@ PAIR_CONV0 = True  # run conv0 of both regularisation branches as one launch (N 
 _ENGINES = {"fp32": N.ENGINE_FP32, "tensor": N.ENGINE_TENSOR}
 
 
+@_on_device
 def conv3d(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = True,
            skip: Optional[torch.Tensor] = None, engine: Optional[str] = None) -> torch.Tensor:
     """One conv block on a [B,Cin,D,H,W] tensor (kd = 1 layers take D as a batch of planes)."""
@@ -649,6 +677,7 @@ def conv3d(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = Tr
 _FMT = {"f32": N.FMT_F32, "ch16": N.FMT_CH16, "ch16p": N.FMT_CH16P}
 
 
+@_on_device
 def to_ch16(x: torch.Tensor, parity_split: bool = False) -> torch.Tensor:
     """fp32 [B,C,D,H,W] -> the tensor path's cell layout (include/dmvs_b200.h DMVS_FMT_CH16 / CH16P), as a flat byte-equal
     fp32-sized buffer viewed as int32 [B, C/4 planes, D, H, W, 4]."""
@@ -661,6 +690,7 @@ def to_ch16(x: torch.Tensor, parity_split: bool = False) -> torch.Tensor:
     return y
 
 
+@_on_device
 def from_ch16(y: torch.Tensor, channels: int, parity_split: bool = False) -> torch.Tensor:
     lib = N.load()
     b, planes, d, h, w, _ = y.shape
@@ -670,6 +700,7 @@ def from_ch16(y: torch.Tensor, channels: int, parity_split: bool = False) -> tor
     return x
 
 
+@_on_device
 def conv3d_ch16(x: torch.Tensor, layer: PackedLayer, stride: int = 1, relu: bool = True, skip: Optional[torch.Tensor] = None,
                 out_fmt: str = "ch16", in_cells: bool = False) -> torch.Tensor:
     """One block of the tensor path.  x: cells from ``to_ch16`` (parity split for stride 2) or fp32 [B,2,D,H,W] for conv0;
@@ -720,6 +751,7 @@ class PackedRegnet:
             self.c_branches[0].conv0_pair = N.ConvLayer(None, self.pair[1].data_ptr(), self.pair[2].data_ptr(), self.pair[0].data_ptr(), None)
 
 
+@_on_device
 def regnet_forward(pack: PackedRegnet, cost: Optional[torch.Tensor], engine: Optional[str] = None,
                    cost_cells: Optional[torch.Tensor] = None, branch_mask: int = 3, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cost [B,2,D,h,w] (and / or its cell form from ``warp_corr(want_cells=True)``) -> logits [B,4,D,h,w].
@@ -757,6 +789,7 @@ def _scalar(v, device) -> torch.Tensor:
     return torch.full((1,), float(v), device=device, dtype=torch.float32)
 
 
+@_on_device
 def depth_head(logits: torch.Tensor, hyp: torch.Tensor, interval, want_prob: bool = True):
     lib = N.load()
     logits = _req(logits, "logits").contiguous()
@@ -777,6 +810,7 @@ def depth_head(logits: torch.Tensor, hyp: torch.Tensor, interval, want_prob: boo
     return prob, d4, hyp_c, conf
 
 
+@_on_device
 def refine_head(logits_c: torch.Tensor, hyp_c: torch.Tensor, interval, alpha: float = 5.0):
     lib = N.load()
     logits_c = _req(logits_c, "logits_c").contiguous()
@@ -797,6 +831,7 @@ def refine_head(logits_c: torch.Tensor, hyp_c: torch.Tensor, interval, alpha: fl
 
 
 # ----------------------------------------------------------------------------- S1
+@_on_device
 def hypotheses_first(depth_values: torch.Tensor, ndepth: int, shape: Sequence[int], inverse: bool):
     lib = N.load()
     dv = _req(depth_values, "depth_values").contiguous()
@@ -811,6 +846,7 @@ def hypotheses_first(depth_values: torch.Tensor, ndepth: int, shape: Sequence[in
     return hyp, interval
 
 
+@_on_device
 def hypotheses_next(last_depth: torch.Tensor, ndepth: int, interval_pixel, shape: Optional[Sequence[int]], inverse: bool):
     """Per-pixel checkerboard ranges around ``last_depth`` [B,h0,w0], upsampled to ``shape`` (None: no upsample)."""
     lib = N.load()

@@ -72,8 +72,7 @@ int dmvs_warp_corr_f32(const float* ref, long long ref_bstride, const float* con
  * channels_last memory format has stride 2C and its channel slices are consumed in place) and `src_bstride` between
  * batches; pointers 16-byte aligned.  The reference view is NCHW when `ref_pixstride` == 0, else channel-last too.  A bilinear footprint row is then one contiguous
  * run of 2*C floats that C/2 lanes fetch with one 16-byte load each (`src_cornerstride` = floats between the two x-corners of a
- * footprint: 0 / src_pixstride for a plain channel-last map; C for the PAIR layout [..][w][2][C] whose entry x stores pixel x
- * followed by a copy of pixel x+1 (pixel stride 2C), so that a footprint row is an aligned run that never straddles a 128-byte line), which is what makes the gather cheap when the
+ * footprint; 0 = `src_pixstride`, the only value the Python layer passes), which is what makes the gather cheap when the
  * per-pixel hypotheses are rough (see csrc/warp_corr_nhwc.cu).  All other arguments as above. */
 int dmvs_warp_corr_nhwc_f32(const float* ref, long long ref_bstride, int ref_pixstride, const float* const* src,
                             long long src_bstride, int src_pixstride, int src_cornerstride, int n_src, const float* rt, const float* hyp, float* cost, void* cost_cells,
@@ -235,7 +234,6 @@ int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* s
 #define DMVS_FMT_CH16 1
 #define DMVS_FMT_CH16P 2
 #define DMVS_FMT_COST2 3 /* conv0 input written by dmvs_warp_corr_f32(cost_cells), see there */
-#define DMVS_FMT_NHWC2P 5 /* like DMVS_FMT_NHWC2 in the pair layout [2][B][D][H][W][2][Cout/2]: entry x = (pixel x | pixel x+1) */
 #define DMVS_FMT_NHWC2 4 /* output only, FeatureNet's 3x3 heads (kd = 1, Cin = 32, Cout = 16 / 32): two channel-last fp32 buffers
                             back to back, [2][B][D][H][W][Cout/2] = the `stageK` / `stageK_c` feature sets */
 

@@ -296,3 +296,22 @@ def test_fusion_matrices_numpy_and_torch_forms_agree():
     assert np.array_equal(b[:9].numpy().reshape(3, 3), inv_k)                      # block 0: inv(K_ref), numpy's own bits
     assert np.array_equal(b[21:30].numpy().reshape(3, 3), ks[1].numpy())           # block 2: K_src
     assert np.array_equal(b[51:60].numpy().reshape(3, 3), ks[0].numpy())           # block 5: K_ref
+
+
+def test_module_copies_and_pickles_like_the_reference():
+    """derived caches (repacked weights as ctypes structs, CUDA streams) must not leak into copy.deepcopy / pickle."""
+    import copy
+    import io
+    import pickle
+    import torch
+    from dmvsnet_b200 import MVSNet
+    net = MVSNet([8, 8, 8], [4, 2, 1]).eval()
+    reg = net.cost_regularization[0]
+    reg._pack, reg._pack_key = object(), ("stale",)          # stand-ins for the ctypes cache a forward leaves behind
+    net.feature._packed, net.feature._packed_key = {"x": lambda: 0}, ("stale",)
+    twin = copy.deepcopy(net)
+    assert twin.cost_regularization[0]._pack is None and not hasattr(twin.feature, "_packed")
+    blob = pickle.dumps(net)
+    assert sorted(pickle.loads(blob).state_dict()) == sorted(net.state_dict())
+    buf = io.BytesIO()
+    torch.save(net, buf)
