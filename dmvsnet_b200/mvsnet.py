@@ -25,6 +25,13 @@ __all__ = ["MVSNet", "CostAgg", "DepthNet", "Align_Corners_Range"]
 Align_Corners_Range = False  # mvsnet.py:8; the fused sampler implements align_corners=False
 
 
+def _as_float_images(imgs: torch.Tensor) -> torch.Tensor:
+    """uint8 photographs -> the fp32 [0,1] images the network is defined on: x / 255 in IEEE fp32, as the reference's loaders."""
+    if imgs.dtype == torch.uint8:
+        return imgs.to(torch.float32).div_(255.0)
+    return imgs
+
+
 def _check_finite(flag: torch.Tensor) -> None:
     if not bool(flag[0]):
         raise FloatingPointError(
@@ -232,6 +239,10 @@ class MVSNet(nn.Module):
               keys: Sequence[str] = ("depth", "photometric_confidence")) -> Dict[str, torch.Tensor]:
         """Host tensors in, host tensors out: H2D of the images, forward, D2H of ``keys`` only.
 
+        ``imgs`` may be uint8 [B,N,3,H,W] (the decoded photographs, 0..255): they cross PCIe as they are (a quarter of the
+        bytes) and are scaled on the device by the same IEEE fp32 division by 255 the reference's loaders do on the host
+        (datasets/general_eval.py:161 ``np.array(img, dtype=np.float32) / 255.``) - identical pixel values.
+
         What ``Model.test`` does around the network (tools.tocuda model.py:333 / tensor2numpy model.py:347), minus the
         D2H of the three probability volumes nobody reads at test time.  The views are uploaded in groups on a side
         stream so that FeatureNet (per-view arithmetic, mvsnet.py:199-202) starts on the first group while the rest is
@@ -243,7 +254,7 @@ class MVSNet(nn.Module):
 
     def _infer(self, imgs, proj_matrices, depth_values, keys, dev):
         if imgs.is_cuda:
-            out = self.forward(imgs, proj_matrices, depth_values)
+            out = self.forward(_as_float_images(imgs), proj_matrices, depth_values)
         else:
             src = imgs if imgs.is_pinned() else imgs.pin_memory()
             b, n = src.shape[0], src.shape[1]
@@ -264,7 +275,7 @@ class MVSNet(nn.Module):
             for lo, part, ev in chunks:
                 main.wait_event(ev)
                 part.record_stream(main)
-                feats.extend(self.extract_features(part))
+                feats.extend(self.extract_features(_as_float_images(part)))
             out = self.cascade(feats, proj_matrices, depth_values, imgs.shape[-2:])
         host = {}
         finite = torch.empty(1, dtype=torch.bool, pin_memory=True)
@@ -317,7 +328,7 @@ class MVSNet(nn.Module):
             with torch.cuda.stream(feat_stream):
                 feat_stream.wait_event(ev)
                 dimgs.record_stream(feat_stream)
-                feats = self.extract_features(dimgs)
+                feats = self.extract_features(_as_float_images(dimgs))
                 fev = torch.cuda.Event()
                 fev.record(feat_stream)
             for view in feats:
@@ -337,7 +348,7 @@ class MVSNet(nn.Module):
                 main.wait_event(ev)
                 dimgs.record_stream(main)
                 cur = upload(nxt) if nxt is not None else None
-                out = self.forward(dimgs, proj, dv)
+                out = self.forward(_as_float_images(dimgs), proj, dv)
             else:
                 feats, hw, fev = cur_feats
                 # enqueue the next item's upload and FeatureNet first, then this item's cascade: they overlap on the device

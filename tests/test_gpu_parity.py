@@ -678,3 +678,23 @@ def test_ops_follow_the_tensors_device_not_the_current_one():
         torch.cuda.set_device(0)
         got = net.to("cuda:1")(imgs.to("cuda:1"), proj, dv.to("cuda:1"))["depth"]
     assert got.device.index == 1 and torch.equal(got.cpu(), want)
+
+
+def test_infer_uint8_images_equal_float_images():
+    """MVSNet.infer / infer_many take the 8-bit photographs as they are (uint8 host tensor, a quarter of the H2D bytes) and
+    scale them on the device: same pixel values as the reference's host-side ``np.array(img, float32) / 255.``
+    (datasets/general_eval.py:161), hence the same depth map bit for bit."""
+    from dmvsnet_b200 import MVSNet, synthetic as syn
+    nd, ratios, H, W, n = [16, 8, 8], [4, 2, 1], 128, 160, 3
+    net = MVSNet(nd, ratios, inverse_depth=True)
+    net.load_state_dict(syn.ridge_regnet_state(net.state_dict(), seed=1))
+    net = net.to(DEV).eval()
+    proj = syn.make_proj_matrices(H, W, n, 1)
+    u8 = (syn.make_scene_images(H, W, n, proj["stage3"], seed=1) * 255).round().to(torch.uint8)
+    f32 = torch.from_numpy(u8.numpy().astype("float32") / 255.0)
+    dv = syn.make_depth_values(1, 192, inverse=True)
+    want = net.infer(f32, proj, dv)
+    got = net.infer(u8, proj, dv)
+    assert torch.equal(got["depth"], want["depth"]) and torch.equal(got["photometric_confidence"], want["photometric_confidence"])
+    many = list(net.infer_many([(u8, proj, dv), (f32, proj, dv)]))
+    assert torch.equal(many[0]["depth"], want["depth"]) and torch.equal(many[1]["depth"], want["depth"])
