@@ -28,7 +28,9 @@ Align_Corners_Range = False  # mvsnet.py:8; the fused sampler implements align_c
 def _as_float_images(imgs: torch.Tensor) -> torch.Tensor:
     """uint8 photographs -> the fp32 [0,1] images the network is defined on: x / 255 in IEEE fp32, as the reference's loaders."""
     if imgs.dtype == torch.uint8:
-        return imgs.to(torch.float32).div_(255.0)
+        # a TENSOR divisor: torch turns division by a Python scalar into a multiplication by 1/255 on CUDA, which is not the
+        # correctly rounded quotient numpy computes on the host
+        return imgs.to(torch.float32) / torch.full((), 255.0, device=imgs.device)
     return imgs
 
 
