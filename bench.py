@@ -356,9 +356,11 @@ def run_gpu_arm(args, cfg_name):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=False):
-        if profile:
-            ops.PROFILE = []
+    def timed(fn, steps, profile=None):
+        # profile: None = no per-op events; "w1:" = CUDA events around the W1 launches only (12 per step: the roofline is measured
+        # inside the timed region); "" = around every op (host time: used in a separate short pass for the breakdown)
+        if profile is not None:
+            ops.PROFILE, ops.PROFILE_ONLY = [], (profile or None)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         l0 = _native.launch_count()
@@ -367,7 +369,7 @@ def run_gpu_arm(args, cfg_name):
             out = fn()
         e1.record()
         barrier()
-        prof, ops.PROFILE = ops.PROFILE, None
+        prof, ops.PROFILE, ops.PROFILE_ONLY = ops.PROFILE, None, None
         return e0.elapsed_time(e1), out, prof, _native.launch_count() - l0
 
     warm = max(args.warmup, 3)
@@ -385,14 +387,17 @@ def run_gpu_arm(args, cfg_name):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    # ---- value: the full forward, images resident in HBM.  The per-op CUDA events of ops.PROFILE ride along (a few us each).
-    ms, out, prof_full, launches = timed(full_step, args.steps, profile=True)
+    # ---- value: the full forward, images resident in HBM; CUDA events around the W1 launches ride along
+    ms, out, prof_full, launches = timed(full_step, args.steps, profile="w1:")
     depth_full = out["depth"].clone()
     # ---- hot_path: the stage loop on the conditioned feature maps
-    hot_ms, out, prof_hot, hot_launches = timed(hot_step, args.steps, profile=True)
+    hot_ms, out, prof_hot, hot_launches = timed(hot_step, args.steps, profile="w1:")
     depth_hot = out["depth"].clone()
     clocks = sampler.stop()
     del out
+    # per-group breakdown: a separate short pass with events around every op (not part of any reported throughput)
+    _, _, prof_full_all, _ = timed(full_step, 3, profile="")
+    _, _, prof_hot_all, _ = timed(hot_step, 3, profile="")
 
     # in-bounds fraction of the six W1 launches (one extra untimed step each, recorded hypotheses)
     inb_hot, inb_full = {}, {}
@@ -451,8 +456,10 @@ def run_gpu_arm(args, cfg_name):
 
     peak, peak_src, _ = peaks()
     n_steps = float(args.steps)
-    roof_hot, rows_hot, groups_hot = w1_roofline(prof_hot, n_steps, views, peak, inb_hot)
-    roof_full, rows_full, groups_full = w1_roofline(prof_full, n_steps, views, peak, inb_full)
+    roof_hot, rows_hot, _ = w1_roofline(prof_hot, n_steps, views, peak, inb_hot)
+    roof_full, rows_full, _ = w1_roofline(prof_full, n_steps, views, peak, inb_full)
+    _, _, groups_hot = w1_roofline(prof_hot_all, 3.0, views, peak)
+    _, _, groups_full = w1_roofline(prof_full_all, 3.0, views, peak)
     sm_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9  # GB/s through the SMs' shared-memory data pipe
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r2_w1_traffic.json")

@@ -17,6 +17,7 @@ from . import _native as N
 # Optional instrumentation for bench.py: when PROFILE is a list, every op appends (tag, start_event, end_event,
 # algorithmic_bytes) recorded on the launching stream; when CAPTURE is a list, warp_corr appends (tag, rt, hyp).
 PROFILE = None
+PROFILE_ONLY = None  # optional tag prefix (e.g. "w1:"): only those ops are timed - a pair of CUDA events per op costs host time
 CAPTURE = None
 
 
@@ -25,14 +26,15 @@ class _timed:
         self.tag, self.nbytes = tag, nbytes
 
     def __enter__(self):
-        if PROFILE is not None:
+        self.on = PROFILE is not None and (PROFILE_ONLY is None or self.tag.startswith(PROFILE_ONLY))
+        if self.on:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
         return self
 
     def __exit__(self, *exc):
-        if PROFILE is not None:
+        if self.on and PROFILE is not None:
             self.e1.record()
             PROFILE.append((self.tag, self.e0, self.e1, self.nbytes))
         return False
