@@ -356,9 +356,15 @@ def run_gpu_arm(args, cfg_name):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=None):
+    def timed(fn, steps, profile=None, settle=2):
         # profile: None = no per-op events; "w1:" = CUDA events around the W1 launches only (12 per step: the roofline is measured
-        # inside the timed region); "" = around every op (host time: used in a separate short pass for the breakdown)
+        # inside the timed region); "" = around every op (host time: used in a separate short pass for the breakdown).
+        # `settle` untimed iterations of the SAME loop body first: the caching allocator reaches the block layout of this loop
+        # (a cudaMalloc inside the timed region is a device-wide stall of milliseconds), and no result outlives its iteration.
+        out = None
+        for _ in range(settle):
+            out = None
+            out = fn()
         if profile is not None:
             ops.PROFILE, ops.PROFILE_ONLY = [], (profile or None)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -366,6 +372,7 @@ def run_gpu_arm(args, cfg_name):
         l0 = _native.launch_count()
         e0.record()
         for _ in range(steps):
+            out = None
             out = fn()
         e1.record()
         barrier()
