@@ -51,6 +51,8 @@ CONFIGS = {
 }
 RATIOS = {1: [4], 3: [4, 2, 1]}
 FEATURE_C = (32, 16, 8)
+# algorithmic flops of the regularisation nets per view (2 * MAC): main + refine nets of all stages
+R1_GFLOP = {"dtu": 708.7, "bmvs": 165.5, "tnt": 758.5, "synth": 6468.6}
 
 
 def peaks():
@@ -461,7 +463,7 @@ def run_gpu_arm(args, cfg_name):
         torch.cuda.empty_cache()
         sharded = sharded_leg(args, world, rank, dev, barrier)
 
-    peak, peak_src, _ = peaks()
+    peak, peak_src, pk = peaks()
     n_steps = float(args.steps)
     roof_hot, rows_hot, _ = w1_roofline(prof_hot, n_steps, views, peak, inb_hot)
     roof_full, rows_full, _ = w1_roofline(prof_full, n_steps, views, peak, inb_full)
@@ -511,6 +513,17 @@ def run_gpu_arm(args, cfg_name):
                                           "frac": (roof_hot["gather_bytes_per_step"] / sm_peak / 1e6) / roof_hot["ms_per_step"] if roof_hot["ms_per_step"] > 0 else None}},
                              **{k: v for k, v in roof_hot.items() if k != "gather_bytes_per_step"}),
             "roofline_per_launch": rows_hot,
+            "roofline_regnet": None if cfg_name not in R1_GFLOP else {
+                "kernel": "R1 = conv_tc2_kernel (tcgen05 implicit GEMM, fp16 hi/lo split operands: 3 products per multiply-add), all regularisation nets of a step "
+                          "(82 % of the hot path's kernel time, profiles/r2j_launches_hot.csv)",
+                "bound": "tensor", "unit": "TFLOP/s", "algorithmic_gflop_per_step": R1_GFLOP[cfg_name],
+                "ms_per_step": groups_hot.get("regnet", 0.0) + groups_hot.get("regnet_refine", 0.0),
+                "achieved": R1_GFLOP[cfg_name] / max(groups_hot.get("regnet", 0.0) + groups_hot.get("regnet_refine", 0.0), 1e-9),
+                "peak": float(pk.get("bf16_tflops_sustained", 1400.0)),
+                "frac": R1_GFLOP[cfg_name] / max(groups_hot.get("regnet", 0.0) + groups_hot.get("regnet_refine", 0.0), 1e-9) / float(pk.get("bf16_tflops_sustained", 1400.0)),
+                "note": "algorithmic flops (one product per multiply-add) over the event-timed net launches against the sustained bf16 peak; the split executes 3x "
+                        "these flops, and at base_channels = 8 the layers are bound by the shared-memory operand read per MMA (N = 16..64) and by HBM at full "
+                        "resolution, not by the tensor pipe (DESIGN.md section 4)"},
             "roofline_full_forward": dict({"workload": "value region: feature maps from the randomly initialised FeatureNet are not discriminative, the regressed "
                                                        "depth is rough and most source footprints miss their staged box (direct global gathers)"},
                                           **{k: v for k, v in roof_full.items() if k != "gather_bytes_per_step"}, per_launch=rows_full),
