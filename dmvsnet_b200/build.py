@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdmvs_b200.so")
-SOURCES = ["api.cu", "warp_corr.cu", "warp_corr_nhwc.cu", "warp_corr_staged.cu", "warp_corr_h16.cu", "warp_corr_bwd.cu", "featurenet.cu", "geo_filter.cu", "heads.cu", "conv3d.cu", "conv_tc2.cu", "regnet.cu"]
+SOURCES = ["api.cu", "warp_corr.cu", "warp_corr_nhwc.cu", "warp_corr_staged.cu", "warp_corr_h16.cu", "warp_corr_bwd.cu", "featurenet.cu", "geo_filter.cu", "heads.cu", "conv3d.cu", "conv_tc2.cu", "conv_kf.cu", "regnet.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -21,6 +21,7 @@ extern int g_head_px;
 extern int g_pb_td8;
 extern int g_tc2_pdl;
 extern int g_regnet_streams;
+extern int g_kf;
 
 }  // namespace dmvs
 
@@ -40,6 +41,10 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
   }
   if (key && !strcmp(key, "regnet_streams") && (value == 0 || value == 1)) {
     dmvs::g_regnet_streams = value;
+    return DMVS_OK;
+  }
+  if (key && !strcmp(key, "kf") && value >= 0 && value <= 2) {
+    dmvs::g_kf = value;
     return DMVS_OK;
   }
   if (key && !strcmp(key, "head_px") && (value == 32 || value == 64 || value == 128)) {

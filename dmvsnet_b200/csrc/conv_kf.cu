@@ -1,0 +1,382 @@
+// R1 tensor-core path, stride-1 3x3x3 layers with the DEPTH TAP FOLDED INTO N and a march along z (sm_100a).
+//
+// conv_tc2.cu issues one tcgen05.mma per (output plane, tap, 8-channel chunk); each of them re-reads its 128-voxel A tile from
+// shared memory (~64 cycles) for 8-32 cycles of math, so those layers are bound by the NUMBER of MMAs.  Here the three depth
+// taps share one MMA: the weight columns are [kd = 0 | kd = 1 | kd = 2] (N = 3 x 2*Cout_p), and the accumulator belongs to the
+// INPUT plane s: P[s][kd] = sum over (kh, kw, c) of in[s] * W[kd].  An output plane is then the sum of three column blocks of
+// three neighbouring accumulators, out[t] = P[t-1][0] + P[t][1] + P[t+1][2], taken in the epilogue (TMEM loads are cheap).
+// 9 * Cin/8 MMAs per plane instead of 27 * Cin/8.
+//
+//   * A CTA owns a contiguous range of the linearised (column, output plane) sequence, column = one 16 x 8 patch over all D planes;
+//     ranges are equal to within one plane whatever the volume shape.  Inside a column fragment [t0, t1] it marches through the
+//     input planes max(t0-1, 0) .. min(t1+1, D-1): every plane is staged once by TMA (one 18 x 10-cell box per hi/lo plane, OOB
+//     zero fill = the padding in y / x; planes outside the volume are simply not visited = the padding in z).
+//   * The accumulators form a ring of R TMEM slots.  Plane number g (counted over the CTA's whole range) lives in slot g % R;
+//     `accfull[slot]` is committed by the issuing thread, `accempty[slot]` collects 3 reader arrivals per epilogue warp (the output planes s-1, s,
+//     s+1; where one of them is outside the fragment its neighbour inside arrives in its place).
+//   * Two issuing threads alternate planes (R is even, so a slot always belongs to the same thread and its barrier phases are
+//     consumed in order); the smem stage ring is split between them the same way.
+//
+// Kinds: S1 = Cin, Cout multiples of 8 on CH16 cells (conv2); C0 = conv0 on the cost cells W1 emits (K packed along kw, 3 MMAs
+// per plane); PB = `prob` (8 -> 2, fp32 logits out).
+#include "conv_tc2.cuh"
+
+namespace dmvs {
+
+enum { KF_S1 = 0, KF_C0 = 1, KF_PB = 2 };
+
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NPART_, int CS_>
+struct KF {
+  static constexpr int NB = 2 * COUT_P;                 // one kd block: [hi(W) | lo(W)] columns
+  static constexpr int NF = (3 * NB + 15) / 16 * 16;    // N of one tcgen05.mma (PB: 12 -> 16)
+  static constexpr int SH = T_H + 2, BW = T_W + 2;
+  static constexpr int BLK_BYTES = SH * BW * 16;
+  static constexpr int PLANE = pad128(BLK_BYTES);
+  static constexpr int CJ = (KIND == KF_C0) ? 1 : CIN / 8;
+  static constexpr int NPLANE = (KIND == KF_C0) ? 1 : 2 * CJ;
+  static constexpr int TAPS = (KIND == KF_C0) ? 3 : 9;
+  static constexpr int A_LBO = (KIND == KF_C0) ? 32 : PLANE;
+  static constexpr int A_SBO = BW * 16;
+  static constexpr int B_TILE = 2 * NF * 16;
+  static constexpr int B_BYTES = CJ * TAPS * B_TILE;
+  static constexpr int STAGE_BYTES = NPLANE * PLANE;
+  static constexpr int TX_BYTES = NPLANE * BLK_BYTES;
+  static constexpr int OFF_B = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_B + pad128(B_BYTES);
+  static constexpr int SMEM = OFF_BAR + 8 * (2 * STAGES + 2 * R) + 16 + 128;
+  static constexpr int TMEM_COLS = pow2c(R * NF);
+  // epilogue: NPART groups of 4 warps interleave the output planes, CS groups share one plane by 8-channel chunk
+  static constexpr int NPART = NPART_, CS = CS_;
+  static constexpr int EPI_WARPS = 4 * NPART * CS;
+  static constexpr int MMA_WARPS = 2;
+  static constexpr int HS = STAGES / MMA_WARPS;
+  static constexpr int THREADS = (1 + MMA_WARPS + EPI_WARPS) * 32;
+  static_assert(R % 2 == 0 && R >= 4, "the accumulator ring is shared by two issuing threads and needs 3 live slots + 1");
+  static_assert(R * NF <= 512, "accumulator ring exceeds TMEM");
+  static_assert(STAGES % 2 == 0, "stage ring is split between two issuing threads");
+  static_assert(SMEM <= 227 * 1024, "pipeline does not fit shared memory");
+  // a group waits only on the accumulators it reads; with more than R/2 plane-interleaved groups one of them can meet a slot a
+  // full phase early and pass the parity test on the previous tenant (tools/experiments/kf_protocol_sim.py)
+  static_assert(2 * NPART <= R, "too many plane-interleaved epilogue groups for the accumulator ring");
+  static_assert(COUT_P % (8 * CS) == 0 || CS == 1, "channel chunks do not split evenly");
+};
+
+struct KfRange {  // the CTA's share of the (column, output plane) sequence
+  long long o, o_end;
+  int D;
+  __device__ __forceinline__ KfRange(const Tc2Params& p) {
+    const long long total = (long long)p.n_tiles * p.Do;
+    o = total * blockIdx.x / gridDim.x;
+    o_end = total * (blockIdx.x + 1) / gridDim.x;
+    D = p.Do;
+  }
+  // next column fragment: outputs [t0, t1] of column `col`, input planes [sa, sb]
+  __device__ __forceinline__ bool next(int& col, int& t0, int& t1, int& sa, int& sb) {
+    if (o >= o_end) return false;
+    col = (int)(o / D);
+    t0 = (int)(o - (long long)col * D);
+    const long long left = o_end - o;
+    t1 = (left >= D - t0) ? D - 1 : t0 + (int)left - 1;
+    sa = t0 > 0 ? t0 - 1 : 0;
+    sb = t1 < D - 1 ? t1 + 1 : D - 1;
+    o += t1 - t0 + 1;
+    return true;
+  }
+};
+
+__device__ __forceinline__ void kf_column(const Tc2Params& p, int col, int& x0, int& y0, int& b) {
+  x0 = (col % p.tiles_x) * T_W;
+  col /= p.tiles_x;
+  y0 = (col % p.tiles_y) * T_H;
+  b = col / p.tiles_y;
+}
+
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS>
+__global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THREADS, 1)
+    conv_kf_kernel(const __grid_constant__ Tc2Params p, const __grid_constant__ CUtensorMap tmap) {
+  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* sB = smem + Cfg::OFF_B;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accfull = empty + STAGES;
+  uint64_t* accempty = accfull + R;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + R);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < R; ++a) {
+      mbar_init(accfull + a, 1);
+      mbar_init(accempty + a, 3 * 4 * CS);  // 3 readers x (4 warps x CS groups), one elected arrival per warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    uint4* wdst = reinterpret_cast<uint4*>(sB);
+    for (int i = tid; i < Cfg::B_BYTES / 16; i += Cfg::THREADS) wdst[i] = __ldg(p.wtc + i);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();
+  pdl_wait();
+
+  KfRange range(p);
+  int col, t0, t1, sa, sb;
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: one TMA box per (input plane, hi/lo plane)
+    if (lane == 0) {
+      prefetch_tmap(&tmap);
+      const int planes_per_b = 2 * CIN / 8;
+      int g = 0;
+      while (range.next(col, t0, t1, sa, sb)) {
+        int x0, y0, b;
+        kf_column(p, col, x0, y0, b);
+        for (int s = sa; s <= sb; ++s, ++g) {
+          const int m = g & 1, j = g >> 1;
+          const int st = Cfg::MMA_WARPS * (j % Cfg::HS) + m, u = j / Cfg::HS;
+          mbar_wait(empty + st, (u & 1) ^ 1);
+          uint8_t* dst = smem + st * Cfg::STAGE_BYTES;
+          mbar_expect_tx(full + st, Cfg::TX_BYTES);
+          if (KIND == KF_C0) {  // cost cells: cell x = [voxel x-1 | voxel x], one plane per batch entry
+            tma_load_4d(dst, &tmap, full + st, 8 * x0, y0 - 1, s, b);
+          } else {
+#pragma unroll 1
+            for (int pl = 0; pl < Cfg::NPLANE; ++pl)
+              tma_load_4d(dst + pl * Cfg::PLANE, &tmap, full + st, 8 * (x0 - 1), y0 - 1, s, b * planes_per_b + pl);
+          }
+        }
+      }
+    }
+  } else if (warp <= Cfg::MMA_WARPS) {
+    // ---------------------------------------------------------------- MMA issuers: thread m takes the planes with g % 2 == m
+    const int me = warp - 1;
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Cfg::NF);
+      const uint64_t bdesc0 = make_desc(smem_u32(sB), Cfg::NF * 16, 128);
+      int g = 0;
+      while (range.next(col, t0, t1, sa, sb)) {
+        for (int s = sa; s <= sb; ++s, ++g) {
+          if ((g & 1) != me) continue;
+          const int slot = g % R, k = g / R;
+          mbar_wait(accempty + slot, (k & 1) ^ 1);
+          const int j = g >> 1;
+          const int st = Cfg::MMA_WARPS * (j % Cfg::HS) + me, u = j / Cfg::HS;
+          mbar_wait(full + st, u & 1);
+          tc_fence_after();
+          const uint64_t adesc0 = make_desc(smem_u32(smem + st * Cfg::STAGE_BYTES), Cfg::A_LBO, Cfg::A_SBO);
+          const uint32_t acc = tmem_base + slot * Cfg::NF;
+#pragma unroll
+          for (int tap = 0; tap < Cfg::TAPS; ++tap) {
+            const int off = (KIND == KF_C0) ? tap * Cfg::BW * 16 : ((tap / 3) * Cfg::BW + tap % 3) * 16;
+#pragma unroll
+            for (int cj = 0; cj < Cfg::CJ; ++cj) {
+              const uint64_t ad = adesc0 + (uint64_t)(((KIND == KF_C0 ? 0 : 2 * cj * Cfg::PLANE) + off) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)(((cj * Cfg::TAPS + tap) * Cfg::B_TILE) >> 4);
+              umma_f16(acc, ad, bd, idesc, (tap == 0 && cj == 0) ? 0u : 1u);
+            }
+          }
+          umma_commit(empty + st);
+          umma_commit(accfull + slot);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue: group (part, cs) takes every NPART-th output plane
+    // and every CS-th channel chunk of it
+    const int ew = warp - 1 - Cfg::MMA_WARPS;
+    const int q = warp & 3, part = (ew >> 2) % Cfg::NPART, cs = (ew >> 2) / Cfg::NPART;
+    const int hl = q * 4 + (lane >> 3), wl = lane & 7;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int npo = p.Cout / 4;
+    int g_base = 0;
+    long long oc = 0;
+    while (range.next(col, t0, t1, sa, sb)) {
+      int x0, y0, b;
+      kf_column(p, col, x0, y0, b);
+      const int oy = y0 + hl, ox = x0 + wl;
+      const bool in_img = (oy < p.Ho) && (ox < p.Wo);
+      for (int t = t0; t <= t1; ++t, ++oc) {
+        if ((int)(oc % Cfg::NPART) != part) continue;
+        const bool has_m = t > 0, has_p = t < p.Do - 1;
+        const int g0 = g_base + (t - sa), gm = g0 - 1, gp = g0 + 1;
+        if (has_m) mbar_wait(accfull + gm % R, (gm / R) & 1);
+        mbar_wait(accfull + g0 % R, (g0 / R) & 1);
+        if (has_p) mbar_wait(accfull + gp % R, (gp / R) & 1);
+        tc_fence_after();
+        // column blocks: kd = 0 of plane t-1, kd = 1 of plane t, kd = 2 of plane t+1 (a missing neighbour re-reads plane t and is
+        // masked out, so the loads stay unconditional)
+        const uint32_t am = lane_addr + (uint32_t)((has_m ? gm : g0) % R) * Cfg::NF;
+        const uint32_t a0 = lane_addr + (uint32_t)(g0 % R) * Cfg::NF + Cfg::NB;
+        const uint32_t ap = lane_addr + (uint32_t)((has_p ? gp : g0) % R) * Cfg::NF + 2 * Cfg::NB;
+        const float fm = has_m ? 1.f : 0.f, fp = has_p ? 1.f : 0.f;
+        // 3 reader arrivals per accumulator: this plane arrives for itself and for the readers outside the fragment it stands in
+        // for.  Called as soon as the group's TMEM loads have landed in registers - the slot is free long before the stores.
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();  // every lane's tcgen05.ld has completed (wait::ld) before lane 0 arrives for the warp
+          if (lane == 0) {
+            if (has_m) mbar_arrive_n(accempty + gm % R, (t == t0) ? 3 : 1);
+            mbar_arrive_n(accempty + g0 % R, 1 + (t == t0 ? 1 : 0) + (t == t1 ? 1 : 0));
+            if (has_p) mbar_arrive_n(accempty + gp % R, (t == t1) ? 3 : 1);
+          }
+        };
+        if (KIND == KF_PB) {
+          // NB = 4: columns [hi co0, hi co1, lo co0, lo co1] per kd; the x8 loads cover kd 0,1 (columns 0..7) and kd 2 (8..15)
+          uint32_t r0[8], r1[8], r2[8];
+          tmem_ld8_issue(am, r0);
+          tmem_ld8_issue(a0 - Cfg::NB, r1);
+          tmem_ld8_issue(ap, r2);
+          tmem_wait_ld();
+          release();
+          if (in_img) {
+            float* yf = reinterpret_cast<float*>(p.y);
+            const long long oplane = (long long)p.Ho * p.Wo;
+#pragma unroll
+            for (int co = 0; co < 2; ++co) {
+              const float vm = __uint_as_float(r0[co]) + __uint_as_float(r0[2 + co]);
+              const float v0 = __uint_as_float(r1[4 + co]) + __uint_as_float(r1[6 + co]);
+              const float vp = __uint_as_float(r2[co]) + __uint_as_float(r2[2 + co]);
+              float v = (fm * vm + v0) + fp * vp;
+              if (p.scale) v = fmaf(v, __ldg(p.scale + co), __ldg(p.shift + co));
+              if (p.relu) v = fmaxf(v, 0.f);
+              if (co < p.Cout) yf[(long long)b * p.y_bs + ((long long)co * p.Do + t) * oplane + (long long)oy * p.Wo + ox] = v;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c0 = 8 * cs; c0 < COUT_P; c0 += 8 * Cfg::CS) {
+            uint32_t rm[8], rml[8], r0[8], r0l[8], rp[8], rpl[8];
+            tmem_ld8_issue(am + c0, rm);
+            tmem_ld8_issue(am + COUT_P + c0, rml);
+            tmem_ld8_issue(a0 + c0, r0);
+            tmem_ld8_issue(a0 + COUT_P + c0, r0l);
+            tmem_ld8_issue(ap + c0, rp);
+            tmem_ld8_issue(ap + COUT_P + c0, rpl);
+            tmem_wait_ld();
+            if (c0 + 8 * Cfg::CS >= COUT_P) release();
+            if (!in_img || c0 >= p.Cout) continue;
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float vm = __uint_as_float(rm[c]) + __uint_as_float(rml[c]);
+              const float v0 = __uint_as_float(r0[c]) + __uint_as_float(r0l[c]);
+              const float vp = __uint_as_float(rp[c]) + __uint_as_float(rpl[c]);
+              float a = (fm * vm + v0) + fp * vp;
+              if (p.scale) a = fmaf(a, __ldg(p.scale + c0 + c), __ldg(p.shift + c0 + c));
+              if (p.relu) a = fmaxf(a, 0.f);
+              v[c] = a;
+            }
+            uint4 hi, lo;
+            split_pack8(v, hi, lo);
+            const int ph = (c0 >> 3) * 2;
+            const long long cell = cell_index(p.out_fmt, b, npo, ph, p.Do, p.Ho, p.Wo, t, oy, ox);
+            const long long pstride = (p.out_fmt == FMT_CH16P) ? (long long)p.Do * p.Ho * (2 * ((p.Wo + 1) >> 1))
+                                                               : (long long)p.Do * p.Ho * p.Wo;
+            uint4* yc = reinterpret_cast<uint4*>(p.y);
+            yc[cell] = hi;
+            yc[cell + pstride] = lo;
+          }
+        }
+      }
+      g_base += sb - sa + 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+extern int g_tc2_max_ctas;
+extern int g_tc2_pdl;
+// dmvs_debug_set("kf", 0 | 1 | 2): 0 = the per-tap kernels of conv_tc2.cu everywhere; 1 = conv2 folded (x1.75 on B200);
+// 2 = conv0 and prob folded as well (measured SLOWER: with 3 / 9 MMAs per plane they are bound by the per-plane hand-off
+// between issuer and epilogue through a ring of only 4 - 8 accumulators, not by the MMA count)
+int g_kf = 1;
+
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS>
+static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
+  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>;
+  p.tiles_x = ceil_div(p.Wo, T_W);
+  p.tiles_y = ceil_div(p.Ho, T_H);
+  p.tiles_z = 1;
+  p.n_tiles = p.tiles_x * p.tiles_y * p.B;  // columns
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  int rc;
+  if (KIND == KF_C0)  // [B][D][H][W+1] cost cells viewed as a CH16 tensor of width W+1 with one plane per batch entry
+    rc = make_tmap(&tmap, x, FMT_CH16, p.B, p.Di, p.Hi, p.Wi + 1, Cfg::BW, Cfg::SH, 1);
+  else
+    rc = make_tmap(&tmap, x, FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, 1);
+  if (rc != DMVS_OK) return rc;
+  auto kern = conv_kf_kernel<KIND, CIN, COUT_P, R, STAGES, NP, CS>;
+  static PerDevice state;  // per template instance
+  const int slot = current_device_slot();
+  DMVS_REQUIRE(slot >= 0, DMVS_ERR_CUDA, "conv_kf: no current CUDA device");
+  if (!state.configured[slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) {
+      set_error("conv_kf: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+      return DMVS_ERR_CUDA;
+    }
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM) != cudaSuccess || occ < 1) occ = 1;
+    const int by_tmem = 512 / Cfg::TMEM_COLS;
+    state.value[slot] = occ < by_tmem ? occ : by_tmem;
+    if (state.value[slot] < 1) state.value[slot] = 1;
+    state.configured[slot] = true;
+  }
+  const int ctas_per_sm = state.value[slot];
+  const long long want = (long long)kNumSMs * (ctas_per_sm < g_tc2_max_ctas ? ctas_per_sm : g_tc2_max_ctas);
+  // every range pays up to two halo planes: no ranges shorter than 4 output planes
+  const long long total = (long long)p.n_tiles * p.Do;
+  long long grid = total / 4 < 1 ? 1 : total / 4;
+  if (grid > want) grid = want;
+  if (g_tc2_pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p, tmap);
+  } else {
+    kern<<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, tmap);
+  }
+  char what[128];
+  snprintf(what, sizeof(what), "conv_kf<kind %d, Cin %d, Cout_p %d, ring %d, stages %d> columns %d x %d planes", KIND, CIN, COUT_P, R, STAGES,
+           p.n_tiles, p.Do);
+  return check_launch(what);
+}
+
+// Stride-1 3x3x3 layers with a folded weight image (dmvs_conv_layer.w_tc_kd).  `p` arrives filled by conv_layer_tc2 (dims, pointers,
+// out_fmt, y_bs) with p.wtc already pointing at the folded image.  Returns +1 if the shape has no folded specialisation.
+int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t st) {
+  if (!g_kf) return 1;
+  if (p.Cin == 16 && p.Cout == 16 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P))
+    return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2>(p, x, st);  // conv2
+  if (g_kf < 2) return 1;
+  if (p.Cin == 2 && in_cells) {
+    if (p.Cout == 16) return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2>(p, x, st);  // conv0 of both branches
+    if (p.Cout == 8) return launch_kf<KF_C0, 2, 8, 8, 8, 4, 1>(p, x, st);    // conv0
+    return 1;
+  }
+  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1>(p, x, st);  // prob
+  return 1;
+}
+
+}  // namespace dmvs

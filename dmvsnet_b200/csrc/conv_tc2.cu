@@ -19,41 +19,9 @@
 //   * prob (8 -> 2, mode PB): the depth tap kd is folded into N.  Cout = 2 uses only 4 of the 16 UMMA columns, so the
 //     columns carry [kd][hi0 hi1 lo0 lo1]: one accumulator per INPUT plane holds the three kd partial sums, the
 //     epilogue adds P[t+kd][kd] - (TD+2)*9 MMAs per tile instead of TD*27 at the same cost each.
-#include <cuda.h>
-#include <string.h>
-
-#include "tc_common.cuh"
+#include "conv_tc2.cuh"
 
 namespace dmvs {
-
-enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2, FMT_NHWC2 = 4 };
-enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4, M2_C0T = 5, M2_TRF = 6 };
-__host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mode == M2_C0T; }
-// TRF: transposed conv with the 27 taps folded by input shift: the taps that read the same shifted A view (shift in {0,1}^3,
-// 8 of them) become ONE MMA whose N spans the 8 parity-class accumulators (zero weight columns where a class has no tap for
-// that shift).  Every MMA re-reads its 4 KB A tile from shared memory at 64 B/clk whatever its N, so 8 MMAs instead of 27.
-__host__ __device__ constexpr bool is_tr(int mode) { return mode == M2_TR || mode == M2_TRF; }
-constexpr int T_H = 16, T_W = 8;
-#ifndef SUBISSUE
-#define SUBISSUE 2
-#endif
-
-struct Tc2Params {
-  const float* x_f32;  // C0 only
-  const uint4* wtc;
-  const float* scale;
-  const float* shift;
-  const uint4* skip;  // CH16P, TR only
-  void* y;
-  long long x_bs;     // C0 only (elements)
-  long long y_bs;     // fp32 output only: batch stride in elements (the logits tensor interleaves two branches)
-  int B, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo;
-  int relu, out_fmt;
-  int tiles_x, tiles_y, tiles_z, n_tiles;
-};
-
-__host__ __device__ constexpr int pad128(int v) { return (v + 127) / 128 * 128; }
-__host__ __device__ constexpr int pow2c(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD = 3>
 struct C2 {
@@ -122,26 +90,6 @@ __device__ __forceinline__ Tile2 decode2(const Tc2Params& p, int lt, int td) {
   t.z0 = (lt % p.tiles_z) * td;
   t.b = lt / p.tiles_z;
   return t;
-}
-
-// ------------------------------------------------------------------------------------------------ cell helpers
-__device__ __forceinline__ void unpack_cell(const uint4& c, float (&v)[8]) {
-  const __half2* h = reinterpret_cast<const __half2*>(&c);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
-}
-// cell index of voxel (z, y, x) of plane `pl` in a CH16 / CH16P tensor with dims (D, H, W) and NP planes per batch entry
-__device__ __forceinline__ long long cell_index(int fmt, int b, int np, int pl, int D, int H, int W, int z, int y, int x) {
-  const long long row = ((long long)(b * np + pl) * D + z) * H + y;
-  if (fmt == FMT_CH16P) {
-    const int we = (W + 1) >> 1;
-    return (row * 2 + (x & 1)) * we + (x >> 1);
-  }
-  return row * W + x;
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issue (one thread)
@@ -579,45 +527,7 @@ __global__ void __launch_bounds__(256) ch16_to_f32_kernel(const uint4* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-  }
-  return fn;
-}
-
-// tensor map over a CH16 (rank 4: {W*8 halfs, H, D, planes}) or CH16P (rank 5: {We*8, 2, H, D, planes}) tensor
-static int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int D, int H, int W, int box_cells, int box_h, int box_d) {
-  EncodeTiledFn enc = encode_fn();
-  DMVS_REQUIRE(enc != nullptr, DMVS_ERR_CUDA, "conv_tc2: cuTensorMapEncodeTiled is not available from the driver");
-  CUresult r;
-  if (fmt == FMT_CH16) {
-    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
-    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    const cuuint32_t box[4] = {(cuuint32_t)box_cells * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
-    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    const cuuint64_t we = (cuuint64_t)(W + 1) / 2;
-    const cuuint64_t dims[5] = {we * 8, 2, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
-    const cuuint64_t strides[4] = {we * 16, 2 * we * 16, (cuuint64_t)H * 2 * we * 16, (cuuint64_t)D * H * 2 * we * 16};
-    const cuuint32_t box[5] = {(cuuint32_t)box_cells * 8, 1, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
-    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
-  DMVS_REQUIRE(r == CUDA_SUCCESS, DMVS_ERR_CUDA, "conv_tc2: cuTensorMapEncodeTiled failed (%d) for dims D=%d H=%d W=%d planes=%d", (int)r,
-               D, H, W, planes);
-  return DMVS_OK;
-}
+int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t st);  // conv_kf.cu
 
 int g_tc2_max_ctas = 1;
 int g_tc2_pdl = 1;      // programmatic dependent launch of the tensor convs (dmvs_debug_set("tc2_pdl", 0 | 1))
@@ -767,6 +677,12 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   }
   p.Do = Di; p.Ho = Hi; p.Wo = Wi;
   if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;
+  if (L.w_tc_kd) {  // depth tap folded into N, march along z (conv_kf.cu): conv0 on cost cells, conv2, prob
+    Tc2Params pk = p;
+    pk.wtc = reinterpret_cast<const uint4*>(L.w_tc_kd);
+    const int rc = conv_layer_kf(pk, x, in_cells, st);
+    if (rc <= 0) return rc;
+  }
   if (Cin == 2 && Cout == 16 && in_cells) {                                          // conv0 of both branches (conv0_pair)
     if (Di >= 8 && g_pb_td8) return launch2<M2_C0T, 2, 2, 32, 8, 4>(p, x, st);
     return launch2<M2_C0T, 2, 2, 32, 4, 4>(p, x, st);

@@ -541,6 +541,10 @@ class PackedLayer:
             self.w_tc_kd = _pack_tensor_core_prob(w[:, :, :cout])
         elif cin == 16 and cout == 8 and taps == 27 and transposed:
             self.w_tc_kd = _pack_tensor_core_tr_fold(w[:, :, :cout])
+        elif cin == 16 and cout == 16 and taps == 27 and not transposed:   # conv2
+            self.w_tc_kd = _pack_tensor_core_kf(self.w_tc)
+        elif cin == 2 and cout == 8 and taps == 27 and not transposed:     # conv0
+            self.w_tc_kd = _pack_tensor_core_kf(self.w_tc, kh_only=True)
         self.kd = 3 if taps == 27 else 1
         self.cin, self.cout = cin, cout
         self.transposed = transposed
@@ -588,6 +592,16 @@ def _pack_tensor_core_prob(w: torch.Tensor) -> torch.Tensor:
             img[0, :, 1, 4 * kd + co] = hi[kd, :, :, co]
             img[0, :, 0, 4 * kd + 2 + co] = lo[kd, :, :, co]
     return img.contiguous()
+
+
+def _pack_tensor_core_kf(per_tap: torch.Tensor, kh_only: bool = False) -> torch.Tensor:
+    """Depth tap folded into N for the z-marching kernels (csrc/conv_kf.cu).  `per_tap` is the image of ``_pack_tensor_core``
+    ([j][27 taps (kd,kh,kw)][kc][nb][8]) or, with ``kh_only``, of ``_pack_tensor_core_kw`` ([1][9 taps (kd,kh)][kc][nb][8]);
+    the result is [j][taps / 3][kc][n = 3*nb][8] with the column blocks ordered kd = 0, 1, 2."""
+    j, taps, kc, nb, e = per_tap.shape
+    assert taps == (9 if kh_only else 27)
+    t = per_tap.reshape(j, 3, taps // 3, kc, nb, e).permute(0, 2, 3, 1, 4, 5)
+    return t.reshape(j, taps // 3, kc, 3 * nb, e).contiguous()
 
 
 def _pack_tensor_core_tr_fold(w: torch.Tensor) -> torch.Tensor:
@@ -749,8 +763,11 @@ class PackedRegnet:
         if (PAIR_CONV0 and a.cin == 2 and a.cout == 8 and b.cin == 2 and b.cout == 8 and a.kd == 3 and not a.transposed
                 and a.scale is not None and b.scale is not None):
             w = torch.cat([a.w[:, :, :8], b.w[:, :, :8]], 2)
-            self.pair = (_pack_tensor_core_kw(w), torch.cat([a.scale, b.scale]).contiguous(), torch.cat([a.shift, b.shift]).contiguous())
-            self.c_branches[0].conv0_pair = N.ConvLayer(None, self.pair[1].data_ptr(), self.pair[2].data_ptr(), self.pair[0].data_ptr(), None)
+            img = _pack_tensor_core_kw(w)
+            self.pair = (img, torch.cat([a.scale, b.scale]).contiguous(), torch.cat([a.shift, b.shift]).contiguous(),
+                         _pack_tensor_core_kf(img, kh_only=True))
+            self.c_branches[0].conv0_pair = N.ConvLayer(None, self.pair[1].data_ptr(), self.pair[2].data_ptr(), self.pair[0].data_ptr(),
+                                                        self.pair[3].data_ptr())
 
 
 @_on_device

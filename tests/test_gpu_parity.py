@@ -362,6 +362,9 @@ def _cost_cells_from_volume(vol):
     (32, 32, (3, 19, 27), 1, False), (32, 64, (3, 18, 26), 2, False), (64, 64, (2, 17, 9), 1, False), (64, 32, (1, 9, 10), 2, True),
     (32, 16, (2, 17, 11), 2, True), (16, 8, (3, 19, 13), 2, True), (8, 2, (7, 33, 41), 1, False), (8, 16, (1, 8, 8), 2, False),
     (16, 8, (1, 40, 100), 2, True),
+    # depth-tap-folded kernels (csrc/conv_kf.cu): one and two planes, ranges that cut columns, odd plane counts
+    (16, 16, (1, 18, 26), 1, False), (16, 16, (2, 37, 50), 1, False), (16, 16, (3, 148, 200), 1, False), (8, 2, (4, 50, 60), 1, False),
+    (8, 2, (1, 20, 30), 1, False), (2, 8, (4, 50, 61), 1, False), (2, 8, (1, 20, 31), 1, False), (2, 8, (9, 150, 200), 1, False),
     # many tiles per persistent CTA: the stage ring and both accumulator sets wrap several times
     (8, 2, (24, 160, 200), 1, False), (2, 8, (16, 160, 200), 1, False), (16, 16, (12, 160, 200), 1, False),
     (8, 16, (12, 160, 200), 2, False), (16, 8, (6, 80, 100), 2, True), (32, 32, (8, 80, 104), 1, False),
@@ -407,6 +410,17 @@ def test_conv_layer_ch16_vs_torch(cfg):
             assert rel_linf(got, want) < 1e-5, (fmt, rel_linf(got, want))
     assert tuple(got.shape) == tuple(want.shape)
     assert rel_linf(got, want) < 1e-5, rel_linf(got, want)
+
+
+@pytest.mark.parametrize("cfg", [(8, 2, (4, 50, 60), 1, False), (8, 2, (24, 160, 200), 1, False), (2, 8, (4, 50, 61), 1, False),
+                                 (2, 8, (9, 150, 200), 1, False), (16, 16, (3, 148, 200), 1, False)])
+def test_conv_depth_tap_folded_kernels_all_kinds(cfg, native_lib):
+    """csrc/conv_kf.cu serves conv2 by default; its conv0 / prob kinds (knob kf = 2, measured slower) stay correct."""
+    try:
+        assert native_lib.dmvs_debug_set(b"kf", 2) == 0
+        test_conv_layer_ch16_vs_torch(cfg)
+    finally:
+        native_lib.dmvs_debug_set(b"kf", 1)
 
 
 @pytest.mark.parametrize("engine", ["fp32", "tensor"])
