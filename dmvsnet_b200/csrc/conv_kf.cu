@@ -198,6 +198,15 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
     const int hl = q * 4 + (lane >> 3), wl = lane & 7;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int npo = p.Cout / 4;
+    // BatchNorm scale / shift of this group's first channel chunk stay in registers (CS groups own one chunk each)
+    float sc[8], sh[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = 8 * cs + c;
+      const bool on = p.scale && ch < p.Cout;
+      sc[c] = on ? __ldg(p.scale + ch) : 1.f;
+      sh[c] = on ? __ldg(p.shift + ch) : 0.f;
+    }
     int g_base = 0;
     long long oc = 0;
     while (range.next(col, t0, t1, sa, sb)) {
@@ -272,7 +281,8 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
               const float v0 = __uint_as_float(r0[c]) + __uint_as_float(r0l[c]);
               const float vp = __uint_as_float(rp[c]) + __uint_as_float(rpl[c]);
               float a = (fm * vm + v0) + fp * vp;
-              if (p.scale) a = fmaf(a, __ldg(p.scale + c0 + c), __ldg(p.shift + c0 + c));
+              if (c0 == 8 * cs) a = fmaf(a, sc[c], sh[c]);
+              else if (p.scale) a = fmaf(a, __ldg(p.scale + c0 + c), __ldg(p.shift + c0 + c));
               if (p.relu) a = fmaxf(a, 0.f);
               v[c] = a;
             }
