@@ -25,7 +25,7 @@ namespace dmvs {
 
 enum { KF_S1 = 0, KF_C0 = 1, KF_PB = 2 };
 
-template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NPART_, int CS_>
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NPART_, int CS_, int MW_ = 2>
 struct KF {
   static constexpr int NB = 2 * COUT_P;                 // one kd block: [hi(W) | lo(W)] columns
   static constexpr int NF = (3 * NB + 15) / 16 * 16;    // N of one tcgen05.mma (PB: 12 -> 16)
@@ -48,15 +48,16 @@ struct KF {
   // epilogue: NPART groups of 4 warps interleave the output planes, CS groups share one plane by 8-channel chunk
   static constexpr int NPART = NPART_, CS = CS_;
   static constexpr int EPI_WARPS = 4 * NPART * CS;
-  static constexpr int MMA_WARPS = 2;
+  static constexpr int MMA_WARPS = MW_;
   static constexpr int HS = STAGES / MMA_WARPS;
   static constexpr int THREADS = (1 + MMA_WARPS + EPI_WARPS) * 32;
-  static_assert(R % 2 == 0 && R >= 4, "the accumulator ring is shared by two issuing threads and needs 3 live slots + 1");
+  static_assert(R % MMA_WARPS == 0 && R >= 4, "a slot must always belong to the same issuing thread; 3 live slots + 1");
   static_assert(R * NF <= 512, "accumulator ring exceeds TMEM");
-  static_assert(STAGES % 2 == 0, "stage ring is split between two issuing threads");
+  static_assert(STAGES % MMA_WARPS == 0, "stage ring is split between the issuing threads");
   static_assert(SMEM <= 227 * 1024, "pipeline does not fit shared memory");
   // a group waits only on the accumulators it reads; with more than R/2 plane-interleaved groups one of them can meet a slot a
   // full phase early and pass the parity test on the previous tenant (tools/experiments/kf_protocol_sim.py)
+  static_assert((NPART & (NPART - 1)) == 0, "plane interleave is a power of two");
   static_assert(2 * NPART <= R, "too many plane-interleaved epilogue groups for the accumulator ring");
   static_assert(COUT_P % (8 * CS) == 0 || CS == 1, "channel chunks do not split evenly");
 };
@@ -91,10 +92,10 @@ __device__ __forceinline__ void kf_column(const Tc2Params& p, int col, int& x0, 
   b = col / p.tiles_y;
 }
 
-template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS>
-__global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THREADS, 1)
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW>
+__global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::THREADS, 1)
     conv_kf_kernel(const __grid_constant__ Tc2Params p, const __grid_constant__ CUtensorMap tmap) {
-  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>;
+  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* sB = smem + Cfg::OFF_B;
@@ -141,8 +142,8 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
         int x0, y0, b;
         kf_column(p, col, x0, y0, b);
         for (int s = sa; s <= sb; ++s, ++g) {
-          const int m = g & 1, j = g >> 1;
-          const int st = Cfg::MMA_WARPS * (j % Cfg::HS) + m, u = j / Cfg::HS;
+          const int m = g % MW, j = g / MW;
+          const int st = MW * (j % Cfg::HS) + m, u = j / Cfg::HS;
           mbar_wait(empty + st, (u & 1) ^ 1);
           uint8_t* dst = smem + st * Cfg::STAGE_BYTES;
           mbar_expect_tx(full + st, Cfg::TX_BYTES);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
       }
     }
   } else if (warp <= Cfg::MMA_WARPS) {
-    // ---------------------------------------------------------------- MMA issuers: thread m takes the planes with g % 2 == m
+    // ---------------------------------------------------------------- MMA issuers: thread m takes the planes with g % MW == m
     const int me = warp - 1;
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(Cfg::NF);
@@ -165,11 +166,11 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
       int g = 0;
       while (range.next(col, t0, t1, sa, sb)) {
         for (int s = sa; s <= sb; ++s, ++g) {
-          if ((g & 1) != me) continue;
+          if ((g % MW) != me) continue;
           const int slot = g % R, k = g / R;
           mbar_wait(accempty + slot, (k & 1) ^ 1);
-          const int j = g >> 1;
-          const int st = Cfg::MMA_WARPS * (j % Cfg::HS) + me, u = j / Cfg::HS;
+          const int j = g / MW;
+          const int st = MW * (j % Cfg::HS) + me, u = j / Cfg::HS;
           mbar_wait(full + st, u & 1);
           tc_fence_after();
           const uint64_t adesc0 = make_desc(smem_u32(smem + st * Cfg::STAGE_BYTES), Cfg::A_LBO, Cfg::A_SBO);
@@ -207,15 +208,18 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
       sc[c] = on ? __ldg(p.scale + ch) : 1.f;
       sh[c] = on ? __ldg(p.shift + ch) : 0.f;
     }
-    int g_base = 0;
-    long long oc = 0;
+    int g_base = 0, oc = 0;
+    // output addressing: per fragment one base (cell or fp32 element of plane 0 at this thread's pixel), per plane one stride
+    const long long zcells = (p.out_fmt == FMT_CH16P) ? (long long)p.Ho * (2 * ((p.Wo + 1) >> 1)) : (long long)p.Ho * p.Wo;
+    const long long pstride = (long long)p.Do * zcells;  // hi plane -> lo plane of a CH16 / CH16P tensor
     while (range.next(col, t0, t1, sa, sb)) {
       int x0, y0, b;
       kf_column(p, col, x0, y0, b);
       const int oy = y0 + hl, ox = x0 + wl;
       const bool in_img = (oy < p.Ho) && (ox < p.Wo);
-      for (int t = t0; t <= t1; ++t, ++oc) {
-        if ((int)(oc % Cfg::NPART) != part) continue;
+      const long long base = (KIND == KF_PB) ? (long long)b * p.y_bs + (long long)oy * p.Wo + ox
+                                             : cell_index(p.out_fmt, b, npo, 0, p.Do, p.Ho, p.Wo, 0, oy, ox);
+      for (int t = t0 + ((part - oc) & (Cfg::NPART - 1)); t <= t1; t += Cfg::NPART) {
         const bool has_m = t > 0, has_p = t < p.Do - 1;
         const int g0 = g_base + (t - sa), gm = g0 - 1, gp = g0 + 1;
         if (has_m) mbar_wait(accfull + gm % R, (gm / R) & 1);
@@ -248,8 +252,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
           tmem_wait_ld();
           release();
           if (in_img) {
-            float* yf = reinterpret_cast<float*>(p.y);
-            const long long oplane = (long long)p.Ho * p.Wo;
+            float* yf = reinterpret_cast<float*>(p.y) + base + (long long)t * zcells;
 #pragma unroll
             for (int co = 0; co < 2; ++co) {
               const float vm = __uint_as_float(r0[co]) + __uint_as_float(r0[2 + co]);
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
               float v = (fm * vm + v0) + fp * vp;
               if (p.scale) v = fmaf(v, __ldg(p.scale + co), __ldg(p.shift + co));
               if (p.relu) v = fmaxf(v, 0.f);
-              if (co < p.Cout) yf[(long long)b * p.y_bs + ((long long)co * p.Do + t) * oplane + (long long)oy * p.Wo + ox] = v;
+              if (co < p.Cout) yf[(long long)co * pstride] = v;
             }
           }
         } else {
@@ -288,17 +291,14 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>::THRE
             }
             uint4 hi, lo;
             split_pack8(v, hi, lo);
-            const int ph = (c0 >> 3) * 2;
-            const long long cell = cell_index(p.out_fmt, b, npo, ph, p.Do, p.Ho, p.Wo, t, oy, ox);
-            const long long pstride = (p.out_fmt == FMT_CH16P) ? (long long)p.Do * p.Ho * (2 * ((p.Wo + 1) >> 1))
-                                                               : (long long)p.Do * p.Ho * p.Wo;
-            uint4* yc = reinterpret_cast<uint4*>(p.y);
-            yc[cell] = hi;
-            yc[cell + pstride] = lo;
+            uint4* yc = reinterpret_cast<uint4*>(p.y) + base + (long long)t * zcells + (long long)(c0 >> 2) * pstride;
+            yc[0] = hi;
+            yc[pstride] = lo;
           }
         }
       }
       g_base += sb - sa + 1;
+      oc += t1 - t0 + 1;
     }
   }
   tc_fence_before();
@@ -312,10 +312,11 @@ extern int g_tc2_pdl;
 // 2 = conv0 and prob folded as well (measured SLOWER: with 3 / 9 MMAs per plane they are bound by the per-plane hand-off
 // between issuer and epilogue through a ring of only 4 - 8 accumulators, not by the MMA count)
 int g_kf = 1;
+int g_kf_mw = 2;  // dmvs_debug_set("kf_mw", 2 | 4): issuing threads of the folded kernels
 
-template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS>
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2>
 static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
-  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS>;
+  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>;
   p.tiles_x = ceil_div(p.Wo, T_W);
   p.tiles_y = ceil_div(p.Ho, T_H);
   p.tiles_z = 1;
@@ -328,7 +329,7 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   else
     rc = make_tmap(&tmap, x, FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, 1);
   if (rc != DMVS_OK) return rc;
-  auto kern = conv_kf_kernel<KIND, CIN, COUT_P, R, STAGES, NP, CS>;
+  auto kern = conv_kf_kernel<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>;
   static PerDevice state;  // per template instance
   const int slot = current_device_slot();
   DMVS_REQUIRE(slot >= 0, DMVS_ERR_CUDA, "conv_kf: no current CUDA device");
@@ -377,15 +378,23 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
 // out_fmt, y_bs) with p.wtc already pointing at the folded image.  Returns +1 if the shape has no folded specialisation.
 int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t st) {
   if (!g_kf) return 1;
-  if (p.Cin == 16 && p.Cout == 16 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P))
-    return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2>(p, x, st);  // conv2
+  if (p.Cin == 16 && p.Cout == 16 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P)) {  // conv2
+    if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 4>(p, x, st);
+    return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 2>(p, x, st);
+  }
   if (g_kf < 2) return 1;
   if (p.Cin == 2 && in_cells) {
-    if (p.Cout == 16) return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2>(p, x, st);  // conv0 of both branches
+    if (p.Cout == 16) {  // conv0 of both branches
+      if (g_kf_mw == 4) return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2, 4>(p, x, st);
+      return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2, 2>(p, x, st);
+    }
     if (p.Cout == 8) return launch_kf<KF_C0, 2, 8, 8, 8, 4, 1>(p, x, st);    // conv0
     return 1;
   }
-  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1>(p, x, st);  // prob
+  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob
+    if (g_kf_mw == 4) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4>(p, x, st);
+    return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 2>(p, x, st);
+  }
   return 1;
 }
 

@@ -18,9 +18,11 @@ ap.add_argument("--stages", default="1,2,3")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 lib = _native.load()
-for kv in filter(None, args.set.split(",")):
-    k_, v_ = kv.split("=")
-    assert lib.dmvs_debug_set(k_.encode(), int(v_)) == 0
+def apply_set():
+    for kv in filter(None, args.set.split(",")):
+        k_, v_ = kv.split("=")
+        assert lib.dmvs_debug_set(k_.encode(), int(v_)) == 0
+apply_set()
 VALUES = [int(v) for v in args.values.split(",")]
 STAGES = [int(v) for v in args.stages.split(",")]
 net = MVSNet([48, 32, 8], [4, 2, 1], inverse_depth=True)
@@ -67,6 +69,7 @@ with torch.no_grad():
             for v in VALUES:
                 print('  running stage %d refine=%d %s=%d' % (stage + 1, refine, args.knob, v), flush=True)
                 assert lib.dmvs_debug_set(args.knob.encode(), v) == 0
+                apply_set()
                 logits = torch.empty(1, 4, dd, h, w, device=dev)
                 ms = timeit(lambda: ops.regnet_forward(pack, None, cost_cells=cells, out=logits), args.reps)
                 out[v] = logits

@@ -30,9 +30,9 @@ def fragments(o, o_end, D):
         yield col, t0, t1, sa, sb
 
 
-def run(D, o, o_end, R, STAGES, NPART, seed):
+def run(D, o, o_end, R, STAGES, NPART, seed, MW=2):
     rnd = random.Random(seed)
-    HS = STAGES // 2
+    HS = STAGES // MW
     full = [Bar(1) for _ in range(STAGES)]
     empty = [Bar(1) for _ in range(STAGES)]
     accfull = [Bar(1) for _ in range(R)]
@@ -45,8 +45,8 @@ def run(D, o, o_end, R, STAGES, NPART, seed):
         g = 0
         for col, t0, t1, sa, sb in fragments(o, o_end, D):
             for s in range(sa, sb + 1):
-                m, j = g & 1, g >> 1
-                st, u = 2 * (j % HS) + m, j // HS
+                m, j = g % MW, g // MW
+                st, u = MW * (j % HS) + m, j // HS
                 while not empty[st].test((u & 1) ^ 1):
                     yield
                 stage_holds[st] = g
@@ -58,12 +58,12 @@ def run(D, o, o_end, R, STAGES, NPART, seed):
         g = 0
         for col, t0, t1, sa, sb in fragments(o, o_end, D):
             for s in range(sa, sb + 1):
-                if (g & 1) == me:
+                if (g % MW) == me:
                     slot, k = g % R, g // R
                     while not accempty[slot].test((k & 1) ^ 1):
                         yield
-                    j = g >> 1
-                    st, u = 2 * (j % HS) + me, j // HS
+                    j = g // MW
+                    st, u = MW * (j % HS) + me, j // HS
                     while not full[st].test(u & 1):
                         yield
                     if stage_holds[st] != g:
@@ -99,7 +99,7 @@ def run(D, o, o_end, R, STAGES, NPART, seed):
                 yield
             g_base += sb - sa + 1
 
-    procs = [producer(), issuer(0), issuer(1)] + [part(i) for i in range(NPART)]
+    procs = [producer()] + [issuer(i) for i in range(MW)] + [part(i) for i in range(NPART)]
     alive = list(range(len(procs)))
     idle = 0
     while alive:
@@ -121,19 +121,19 @@ def run(D, o, o_end, R, STAGES, NPART, seed):
 if __name__ == "__main__":
     bad = 0
     perconf = {}
-    for R, NPART in ((4, 1), (4, 2), (4, 3), (4, 4), (6, 2), (6, 3), (8, 2), (8, 3), (8, 4), (8, 6)):
+    for R, NPART, MW in ((4, 1, 2), (4, 2, 2), (4, 2, 4), (4, 4, 2), (6, 2, 2), (8, 2, 2), (8, 4, 2), (8, 4, 4), (8, 2, 4)):
         for D in (1, 2, 3, 4, 5, 8):
             for trial in range(200):
                 rnd = random.Random(trial)
                 o = rnd.randrange(0, 3 * D)
                 n = rnd.randrange(1, 40)
                 try:
-                    res, errs = run(D, o, o + n, R, 8, NPART, trial)
+                    res, errs = run(D, o, o + n, R, 8, NPART, trial, MW)
                 except OverflowError:
                     res, errs = "OVER-ARRIVAL", []
                 if res != "ok" or errs:
                     bad += 1
-                    perconf[(R, NPART)] = perconf.get((R, NPART), 0) + 1
+                    perconf[(R, NPART, MW)] = perconf.get((R, NPART, MW), 0) + 1
                     if bad < 0:
                         print("R=%d NPART=%d D=%d range [%d,%d): %s %s" % (R, NPART, D, o, o + n, res, errs[:2]))
     print("bad cases:", bad, perconf)
