@@ -314,6 +314,35 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
   }
 }
 
+// Transposed layers: the skip cells of a tile do not depend on its accumulators, but their loads sit on the epilogue's critical
+// path (HBM latency per unit, 2 units per warp and tile).  While the MMAs of tile k run, the epilogue warps pull the skip lines of
+// tile k + 1 into L2; one lane per 8-pixel row segment touches each 128-byte line (hi / lo plane x even / odd columns).
+template <int MODE, int NB, int TD, int KD, int NPART>
+__device__ __forceinline__ void prefetch_skip2(const Tc2Params& p, const Tile2& tc, int q, int lane, int part) {
+  if (!is_tr(MODE) || !p.skip || (lane & 7) != 0) return;
+  constexpr int COUT_P = NB / 2;
+  const int hl = q * 4 + (lane >> 3);
+  const int iy = tc.y0 + hl, ix = tc.x0;
+  if (iy >= p.Hi || ix >= p.Wi) return;
+  const int npo = p.Cout / 4;
+  constexpr int NZY = (KD == 3) ? 4 : 2;
+  const long long pstride = (long long)p.Do * p.Ho * (2 * ((p.Wo + 1) >> 1));
+  for (int u = part; u < TD * NZY; u += NPART) {
+    const int t = u / NZY, pzy = u % NZY;
+    if (tc.z0 + t >= p.Di) break;
+    const int oz = (KD == 3) ? 2 * (tc.z0 + t) + (pzy >> 1) : tc.z0 + t, oy = 2 * iy + (pzy & 1);
+    for (int c0 = 0; c0 < COUT_P && c0 < p.Cout; c0 += 8) {
+      const int ph = (c0 >> 3) * 2;
+      const uint4* ce = p.skip + cell_index(FMT_CH16P, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, 2 * ix);
+      const uint4* co_ = p.skip + cell_index(FMT_CH16P, tc.b, npo, ph, p.Do, p.Ho, p.Wo, oz, oy, 2 * ix + 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ce));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ce + pstride));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(co_));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(co_ + pstride));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD>
 __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THREADS, 1)
@@ -469,6 +498,8 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
     int tile_k = 0;
     for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
       const int a = (Cfg::ACC_SETS == 2) ? (tile_k & 1) : 0, v = (Cfg::ACC_SETS == 2) ? (tile_k >> 1) : tile_k;
+      if (is_tr(MODE) && p.skip_prefetch && lt + (int)gridDim.x < p.n_tiles)
+        prefetch_skip2<MODE, NB, TD, KD, Cfg::NPART>(p, decode2(p, lt + gridDim.x, TD), q, lane, part);
       mbar_wait(accfull + a, v & 1);
       tc_fence_after();
       epilogue2<MODE, NB, TD, KD, Cfg::NPART>(p, decode2(p, lt, TD), tmem_base + a * Cfg::COLS, q, lane, part);
@@ -530,6 +561,7 @@ __global__ void __launch_bounds__(256) ch16_to_f32_kernel(const uint4* __restric
 int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t st);  // conv_kf.cu
 
 int g_tc2_max_ctas = 1;
+int g_tc2_skip_prefetch = 1;  // dmvs_debug_set("tc2_skip_prefetch", 0 | 1): transposed layers pull the next tile's skip lines into L2
 int g_tc2_pdl = 1;      // programmatic dependent launch of the tensor convs (dmvs_debug_set("tc2_pdl", 0 | 1))
 int g_pb_td8 = 1;       // debug knob (dmvs_debug_set("pb_td8", 0 | 1)): prob layer with 8-plane tiles  // debug knob (dmvs_debug_set("tc2_max_ctas", n))
 
@@ -616,6 +648,7 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   p.skip = reinterpret_cast<const uint4*>(skip); p.y = y;
   p.B = B; p.Cin = Cin; p.Cout = Cout; p.Di = Di; p.Hi = Hi; p.Wi = Wi; p.relu = relu; p.out_fmt = out_fmt;
   p.y_bs = y_bs_f32;
+  p.skip_prefetch = g_tc2_skip_prefetch;
   if (kd == 1) {  // 2-D layers (the refine net's bottleneck, FeatureNet's 3x3 heads): depth is a batch of planes
     p.Do = Di;
     if (!transposed && stride == 1 && Cin == 64 && Cout == 32) {  // FeatureNet conv2.0 (5x5 stride 2 on 16 ch = 3x3 on 64 unshuffled ch)
