@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
           tc_fence_after();
           const uint64_t adesc0 = make_desc(smem_u32(smem + st * Cfg::STAGE_BYTES), Cfg::A_LBO, Cfg::A_SBO);
           const uint32_t acc = tmem_base + slot * Cfg::NF;
+          if (!(p.dbg & 2))
 #pragma unroll
           for (int tap = 0; tap < Cfg::TAPS; ++tap) {
             const int off = (KIND == KF_C0) ? tap * Cfg::BW * 16 : ((tap / 3) * Cfg::BW + tap % 3) * 16;
@@ -243,6 +244,10 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
             if (has_p) mbar_arrive_n(accempty + gp % R, (t == t1) ? 3 : 1);
           }
         };
+        if (p.dbg & 1) {
+          release();
+          continue;
+        }
         if (KIND == KF_PB) {
           // NB = 4: columns [hi co0, hi co1, lo co0, lo co1] per kd; the x8 loads cover kd 0,1 (columns 0..7) and kd 2 (8..15)
           uint32_t r0[8], r1[8], r2[8];
@@ -312,11 +317,13 @@ extern int g_tc2_pdl;
 // 2 = conv0 and prob folded as well (measured SLOWER: with 3 / 9 MMAs per plane they are bound by the per-plane hand-off
 // between issuer and epilogue through a ring of only 4 - 8 accumulators, not by the MMA count)
 int g_kf = 1;
+int g_kf_dbg = 0;  // dmvs_debug_set("kf_dbg", bits): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
 int g_kf_mw = 2;  // dmvs_debug_set("kf_mw", 2 | 4): issuing threads of the folded kernels
 
 template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2>
 static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>;
+  p.dbg = g_kf_dbg;
   p.tiles_x = ceil_div(p.Wo, T_W);
   p.tiles_y = ceil_div(p.Ho, T_H);
   p.tiles_z = 1;

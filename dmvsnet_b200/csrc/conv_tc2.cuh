@@ -31,6 +31,7 @@ struct Tc2Params {
   long long y_bs;     // fp32 output only: batch stride in elements (the logits tensor interleaves two branches)
   int B, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo;
   int relu, out_fmt;
+  int dbg;            // experiments (dmvs_debug_set("kf_dbg", bits)): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
   int skip_prefetch;  // transposed layers: L2 prefetch of the next tile's skip cells
   int tiles_x, tiles_y, tiles_z, n_tiles;
 };
