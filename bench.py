@@ -17,7 +17,7 @@ the N images, then the 3-stage cascade (S1 -> W1 -> R1 -> E1 -> W1 -> R1 -> E2 p
   roofline   the fused warp+corr kernel W1 inside the hot_path region: algorithmic bytes 4*h*w*(N*C + 3*D) per launch over
              its CUDA-event time, six launches per step pooled, against the measured HBM peak; per launch under
              "roofline_per_launch".  "roofline_full_forward": the same kernel inside the `value` region, where the feature maps
-             come from the randomly initialised FeatureNet (not discriminative -> rough regressed depth: the adversarial case)
+             come from FeatureNet itself (random weights; output heads calibrated on the synthetic images unless --featnet-heads random)
   cpu_baseline / --impl reference
              the oracle port of the reference's PyTorch-CPU path (oracle/dmvs_oracle.py; the reference itself is pure Python and
              does not exist on the GPU box) on all host cores, on the SAME full view (no band, no scaling)
@@ -25,7 +25,9 @@ the N images, then the 3-stage cascade (S1 -> W1 -> R1 -> E1 -> W1 -> R1 -> E2 p
              the same restatement with its tensors on the B200 (the reference's PyTorch-CUDA / cuDNN path), TF32 off and on
   check      final depth of the benchmarked view against the oracle's (computed once, untimed)
 
-Weights: FeatureNet random, regularisation nets synthetic.ridge_regnet_state (follow the cost ridge like trained
+Weights: FeatureNet random with its three bias-free output heads calibrated to zero-mean, unit-variance descriptors
+on the synthetic images (synthetic.calibrate_feature_heads: without it the correlation is dominated by the common mode of the post-ReLU
+activations, the cost volume has no ridge and the cascade regresses noise), regularisation nets synthetic.ridge_regnet_state (follow the cost ridge like trained
 ones; all layers dense).  N > 1: torchrun, one process per GPU, independent replicas (one view set each; the path has no
 data-path collective - DESIGN.md "Multi-GPU"), barrier + max-over-ranks timing, scaling "weak"; rank 0 additionally times the
 single-view sharded mode when --sharded is given.
@@ -101,6 +103,9 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ workload (both arms)
+FEATNET_HEADS = "calibrated"  # --featnet-heads: "calibrated" (synthetic.calibrate_feature_heads) | "random"
+
+
 def make_workload(cfg_name, seed, want_features=True):
     """The inputs of one step: images of the rendered scene, cameras, depth range, the network state - identical for both arms -
     and (GPU arm) the conditioned feature maps of the hot_path region."""
@@ -116,6 +121,8 @@ def make_workload(cfg_name, seed, want_features=True):
     imgs = imgs_u8.to(torch.float32) / 255.0
     net = MVSNet(ndepths, ratios, inverse_depth=True)
     state = syn.ridge_regnet_state(net.state_dict(), seed=0)
+    if FEATNET_HEADS == "calibrated":
+        state = syn.calibrate_feature_heads(state, imgs)
     feats = syn.make_scene_features(H, W, views, proj, seed=seed, num_stages=len(ndepths)) if want_features else None
     return dict(H=H, W=W, views=views, ndepths=ndepths, ratios=ratios, proj=proj, dv=dv, imgs=imgs, imgs_u8=imgs_u8, net=net, state=state,
                 feats=feats)
@@ -491,7 +498,9 @@ def run_gpu_arm(args, cfg_name):
                        "scope_hot_path": "stage loop mvsnet.py:208-258 (scope H) on photo-consistent feature maps resident in HBM",
                        "l2": "inputs (113 MB of images, 1.06 GB of features, >1 GB of activations per step) exceed the 126 MB L2; no flush needed",
                        "parallelism": "replicas x%d (one view set per GPU, no collective)" % world,
-                       "weights": "FeatureNet random (SURVEY App. D); regularisation nets follow the cost ridge like trained ones (synthetic.ridge_regnet_state)",
+                       "weights": "FeatureNet random (SURVEY App. D)%s; regularisation nets follow the cost ridge like trained ones (synthetic.ridge_regnet_state)"
+                                  % (", output heads calibrated to zero-mean unit-variance descriptors on the synthetic images (synthetic.calibrate_feature_heads)"
+                                     if FEATNET_HEADS == "calibrated" else ""),
                        "images": "renderings of a textured tilted plane seen by the rig's cameras (synthetic.make_scene_images)",
                        "prob_volume": "kept (reference default)"},
             "clocks": clocks,
@@ -524,8 +533,7 @@ def run_gpu_arm(args, cfg_name):
                 "note": "algorithmic flops (one product per multiply-add) over the event-timed net launches against the sustained bf16 peak; the split executes 3x "
                         "these flops, and at base_channels = 8 the layers are bound by the shared-memory operand read per MMA (N = 16..64) and by HBM at full "
                         "resolution, not by the tensor pipe (DESIGN.md section 4)"},
-            "roofline_full_forward": dict({"workload": "value region: feature maps from the randomly initialised FeatureNet are not discriminative, the regressed "
-                                                       "depth is rough and most source footprints miss their staged box (direct global gathers)"},
+            "roofline_full_forward": dict({"workload": "value region: feature maps computed by FeatureNet from the rendered images (heads: %s)" % FEATNET_HEADS},
                                           **{k: v for k, v in roof_full.items() if k != "gather_bytes_per_step"}, per_launch=rows_full),
             "breakdown_ms_per_step": groups_full,
             "check": {"depth_mean": float(depth_full.mean()), "depth_mean_hot_path": float(depth_hot.mean())},
@@ -595,9 +603,14 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the single-view sharded leg")
     ap.add_argument("--sharded-config", default="tnt", choices=sorted(CONFIGS), help="N > 1: the view set of the single-view sharded leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / check / gpu_library_baseline legs")
+    ap.add_argument("--featnet-heads", default="calibrated", choices=["calibrated", "random"],
+                    help="FeatureNet's bias-free output heads: calibrated on the synthetic images (zero-mean, unit-variance descriptors, "
+                         "synthetic.calibrate_feature_heads) or plain random")
     ap.add_argument("--profile-step", nargs="?", const="hot", default=None, choices=["hot", "full"],
                     help="run one step (hot path or full forward) inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
+    global FEATNET_HEADS
+    FEATNET_HEADS = args.featnet_heads
     if args.impl == "reference":
         return run_reference_arm(args, args.config)
     return run_gpu_arm(args, args.config)

@@ -25,7 +25,7 @@ namespace dmvs {
 
 enum { KF_S1 = 0, KF_C0 = 1, KF_PB = 2 };
 
-template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NPART_, int CS_, int MW_ = 2>
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NPART_, int CS_, int MW_ = 2, int NPROD_ = 1>
 struct KF {
   static constexpr int NB = 2 * COUT_P;                 // one kd block: [hi(W) | lo(W)] columns
   static constexpr int NF = (3 * NB + 15) / 16 * 16;    // N of one tcgen05.mma (PB: 12 -> 16)
@@ -50,7 +50,8 @@ struct KF {
   static constexpr int EPI_WARPS = 4 * NPART * CS;
   static constexpr int MMA_WARPS = MW_;
   static constexpr int HS = STAGES / MMA_WARPS;
-  static constexpr int THREADS = (1 + MMA_WARPS + EPI_WARPS) * 32;
+  static constexpr int NPROD = NPROD_;  // TMA-issuing threads (one per warp): plane g is fetched by thread g % NPROD
+  static constexpr int THREADS = (NPROD + MMA_WARPS + EPI_WARPS) * 32;
   static_assert(R % MMA_WARPS == 0 && R >= 4, "a slot must always belong to the same issuing thread; 3 live slots + 1");
   static_assert(R * NF <= 512, "accumulator ring exceeds TMEM");
   static_assert(STAGES % MMA_WARPS == 0, "stage ring is split between the issuing threads");
@@ -92,10 +93,10 @@ __device__ __forceinline__ void kf_column(const Tc2Params& p, int col, int& x0, 
   b = col / p.tiles_y;
 }
 
-template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW>
-__global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::THREADS, 1)
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW, int NPR>
+__global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>::THREADS, 1)
     conv_kf_kernel(const __grid_constant__ Tc2Params p, const __grid_constant__ CUtensorMap tmap) {
-  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>;
+  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* sB = smem + Cfg::OFF_B;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + R);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == NPR) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full + s, 1);
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
 
   KfRange range(p);
   int col, t0, t1, sa, sb;
-  if (warp == 0) {
+  if (warp < NPR) {
     // ---------------------------------------------------------------- producer: one TMA box per (input plane, hi/lo plane)
     if (lane == 0) {
       prefetch_tmap(&tmap);
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
         int x0, y0, b;
         kf_column(p, col, x0, y0, b);
         for (int s = sa; s <= sb; ++s, ++g) {
+          if (NPR > 1 && (g % NPR) != warp) continue;
           const int m = g % MW, j = g / MW;
           const int st = MW * (j % Cfg::HS) + m, u = j / Cfg::HS;
           mbar_wait(empty + st, (u & 1) ^ 1);
@@ -157,9 +159,9 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
         }
       }
     }
-  } else if (warp <= Cfg::MMA_WARPS) {
+  } else if (warp < NPR + Cfg::MMA_WARPS) {
     // ---------------------------------------------------------------- MMA issuers: thread m takes the planes with g % MW == m
-    const int me = warp - 1;
+    const int me = warp - NPR;
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(Cfg::NF);
       const uint64_t bdesc0 = make_desc(smem_u32(sB), Cfg::NF * 16, 128);
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
   } else {
     // ---------------------------------------------------------------- epilogue: group (part, cs) takes every NPART-th output plane
     // and every CS-th channel chunk of it
-    const int ew = warp - 1 - Cfg::MMA_WARPS;
+    const int ew = warp - NPR - Cfg::MMA_WARPS;
     const int q = warp & 3, part = (ew >> 2) % Cfg::NPART, cs = (ew >> 2) / Cfg::NPART;
     const int hl = q * 4 + (lane >> 3), wl = lane & 7;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>::
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == NPR) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 extern int g_tc2_max_ctas;
@@ -318,11 +320,12 @@ extern int g_tc2_pdl;
 // between issuer and epilogue through a ring of only 4 - 8 accumulators, not by the MMA count)
 int g_kf = 1;
 int g_kf_dbg = 0;  // dmvs_debug_set("kf_dbg", bits): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
+int g_kf_prod = 1;  // dmvs_debug_set("kf_prod", 1 | 2): TMA-issuing threads
 int g_kf_mw = 2;  // dmvs_debug_set("kf_mw", 2 | 4): issuing threads of the folded kernels
 
-template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2>
+template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2, int NPR = 1>
 static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
-  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>;
+  using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>;
   p.dbg = g_kf_dbg;
   p.tiles_x = ceil_div(p.Wo, T_W);
   p.tiles_y = ceil_div(p.Ho, T_H);
@@ -336,7 +339,7 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   else
     rc = make_tmap(&tmap, x, FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, 1);
   if (rc != DMVS_OK) return rc;
-  auto kern = conv_kf_kernel<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW>;
+  auto kern = conv_kf_kernel<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>;
   static PerDevice state;  // per template instance
   const int slot = current_device_slot();
   DMVS_REQUIRE(slot >= 0, DMVS_ERR_CUDA, "conv_kf: no current CUDA device");
@@ -386,6 +389,7 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
 int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t st) {
   if (!g_kf) return 1;
   if (p.Cin == 16 && p.Cout == 16 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P)) {  // conv2
+    if (g_kf_prod == 2) return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 2, 2>(p, x, st);
     if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 4>(p, x, st);
     return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 2>(p, x, st);
   }
@@ -399,6 +403,7 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
     return 1;
   }
   if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob
+    if (g_kf_prod == 2) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4, 2>(p, x, st);
     if (g_kf_mw == 4) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4>(p, x, st);
     return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 2>(p, x, st);
   }

@@ -368,5 +368,52 @@ def ridge_regnet_state(state: Dict[str, torch.Tensor], seed: int = 0, gain: floa
     return out
 
 
+def calibrate_feature_heads(state: Dict[str, torch.Tensor], imgs: torch.Tensor, crop: Tuple[int, int] = (256, 320)) -> Dict[str, torch.Tensor]:
+    """Make a randomly initialised FeatureNet DISCRIMINATIVE on ``imgs`` ([1,N,3,H,W] in [0,1]) the way a trained one is, without a
+    checkpoint: the three bias-free output heads (``feature.out1/2/3``, module.py:274-340) are made orthogonal to the mean
+    activation vector of their input and scaled to unit output variance, measured on a centre crop of view 0.
+
+    Random heads on post-ReLU activations return feature maps with a large common-mode component; the group-wise correlation
+    of two such maps is dominated by it, the cost volume has no ridge, and the ridge-following regularisation nets regress
+    noise (24 % mean deviation from the rendered scene; 2 % with calibrated heads at 256 x 320, CPU restatement).  A trained
+    FeatureNet's descriptors are centred by training; here the same is obtained from the statistics of the synthetic images.
+    Every layer keeps dense random weights and runs exactly as with a checkpoint; workload generator code (plain torch on
+    the host), not part of the CUDA path."""
+    import torch.nn.functional as F
+    st = dict(state)
+    h, w = imgs.shape[-2:]
+    ch, cw = min(crop[0], h) // 8 * 8, min(crop[1], w) // 8 * 8
+    y0, x0 = (h - ch) // 2, (w - cw) // 2
+    x = imgs[0, :1, :, y0:y0 + ch, x0:x0 + cw].to("cpu", torch.float32)
+    if imgs.dtype == torch.uint8:
+        x = x / 255.0
+    p = {k[len("feature."):]: v.detach().to("cpu", torch.float32) for k, v in st.items() if k.startswith("feature.")}
+
+    def seq(t, base, specs):
+        for i, (stride, pad) in enumerate(specs):
+            n = "%s.%d" % (base, i)
+            t = F.conv2d(t, p[n + ".conv.weight"], None, stride=stride, padding=pad)
+            t = F.relu(F.batch_norm(t, p[n + ".bn.running_mean"], p[n + ".bn.running_var"], p[n + ".bn.weight"], p[n + ".bn.bias"],
+                                    False, 0.1, 1e-5))
+        return t
+    with torch.no_grad():
+        c0 = seq(x, "conv0", [(1, 1), (1, 1)])
+        c1 = seq(c0, "conv1", [(2, 2), (1, 1), (1, 1)])
+        c2 = seq(c1, "conv2", [(2, 2), (1, 1), (1, 1)])
+        top2 = F.interpolate(c2, scale_factor=2, mode="nearest") + F.conv2d(c1, p["inner1.weight"], p["inner1.bias"])
+        top3 = F.interpolate(top2, scale_factor=2, mode="nearest") + F.conv2d(c0, p["inner2.weight"], p["inner2.bias"])
+        for head, inp in (("out1", c2), ("out2", top2), ("out3", top3)):
+            wgt = p[head + ".weight"].clone()
+            m = inp.mean(dim=(0, 2, 3))
+            taps = wgt.shape[2] * wgt.shape[3]
+            dc = (wgt.sum(dim=(2, 3)) * m[None]).sum(1)  # response of each filter to the mean input
+            wgt = wgt - (dc / (taps * (m * m).sum()))[:, None, None, None] * m[None, :, None, None]
+            out = F.conv2d(inp, wgt, None, padding=wgt.shape[-1] // 2)
+            wgt = wgt / out.std(dim=(0, 2, 3)).clamp_min(1e-6)[:, None, None, None]
+            key = "feature.%s.weight" % head
+            st[key] = wgt.to(state[key].device, state[key].dtype)
+    return st
+
+
 def stage_shapes(height: int, width: int, num_stages: int = 3) -> List[Tuple[int, int]]:
     return [(height // 2 ** (3 - s - 1), width // 2 ** (3 - s - 1)) for s in range(num_stages)]
