@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 
-ABI_VERSION = 19
+ABI_VERSION = 20
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 FMT_NHWC2 = 4
 ENGINE_FP32, ENGINE_TENSOR = 0, 1
@@ -26,7 +26,7 @@ class NativeLibraryError(RuntimeError):
 
 
 class ConvLayer(ctypes.Structure):
-    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("w_tc", c_void_p), ("w_tc_kd", c_void_p)]
+    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("w_tc", c_void_p), ("w_tc_kd", c_void_p), ("w_tc_kw", c_void_p)]
 
 
 class RegnetBranch(ctypes.Structure):

@@ -18,28 +18,38 @@
 //     consumed in order); the smem stage ring is split between them the same way.
 //
 // Kinds: S1 = Cin, Cout multiples of 8 on CH16 cells (conv2); C0 = conv0 on the cost cells W1 emits (K packed along kw, 3 MMAs
-// per plane); PB = `prob` (8 -> 2, fp32 logits out).
+// per plane); PB = `prob` (8 -> 2, fp32 logits out); PW = `prob` with kw folded into N as well, on wide tiles:
+//
+//   * The full-resolution layers are bound by the TMA engine's rate for narrow rows (18 x 160-byte rows per box: ~235 cycles,
+//     profiles/r2l_kf_probe.txt) and by the MMA count at about the same level.  PW attacks both: the tile is 4 rows x 32 voxels
+//     (M row = y * 32 + x, so the 8-row core matrices are consecutive 128-byte pieces of 512-byte box rows: SBO = 128, no x halo in
+//     shared memory), the box is 6 rows x 512 bytes, and A is never shifted in x: the accumulator of input voxel x carries all nine
+//     (kd, kw) column blocks, out[t][x] = sum_kd sum_kw P[t+kd-1][x+kw-1][kd][kw].  The x shift is a lane shuffle in the epilogue
+//     (an epilogue warp owns one 32-voxel row; lanes 0 and 31 are halo: tiles advance by 30 voxels).  3 MMAs of N = 48 per plane.
 #include "conv_tc2.cuh"
 
 namespace dmvs {
 
-enum { KF_S1 = 0, KF_C0 = 1, KF_PB = 2 };
+enum { KF_S1 = 0, KF_C0 = 1, KF_PB = 2, KF_PW = 3 };
 
 template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NPART_, int CS_, int MW_ = 2, int NPROD_ = 1>
 struct KF {
-  static constexpr int NB = 2 * COUT_P;                 // one kd block: [hi(W) | lo(W)] columns
-  static constexpr int NF = (3 * NB + 15) / 16 * 16;    // N of one tcgen05.mma (PB: 12 -> 16)
-  static constexpr int SH = T_H + 2, BW = T_W + 2;
+  static constexpr bool WIDE = KIND == KF_PW;
+  static constexpr int NB = WIDE ? 16 : 2 * COUT_P;     // one kd block: [hi(W) | lo(W)] columns (PW: 3 kw x 4, padded to 16)
+  static constexpr int NF = (3 * NB + 15) / 16 * 16;    // N of one tcgen05.mma (PB: 12 -> 16, PW: 36 -> 48)
+  static constexpr int TW = WIDE ? 32 : T_W, TH = WIDE ? 4 : T_H;  // tile: TH rows x TW voxels = 128 accumulator lanes
+  static constexpr int XSTEP = WIDE ? 30 : T_W;                    // valid output voxels per tile row
+  static constexpr int SH = TH + 2, BW = WIDE ? TW : TW + 2;
   static constexpr int BLK_BYTES = SH * BW * 16;
-  static constexpr int PLANE = pad128(BLK_BYTES);
+  static constexpr int PLANE = BLK_BYTES;  // the hi / lo planes of all channel chunks arrive as ONE 4-D box: dense plane pitch
   static constexpr int CJ = (KIND == KF_C0) ? 1 : CIN / 8;
   static constexpr int NPLANE = (KIND == KF_C0) ? 1 : 2 * CJ;
-  static constexpr int TAPS = (KIND == KF_C0) ? 3 : 9;
+  static constexpr int TAPS = (KIND == KF_C0 || WIDE) ? 3 : 9;
   static constexpr int A_LBO = (KIND == KF_C0) ? 32 : PLANE;
-  static constexpr int A_SBO = BW * 16;
+  static constexpr int A_SBO = WIDE ? 128 : BW * 16;
   static constexpr int B_TILE = 2 * NF * 16;
   static constexpr int B_BYTES = CJ * TAPS * B_TILE;
-  static constexpr int STAGE_BYTES = NPLANE * PLANE;
+  static constexpr int STAGE_BYTES = pad128(NPLANE * PLANE);
   static constexpr int TX_BYTES = NPLANE * BLK_BYTES;
   static constexpr int OFF_B = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_B + pad128(B_BYTES);
@@ -86,10 +96,12 @@ struct KfRange {  // the CTA's share of the (column, output plane) sequence
   }
 };
 
+// x0: first voxel of the accumulator rows (PW: one halo voxel left of the first output)
+template <class Cfg>
 __device__ __forceinline__ void kf_column(const Tc2Params& p, int col, int& x0, int& y0, int& b) {
-  x0 = (col % p.tiles_x) * T_W;
+  x0 = (col % p.tiles_x) * Cfg::XSTEP - (Cfg::WIDE ? 1 : 0);
   col /= p.tiles_x;
-  y0 = (col % p.tiles_y) * T_H;
+  y0 = (col % p.tiles_y) * Cfg::TH;
   b = col / p.tiles_y;
 }
 
@@ -141,7 +153,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
       int g = 0;
       while (range.next(col, t0, t1, sa, sb)) {
         int x0, y0, b;
-        kf_column(p, col, x0, y0, b);
+        kf_column<Cfg>(p, col, x0, y0, b);
         for (int s = sa; s <= sb; ++s, ++g) {
           if (NPR > 1 && (g % NPR) != warp) continue;
           const int m = g % MW, j = g / MW;
@@ -152,9 +164,8 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
           if (KIND == KF_C0) {  // cost cells: cell x = [voxel x-1 | voxel x], one plane per batch entry
             tma_load_4d(dst, &tmap, full + st, 8 * x0, y0 - 1, s, b);
           } else {
-#pragma unroll 1
-            for (int pl = 0; pl < Cfg::NPLANE; ++pl)
-              tma_load_4d(dst + pl * Cfg::PLANE, &tmap, full + st, 8 * (x0 - 1), y0 - 1, s, b * planes_per_b + pl);
+            // one box over the NPLANE consecutive planes of this batch entry (a TMA instruction costs ~235 cycles whatever its box)
+            tma_load_4d(dst, &tmap, full + st, 8 * (Cfg::WIDE ? x0 : x0 - 1), y0 - 1, s, b * planes_per_b);
           }
         }
       }
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
           if (!(p.dbg & 2))
 #pragma unroll
           for (int tap = 0; tap < Cfg::TAPS; ++tap) {
-            const int off = (KIND == KF_C0) ? tap * Cfg::BW * 16 : ((tap / 3) * Cfg::BW + tap % 3) * 16;
+            const int off = (KIND == KF_C0 || Cfg::WIDE) ? tap * Cfg::BW * 16 : ((tap / 3) * Cfg::BW + tap % 3) * 16;
 #pragma unroll
             for (int cj = 0; cj < Cfg::CJ; ++cj) {
               const uint64_t ad = adesc0 + (uint64_t)(((KIND == KF_C0 ? 0 : 2 * cj * Cfg::PLANE) + off) >> 4);
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
     // and every CS-th channel chunk of it
     const int ew = warp - NPR - Cfg::MMA_WARPS;
     const int q = warp & 3, part = (ew >> 2) % Cfg::NPART, cs = (ew >> 2) / Cfg::NPART;
-    const int hl = q * 4 + (lane >> 3), wl = lane & 7;
+    const int hl = Cfg::WIDE ? q : q * 4 + (lane >> 3), wl = Cfg::WIDE ? lane : lane & 7;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int npo = p.Cout / 4;
     // BatchNorm scale / shift of this group's first channel chunk stay in registers (CS groups own one chunk each)
@@ -217,10 +228,10 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
     const long long pstride = (long long)p.Do * zcells;  // hi plane -> lo plane of a CH16 / CH16P tensor
     while (range.next(col, t0, t1, sa, sb)) {
       int x0, y0, b;
-      kf_column(p, col, x0, y0, b);
+      kf_column<Cfg>(p, col, x0, y0, b);
       const int oy = y0 + hl, ox = x0 + wl;
-      const bool in_img = (oy < p.Ho) && (ox < p.Wo);
-      const long long base = (KIND == KF_PB) ? (long long)b * p.y_bs + (long long)oy * p.Wo + ox
+      const bool in_img = (oy < p.Ho) && (ox < p.Wo) && (!Cfg::WIDE || (lane >= 1 && lane <= 30));
+      const long long base = (KIND == KF_PB || KIND == KF_PW) ? (long long)b * p.y_bs + (long long)oy * p.Wo + ox
                                              : cell_index(p.out_fmt, b, npo, 0, p.Do, p.Ho, p.Wo, 0, oy, ox);
       for (int t = t0 + ((part - oc) & (Cfg::NPART - 1)); t <= t1; t += Cfg::NPART) {
         const bool has_m = t > 0, has_p = t < p.Do - 1;
@@ -250,7 +261,39 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
           release();
           continue;
         }
-        if (KIND == KF_PB) {
+        if (KIND == KF_PW) {
+          // NB = 16: columns [kw][hi co0, hi co1, lo co0, lo co1] (12 used) per kd.  s[kw][co] = sum over kd, then the x shift across lanes.
+          uint32_t ra[8], rb[4], rc[8], rd[4], re[8], rf[4];
+          tmem_ld8_issue(am, ra);
+          tmem_ld4_issue(am + 8, rb);
+          tmem_ld8_issue(a0, rc);
+          tmem_ld4_issue(a0 + 8, rd);
+          tmem_ld8_issue(ap, re);
+          tmem_ld4_issue(ap + 8, rf);
+          tmem_wait_ld();
+          release();
+          float sk[3][2];
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int co = 0; co < 2; ++co) {
+              const int c = 4 * kw + co;  // hi column; lo column = c + 2
+              const float vm = __uint_as_float(c < 8 ? ra[c] : rb[c - 8]) + __uint_as_float(c + 2 < 8 ? ra[c + 2] : rb[c + 2 - 8]);
+              const float v0 = __uint_as_float(c < 8 ? rc[c] : rd[c - 8]) + __uint_as_float(c + 2 < 8 ? rc[c + 2] : rd[c + 2 - 8]);
+              const float vp = __uint_as_float(c < 8 ? re[c] : rf[c - 8]) + __uint_as_float(c + 2 < 8 ? re[c + 2] : rf[c + 2 - 8]);
+              sk[kw][co] = (fm * vm + v0) + fp * vp;
+            }
+          float* yf = reinterpret_cast<float*>(p.y) + base + (long long)t * zcells;
+#pragma unroll
+          for (int co = 0; co < 2; ++co) {
+            // out[x] = P[x-1][kw = 0] + P[x][kw = 1] + P[x+1][kw = 2]
+            const float left = __shfl_up_sync(0xffffffffu, sk[0][co], 1), right = __shfl_down_sync(0xffffffffu, sk[2][co], 1);
+            float v = (left + sk[1][co]) + right;
+            if (p.scale) v = fmaf(v, __ldg(p.scale + co), __ldg(p.shift + co));
+            if (p.relu) v = fmaxf(v, 0.f);
+            if (in_img && co < p.Cout) yf[(long long)co * pstride] = v;
+          }
+        } else if (KIND == KF_PB) {
           // NB = 4: columns [hi co0, hi co1, lo co0, lo co1] per kd; the x8 loads cover kd 0,1 (columns 0..7) and kd 2 (8..15)
           uint32_t r0[8], r1[8], r2[8];
           tmem_ld8_issue(am, r0);
@@ -319,6 +362,9 @@ extern int g_tc2_pdl;
 // 2 = conv0 and prob folded as well (measured SLOWER: with 3 / 9 MMAs per plane they are bound by the per-plane hand-off
 // between issuer and epilogue through a ring of only 4 - 8 accumulators, not by the MMA count)
 int g_kf = 1;
+// dmvs_debug_set("kf_wide", 0 | 1): `prob` on the wide-tile kernel (kd and kw folded).  Measured equal to the per-tap kernel (265 vs
+// 262 us at 32 x 592 x 800): with 3 MMAs per plane the kernel is bound by its per-plane hand-offs, not by MMAs or TMA - off by default
+int g_kf_wide = 0;
 int g_kf_dbg = 0;  // dmvs_debug_set("kf_dbg", bits): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
 int g_kf_prod = 1;  // dmvs_debug_set("kf_prod", 1 | 2): TMA-issuing threads
 int g_kf_mw = 2;  // dmvs_debug_set("kf_mw", 2 | 4): issuing threads of the folded kernels
@@ -327,8 +373,8 @@ template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int 
 static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>;
   p.dbg = g_kf_dbg;
-  p.tiles_x = ceil_div(p.Wo, T_W);
-  p.tiles_y = ceil_div(p.Ho, T_H);
+  p.tiles_x = ceil_div(p.Wo, Cfg::XSTEP);
+  p.tiles_y = ceil_div(p.Ho, Cfg::TH);
   p.tiles_z = 1;
   p.n_tiles = p.tiles_x * p.tiles_y * p.B;  // columns
   CUtensorMap tmap;
@@ -337,7 +383,7 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   if (KIND == KF_C0)  // [B][D][H][W+1] cost cells viewed as a CH16 tensor of width W+1 with one plane per batch entry
     rc = make_tmap(&tmap, x, FMT_CH16, p.B, p.Di, p.Hi, p.Wi + 1, Cfg::BW, Cfg::SH, 1);
   else
-    rc = make_tmap(&tmap, x, FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, 1);
+    rc = make_tmap(&tmap, x, FMT_CH16, p.B * 2 * CIN / 8, p.Di, p.Hi, p.Wi, Cfg::BW, Cfg::SH, 1, Cfg::NPLANE);
   if (rc != DMVS_OK) return rc;
   auto kern = conv_kf_kernel<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>;
   static PerDevice state;  // per template instance
@@ -393,8 +439,8 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
     if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 4>(p, x, st);
     return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 2>(p, x, st);
   }
-  if (g_kf < 2) return 1;
   if (p.Cin == 2 && in_cells) {
+    if (g_kf < 2) return 1;
     if (p.Cout == 16) {  // conv0 of both branches
       if (g_kf_mw == 4) return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2, 4>(p, x, st);
       return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2, 2>(p, x, st);
@@ -402,6 +448,13 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
     if (p.Cout == 8) return launch_kf<KF_C0, 2, 8, 8, 8, 4, 1>(p, x, st);    // conv0
     return 1;
   }
+  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32 && p.wtc_wide && g_kf_wide) {  // prob, kd and kw folded, wide tiles
+    Tc2Params pw = p;
+    pw.wtc = p.wtc_wide;
+    if (g_kf_prod == 2) return launch_kf<KF_PW, 8, 2, 10, 10, 4, 1, 2, 2>(pw, x, st);
+    return launch_kf<KF_PW, 8, 2, 10, 10, 4, 1, 2, 1>(pw, x, st);
+  }
+  if (g_kf < 2) return 1;
   if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob
     if (g_kf_prod == 2) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4, 2>(p, x, st);
     if (g_kf_mw == 4) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4>(p, x, st);

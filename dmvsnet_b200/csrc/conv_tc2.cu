@@ -634,7 +634,7 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
                    int Cout, int Di, int Hi, int Wi, int kd, int stride, int transposed, int relu, int out_fmt, cudaStream_t st) {
   if (!L.w_tc || (kd != 1 && kd != 3)) return 1;
   DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc2: null pointer");
-  DMVS_REQUIRE(aligned16(L.w_tc) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
+  DMVS_REQUIRE(aligned16(L.w_tc) && (!L.w_tc_kw || aligned16(L.w_tc_kw)) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
                "conv_tc2: pointers must be 16-byte aligned");
   DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P || out_fmt == FMT_NHWC2,
                DMVS_ERR_BAD_SHAPE,
@@ -713,6 +713,7 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   if (L.w_tc_kd) {  // depth tap folded into N, march along z (conv_kf.cu): conv0 on cost cells, conv2, prob
     Tc2Params pk = p;
     pk.wtc = reinterpret_cast<const uint4*>(L.w_tc_kd);
+    pk.wtc_wide = reinterpret_cast<const uint4*>(L.w_tc_kw);
     const int rc = conv_layer_kf(pk, x, in_cells, st);
     if (rc <= 0) return rc;
   }

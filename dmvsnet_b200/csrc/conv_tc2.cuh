@@ -23,6 +23,7 @@ constexpr int T_H = 16, T_W = 8;
 struct Tc2Params {
   const float* x_f32;  // C0 only
   const uint4* wtc;
+  const uint4* wtc_wide;  // `prob` only: image for the wide-tile kernel (dmvs_conv_layer.w_tc_kw), may be null
   const float* scale;
   const float* shift;
   const uint4* skip;  // CH16P, TR only
@@ -75,14 +76,15 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // tensor map over a CH16 (rank 4: {W*8 halfs, H, D, planes}) or CH16P (rank 5: {We*8, 2, H, D, planes}) tensor
-inline int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int D, int H, int W, int box_cells, int box_h, int box_d) {
+inline int make_tmap(CUtensorMap* m, const void* base, int fmt, int planes, int D, int H, int W, int box_cells, int box_h, int box_d,
+                     int box_planes = 1) {
   EncodeTiledFn enc = encode_fn();
   DMVS_REQUIRE(enc != nullptr, DMVS_ERR_CUDA, "conv_tc2: cuTensorMapEncodeTiled is not available from the driver");
   CUresult r;
   if (fmt == FMT_CH16) {
     const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
     const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    const cuuint32_t box[4] = {(cuuint32_t)box_cells * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)box_cells * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, (cuuint32_t)box_planes};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

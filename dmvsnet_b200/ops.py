@@ -537,8 +537,10 @@ class PackedLayer:
         else:
             self.w_tc = None
         self.w_tc_kd = None
+        self.w_tc_kw = None
         if cin == 8 and cout == 2 and taps == 27 and not transposed:
             self.w_tc_kd = _pack_tensor_core_prob(w[:, :, :cout])
+            self.w_tc_kw = _pack_tensor_core_prob_wide(w[:, :, :cout])
         elif cin == 16 and cout == 8 and taps == 27 and transposed:
             self.w_tc_kd = _pack_tensor_core_tr_fold(w[:, :, :cout])
         elif cin == 16 and cout == 16 and taps == 27 and not transposed:   # conv2
@@ -556,7 +558,7 @@ class PackedLayer:
             self.scale = self.shift = None
 
     def c_struct(self) -> N.ConvLayer:
-        return N.ConvLayer(self.w.data_ptr(), _ptr(self.scale), _ptr(self.shift), _ptr(self.w_tc), _ptr(self.w_tc_kd))
+        return N.ConvLayer(self.w.data_ptr(), _ptr(self.scale), _ptr(self.shift), _ptr(self.w_tc), _ptr(self.w_tc_kd), _ptr(self.w_tc_kw))
 
 
 def _pack_tensor_core(w: torch.Tensor) -> torch.Tensor:
@@ -591,6 +593,26 @@ def _pack_tensor_core_prob(w: torch.Tensor) -> torch.Tensor:
             img[0, :, 0, 4 * kd + co] = hi[kd, :, :, co]
             img[0, :, 1, 4 * kd + co] = hi[kd, :, :, co]
             img[0, :, 0, 4 * kd + 2 + co] = lo[kd, :, :, co]
+    return img.contiguous()
+
+
+def _pack_tensor_core_prob_wide(w: torch.Tensor) -> torch.Tensor:
+    """`prob` (8 -> 2) for the wide-tile kernel: depth tap and kw folded into N.  [27][8][2] -> [1][3 (kh)][kc][n = 48][8 halfs];
+    column n = 16*kd + 4*kw + co holds hi(W) (both K halves), n = 16*kd + 4*kw + 2 + co holds lo(W) (A_hi half only)."""
+    taps, cin, cout = w.shape
+    assert taps == 27 and cin == 8 and cout == 2
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    hi = hi.reshape(3, 3, 3, 8, 2)  # [kd][kh][kw][k][co]
+    lo = lo.reshape(3, 3, 3, 8, 2)
+    img = torch.zeros(1, 3, 2, 48, 8, dtype=torch.float16, device=w.device)
+    for kd in range(3):
+        for kw in range(3):
+            for co in range(2):
+                n = 16 * kd + 4 * kw + co
+                img[0, :, 0, n] = hi[kd, :, kw, :, co]
+                img[0, :, 1, n] = hi[kd, :, kw, :, co]
+                img[0, :, 0, n + 2] = lo[kd, :, kw, :, co]
     return img.contiguous()
 
 
@@ -767,7 +789,7 @@ class PackedRegnet:
             self.pair = (img, torch.cat([a.scale, b.scale]).contiguous(), torch.cat([a.shift, b.shift]).contiguous(),
                          _pack_tensor_core_kf(img, kh_only=True))
             self.c_branches[0].conv0_pair = N.ConvLayer(None, self.pair[1].data_ptr(), self.pair[2].data_ptr(), self.pair[0].data_ptr(),
-                                                        self.pair[3].data_ptr())
+                                                        self.pair[3].data_ptr(), None)
 
 
 @_on_device

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 19
+#define DMVS_ABI_VERSION 20
 #define DMVS_MAX_SRC 16 /* source views per call (reference configs use 2..10) */
 
 typedef enum {
@@ -173,12 +173,18 @@ typedef struct {
    * n < Cout_p: hi(W[tap][8j+k][n]) for kc = 0 and 1;  n >= Cout_p: lo(W[tap][8j+k][n-Cout_p]) for kc = 0, zero for kc = 1.
    * NULL: the layer always runs on the fp32 path. */
   const void* w_tc;
-  /* optional, Cin = 8 / Cout = 2 (`prob`) only: the depth tap folded into the UMMA N dimension,
+  /* optional folded images.  Cin = 16 / Cout = 16 (`conv2`) and Cin = 2 (`conv0`, `conv0_pair`): the w_tc image with the depth tap
+   * folded into N, [chunk j][tap (kh,kw) | (kh)][kc = 2][n = 3 x 2*Cout_p, kd-major][8 halfs] (csrc/conv_kf.cu).
+   * Cin = 8 / Cout = 2 (`prob`): the depth tap folded into the UMMA N dimension,
    * [1][9 taps (kh,kw)][kc = 2][n = 16][8 halfs] with n = 4*kd + co (hi, both kc) and n = 4*kd + 2 + co (lo, kc = 0).
    * Also, Cin = 16 / Cout = 8 transposed (`conv11`): the 27 taps folded by input shift,
    * [chunk j = 2][shift (sz,sy,sx) = 8][kc = 2][n = 8 parity classes x 16][8 halfs]: class block c = (pz,py,px) holds the w_tc
    * columns of tap k with k = 1 (p = 0, s = 0), 2 (p = 1, s = 0), 0 (p = 1, s = 1) per axis, zeros where p = 0 and s = 1. */
   const void* w_tc_kd;
+  /* optional, Cin = 8 / Cout = 2 (`prob`) only: depth tap AND kw folded into N for the wide-tile kernel (csrc/conv_kf.cu),
+   * [1][3 taps (kh)][kc = 2][n = 48][8 halfs] with n = 16*kd + 4*kw + co (hi, both kc) and n = 16*kd + 4*kw + 2 + co (lo, kc = 0);
+   * columns 16*kd + 12 .. 16*kd + 15 stay zero.  NULL: `prob` runs on the w_tc_kd / w_tc kernels. */
+  const void* w_tc_kw;
 } dmvs_conv_layer;
 
 /* which arithmetic a convolution call uses */

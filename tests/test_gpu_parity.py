@@ -415,12 +415,17 @@ def test_conv_layer_ch16_vs_torch(cfg):
 @pytest.mark.parametrize("cfg", [(8, 2, (4, 50, 60), 1, False), (8, 2, (24, 160, 200), 1, False), (2, 8, (4, 50, 61), 1, False),
                                  (2, 8, (9, 150, 200), 1, False), (16, 16, (3, 148, 200), 1, False)])
 def test_conv_depth_tap_folded_kernels_all_kinds(cfg, native_lib):
-    """csrc/conv_kf.cu serves conv2 by default; its conv0 / prob kinds (knob kf = 2, measured slower) stay correct."""
+    """csrc/conv_kf.cu serves conv2 by default; its conv0 / prob kinds (knob kf = 2) and the wide-tile prob kernel (knob kf_wide;
+    measured no faster than the per-tap kernels) stay correct."""
     try:
         assert native_lib.dmvs_debug_set(b"kf", 2) == 0
         test_conv_layer_ch16_vs_torch(cfg)
+        if cfg[:2] == (8, 2):
+            assert native_lib.dmvs_debug_set(b"kf_wide", 1) == 0
+            test_conv_layer_ch16_vs_torch(cfg)
     finally:
         native_lib.dmvs_debug_set(b"kf", 1)
+        native_lib.dmvs_debug_set(b"kf_wide", 0)
 
 
 @pytest.mark.parametrize("engine", ["fp32", "tensor"])

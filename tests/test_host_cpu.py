@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for name in declared:
         assert hasattr(native_lib, name), "libdmvs_b200.so does not export %s" % name
     assert sorted(_native.SIGNATURES) == declared, "ctypes binding and header disagree"
-    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 19
+    assert native_lib.dmvs_abi_version() == _native.ABI_VERSION == 20
     assert native_lib.dmvs_launch_count() >= 0  # a process-wide counter: other tests of the same session may have launched already
 
 

@@ -9,6 +9,9 @@ lib = _native.load()
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 d, h, w = 32, 592, 800
+if len(sys.argv) > 1:
+    d, h, w = [int(v) for v in sys.argv[1].split("x")]
+print("prob volume %d x %d x %d (%.0f MB of cells), conv2 at half of it" % (d, h, w, d * h * w * 32 / 1e6), flush=True)
 
 
 def timeit(fn, n=10):
@@ -30,12 +33,12 @@ w2 = torch.randn(16, 16, 3, 3, 3, generator=g) * 0.05
 bn = tuple(t.to(dev) for t in (torch.ones(16), torch.zeros(16), torch.zeros(16), torch.ones(16)))
 conv2 = ops.PackedLayer(w2.to(dev), False, bn)
 x16 = ops.to_ch16(torch.randn(1, 16, d // 2, h // 2, w // 2, device=dev))
-for kf, mw, npr in ((0, 2, 1), (2, 2, 1), (2, 4, 1), (2, 4, 2)):
-    for dbg in (0, 3):
+for kf, mw, npr, wide in ((0, 2, 1, 0), (2, 4, 1, 0), (1, 2, 1, 1), (1, 2, 2, 1)):
+    for dbg in (0, 1, 2, 3):
         if kf == 0 and dbg:
             continue
-        lib.dmvs_debug_set(b"kf", kf); lib.dmvs_debug_set(b"kf_mw", mw); lib.dmvs_debug_set(b"kf_dbg", dbg); lib.dmvs_debug_set(b"kf_prod", npr)
+        lib.dmvs_debug_set(b"kf", kf); lib.dmvs_debug_set(b"kf_mw", mw); lib.dmvs_debug_set(b"kf_dbg", dbg); lib.dmvs_debug_set(b"kf_prod", npr); lib.dmvs_debug_set(b"kf_wide", wide)
         tp = timeit(lambda: ops.conv3d_ch16(x8, prob, relu=False, out_fmt="f32"))
         t2 = timeit(lambda: ops.conv3d_ch16(x16, conv2, relu=True, out_fmt="ch16p")) if kf else float("nan")
-        print("kf=%d issuers=%d producers=%d dbg=%d (1: no epilogue work, 2: no MMAs)  prob %.1f us   conv2 %.1f us" % (kf, mw, npr, dbg, tp, t2), flush=True)
-lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_mw", 2); lib.dmvs_debug_set(b"kf_dbg", 0); lib.dmvs_debug_set(b"kf_prod", 1)
+        print("wide=%d kf=%d issuers=%d producers=%d dbg=%d (1: no epilogue work, 2: no MMAs)  prob %.1f us   conv2 %.1f us" % (wide, kf, mw, npr, dbg, tp, t2), flush=True)
+lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_mw", 2); lib.dmvs_debug_set(b"kf_dbg", 0); lib.dmvs_debug_set(b"kf_prod", 1); lib.dmvs_debug_set(b"kf_wide", 0)

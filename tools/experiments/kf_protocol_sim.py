@@ -121,7 +121,7 @@ def run(D, o, o_end, R, STAGES, NPART, seed, MW=2):
 if __name__ == "__main__":
     bad = 0
     perconf = {}
-    for R, NPART, MW in ((4, 1, 2), (4, 2, 2), (4, 2, 4), (4, 4, 2), (6, 2, 2), (8, 2, 2), (8, 4, 2), (8, 4, 4), (8, 2, 4)):
+    for R, NPART, MW in ((4, 1, 2), (4, 2, 2), (4, 2, 4), (4, 4, 2), (6, 2, 2), (8, 2, 2), (8, 4, 2), (8, 4, 4), (8, 2, 4), (10, 4, 2)):
         for D in (1, 2, 3, 4, 5, 8):
             for trial in range(200):
                 rnd = random.Random(trial)
