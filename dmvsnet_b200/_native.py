@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdmvs_b200.so")
 ABI_VERSION = 20
 FMT_F32, FMT_CH16, FMT_CH16P = 0, 1, 2
 FMT_NHWC2 = 4
+FMT_NHWC2_F16 = 5
 ENGINE_FP32, ENGINE_TENSOR = 0, 1
 MAX_SRC = 16
 REGNET_LAYERS = 11

@@ -290,14 +290,22 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
           for (int c = 0; c < 8; ++c)
             if (c0 + c < p.Cout)
               yf[(long long)tc.b * p.y_bs + ((long long)(c0 + c) * p.Do + oz) * oplane + (long long)oy * p.Wo + ox] = v[c];
-        } else if (p.out_fmt == FMT_NHWC2) {
+        } else if (p.out_fmt == FMT_NHWC2 || p.out_fmt == FMT_NHWC2H) {
           // two channel-last fp32 buffers back to back, [2][B][Do][Ho][Wo][Cout/2]: the lane's 8 channels are 32 contiguous bytes
           const int half = p.Cout >> 1;
           const int hsel = c0 >= half ? 1 : 0, cc = c0 - hsel * half;
-          float* yb = reinterpret_cast<float*>(p.y) + (long long)hsel * p.B * p.Do * p.Ho * p.Wo * half +
-                      ((((long long)tc.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * half + cc;
+          const long long set = (long long)p.B * p.Do * p.Ho * p.Wo * half;
+          const long long at = (long long)hsel * set + ((((long long)tc.b * p.Do + oz) * p.Ho + oy) * p.Wo + ox) * half + cc;
+          float* yb = reinterpret_cast<float*>(p.y) + at;
           *reinterpret_cast<float4*>(yb) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(yb + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          if (p.out_fmt == FMT_NHWC2H) {  // + the same two sets rounded to fp16 behind them (W1's source-map format): 16 bytes per lane
+            __half* yh = reinterpret_cast<__half*>(reinterpret_cast<float*>(p.y) + 2 * set) + at;
+            const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+            const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+            *reinterpret_cast<uint4*>(yh) = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                       *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          }
         } else {
           uint4 hi, lo;
           split_pack8(v, hi, lo);
@@ -636,10 +644,10 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
   DMVS_REQUIRE(x && y, DMVS_ERR_BAD_POINTER, "conv_tc2: null pointer");
   DMVS_REQUIRE(aligned16(L.w_tc) && (!L.w_tc_kw || aligned16(L.w_tc_kw)) && aligned16(x) && aligned16(y) && (!skip || aligned16(skip)), DMVS_ERR_BAD_POINTER,
                "conv_tc2: pointers must be 16-byte aligned");
-  DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P || out_fmt == FMT_NHWC2,
+  DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_CH16 || out_fmt == FMT_CH16P || out_fmt == FMT_NHWC2 || out_fmt == FMT_NHWC2H,
                DMVS_ERR_BAD_SHAPE,
                "conv_tc2: bad out_fmt %d", out_fmt);
-  DMVS_REQUIRE((out_fmt != FMT_NHWC2) || (kd == 1 && !transposed && stride == 1 && Cin == 32 && (Cout == 16 || Cout == 32)),
+  DMVS_REQUIRE((out_fmt != FMT_NHWC2 && out_fmt != FMT_NHWC2H) || (kd == 1 && !transposed && stride == 1 && Cin == 32 && (Cout == 16 || Cout == 32)),
                DMVS_ERR_BAD_SHAPE,
                "conv_tc2: the split channel-last output exists for FeatureNet's 32-channel 3x3 heads only");
   Tc2Params p;
@@ -659,7 +667,7 @@ int conv_layer_tc2(const void* x, int in_cells, const dmvs_conv_layer& L, const 
     if (!transposed && stride == 1 && ((Cin == 32 && (Cout == 16 || Cout == 32)) || (Cin == 16 && Cout == 16) || (Cin == 8 && Cout == 8))) {
       // FeatureNet's 3x3 layers (out3 / out2 and conv2.1-2 / conv1.1-2): weights resident, all channel chunks in one pass
       DMVS_REQUIRE(skip == nullptr, DMVS_ERR_BAD_SHAPE, "conv_tc2: only transposed convs take a skip input");
-      DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2 || out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE,
+      DMVS_REQUIRE(out_fmt == FMT_F32 || out_fmt == FMT_NHWC2 || out_fmt == FMT_NHWC2H || out_fmt == FMT_CH16, DMVS_ERR_BAD_SHAPE,
                    "conv_tc2: FeatureNet layers write fp32 (NCHW or split channel-last) or CH16");
       p.Ho = Hi; p.Wo = Wi;
       if (p.y_bs == 0) p.y_bs = (long long)Cout * Di * Hi * Wi;

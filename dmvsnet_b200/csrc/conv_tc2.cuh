@@ -8,7 +8,7 @@
 
 namespace dmvs {
 
-enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2, FMT_NHWC2 = 4 };
+enum { FMT_F32 = 0, FMT_CH16 = 1, FMT_CH16P = 2, FMT_NHWC2 = 4, FMT_NHWC2H = 5 };
 enum { M2_S1 = 0, M2_S2 = 1, M2_TR = 2, M2_C0 = 3, M2_PB = 4, M2_C0T = 5, M2_TRF = 6 };
 __host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mode == M2_C0T; }
 // TRF: transposed conv with the 27 taps folded by input shift: the taps that read the same shifted A view (shift in {0,1}^3,

@@ -112,6 +112,10 @@ class FeatureNet(nn.Module):
     # fp32 FMA kernels, 2.6x faster); False keeps them on the fp32 direct convolution
     tensor_heads = True
     tensor_s2 = True  # the two 5x5 stride-2 layers on the tensor engine through a 2x2 pixel-unshuffle (space-to-depth)
+    # native engine with tensor heads: the out2 / out3 epilogues also write their maps rounded to fp16 (extra ``stageK_h16`` /
+    # ``stageK_c_h16`` entries, ops.HalfFeatures: W1's source-map format).  Set by MVSNet.extract_features around its call;
+    # off by default so that FeatureNet.forward returns exactly the reference's keys
+    emit_f16 = False
 
     def forward(self, x):
         if x.is_cuda and self.engine == "native" and not self.training and self.mode == "fpn" and self.num_stage == 3:
@@ -214,9 +218,15 @@ class FeatureNet(nn.Module):
             # the two 32-channel 3x3 heads (57 % of FeatureNet's flops) on the tcgen05 engine: the laterals emit their sums as
             # fp16 hi/lo cells (top2 only as cells: nobody else reads it), the heads write the channel-last feature sets
             top, cells = ops.conv2d(c1, pk["inner1"], up_add=c2, cells=True)
-            out["stage2"], out["stage2_c"] = ops.conv2d_head_tensor(cells, pk["out2_tc"])
+            if self.emit_f16:  # the heads' epilogues also write W1's fp16 source maps (``<key>_h16``: ops.HalfFeatures)
+                out["stage2"], out["stage2_c"], out["stage2_h16"], out["stage2_c_h16"] = ops.conv2d_head_tensor(cells, pk["out2_tc"], True)
+            else:
+                out["stage2"], out["stage2_c"] = ops.conv2d_head_tensor(cells, pk["out2_tc"])
             _, cells = ops.conv2d(c0, pk["inner2"], up_add=top, nchw=False, cells=True)
-            out["stage3"], out["stage3_c"] = ops.conv2d_head_tensor(cells, pk["out3_tc"])
+            if self.emit_f16:
+                out["stage3"], out["stage3_c"], out["stage3_h16"], out["stage3_c_h16"] = ops.conv2d_head_tensor(cells, pk["out3_tc"], True)
+            else:
+                out["stage3"], out["stage3_c"] = ops.conv2d_head_tensor(cells, pk["out3_tc"])
             return out
         top = ops.conv2d(c1, pk["inner1"], up_add=c2)
         _, out["stage2"], out["stage2_c"] = ops.conv2d(top, pk["out2"], nchw=False, split_nhwc=True)

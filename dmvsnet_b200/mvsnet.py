@@ -211,14 +211,20 @@ class MVSNet(nn.Module):
         arithmetic, but 5 small cuDNN launches per layer become one: 39 -> 23 ms at DTU size on B200).  Returns the
         reference's per-view list of dicts; every entry is a strided view into the batched output (no copies)."""
         b, n = imgs.shape[0], imgs.shape[1]
-        out = self.feature(imgs.reshape(b * n, *imgs.shape[2:]))
+        want16 = self.w1_precision == "fp16" and imgs.is_cuda and n > 1
+        self.feature.emit_f16 = want16  # the tensor heads' epilogues write the fp16 source maps themselves
+        try:
+            out = self.feature(imgs.reshape(b * n, *imgs.shape[2:]))
+        finally:
+            self.feature.emit_f16 = False
+        halves = {k[:-4]: out.pop(k) for k in [k for k in out if k.endswith("_h16")]}
 
         def view_of(t, v):
             return t.view(b, n, *t.shape[1:])[:, v]
         views = [{k: view_of(t, v) for k, t in out.items()} for v in range(n)]
-        if self.w1_precision == "fp16" and imgs.is_cuda and n > 1:
-            for k, t in out.items():  # one conversion launch per map for all views; the source views take their slices
-                half = ops.features_nhwc_f16(t)
+        if want16:
+            for k, t in out.items():  # maps without an emitted copy: one conversion launch per map for all views
+                half = halves[k] if k in halves else ops.features_nhwc_f16(t)
                 for v in range(1, n):
                     views[v][k + "_h16"] = half.view_of(b, n, v)
         return views

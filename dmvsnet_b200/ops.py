@@ -486,20 +486,27 @@ def s2d_weight(w5: torch.Tensor) -> torch.Tensor:
 
 
 @_on_device
-def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer"):
+def conv2d_head_tensor(cells: torch.Tensor, layer: "PackedLayer", want_f16: bool = False):
     """FeatureNet's bare 3x3 heads out2 / out3 (module.py:326-336, Cin = 32, no BN / ReLU / bias) on the tcgen05 engine:
-    CH16 cells [B, 8, 1, H, W, 4] -> the two feature sets as channel-last maps, returned as [B,Cout/2,H,W] views."""
+    CH16 cells [B, 8, 1, H, W, 4] -> the two feature sets as channel-last maps, returned as [B,Cout/2,H,W] views.
+    ``want_f16``: the epilogue also writes both sets rounded to fp16 (DMVS_FMT_NHWC2_F16) - W1's source-map format - and the call
+    returns ``(set0, set1, HalfFeatures0, HalfFeatures1)``."""
     lib = N.load()
     b, planes, d, h, w, _ = cells.shape
     if planes != 8 or d != 1 or layer.cin != 32 or layer.kd != 1 or layer.w_tc is None:
         raise ValueError("conv2d_head_tensor: expects 32-channel cells and a packed 2-D 3x3 layer")
     half = layer.cout // 2
-    y = torch.empty(2, b, h, w, half, device=cells.device, dtype=torch.float32)
+    n = 2 * b * h * w * half
+    buf = torch.empty(n + (n // 2 if want_f16 else 0), device=cells.device, dtype=torch.float32)
+    y = buf[:n].view(2, b, h, w, half)
     cl = layer.c_struct()
     with _timed("featnet:tc3x3_32to%d_%dx%d" % (layer.cout, h, w)):
-        rc = lib.dmvs_conv3d_ch16(cells.data_ptr(), 0, ctypes.byref(cl), None, y.data_ptr(), b, 32, layer.cout, 1, h, w, 1, 1, 0, 0,
-                                  N.FMT_NHWC2, _stream())
+        rc = lib.dmvs_conv3d_ch16(cells.data_ptr(), 0, ctypes.byref(cl), None, buf.data_ptr(), b, 32, layer.cout, 1, h, w, 1, 1, 0, 0,
+                                  N.FMT_NHWC2_F16 if want_f16 else N.FMT_NHWC2, _stream())
     N.check(rc, "dmvs_conv3d_ch16")
+    if want_f16:
+        y16 = buf[n:].view(torch.float16).view(2, b, h, w, half)
+        return y[0].permute(0, 3, 1, 2), y[1].permute(0, 3, 1, 2), HalfFeatures(y16[0]), HalfFeatures(y16[1])
     return y[0].permute(0, 3, 1, 2), y[1].permute(0, 3, 1, 2)
 
 

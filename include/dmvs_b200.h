@@ -242,6 +242,9 @@ int dmvs_conv3d_f32(const float* x, const dmvs_conv_layer* layer, const float* s
 #define DMVS_FMT_COST2 3 /* conv0 input written by dmvs_warp_corr_f32(cost_cells), see there */
 #define DMVS_FMT_NHWC2 4 /* output only, FeatureNet's 3x3 heads (kd = 1, Cin = 32, Cout = 16 / 32): two channel-last fp32 buffers
                             back to back, [2][B][D][H][W][Cout/2] = the `stageK` / `stageK_c` feature sets */
+#define DMVS_FMT_NHWC2_F16 5 /* DMVS_FMT_NHWC2 followed, in the same buffer, by the same two sets rounded to fp16 ([2][B][D][H][W][Cout/2]
+                                halfs): the source-map format of dmvs_warp_corr_h16_f32, written by the head's epilogue instead of a
+                                separate dmvs_features_nhwc_f16 pass.  Buffer size: 2*B*D*H*W*(Cout/2) * (4 + 2) bytes */
 
 /* fp32 NCDHW <-> CH16 / CH16P (C % 8 == 0; CH16P: W even).  to_ch16 != 0: x fp32 -> y cells; else x cells -> y fp32. */
 int dmvs_convert_layout(const void* x, void* y, int B, int C, int D, int H, int W, int fmt, int to_ch16, void* stream);

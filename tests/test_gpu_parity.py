@@ -265,9 +265,12 @@ def test_feature_net_native_vs_oracle(b, n, h, w):
         with torch.no_grad():
             got = net.extract_features(cuda(imgs))
         # 13 layers + the pixel-unshuffle of c1 for the second 5x5 stride-2 layer; the cuDNN engine launches nothing of ours
-        # ... + one fp16 conversion per map for the source views (w1_precision = "fp16", the default)
+        # ... + one fp16 conversion per map for the source views (w1_precision = "fp16", the default); the native tensor heads
+        # (out2 / out3) write the fp16 copies of their four maps themselves, so only the two stage-1 maps are converted
         assert net.w1_precision == "fp16"
-        assert _lib_launches() - launches == (14 if engine == "native" else 0) + 6
+        assert _lib_launches() - launches == ((14 + 2) if engine == "native" else 6)
+        assert torch.equal(got[1]["stage2_h16"].float(), got[1]["stage2"].half().float())
+        assert "stage2_h16" not in net.feature(cuda(imgs[:, 0]))  # FeatureNet.forward itself returns the reference's keys only
         assert got[1]["stage2_h16"].shape == got[1]["stage2"].shape and "stage2_h16" not in got[0]
         assert torch.equal(got[1]["stage3_c_h16"].float(), got[1]["stage3_c"].half().float())
         if engine == "native":  # ... and with the 3x3 heads on the fp32 kernels instead of the tensor cores
