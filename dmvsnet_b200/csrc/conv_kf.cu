@@ -20,6 +20,11 @@
 // Kinds: S1 = Cin, Cout multiples of 8 on CH16 cells (conv2); C0 = conv0 on the cost cells W1 emits (K packed along kw, 3 MMAs
 // per plane); PB = `prob` (8 -> 2, fp32 logits out); PW = `prob` with kw folded into N as well, on wide tiles:
 //
+// SW = S1 for Cout_p = 32 (conv4), where 3 x 2*Cout_p columns per plane would leave room for two accumulators only: the lo(W) product
+// moves from the N to the K dimension.  Columns are [kd][Cout_p] (N = 96); per tap and 8-channel chunk one MMA multiplies
+// [A_hi | A_lo] with [hi(W); hi(W)], and per tap and PAIR of chunks one MMA multiplies [A_hi(chunk 2i) | A_hi(chunk 2i+1)] (the K
+// halves are the two chunks' hi planes: LBO = 2 planes) with [lo(W, 2i); lo(W, 2i+1)].  1.5 MMAs per (tap, chunk) instead of 3.
+//
 //   * The full-resolution layers are bound by the TMA engine's rate for narrow rows (18 x 160-byte rows per box: ~235 cycles,
 //     profiles/r2l_kf_probe.txt) and by the MMA count at about the same level.  PW attacks both: the tile is 4 rows x 32 voxels
 //     (M row = y * 32 + x, so the 8-row core matrices are consecutive 128-byte pieces of 512-byte box rows: SBO = 128, no x halo in
@@ -30,12 +35,13 @@
 
 namespace dmvs {
 
-enum { KF_S1 = 0, KF_C0 = 1, KF_PB = 2, KF_PW = 3 };
+enum { KF_S1 = 0, KF_C0 = 1, KF_PB = 2, KF_PW = 3, KF_SW = 4 };
 
 template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NPART_, int CS_, int MW_ = 2, int NPROD_ = 1>
 struct KF {
   static constexpr bool WIDE = KIND == KF_PW;
-  static constexpr int NB = WIDE ? 16 : 2 * COUT_P;     // one kd block: [hi(W) | lo(W)] columns (PW: 3 kw x 4, padded to 16)
+  static constexpr bool SPLITW = KIND == KF_SW;
+  static constexpr int NB = WIDE ? 16 : SPLITW ? COUT_P : 2 * COUT_P;  // one kd block: [hi(W) | lo(W)] columns (PW: 3 kw x 4, padded to 16; SW: one column per output channel)
   static constexpr int NF = (3 * NB + 15) / 16 * 16;    // N of one tcgen05.mma (PB: 12 -> 16, PW: 36 -> 48)
   static constexpr int TW = WIDE ? 32 : T_W, TH = WIDE ? 4 : T_H;  // tile: TH rows x TW voxels = 128 accumulator lanes
   static constexpr int XSTEP = WIDE ? 30 : T_W;                    // valid output voxels per tile row
@@ -48,7 +54,7 @@ struct KF {
   static constexpr int A_LBO = (KIND == KF_C0) ? 32 : PLANE;
   static constexpr int A_SBO = WIDE ? 128 : BW * 16;
   static constexpr int B_TILE = 2 * NF * 16;
-  static constexpr int B_BYTES = CJ * TAPS * B_TILE;
+  static constexpr int B_BYTES = (SPLITW ? CJ + CJ / 2 : CJ) * TAPS * B_TILE;  // SW: the hi(W) image, then the lo(W) image of the chunk pairs
   static constexpr int STAGE_BYTES = pad128(NPLANE * PLANE);
   static constexpr int TX_BYTES = NPLANE * BLK_BYTES;
   static constexpr int OFF_B = STAGES * STAGE_BYTES;
@@ -198,6 +204,15 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
               const uint64_t bd = bdesc0 + (uint64_t)(((cj * Cfg::TAPS + tap) * Cfg::B_TILE) >> 4);
               umma_f16(acc, ad, bd, idesc, (tap == 0 && cj == 0) ? 0u : 1u);
             }
+            if (Cfg::SPLITW) {  // [A_hi(chunk 2i) | A_hi(chunk 2i+1)] x [lo(W, 2i); lo(W, 2i+1)]
+              const uint64_t adesc_p = make_desc(smem_u32(smem + st * Cfg::STAGE_BYTES), 2 * Cfg::PLANE, Cfg::A_SBO);
+#pragma unroll
+              for (int ci = 0; ci < Cfg::CJ / 2; ++ci) {
+                const uint64_t ad = adesc_p + (uint64_t)((4 * ci * Cfg::PLANE + off) >> 4);
+                const uint64_t bd = bdesc0 + (uint64_t)((((Cfg::CJ + ci) * Cfg::TAPS + tap) * Cfg::B_TILE) >> 4);
+                umma_f16(acc, ad, bd, idesc, 1u);
+              }
+            }
           }
           umma_commit(empty + st);
           umma_commit(accfull + slot);
@@ -319,12 +334,18 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
           for (int c0 = 8 * cs; c0 < COUT_P; c0 += 8 * Cfg::CS) {
             uint32_t rm[8], rml[8], r0[8], r0l[8], rp[8], rpl[8];
             tmem_ld8_issue(am + c0, rm);
-            tmem_ld8_issue(am + COUT_P + c0, rml);
             tmem_ld8_issue(a0 + c0, r0);
-            tmem_ld8_issue(a0 + COUT_P + c0, r0l);
             tmem_ld8_issue(ap + c0, rp);
-            tmem_ld8_issue(ap + COUT_P + c0, rpl);
+            if (!Cfg::SPLITW) {
+              tmem_ld8_issue(am + COUT_P + c0, rml);
+              tmem_ld8_issue(a0 + COUT_P + c0, r0l);
+              tmem_ld8_issue(ap + COUT_P + c0, rpl);
+            }
             tmem_wait_ld();
+            if (Cfg::SPLITW) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) rml[c] = r0l[c] = rpl[c] = 0u;  // the lo(W) product sits in the same columns
+            }
             if (c0 + 8 * Cfg::CS >= COUT_P) release();
             if (!in_img || c0 >= p.Cout) continue;
             float v[8];
@@ -439,6 +460,8 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
     if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 4>(p, x, st);
     return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 2>(p, x, st);
   }
+  if (p.Cin == 32 && p.Cout == 32 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P))  // conv4
+    return launch_kf<KF_SW, 32, 32, 4, 2, 2, 2, 2>(p, x, st);
   if (p.Cin == 2 && in_cells) {
     if (g_kf < 2) return 1;
     if (p.Cout == 16) {  // conv0 of both branches

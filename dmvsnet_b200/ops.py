@@ -552,6 +552,8 @@ class PackedLayer:
             self.w_tc_kd = _pack_tensor_core_tr_fold(w[:, :, :cout])
         elif cin == 16 and cout == 16 and taps == 27 and not transposed:   # conv2
             self.w_tc_kd = _pack_tensor_core_kf(self.w_tc)
+        elif cin == 32 and cout == 32 and taps == 27 and not transposed:   # conv4
+            self.w_tc_kd = _pack_tensor_core_kf_split(w[:, :, :cout])
         elif cin == 2 and cout == 8 and taps == 27 and not transposed:     # conv0
             self.w_tc_kd = _pack_tensor_core_kf(self.w_tc, kh_only=True)
         self.kd = 3 if taps == 27 else 1
@@ -631,6 +633,26 @@ def _pack_tensor_core_kf(per_tap: torch.Tensor, kh_only: bool = False) -> torch.
     assert taps == (9 if kh_only else 27)
     t = per_tap.reshape(j, 3, taps // 3, kc, nb, e).permute(0, 2, 3, 1, 4, 5)
     return t.reshape(j, taps // 3, kc, 3 * nb, e).contiguous()
+
+
+def _pack_tensor_core_kf_split(w: torch.Tensor) -> torch.Tensor:
+    """Depth tap folded into N with the lo(W) product in the K dimension (csrc/conv_kf.cu, kind SW: conv4, 32 -> 32).
+    [27][Cin][Cout] -> one flat buffer holding two images with columns n = kd * Cout + co:
+      hi image [chunk j = Cin/8][9 taps (kh,kw)][kc = 2][n][8 halfs]: hi(W[8j+k]) for kc = 0 AND 1 (the A_hi and A_lo halves of chunk j);
+      lo image [pair i = Cin/16][9 taps][kc = 2][n][8 halfs]: lo(W[16i+k]) for kc = 0, lo(W[16i+8+k]) for kc = 1 (the A_hi halves of the
+      pair's two chunks)."""
+    taps, cin, cout = w.shape
+    assert taps == 27 and cin % 16 == 0 and cout % 8 == 0
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    cj = cin // 8
+    hi_r = hi.reshape(3, 9, cj, 8, cout).permute(2, 1, 0, 4, 3)       # [j][tap9][kd][co][k]
+    lo_r = lo.reshape(3, 9, cj // 2, 2, 8, cout).permute(2, 1, 3, 0, 5, 4)  # [pair][tap9][kc][kd][co][k]
+    img_hi = torch.empty(cj, 9, 2, 3 * cout, 8, dtype=torch.float16, device=w.device)
+    img_hi[:, :, 0] = hi_r.reshape(cj, 9, 3 * cout, 8)
+    img_hi[:, :, 1] = hi_r.reshape(cj, 9, 3 * cout, 8)
+    img_lo = lo_r.reshape(cj // 2, 9, 2, 3 * cout, 8)
+    return torch.cat([img_hi.reshape(-1), img_lo.reshape(-1)]).contiguous()
 
 
 def _pack_tensor_core_tr_fold(w: torch.Tensor) -> torch.Tensor:

@@ -367,6 +367,7 @@ def _cost_cells_from_volume(vol):
     (16, 8, (1, 40, 100), 2, True),
     # depth-tap-folded kernels (csrc/conv_kf.cu): one and two planes, ranges that cut columns, odd plane counts
     (16, 16, (1, 18, 26), 1, False), (16, 16, (2, 37, 50), 1, False), (16, 16, (3, 148, 200), 1, False), (8, 2, (4, 50, 60), 1, False),
+    (32, 32, (1, 20, 30), 1, False), (32, 32, (2, 37, 50), 1, False), (32, 32, (5, 74, 100), 1, False),
     (8, 2, (1, 20, 30), 1, False), (2, 8, (4, 50, 61), 1, False), (2, 8, (1, 20, 31), 1, False), (2, 8, (9, 150, 200), 1, False),
     # many tiles per persistent CTA: the stage ring and both accumulator sets wrap several times
     (8, 2, (24, 160, 200), 1, False), (2, 8, (16, 160, 200), 1, False), (16, 16, (12, 160, 200), 1, False),
