@@ -478,7 +478,7 @@ def run_gpu_arm(args, cfg_name):
     _, _, groups_full = w1_roofline(prof_full_all, 3.0, views, peak)
     sm_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9  # GB/s through the SMs' shared-memory data pipe
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r2_w1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2m_w1_traffic.json")
     if os.path.exists(tp) and cfg_name == "dtu":
         traffic = json.load(open(tp)).get("dram_bytes_per_step")
 
@@ -523,16 +523,16 @@ def run_gpu_arm(args, cfg_name):
                              **{k: v for k, v in roof_hot.items() if k != "gather_bytes_per_step"}),
             "roofline_per_launch": rows_hot,
             "roofline_regnet": None if cfg_name not in R1_GFLOP else {
-                "kernel": "R1 = conv_tc2_kernel (tcgen05 implicit GEMM, fp16 hi/lo split operands: 3 products per multiply-add), all regularisation nets of a step "
-                          "(82 % of the hot path's kernel time, profiles/r2j_launches_hot.csv)",
+                "kernel": "R1 = conv_tc2_kernel / conv_kf_kernel (tcgen05 implicit GEMM, fp16 hi/lo split operands: 3 products per multiply-add), all regularisation "
+                          "nets of a step (77 % of the hot path's kernel time, profiles/r2m_launches_hot.csv)",
                 "bound": "tensor", "unit": "TFLOP/s", "algorithmic_gflop_per_step": R1_GFLOP[cfg_name],
                 "ms_per_step": groups_hot.get("regnet", 0.0) + groups_hot.get("regnet_refine", 0.0),
                 "achieved": R1_GFLOP[cfg_name] / max(groups_hot.get("regnet", 0.0) + groups_hot.get("regnet_refine", 0.0), 1e-9),
                 "peak": float(pk.get("bf16_tflops_sustained", 1400.0)),
                 "frac": R1_GFLOP[cfg_name] / max(groups_hot.get("regnet", 0.0) + groups_hot.get("regnet_refine", 0.0), 1e-9) / float(pk.get("bf16_tflops_sustained", 1400.0)),
                 "note": "algorithmic flops (one product per multiply-add) over the event-timed net launches against the sustained bf16 peak; the split executes 3x "
-                        "these flops, and at base_channels = 8 the layers are bound by the shared-memory operand read per MMA (N = 16..64) and by HBM at full "
-                        "resolution, not by the tensor pipe (DESIGN.md section 4)"},
+                        "these flops, and at base_channels = 8 the layers are bound by the shared-memory operand fetch per MMA (A 4 KB + B, ~68 B/clk: N = 16..96 "
+                        "leaves the pipe 16-51 % busy) and by the per-plane hand-offs of the full-resolution layers, not by the tensor pipe (DESIGN.md section 4)"},
             "roofline_full_forward": dict({"workload": "value region: feature maps computed by FeatureNet from the rendered images (heads: %s)" % FEATNET_HEADS},
                                           **{k: v for k, v in roof_full.items() if k != "gather_bytes_per_step"}, per_launch=rows_full),
             "breakdown_ms_per_step": groups_full,

@@ -2,7 +2,7 @@
 # One GPU-box call that produces the round's tracked evidence (copied from gpurun_out/ into profiles/ afterwards).
 #   tools/capture_round.sh <tag>
 set -u
-T=${1:-r2j}
+T=${1:-r2m}
 O=gpurun_out
 python bench.py --steps 20 --warmup 5 > $O/${T}_bench.json 2> $O/${T}_bench.err
 python bench.py --impl reference --steps 20 --warmup 5 > $O/${T}_bench_reference.json 2>> $O/${T}_bench.err
@@ -18,7 +18,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:warp_corr_h16 -o $O/${T}_w1_step \
     python bench.py --profile-step hot --no-cpu > /dev/null 2>> $O/${T}_bench.err
 # the regularisation launches of stage 2 (main net): conv0 pair + 10 layers of the first branch
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_tc2 -s 44 -c 11 -o $O/${T}_tc2_stage2 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k 'regex:conv_(tc2|kf)' -s 42 -c 11 -o $O/${T}_tc2_stage2 \
     python bench.py --profile-step hot --no-cpu > /dev/null 2>> $O/${T}_bench.err
 tail -c 400 $O/${T}_bench.err
 ls -la $O/${T}_*
