@@ -40,6 +40,7 @@ SIGNATURES = {
     "dmvs_last_error": (c_char_p, []),
     "dmvs_launch_count": (c_ulonglong, []),
     "dmvs_debug_set": (c_int, [c_char_p, c_int]),
+    "dmvs_debug_set_ptr": (c_int, [c_char_p, c_void_p]),
     "dmvs_warp_corr_f32": (c_int, [c_void_p, c_longlong, POINTER(c_void_p), c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dmvs_warp_corr_nhwc_f32": (c_int, [c_void_p, c_longlong, c_int, POINTER(c_void_p), c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

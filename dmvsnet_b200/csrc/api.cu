@@ -23,6 +23,7 @@ extern int g_tc2_pdl;
 extern int g_regnet_streams;
 extern int g_kf;
 extern int g_kf_dbg;
+extern long long* g_kf_trace;
 extern int g_kf_wide;
 extern int g_kf_prod;
 extern int g_tc2_skip_prefetch;
@@ -56,7 +57,7 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
     dmvs::g_tc2_skip_prefetch = value;
     return DMVS_OK;
   }
-  if (key && !strcmp(key, "kf_dbg") && value >= 0 && value <= 3) {
+  if (key && !strcmp(key, "kf_dbg") && value >= 0 && value <= 15) {
     dmvs::g_kf_dbg = value;
     return DMVS_OK;
   }
@@ -68,7 +69,7 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
     dmvs::g_kf_wide = value;
     return DMVS_OK;
   }
-  if (key && !strcmp(key, "kf_mw") && (value == 2 || value == 4)) {
+  if (key && !strcmp(key, "kf_mw") && (value == 0 || value == 2 || value == 4)) {
     dmvs::g_kf_mw = value;
     return DMVS_OK;
   }
@@ -77,6 +78,16 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
     return DMVS_OK;
   }
   dmvs::set_error("dmvs_debug_set: unknown key or bad value");
+  return DMVS_ERR_BAD_SHAPE;
+}
+
+// experiments: device buffers handed to instrumented kernels ("kf_trace": >= 512 x 16 int64 clock stamps of CTA 0, conv_kf.cu)
+extern "C" int dmvs_debug_set_ptr(const char* key, void* ptr) {
+  if (key && !strcmp(key, "kf_trace")) {
+    dmvs::g_kf_trace = static_cast<long long*>(ptr);
+    return DMVS_OK;
+  }
+  dmvs::set_error("dmvs_debug_set_ptr: unknown key");
   return DMVS_ERR_BAD_SHAPE;
 }
 

@@ -66,10 +66,15 @@ struct KF {
   static constexpr int EPI_WARPS = 4 * NPART * CS;
   static constexpr int MMA_WARPS = MW_;
   static constexpr int HS = STAGES / MMA_WARPS;
+  // ONE commit per plane: with as many smem stages as accumulator slots (stage = slot = g % R) "the MMAs of plane g are done" frees
+  // the stage for the producer AND hands the accumulator to the epilogue - both wait on accfull[slot].  A tcgen05.commit costs
+  // ~200 cycles and commits serialise per SM (tools/experiments/kf_trace.py): two per plane were the floor of the per-plane hand-off
+  static constexpr bool ONEBAR = (STAGES == R);
   static constexpr int NPROD = NPROD_;  // TMA-issuing threads (one per warp): plane g is fetched by thread g % NPROD
   static constexpr int THREADS = (NPROD + MMA_WARPS + EPI_WARPS) * 32;
   static_assert(R % MMA_WARPS == 0 && R >= 4, "a slot must always belong to the same issuing thread; 3 live slots + 1");
   static_assert(R * NF <= 512, "accumulator ring exceeds TMEM");
+  static_assert((MMA_WARPS & (MMA_WARPS - 1)) == 0 && (NPROD & (NPROD - 1)) == 0, "role strides are powers of two");
   static_assert(STAGES % MMA_WARPS == 0, "stage ring is split between the issuing threads");
   static_assert(SMEM <= 227 * 1024, "pipeline does not fit shared memory");
   // a group waits only on the accumulators it reads; with more than R/2 plane-interleaved groups one of them can meet a slot a
@@ -103,6 +108,12 @@ struct KfRange {  // the CTA's share of the (column, output plane) sequence
 };
 
 // x0: first voxel of the accumulator rows (PW: one halo voxel left of the first output)
+// experiment: time stamps of the first KF_TRACE_PLANES planes of CTA 0, 16 slots per plane
+constexpr int KF_TRACE_PLANES = 512;
+__device__ __forceinline__ void kf_stamp(const Tc2Params& p, int g, int ev) {
+  if ((p.dbg & 8) && p.trace && blockIdx.x == 0 && g < KF_TRACE_PLANES) p.trace[g * 16 + ev] = clock64();
+}
+
 template <class Cfg>
 __device__ __forceinline__ void kf_column(const Tc2Params& p, int col, int& x0, int& y0, int& b) {
   x0 = (col % p.tiles_x) * Cfg::XSTEP - (Cfg::WIDE ? 1 : 0);
@@ -156,15 +167,25 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
     if (lane == 0) {
       prefetch_tmap(&tmap);
       const int planes_per_b = 2 * CIN / 8;
-      int g = 0;
+      // a single thread runs this loop: every instruction and every taken branch of it is serial latency per plane, so each producer
+      // steps straight to its own planes
+      int g_frag = 0;
       while (range.next(col, t0, t1, sa, sb)) {
         int x0, y0, b;
         kf_column<Cfg>(p, col, x0, y0, b);
-        for (int s = sa; s <= sb; ++s, ++g) {
-          if (NPR > 1 && (g % NPR) != warp) continue;
+        const int first = (warp - g_frag) & (NPR - 1);
+#pragma unroll 1
+        for (int s = sa + first; s <= sb; s += NPR) {
+          const int g = g_frag + (s - sa);
           const int m = g % MW, j = g / MW;
-          const int st = MW * (j % Cfg::HS) + m, u = j / Cfg::HS;
-          mbar_wait(empty + st, (u & 1) ^ 1);
+          const int st = Cfg::ONEBAR ? g % R : MW * (j % Cfg::HS) + m, u = Cfg::ONEBAR ? g / R : j / Cfg::HS;
+          kf_stamp(p, g, 8);
+          if (Cfg::ONEBAR) {
+            if (g >= R) mbar_wait(accfull + st, (u - 1) & 1);  // plane g - R (the stage's previous tenant) has been multiplied
+          } else {
+            mbar_wait(empty + st, (u & 1) ^ 1);
+          }
+          kf_stamp(p, g, 0);
           uint8_t* dst = smem + st * Cfg::STAGE_BYTES;
           mbar_expect_tx(full + st, Cfg::TX_BYTES);
           if (KIND == KF_C0) {  // cost cells: cell x = [voxel x-1 | voxel x], one plane per batch entry
@@ -173,7 +194,9 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
             // one box over the NPLANE consecutive planes of this batch entry (a TMA instruction costs ~235 cycles whatever its box)
             tma_load_4d(dst, &tmap, full + st, 8 * (Cfg::WIDE ? x0 : x0 - 1), y0 - 1, s, b * planes_per_b);
           }
+          kf_stamp(p, g, 7);
         }
+        g_frag += sb - sa + 1;
       }
     }
   } else if (warp < NPR + Cfg::MMA_WARPS) {
@@ -182,15 +205,20 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(Cfg::NF);
       const uint64_t bdesc0 = make_desc(smem_u32(sB), Cfg::NF * 16, 128);
-      int g = 0;
+      int g_frag = 0;
       while (range.next(col, t0, t1, sa, sb)) {
-        for (int s = sa; s <= sb; ++s, ++g) {
-          if ((g % MW) != me) continue;
+        const int first = (me - g_frag) & (MW - 1);
+#pragma unroll 1
+        for (int s = sa + first; s <= sb; s += MW) {
+          const int g = g_frag + (s - sa);
           const int slot = g % R, k = g / R;
+          kf_stamp(p, g, 9);
           mbar_wait(accempty + slot, (k & 1) ^ 1);
+          kf_stamp(p, g, 1);
           const int j = g / MW;
-          const int st = MW * (j % Cfg::HS) + me, u = j / Cfg::HS;
+          const int st = Cfg::ONEBAR ? slot : MW * (j % Cfg::HS) + me, u = Cfg::ONEBAR ? k : j / Cfg::HS;
           mbar_wait(full + st, u & 1);
+          kf_stamp(p, g, 2);
           tc_fence_after();
           const uint64_t adesc0 = make_desc(smem_u32(smem + st * Cfg::STAGE_BYTES), Cfg::A_LBO, Cfg::A_SBO);
           const uint32_t acc = tmem_base + slot * Cfg::NF;
@@ -214,9 +242,11 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
               }
             }
           }
-          umma_commit(empty + st);
+          if (!Cfg::ONEBAR) umma_commit(empty + st);
           umma_commit(accfull + slot);
+          kf_stamp(p, g, 3);
         }
+        g_frag += sb - sa + 1;
       }
     }
     __syncwarp();
@@ -254,6 +284,7 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
         if (has_m) mbar_wait(accfull + gm % R, (gm / R) & 1);
         mbar_wait(accfull + g0 % R, (g0 / R) & 1);
         if (has_p) mbar_wait(accfull + gp % R, (gp / R) & 1);
+        if (q == 0 && lane == 0 && cs == 0) kf_stamp(p, g0, 4);
         tc_fence_after();
         // column blocks: kd = 0 of plane t-1, kd = 1 of plane t, kd = 2 of plane t+1 (a missing neighbour re-reads plane t and is
         // masked out, so the loads stay unconditional)
@@ -264,8 +295,10 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
         // 3 reader arrivals per accumulator: this plane arrives for itself and for the readers outside the fragment it stands in
         // for.  Called as soon as the group's TMEM loads have landed in registers - the slot is free long before the stores.
         auto release = [&]() {
+          if (q == 0 && lane == 0 && cs == 0) kf_stamp(p, g0, 5);
           tc_fence_before();
           __syncwarp();  // every lane's tcgen05.ld has completed (wait::ld) before lane 0 arrives for the warp
+          if (q == 0 && lane == 0 && cs == 0) kf_stamp(p, g0, 6);
           if (lane == 0) {
             if (has_m) mbar_arrive_n(accempty + gm % R, (t == t0) ? 3 : 1);
             mbar_arrive_n(accempty + g0 % R, 1 + (t == t0 ? 1 : 0) + (t == t1 ? 1 : 0));
@@ -386,14 +419,16 @@ int g_kf = 1;
 // dmvs_debug_set("kf_wide", 0 | 1): `prob` on the wide-tile kernel (kd and kw folded).  Measured equal to the per-tap kernel (265 vs
 // 262 us at 32 x 592 x 800): with 3 MMAs per plane the kernel is bound by its per-plane hand-offs, not by MMAs or TMA - off by default
 int g_kf_wide = 0;
+long long* g_kf_trace = nullptr;
 int g_kf_dbg = 0;  // dmvs_debug_set("kf_dbg", bits): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
-int g_kf_prod = 1;  // dmvs_debug_set("kf_prod", 1 | 2): TMA-issuing threads
-int g_kf_mw = 2;  // dmvs_debug_set("kf_mw", 2 | 4): issuing threads of the folded kernels
+int g_kf_prod = 1;  // (unused; kept so that dmvs_debug_set("kf_prod") stays valid)
+int g_kf_mw = 0;    // dmvs_debug_set("kf_mw", 0 | 2 | 4): MMA-issuing threads of the folded kernels, 0 = the default of each kind (conv2: 2, prob: 4 + two TMA threads)
 
 template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2, int NPR = 1>
 static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>;
   p.dbg = g_kf_dbg;
+  p.trace = g_kf_trace;
   p.tiles_x = ceil_div(p.Wo, Cfg::XSTEP);
   p.tiles_y = ceil_div(p.Ho, Cfg::TH);
   p.tiles_z = 1;
@@ -456,17 +491,16 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
 int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t st) {
   if (!g_kf) return 1;
   if (p.Cin == 16 && p.Cout == 16 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P)) {  // conv2
-    if (g_kf_prod == 2) return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 2, 2>(p, x, st);
-    if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 4>(p, x, st);
-    return launch_kf<KF_S1, 16, 16, 4, 8, 2, 2, 2>(p, x, st);
+    if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 4, 2>(p, x, st);
+    return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 2>(p, x, st);
   }
   if (p.Cin == 32 && p.Cout == 32 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P))  // conv4
     return launch_kf<KF_SW, 32, 32, 4, 2, 2, 2, 2>(p, x, st);
   if (p.Cin == 2 && in_cells) {
     if (g_kf < 2) return 1;
     if (p.Cout == 16) {  // conv0 of both branches
-      if (g_kf_mw == 4) return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2, 4>(p, x, st);
-      return launch_kf<KF_C0, 2, 16, 4, 8, 2, 2, 2>(p, x, st);
+      if (g_kf_mw == 4) return launch_kf<KF_C0, 2, 16, 4, 4, 2, 2, 4, 2>(p, x, st);
+      return launch_kf<KF_C0, 2, 16, 4, 4, 2, 2, 2>(p, x, st);
     }
     if (p.Cout == 8) return launch_kf<KF_C0, 2, 8, 8, 8, 4, 1>(p, x, st);    // conv0
     return 1;
@@ -474,14 +508,12 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
   if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32 && p.wtc_wide && g_kf_wide) {  // prob, kd and kw folded, wide tiles
     Tc2Params pw = p;
     pw.wtc = p.wtc_wide;
-    if (g_kf_prod == 2) return launch_kf<KF_PW, 8, 2, 10, 10, 4, 1, 2, 2>(pw, x, st);
-    return launch_kf<KF_PW, 8, 2, 10, 10, 4, 1, 2, 1>(pw, x, st);
+    if (g_kf_mw == 2) return launch_kf<KF_PW, 8, 2, 10, 10, 4, 1, 2, 1>(pw, x, st);
+    return launch_kf<KF_PW, 8, 2, 8, 8, 4, 1, 4, 2>(pw, x, st);
   }
-  if (g_kf < 2) return 1;
-  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob
-    if (g_kf_prod == 2) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4, 2>(p, x, st);
-    if (g_kf_mw == 4) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4>(p, x, st);
-    return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 2>(p, x, st);
+  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob: four issuing and two TMA threads (214 vs 268 us at DTU stage 2)
+    if (g_kf_mw == 2) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 2, 1>(p, x, st);
+    return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4, 2>(p, x, st);
   }
   return 1;
 }

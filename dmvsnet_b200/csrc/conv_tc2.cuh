@@ -33,6 +33,7 @@ struct Tc2Params {
   int B, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo;
   int relu, out_fmt;
   int dbg;            // experiments (dmvs_debug_set("kf_dbg", bits)): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
+  long long* trace;   // experiments: clock64() stamps of CTA 0's pipeline events (dmvs_debug_set_ptr("kf_trace", buffer), kf_dbg bit 3)
   int skip_prefetch;  // transposed layers: L2 prefetch of the next tile's skip cells
   int tiles_x, tiles_y, tiles_z, n_tiles;
 };

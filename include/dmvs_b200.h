@@ -45,6 +45,8 @@ unsigned long long dmvs_launch_count(void);
 /* tuning knobs for experiments: "tc2_max_ctas" (persistent CTAs per SM of the tensor-core convolutions, default 1; 2 measured no
  * gain), "head_px" (pixels per block of the depth head: 32 | 64 | 128, default 32), "pb_td8" (prob / conv0 on 8-plane tiles, default 1) */
 int dmvs_debug_set(const char* key, int value);
+/* experiments: a device buffer for an instrumented kernel ("kf_trace": 512 x 16 int64 clock stamps of CTA 0 of the folded convolutions) */
+int dmvs_debug_set_ptr(const char* key, void* ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * W1  fused homography warp + 2-group correlation, summed over source views.

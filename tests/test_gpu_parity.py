@@ -423,13 +423,17 @@ def test_conv_depth_tap_folded_kernels_all_kinds(cfg, native_lib):
     measured no faster than the per-tap kernels) stay correct."""
     try:
         assert native_lib.dmvs_debug_set(b"kf", 2) == 0
-        test_conv_layer_ch16_vs_torch(cfg)
-        if cfg[:2] == (8, 2):
-            assert native_lib.dmvs_debug_set(b"kf_wide", 1) == 0
+        for mw in (0, 2, 4):  # issuing-thread variants of every kind
+            assert native_lib.dmvs_debug_set(b"kf_mw", mw) == 0
             test_conv_layer_ch16_vs_torch(cfg)
+            if cfg[:2] == (8, 2):
+                assert native_lib.dmvs_debug_set(b"kf_wide", 1) == 0
+                test_conv_layer_ch16_vs_torch(cfg)
+                assert native_lib.dmvs_debug_set(b"kf_wide", 0) == 0
     finally:
         native_lib.dmvs_debug_set(b"kf", 1)
         native_lib.dmvs_debug_set(b"kf_wide", 0)
+        native_lib.dmvs_debug_set(b"kf_mw", 0)
 
 
 @pytest.mark.parametrize("engine", ["fp32", "tensor"])

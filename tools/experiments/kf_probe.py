@@ -33,7 +33,7 @@ w2 = torch.randn(16, 16, 3, 3, 3, generator=g) * 0.05
 bn = tuple(t.to(dev) for t in (torch.ones(16), torch.zeros(16), torch.zeros(16), torch.ones(16)))
 conv2 = ops.PackedLayer(w2.to(dev), False, bn)
 x16 = ops.to_ch16(torch.randn(1, 16, d // 2, h // 2, w // 2, device=dev))
-for kf, mw, npr, wide in ((0, 2, 1, 0), (2, 4, 1, 0), (1, 2, 1, 1), (1, 2, 2, 1)):
+for kf, mw, npr, wide in ((0, 0, 0, 0), (1, 2, 1, 0), (1, 4, 2, 0), (1, 2, 1, 1), (1, 4, 2, 1)):  # npr follows mw (2 -> 1 TMA thread, 4 -> 2)
     for dbg in (0, 1, 2, 3):
         if kf == 0 and dbg:
             continue
@@ -41,4 +41,4 @@ for kf, mw, npr, wide in ((0, 2, 1, 0), (2, 4, 1, 0), (1, 2, 1, 1), (1, 2, 2, 1)
         tp = timeit(lambda: ops.conv3d_ch16(x8, prob, relu=False, out_fmt="f32"))
         t2 = timeit(lambda: ops.conv3d_ch16(x16, conv2, relu=True, out_fmt="ch16p")) if kf else float("nan")
         print("wide=%d kf=%d issuers=%d producers=%d dbg=%d (1: no epilogue work, 2: no MMAs)  prob %.1f us   conv2 %.1f us" % (wide, kf, mw, npr, dbg, tp, t2), flush=True)
-lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_mw", 2); lib.dmvs_debug_set(b"kf_dbg", 0); lib.dmvs_debug_set(b"kf_prod", 1); lib.dmvs_debug_set(b"kf_wide", 0)
+lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_mw", 0); lib.dmvs_debug_set(b"kf_dbg", 0); lib.dmvs_debug_set(b"kf_prod", 1); lib.dmvs_debug_set(b"kf_wide", 0)
