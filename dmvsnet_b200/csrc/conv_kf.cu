@@ -201,8 +201,11 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
     }
   } else if (warp < NPR + Cfg::MMA_WARPS) {
     // ---------------------------------------------------------------- MMA issuers: thread m takes the planes with g % MW == m
+    // The WHOLE warp runs this loop and one elected lane issues: descriptors and addresses computed in warp-uniform code live in
+    // uniform registers, whereas under `if (lane == 0)` the compiler keeps them in vector registers and wraps every tcgen05.mma in
+    // a R2UR / ELECT waterfall (~11 instructions and a branch per MMA on the serial path of the issuing thread)
     const int me = warp - NPR;
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc(Cfg::NF);
       const uint64_t bdesc0 = make_desc(smem_u32(sB), Cfg::NF * 16, 128);
       int g_frag = 0;
@@ -212,16 +215,17 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
         for (int s = sa + first; s <= sb; s += MW) {
           const int g = g_frag + (s - sa);
           const int slot = g % R, k = g / R;
-          kf_stamp(p, g, 9);
+          if (lane == 0) kf_stamp(p, g, 9);
           mbar_wait(accempty + slot, (k & 1) ^ 1);
-          kf_stamp(p, g, 1);
+          if (lane == 0) kf_stamp(p, g, 1);
           const int j = g / MW;
           const int st = Cfg::ONEBAR ? slot : MW * (j % Cfg::HS) + me, u = Cfg::ONEBAR ? k : j / Cfg::HS;
           mbar_wait(full + st, u & 1);
-          kf_stamp(p, g, 2);
+          if (lane == 0) kf_stamp(p, g, 2);
           tc_fence_after();
           const uint64_t adesc0 = make_desc(smem_u32(smem + st * Cfg::STAGE_BYTES), Cfg::A_LBO, Cfg::A_SBO);
           const uint32_t acc = tmem_base + slot * Cfg::NF;
+          if (elect_one()) {
           if (!(p.dbg & 2))
 #pragma unroll
           for (int tap = 0; tap < Cfg::TAPS; ++tap) {
@@ -245,6 +249,8 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
           if (!Cfg::ONEBAR) umma_commit(empty + st);
           umma_commit(accfull + slot);
           kf_stamp(p, g, 3);
+          }
+          __syncwarp();
         }
         g_frag += sb - sa + 1;
       }
