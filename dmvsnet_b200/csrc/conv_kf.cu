@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
   int col, t0, t1, sa, sb;
   if (warp < NPR) {
     // ---------------------------------------------------------------- producer: one TMA box per (input plane, hi/lo plane)
-    if (lane == 0) {
-      prefetch_tmap(&tmap);
+    {  // the whole warp walks the loop, one elected lane issues (uniform registers, see the MMA issuers below)
+      if (lane == 0) prefetch_tmap(&tmap);
       const int planes_per_b = 2 * CIN / 8;
       // a single thread runs this loop: every instruction and every taken branch of it is serial latency per plane, so each producer
       // steps straight to its own planes
@@ -179,14 +179,15 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
           const int g = g_frag + (s - sa);
           const int m = g % MW, j = g / MW;
           const int st = Cfg::ONEBAR ? g % R : MW * (j % Cfg::HS) + m, u = Cfg::ONEBAR ? g / R : j / Cfg::HS;
-          kf_stamp(p, g, 8);
+          if (lane == 0) kf_stamp(p, g, 8);
           if (Cfg::ONEBAR) {
             if (g >= R) mbar_wait(accfull + st, (u - 1) & 1);  // plane g - R (the stage's previous tenant) has been multiplied
           } else {
             mbar_wait(empty + st, (u & 1) ^ 1);
           }
-          kf_stamp(p, g, 0);
+          if (lane == 0) kf_stamp(p, g, 0);
           uint8_t* dst = smem + st * Cfg::STAGE_BYTES;
+          if (elect_one()) {
           mbar_expect_tx(full + st, Cfg::TX_BYTES);
           if (KIND == KF_C0) {  // cost cells: cell x = [voxel x-1 | voxel x], one plane per batch entry
             tma_load_4d(dst, &tmap, full + st, 8 * x0, y0 - 1, s, b);
@@ -195,6 +196,8 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
             tma_load_4d(dst, &tmap, full + st, 8 * (Cfg::WIDE ? x0 : x0 - 1), y0 - 1, s, b * planes_per_b);
           }
           kf_stamp(p, g, 7);
+          }
+          __syncwarp();
         }
         g_frag += sb - sa + 1;
       }

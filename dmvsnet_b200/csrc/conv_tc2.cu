@@ -97,11 +97,9 @@ __device__ __forceinline__ Tile2 decode2(const Tc2Params& p, int lt, int td) {
 // compile time: every descriptor is "base descriptor + constant" (the 14-bit address field never carries: smem < 256 KB),
 // i.e. one 64-bit add per operand and the tcgen05.mma itself.
 template <int MODE, int CIN, int CIN_P, int NB, int TD, int STAGES, int KD>
-__device__ __forceinline__ void issue2(uint32_t a0, uint32_t b0, uint32_t acc_base, bool fresh, int sub) {
+__device__ __forceinline__ void issue2(uint64_t adesc0, uint64_t bdesc0, uint32_t acc_base, bool fresh, int sub) {
   using Cfg = C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>;
   constexpr uint32_t idesc = make_idesc(Cfg::NMMA);
-  const uint64_t adesc0 = make_desc(a0, Cfg::A_LBO, Cfg::A_SBO);
-  const uint64_t bdesc0 = make_desc(b0, Cfg::NMMA * 16, 128);
   const uint32_t fresh_acc = fresh ? 0u : 1u;
 #pragma unroll
   for (int t = 0; t < ((MODE == M2_PB) ? TD + 2 : TD); ++t) {
@@ -443,9 +441,10 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
         fence_proxy_async();
         mbar_arrive(full + s);
       }
-    } else if (lane == 0) {
-      // one thread: TMA box loads into the UMMA layout; OOB zero fill is the convolution's padding
-      prefetch_tmap(&tmap);
+    } else {
+      // the whole warp walks the tile loop, one elected lane issues the TMA box loads into the UMMA layout (coordinates and
+      // addresses stay in uniform registers); OOB zero fill is the convolution's padding
+      if (lane == 0) prefetch_tmap(&tmap);
       const int planes_per_b = 2 * CIN / 8;
       int tile_k = 0;
       for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
@@ -455,6 +454,7 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
           const int s = Cfg::MMA_WARPS * (j % Cfg::HS) + m, u = j / Cfg::HS;
           mbar_wait(empty + s, (u & 1) ^ 1);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          if (elect_one()) {
           mbar_expect_tx(full + s, Cfg::TX_BYTES);
 #pragma unroll 1
           for (int pl = 0; pl < Cfg::NPLANE; ++pl) {
@@ -474,6 +474,8 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
           }
           if (!Cfg::RESIDENT)
             bulk_load(st + Cfg::A_BYTES, p.wtc + (size_t)pass * (Cfg::B_BYTES / 16), Cfg::B_BYTES, full + s);
+          }
+          __syncwarp();
         }
       }
     }
@@ -482,7 +484,10 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
     const int me = (warp - MMA_WARP) % Cfg::MMA_WARPS, sub = (warp - MMA_WARP) / Cfg::MMA_WARPS;
     int tile_k = 0;
     for (int lt = blockIdx.x; lt < p.n_tiles; lt += gridDim.x, ++tile_k) {
-      if (lane == 0 && (tile_k % Cfg::MMA_WARPS) == me) {
+      // The WHOLE warp walks the tile loop and one elected lane issues: descriptors computed in warp-uniform code stay in uniform
+      // registers (one UTCHMMA per MMA in SASS); under `if (lane == 0)` every tcgen05.mma was wrapped in an ~11-instruction R2UR / ELECT
+      // waterfall on the serial path of the issuing thread
+      if ((tile_k % Cfg::MMA_WARPS) == me) {
         const int a = (Cfg::ACC_SETS == 2) ? (tile_k & 1) : 0, v = (Cfg::ACC_SETS == 2) ? (tile_k >> 1) : tile_k;
         mbar_wait(accempty + a, (v & 1) ^ 1);
         for (int pass = 0; pass < Cfg::NPASS; ++pass) {
@@ -491,11 +496,15 @@ __global__ void __launch_bounds__(C2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>::THRE
           mbar_wait(full + s, u & 1);
           tc_fence_after();
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          issue2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>(smem_u32(st), Cfg::RESIDENT ? smem_u32(sB) : smem_u32(st + Cfg::A_BYTES),
-                                                   tmem_base + a * Cfg::COLS, pass == 0, sub);
-          umma_commit(empty + s);
+          const uint64_t adesc0 = make_desc(smem_u32(st), Cfg::A_LBO, Cfg::A_SBO);
+          const uint64_t bdesc0 = make_desc(Cfg::RESIDENT ? smem_u32(sB) : smem_u32(st + Cfg::A_BYTES), Cfg::NMMA * 16, 128);
+          if (elect_one()) {
+            issue2<MODE, CIN, CIN_P, NB, TD, STAGES, KD>(adesc0, bdesc0, tmem_base + a * Cfg::COLS, pass == 0, sub);
+            umma_commit(empty + s);
+          }
+          __syncwarp();
         }
-        umma_commit(accfull + a);
+        if (elect_one()) umma_commit(accfull + a);
       }
       __syncwarp();
     }
