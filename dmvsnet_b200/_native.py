@@ -106,6 +106,11 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
     if lib.dmvs_abi_version() != ABI_VERSION:
         raise NativeLibraryError("ABI version mismatch: library %d, binding %d" % (lib.dmvs_abi_version(), ABI_VERSION))
+    # experiments on the GPU box: DMVS_DEBUG_SET="key=value,key=value" applies dmvs_debug_set knobs at load time
+    for kv in filter(None, os.environ.get("DMVS_DEBUG_SET", "").split(",")):
+        key, _, val = kv.partition("=")
+        if lib.dmvs_debug_set(key.strip().encode(), int(val)) != 0:
+            raise NativeLibraryError("DMVS_DEBUG_SET: %r rejected (%s)" % (kv, lib.dmvs_last_error().decode()))
     _lib = lib
     return lib
 

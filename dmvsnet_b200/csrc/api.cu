@@ -23,6 +23,7 @@ extern int g_tc2_pdl;
 extern int g_regnet_streams;
 extern int g_kf;
 extern int g_kf_dbg;
+extern int g_kf_pdl;
 extern long long* g_kf_trace;
 extern int g_kf_wide;
 extern int g_kf_prod;
@@ -63,6 +64,10 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
   }
   if (key && !strcmp(key, "kf_prod") && (value == 1 || value == 2)) {
     dmvs::g_kf_prod = value;
+    return DMVS_OK;
+  }
+  if (key && !strcmp(key, "kf_pdl") && (value == 0 || value == 1)) {
+    dmvs::g_kf_pdl = value;
     return DMVS_OK;
   }
   if (key && !strcmp(key, "kf_wide") && (value == 0 || value == 1)) {

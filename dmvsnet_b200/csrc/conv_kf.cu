@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, N
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_launch();
+  // p.dbg bit 4: this launch takes part in programmatic dependent launch (see launch_kf)
+  if (p.dbg & 16) pdl_launch();
   pdl_wait();
 
   KfRange range(p);
@@ -429,6 +430,7 @@ int g_kf = 1;
 // 262 us at 32 x 592 x 800): with 3 MMAs per plane the kernel is bound by its per-plane hand-offs, not by MMAs or TMA - off by default
 int g_kf_wide = 0;
 long long* g_kf_trace = nullptr;
+int g_kf_pdl = 0;
 int g_kf_dbg = 0;  // dmvs_debug_set("kf_dbg", bits): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
 int g_kf_prod = 1;  // (unused; kept so that dmvs_debug_set("kf_prod") stays valid)
 int g_kf_mw = 0;    // dmvs_debug_set("kf_mw", 0 | 2 | 4): MMA-issuing threads of the folded kernels, 0 = the default of each kind (conv2: 2, prob: 4 + two TMA threads)
@@ -436,7 +438,11 @@ int g_kf_mw = 0;    // dmvs_debug_set("kf_mw", 0 | 2 | 4): MMA-issuing threads o
 template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2, int NPR = 1>
 static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   using Cfg = KF<KIND, CIN, COUT_P, R, STAGES, NP, CS, MW, NPR>;
-  p.dbg = g_kf_dbg;
+  // Programmatic dependent launch is OFF for the folded kernels by default (dmvs_debug_set("kf_pdl", 1) turns it on): with it, and
+  // only with the cascade and FeatureNet running on concurrent streams (MVSNet.infer_many), one run in ~60 T&T view sets ended in an
+  // `unspecified launch failure` (0 of 20 runs without it, tools/experiments/repro_tnt.py); the gain was ~0.03 ms per view
+  const bool pdl = g_tc2_pdl && g_kf_pdl;
+  p.dbg = g_kf_dbg | (pdl ? 16 : 0);
   p.trace = g_kf_trace;
   p.tiles_x = ceil_div(p.Wo, Cfg::XSTEP);
   p.tiles_y = ceil_div(p.Ho, Cfg::TH);
@@ -473,7 +479,7 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
   const long long total = (long long)p.n_tiles * p.Do;
   long long grid = total / 4 < 1 ? 1 : total / 4;
   if (grid > want) grid = want;
-  if (g_tc2_pdl) {
+  if (pdl) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
