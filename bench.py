@@ -478,7 +478,7 @@ def run_gpu_arm(args, cfg_name):
     _, _, groups_full = w1_roofline(prof_full_all, 3.0, views, peak)
     sm_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9  # GB/s through the SMs' shared-memory data pipe
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r2m_w1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2n_w1_traffic.json")
     if os.path.exists(tp) and cfg_name == "dtu":
         traffic = json.load(open(tp)).get("dram_bytes_per_step")
 
