@@ -507,10 +507,13 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
   if (!g_kf) return 1;
   if (p.Cin == 16 && p.Cout == 16 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P)) {  // conv2
     if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 4, 2>(p, x, st);
+    if (g_kf_mw == 1) return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 1, 1>(p, x, st);
     return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 2>(p, x, st);
   }
-  if (p.Cin == 32 && p.Cout == 32 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P))  // conv4
+  if (p.Cin == 32 && p.Cout == 32 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P)) {  // conv4
+    if (g_kf_mw == 1) return launch_kf<KF_SW, 32, 32, 4, 2, 2, 2, 1, 1>(p, x, st);
     return launch_kf<KF_SW, 32, 32, 4, 2, 2, 2, 2>(p, x, st);
+  }
   if (p.Cin == 2 && in_cells) {
     if (g_kf < 2) return 1;
     if (p.Cout == 16) {  // conv0 of both branches
@@ -528,6 +531,7 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
   }
   if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob: four issuing and two TMA threads (214 vs 268 us at DTU stage 2)
     if (g_kf_mw == 2) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 2, 1>(p, x, st);
+    if (g_kf_mw == 1) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 1, 1>(p, x, st);
     return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4, 2>(p, x, st);
   }
   return 1;

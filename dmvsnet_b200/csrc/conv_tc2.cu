@@ -63,7 +63,7 @@ struct C2 {
   // single-thread) descriptor arithmetic of consecutive tiles overlaps
   // Each issuing warp owns a private slice of the stage ring (stage = MMA_WARPS*(j % HS) + warp, j = its own item count):
   // a full/empty mbarrier is then always consumed by one warp in order - parity waits cannot alias a phase two uses away.
-  static constexpr int MMA_WARPS = (ACC_SETS == 2 && STAGES % 2 == 0) ? 2 : 1;
+  static constexpr int MMA_WARPS = (TC2_MMA_WARPS == 2 && ACC_SETS == 2 && STAGES % 2 == 0) ? 2 : 1;
   static constexpr int HS = STAGES / MMA_WARPS;
   // SUB issuing threads share one tile: thread `sub` issues the accumulator rows (planes) t with t % SUB == sub.  The MMAs of
   // different planes write different accumulators, so no order is needed between the threads; both commit to the stage's

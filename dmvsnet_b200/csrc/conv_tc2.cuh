@@ -16,8 +16,15 @@ __host__ __device__ constexpr bool is_c0(int mode) { return mode == M2_C0 || mod
 // that shift).  Every MMA re-reads its 4 KB A tile from shared memory at 64 B/clk whatever its N, so 8 MMAs instead of 27.
 __host__ __device__ constexpr bool is_tr(int mode) { return mode == M2_TR || mode == M2_TRF; }
 constexpr int T_H = 16, T_W = 8;
+// issuing threads per tile for the prob / conv0 kernels.  2 paid while every tcgen05.mma cost the issuing thread ~11 instructions; with the
+// elected-lane issue (one UTCHMMA per MMA) one thread per accumulator set is faster (R1 6.76 -> 6.66 ms per DTU view)
 #ifndef SUBISSUE
-#define SUBISSUE 2
+#define SUBISSUE 1
+#endif
+// issuing warps per kernel (tiles alternate between them).  Same story: with the elected-lane issue ONE warp keeps up and the second only
+// takes issue slots from the epilogue (R1 6.66 -> 6.52 ms per DTU view)
+#ifndef TC2_MMA_WARPS
+#define TC2_MMA_WARPS 1
 #endif
 
 struct Tc2Params {
