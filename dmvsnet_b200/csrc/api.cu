@@ -26,7 +26,6 @@ extern int g_kf_dbg;
 extern int g_kf_pdl;
 extern long long* g_kf_trace;
 extern int g_kf_wide;
-extern int g_kf_prod;
 extern int g_tc2_skip_prefetch;
 extern int g_kf_mw;
 
@@ -60,10 +59,6 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
   }
   if (key && !strcmp(key, "kf_dbg") && value >= 0 && value <= 15) {
     dmvs::g_kf_dbg = value;
-    return DMVS_OK;
-  }
-  if (key && !strcmp(key, "kf_prod") && (value == 1 || value == 2)) {
-    dmvs::g_kf_prod = value;
     return DMVS_OK;
   }
   if (key && !strcmp(key, "kf_pdl") && (value == 0 || value == 1)) {

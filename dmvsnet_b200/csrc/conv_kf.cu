@@ -432,7 +432,6 @@ int g_kf_wide = 0;
 long long* g_kf_trace = nullptr;
 int g_kf_pdl = 0;
 int g_kf_dbg = 0;  // dmvs_debug_set("kf_dbg", bits): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
-int g_kf_prod = 1;  // (unused; kept so that dmvs_debug_set("kf_prod") stays valid)
 int g_kf_mw = 0;    // dmvs_debug_set("kf_mw", 0 | 2 | 4): MMA-issuing threads of the folded kernels, 0 = the default of each kind (conv2: 2, prob: 4 + two TMA threads)
 
 template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2, int NPR = 1>

@@ -37,8 +37,8 @@ for kf, mw, npr, wide in ((0, 0, 0, 0), (1, 2, 1, 0), (1, 4, 2, 0), (1, 2, 1, 1)
     for dbg in (0, 1, 2, 3):
         if kf == 0 and dbg:
             continue
-        lib.dmvs_debug_set(b"kf", kf); lib.dmvs_debug_set(b"kf_mw", mw); lib.dmvs_debug_set(b"kf_dbg", dbg); lib.dmvs_debug_set(b"kf_prod", npr); lib.dmvs_debug_set(b"kf_wide", wide)
+        lib.dmvs_debug_set(b"kf", kf); lib.dmvs_debug_set(b"kf_mw", mw); lib.dmvs_debug_set(b"kf_dbg", dbg); lib.dmvs_debug_set(b"kf_wide", wide)
         tp = timeit(lambda: ops.conv3d_ch16(x8, prob, relu=False, out_fmt="f32"))
         t2 = timeit(lambda: ops.conv3d_ch16(x16, conv2, relu=True, out_fmt="ch16p")) if kf else float("nan")
         print("wide=%d kf=%d issuers=%d producers=%d dbg=%d (1: no epilogue work, 2: no MMAs)  prob %.1f us   conv2 %.1f us" % (wide, kf, mw, npr, dbg, tp, t2), flush=True)
-lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_mw", 0); lib.dmvs_debug_set(b"kf_dbg", 0); lib.dmvs_debug_set(b"kf_prod", 1); lib.dmvs_debug_set(b"kf_wide", 0)
+lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_mw", 0); lib.dmvs_debug_set(b"kf_dbg", 0); lib.dmvs_debug_set(b"kf_wide", 0)

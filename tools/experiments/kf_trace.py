@@ -19,7 +19,6 @@ NAMES = ["prod past empty", "issuer past accempty", "issuer past full", "issuer 
 for label, kf, wide, mw, npr, dbg in (("PW 2 issuers 1 producer, full", 1, 1, 2, 1, 8), ("PW 4 issuers 2 producers, full", 1, 1, 4, 2, 8),
                                       ("PW 4 issuers 2 producers, no MMAs", 1, 1, 4, 2, 10), ("PW 4 issuers 2 producers, skeleton", 1, 1, 4, 2, 11)):
     lib.dmvs_debug_set(b"kf", kf); lib.dmvs_debug_set(b"kf_wide", wide); lib.dmvs_debug_set(b"kf_mw", mw); lib.dmvs_debug_set(b"kf_dbg", dbg)
-    lib.dmvs_debug_set(b"kf_prod", npr)
     for _ in range(3):
         trace.zero_()
         ops.conv3d_ch16(x8, prob, relu=False, out_fmt="f32")
@@ -45,5 +44,5 @@ for label, kf, wide, mw, npr, dbg in (("PW 2 issuers 1 producer, full", 1, 1, 2,
     print("              TMEM loads           %s" % m(t[lo:hi, 5] - t[lo:hi, 4]))
     print("              warp sync            %s" % m(t[lo:hi, 6] - t[lo:hi, 5]))
     print("   slot     : last reader synced (output g+1) -> issuer past `accempty` for plane g+R %s" % m(t[lo + R:hi + R, 1] - t[lo + 1:hi + 1, 6]))
-lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_wide", 0); lib.dmvs_debug_set(b"kf_mw", 0); lib.dmvs_debug_set(b"kf_dbg", 0); lib.dmvs_debug_set(b"kf_prod", 1)
+lib.dmvs_debug_set(b"kf", 1); lib.dmvs_debug_set(b"kf_wide", 0); lib.dmvs_debug_set(b"kf_mw", 0); lib.dmvs_debug_set(b"kf_dbg", 0)
 lib.dmvs_debug_set_ptr(b"kf_trace", None)
