@@ -315,3 +315,62 @@ def test_module_copies_and_pickles_like_the_reference():
     assert sorted(pickle.loads(blob).state_dict()) == sorted(net.state_dict())
     buf = io.BytesIO()
     torch.save(net, buf)
+
+
+def _emulate_folded(x, img, cout, cout_p, lo_in_k=False):
+    """Numerical model of csrc/conv_kf.cu on the CPU: x [Cin, D, H, W] fp32; `img` a folded weight image.  Every input plane s gets
+    the accumulator P[s][n] (n = kd * nb + column); the output plane t is P[t-1][kd=0] + P[t][kd=1] + P[t+1][kd=2]."""
+    import torch.nn.functional as F
+    cin, d, h, w = x.shape
+    hi = x.to(torch.float16).float()
+    lo = (x - hi).to(torch.float16).float()
+    xp_hi, xp_lo = F.pad(hi, (1, 1, 1, 1)), F.pad(lo, (1, 1, 1, 1))
+    cj = cin // 8
+    if lo_in_k:   # kind SW: [hi image (cj chunks) | lo image (cj / 2 chunk pairs)], columns [kd][cout]
+        nb = cout
+        n_hi = cj * 9 * 2 * 3 * nb * 8
+        img_hi = img[:n_hi].float().view(cj, 9, 2, 3 * nb, 8)
+        img_lo = img[n_hi:].float().view(cj // 2, 9, 2, 3 * nb, 8)
+    else:
+        nb = 2 * cout_p
+        img_hi = img.float().view(cj, 9, 2, 3 * nb, 8)
+    acc = torch.zeros(d, 3 * nb, h, w)
+    for tap in range(9):
+        kh, kw = divmod(tap, 3)
+        a_hi = xp_hi[:, :, kh:kh + h, kw:kw + w]
+        a_lo = xp_lo[:, :, kh:kh + h, kw:kw + w]
+        for j in range(cj):
+            acc += torch.einsum("nk,kdhw->dnhw", img_hi[j, tap, 0], a_hi[8 * j:8 * j + 8])
+            acc += torch.einsum("nk,kdhw->dnhw", img_hi[j, tap, 1], a_lo[8 * j:8 * j + 8])
+        if lo_in_k:
+            for i in range(cj // 2):
+                acc += torch.einsum("nk,kdhw->dnhw", img_lo[i, tap, 0], a_hi[16 * i:16 * i + 8])
+                acc += torch.einsum("nk,kdhw->dnhw", img_lo[i, tap, 1], a_hi[16 * i + 8:16 * i + 16])
+    out = torch.zeros(cout, d, h, w)
+    for t in range(d):
+        for kd in range(3):
+            s = t + kd - 1
+            if 0 <= s < d:
+                blk = acc[s, kd * nb:(kd + 1) * nb]
+                out[:, t] += blk[:cout] if lo_in_k else blk[:cout] + blk[cout_p:cout_p + cout]
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,split", [(16, 16, False), (32, 32, True)])
+def test_folded_weight_images_reproduce_the_convolution(cin, cout, split):
+    """The depth-tap-folded weight images of ops.PackedLayer (conv2: [hi|lo] column blocks per kd; conv4: lo(W) in the K dimension)
+    under a CPU model of the kernel's accumulate-per-input-plane scheme == F.conv3d, to the 2^-22 of the dropped lo*lo product."""
+    import torch.nn.functional as F
+    from dmvsnet_b200 import ops
+    g = torch.Generator().manual_seed(cin)
+    wgt = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.1
+    x = torch.randn(cin, 4, 6, 7, generator=g)
+    w = wgt.permute(2, 3, 4, 1, 0).reshape(27, cin, cout).contiguous()
+    if split:
+        img = ops._pack_tensor_core_kf_split(w)
+    else:
+        img = ops._pack_tensor_core_kf(ops._pack_tensor_core(w))
+    got = _emulate_folded(x, img.reshape(-1) if split else img, cout, max(8, (cout + 7) // 8 * 8), lo_in_k=split)
+    want = F.conv3d(x[None], wgt, None, padding=1)[0]
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 2e-6, err
