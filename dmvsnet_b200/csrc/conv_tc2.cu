@@ -260,16 +260,12 @@ __device__ __forceinline__ void epilogue2(const Tc2Params& p, const Tile2& tc, u
   } else {
     const int oy = tc.y0 + hl, ox = tc.x0 + wl;
     const bool in_img = (oy < p.Ho) && (ox < p.Wo);
-    // work units = (plane, 8-channel chunk): with TD = 1 (the coarse layers) the NPART groups of epilogue warps share the chunks of the
-    // one plane instead of leaving all but the first group idle
-    constexpr int NCH = COUT_P / 8;
-#pragma unroll 1
-    for (int u = part; u < TD * NCH; u += NPART) {
-      const int t = u / NCH, c0 = (u % NCH) * 8;
+    for (int t = part; t < TD; t += NPART) {
       const int oz = tc.z0 + t;
-      if (oz >= p.Do) break;  // warp-uniform; units are plane-major
+      if (oz >= p.Do) break;  // warp-uniform
       const uint32_t taddr = lane_addr + t * NB;
-      {
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT_P; c0 += 8) {
         uint32_t rv[8], rl[8];
         tmem_ld8_issue(taddr + c0, rv);
         tmem_ld8_issue(taddr + COUT_P + c0, rl);
