@@ -69,7 +69,7 @@ extern "C" int dmvs_debug_set(const char* key, int value) {
     dmvs::g_kf_wide = value;
     return DMVS_OK;
   }
-  if (key && !strcmp(key, "kf_mw") && (value == 0 || value == 1 || value == 2 || value == 4)) {
+  if (key && !strcmp(key, "kf_mw") && (value == 0 || value == 1 || value == 2)) {
     dmvs::g_kf_mw = value;
     return DMVS_OK;
   }

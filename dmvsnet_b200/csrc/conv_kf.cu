@@ -73,6 +73,7 @@ struct KF {
   static constexpr int NPROD = NPROD_;  // TMA-issuing threads (one per warp): plane g is fetched by thread g % NPROD
   static constexpr int THREADS = (NPROD + MMA_WARPS + EPI_WARPS) * 32;
   static_assert(R % MMA_WARPS == 0 && R >= 4, "a slot must always belong to the same issuing thread; 3 live slots + 1");
+  static_assert(MMA_WARPS <= 2, "more than two issuing threads make the readers' parity waits unsound (kf_protocol_sim.py)");
   static_assert(R * NF <= 512, "accumulator ring exceeds TMEM");
   static_assert((MMA_WARPS & (MMA_WARPS - 1)) == 0 && (NPROD & (NPROD - 1)) == 0, "role strides are powers of two");
   static_assert(STAGES % MMA_WARPS == 0, "stage ring is split between the issuing threads");
@@ -432,7 +433,7 @@ int g_kf_wide = 0;
 long long* g_kf_trace = nullptr;
 int g_kf_pdl = 0;
 int g_kf_dbg = 0;  // dmvs_debug_set("kf_dbg", bits): 1 = epilogue releases without loading / storing, 2 = issuers commit without MMAs
-int g_kf_mw = 0;    // dmvs_debug_set("kf_mw", 0 | 2 | 4): MMA-issuing threads of the folded kernels, 0 = the default of each kind (conv2: 2, prob: 4 + two TMA threads)
+int g_kf_mw = 0;    // dmvs_debug_set("kf_mw", 0 | 1 | 2): MMA-issuing threads of the folded kernels, 0 = the default (2)
 
 template <int KIND, int CIN, int COUT_P, int R, int STAGES, int NP, int CS, int MW = 2, int NPR = 1>
 static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
@@ -503,9 +504,12 @@ static int launch_kf(Tc2Params p, const void* x, cudaStream_t st) {
 // Stride-1 3x3x3 layers with a folded weight image (dmvs_conv_layer.w_tc_kd).  `p` arrives filled by conv_layer_tc2 (dims, pointers,
 // out_fmt, y_bs) with p.wtc already pointing at the folded image.  Returns +1 if the shape has no folded specialisation.
 int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t st) {
+  // Issuing threads: at most TWO.  A reader polls only the accumulators it reads, and its parity wait is sound only if the previous
+  // tenant of the slot is known to be complete; with two issuers (planes alternate, each issuer completes its planes in order) every
+  // output has just seen a plane of either issuer, with four it has not (tools/experiments/kf_protocol_sim.py with a starved issuer:
+  // over-arrivals for (R, groups, issuers) = (8, 4, 4) and (4, 2, 4), none in 4000 adversarial schedules for the kinds below).
   if (!g_kf) return 1;
   if (p.Cin == 16 && p.Cout == 16 && (p.out_fmt == FMT_CH16 || p.out_fmt == FMT_CH16P)) {  // conv2
-    if (g_kf_mw == 4) return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 4, 2>(p, x, st);
     if (g_kf_mw == 1) return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 1, 1>(p, x, st);
     return launch_kf<KF_S1, 16, 16, 4, 4, 2, 2, 2>(p, x, st);
   }
@@ -515,23 +519,18 @@ int conv_layer_kf(const Tc2Params& p, const void* x, int in_cells, cudaStream_t 
   }
   if (p.Cin == 2 && in_cells) {
     if (g_kf < 2) return 1;
-    if (p.Cout == 16) {  // conv0 of both branches
-      if (g_kf_mw == 4) return launch_kf<KF_C0, 2, 16, 4, 4, 2, 2, 4, 2>(p, x, st);
-      return launch_kf<KF_C0, 2, 16, 4, 4, 2, 2, 2>(p, x, st);
-    }
-    if (p.Cout == 8) return launch_kf<KF_C0, 2, 8, 8, 8, 4, 1>(p, x, st);    // conv0
+    if (p.Cout == 16) return launch_kf<KF_C0, 2, 16, 4, 4, 2, 2, 2>(p, x, st);  // conv0 of both branches
+    if (p.Cout == 8) return launch_kf<KF_C0, 2, 8, 8, 8, 4, 1>(p, x, st);       // conv0
     return 1;
   }
   if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32 && p.wtc_wide && g_kf_wide) {  // prob, kd and kw folded, wide tiles
     Tc2Params pw = p;
     pw.wtc = p.wtc_wide;
-    if (g_kf_mw == 2) return launch_kf<KF_PW, 8, 2, 10, 10, 4, 1, 2, 1>(pw, x, st);
-    return launch_kf<KF_PW, 8, 2, 8, 8, 4, 1, 4, 2>(pw, x, st);
+    return launch_kf<KF_PW, 8, 2, 10, 10, 4, 1, 2, 1>(pw, x, st);
   }
-  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob: four issuing and two TMA threads (214 vs 268 us at DTU stage 2)
-    if (g_kf_mw == 2) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 2, 1>(p, x, st);
+  if (p.Cin == 8 && p.Cout == 2 && p.out_fmt == FMT_F32) {  // prob
     if (g_kf_mw == 1) return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 1, 1>(p, x, st);
-    return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 4, 2>(p, x, st);
+    return launch_kf<KF_PB, 8, 2, 8, 8, 4, 1, 2, 1>(p, x, st);
   }
   return 1;
 }

@@ -30,7 +30,10 @@ def fragments(o, o_end, D):
         yield col, t0, t1, sa, sb
 
 
-def run(D, o, o_end, R, STAGES, NPART, seed, MW=2):
+def run(D, o, o_end, R, STAGES, NPART, seed, MW=2, NPR=1):
+    """STAGES == R models the one-commit scheme of the kernel (stage = slot = g % R, the producer waits on accfull of plane g - R);
+    otherwise the stage ring has its own `empty` barriers and is split between the issuers."""
+    onebar = STAGES == R
     rnd = random.Random(seed)
     HS = STAGES // MW
     full = [Bar(1) for _ in range(STAGES)]
@@ -41,16 +44,25 @@ def run(D, o, o_end, R, STAGES, NPART, seed, MW=2):
     stage_holds = [None] * STAGES
     errors = []
 
-    def producer():
+    def producer(me=0):
         g = 0
         for col, t0, t1, sa, sb in fragments(o, o_end, D):
             for s in range(sa, sb + 1):
-                m, j = g % MW, g // MW
-                st, u = MW * (j % HS) + m, j // HS
-                while not empty[st].test((u & 1) ^ 1):
-                    yield
-                stage_holds[st] = g
-                full[st].arrive()
+                if g % NPR == me:
+                    m, j = g % MW, g // MW
+                    if onebar:
+                        st, u = g % R, g // R
+                        if g >= R:
+                            while not accfull[st].test((u - 1) & 1):
+                                yield
+                            if slot_holds[st] != g - R:
+                                errors.append("producer: stage %d last multiplied %s, wanted %d" % (st, slot_holds[st], g - R))
+                    else:
+                        st, u = MW * (j % HS) + m, j // HS
+                        while not empty[st].test((u & 1) ^ 1):
+                            yield
+                    stage_holds[st] = g
+                    full[st].arrive()
                 g += 1
                 yield
 
@@ -63,14 +75,15 @@ def run(D, o, o_end, R, STAGES, NPART, seed, MW=2):
                     while not accempty[slot].test((k & 1) ^ 1):
                         yield
                     j = g // MW
-                    st, u = MW * (j % HS) + me, j // HS
+                    st, u = (slot, k) if onebar else (MW * (j % HS) + me, j // HS)
                     while not full[st].test(u & 1):
                         yield
                     if stage_holds[st] != g:
                         errors.append("issuer %d: stage %d holds %s, wanted %d" % (me, st, stage_holds[st], g))
                     yield
                     slot_holds[slot] = g
-                    empty[st].arrive()
+                    if not onebar:
+                        empty[st].arrive()
                     accfull[slot].arrive()
                 g += 1
                 yield
@@ -99,11 +112,13 @@ def run(D, o, o_end, R, STAGES, NPART, seed, MW=2):
                 yield
             g_base += sb - sa + 1
 
-    procs = [producer()] + [issuer(i) for i in range(MW)] + [part(i) for i in range(NPART)]
+    procs = [producer(i) for i in range(NPR)] + [issuer(i) for i in range(MW)] + [part(i) for i in range(NPART)]
     alive = list(range(len(procs)))
     idle = 0
+    # adversarial schedules: every role gets a random speed (a starved issuing thread is what exposes an early parity wait)
+    speed = [rnd.choice((1, 1, 1, 4, 20, 100)) for _ in procs]
     while alive:
-        i = rnd.choice(alive)
+        i = rnd.choices(alive, weights=[1.0 / speed[a] for a in alive])[0]
         state = (tuple(b.phase for b in full + empty + accfull + accempty), tuple(b.pending for b in accempty))
         try:
             next(procs[i])
@@ -121,19 +136,22 @@ def run(D, o, o_end, R, STAGES, NPART, seed, MW=2):
 if __name__ == "__main__":
     bad = 0
     perconf = {}
-    for R, NPART, MW in ((4, 1, 2), (4, 2, 2), (4, 2, 4), (4, 4, 2), (6, 2, 2), (8, 2, 2), (8, 4, 2), (8, 4, 4), (8, 2, 4), (10, 4, 2)):
+    # (R, NPART, MW, STAGES, NPR): the shipped kinds are conv2 (4, 2, 2, 4, 1), conv4 (4, 2, 2, 2, 1), prob (8, 4, 4, 8, 2), prob wide
+    # (8, 4, 4, 8, 2) / (10, 4, 2, 10, 1), conv0 (4, 2, 2, 4, 1); (4, 4, ...) is the configuration that fails
+    for R, NPART, MW, STAGES, NPR in ((4, 2, 2, 4, 1), (4, 2, 2, 2, 1), (8, 4, 4, 8, 2), (10, 4, 2, 10, 1), (4, 2, 4, 4, 2), (8, 4, 2, 8, 1),
+                                     (8, 2, 2, 8, 2), (4, 1, 2, 8, 1), (6, 2, 2, 8, 1), (4, 4, 2, 8, 1)):
         for D in (1, 2, 3, 4, 5, 8):
             for trial in range(200):
                 rnd = random.Random(trial)
                 o = rnd.randrange(0, 3 * D)
                 n = rnd.randrange(1, 40)
                 try:
-                    res, errs = run(D, o, o + n, R, 8, NPART, trial, MW)
+                    res, errs = run(D, o, o + n, R, STAGES, NPART, trial, MW, NPR)
                 except OverflowError:
                     res, errs = "OVER-ARRIVAL", []
                 if res != "ok" or errs:
                     bad += 1
-                    perconf[(R, NPART, MW)] = perconf.get((R, NPART, MW), 0) + 1
+                    perconf[(R, NPART, MW, STAGES, NPR)] = perconf.get((R, NPART, MW, STAGES, NPR), 0) + 1
                     if bad < 0:
                         print("R=%d NPART=%d D=%d range [%d,%d): %s %s" % (R, NPART, D, o, o + n, res, errs[:2]))
     print("bad cases:", bad, perconf)

@@ -16,8 +16,8 @@ x8 = ops.to_ch16(torch.randn(1, 8, d, h, w, device=dev))
 trace = torch.zeros(512, 16, dtype=torch.int64, device=dev)
 assert lib.dmvs_debug_set_ptr(b"kf_trace", trace.data_ptr()) == 0
 NAMES = ["prod past empty", "issuer past accempty", "issuer past full", "issuer committed", "epi past accfull", "epi loads landed", "epi warp synced"]
-for label, kf, wide, mw, npr, dbg in (("PW 2 issuers 1 producer, full", 1, 1, 2, 1, 8), ("PW 4 issuers 2 producers, full", 1, 1, 4, 2, 8),
-                                      ("PW 4 issuers 2 producers, no MMAs", 1, 1, 4, 2, 10), ("PW 4 issuers 2 producers, skeleton", 1, 1, 4, 2, 11)):
+for label, kf, wide, mw, npr, dbg in (("PB 2 issuers, full", 1, 0, 2, 1, 8), ("PB 2 issuers, skeleton", 1, 0, 2, 1, 11),
+                                      ("PW 2 issuers, full", 1, 1, 2, 1, 8), ("PW 2 issuers, skeleton", 1, 1, 2, 1, 11)):
     lib.dmvs_debug_set(b"kf", kf); lib.dmvs_debug_set(b"kf_wide", wide); lib.dmvs_debug_set(b"kf_mw", mw); lib.dmvs_debug_set(b"kf_dbg", dbg)
     for _ in range(3):
         trace.zero_()
@@ -26,7 +26,7 @@ for label, kf, wide, mw, npr, dbg in (("PW 2 issuers 1 producer, full", 1, 1, 2,
     t = trace.cpu().double()
     lo, hi = 64, 448   # steady state
     per_plane = (t[hi, 3] - t[lo, 3]) / (hi - lo)
-    R = 8 if (wide and mw == 4) or not wide else 10
+    R = 10 if wide else 8
     NP = 4
     def m(x):
         return "%6.0f (min %5.0f max %6.0f)" % (x.mean(), x.min(), x.max())
